@@ -1,0 +1,1239 @@
+// Host side of the engine behind the C ABI (include/deeparc_ba.h): problem upload and
+// re-ordering, the GPU-resident Levenberg-Marquardt driver, parameter read-back.
+//
+// The LM control flow restates ceres::Solve as the reference configures it
+// (reference src/sfm.cc:66-73; upstream ceres-solver 2.x trust_region_minimizer.cc and
+// levenberg_marquardt_strategy.cc, see oracle/mini_ceres.cc for the CPU restatement the
+// parity tests compare against).  All O(n_obs)/O(n_pts) work runs in the kernels of
+// ba_kernels.cu; the host only sequences launches and reads ~20 scalars per LM iteration.
+// There is no CPU fallback: any CUDA failure is reported through the status code.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/deeparc_ba.h"
+#include "ba_kernels.cuh"
+#include "nccl_dyn.h"
+
+using namespace dba;
+
+int hemisphere_fit_device(const double* centres_host, int n, double centre_io[3], double* rho_io,
+                          const dba_solve_options* o, dba_summary* s, cudaStream_t st, std::string* err,
+                          int64_t* launches);
+
+namespace {
+
+thread_local std::string g_create_error;
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// scalar buffer layout (see DESIGN.md "LM scalars")
+enum {
+  S_COST = 0, S_CAND = 1, S_GSQ_PT = 2, S_MODEL = 3, S_STEP_PT = 4, S_X_PT = 5, S_BAD_PT = 6,  // sum over ranks
+  S_GMAX_PT = 8,                                                                                 // max over ranks
+  S_GSQ_CAM = 12, S_GMAX_CAM = 13, S_BAD_CAM = 14, S_STEP_CAM = 15, S_X_CAM = 16,                // replicated
+  S_TOTAL = 24
+};
+
+struct KernelRecord {
+  std::string name;
+  int64_t launches = 0;
+  double total_ms = 0.0;
+  double algorithmic_bytes = 0.0;
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    free();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+  }
+  void free() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { free(); }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+}  // namespace
+
+struct dba_handle {
+  int device = 0, rank = 0, world = 1, verbose = 0;
+  cudaStream_t st = nullptr;
+  NcclComm comm = nullptr;
+  std::string error;
+  bool have_problem = false;
+
+  // problem (host copies needed later)
+  int64_t n_obs_global = 0, n_obs = 0;
+  int n_pts_global = 0, n_pts = 0, pt_lo = 0, n_ext = 0, n_intr = 0;
+  int cb = 0, two = 0, freeze = 0, free_intr = 0;
+  std::vector<int64_t> perm;  // local sorted position -> caller's observation index
+  bool any_const = false;
+
+  DeviceProblem D{};
+  ParamSet P[2]{};
+  int cur = 0;
+  WorkArrays W{};
+
+  // device storage
+  DevBuf<double2> d_obs_xy, d_J;
+  DevBuf<int2> d_obs_idx;
+  DevBuf<ObsView> d_views;
+  DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_nf, d_nd, d_pcg_state;
+  DevBuf<int4> d_cam_chunks;
+  DevBuf<uint8_t> d_ext_const;
+  DevBuf<double> d_center, d_pts[3], d_rot[3], d_trans[3], d_focal[3], d_dist[3];  // [2] = initial copy
+  DevBuf<PoseRow> d_pose_rows[2];
+  DevBuf<IntrRow> d_intr_rows[2];
+  DevBuf<double> d_sp, d_sc, d_cinv, d_tp, d_dp, d_cam_acc, d_minv, d_dc2, d_x, d_r, d_z, d_p, d_q;
+  DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts;
+  double* h_scalars = nullptr;  // pinned
+  int* h_pcg_state = nullptr;   // pinned
+  size_t j_planes = 0;
+
+  // accounting
+  int64_t launches = 0;
+  bool stats_enabled = false;
+  std::vector<KernelRecord> records;
+  std::map<std::string, int> record_index;
+  struct Pending {
+    int rec;
+    cudaEvent_t a, b;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
+
+  int fail(int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    error = buf;
+    return status;
+  }
+};
+
+#define CU(h, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess)                                                                           \
+      return (h)->fail(DBA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+// ---- kernel accounting ------------------------------------------------------------
+int record_id(dba_handle* h, const char* name, double bytes) {
+  auto it = h->record_index.find(name);
+  if (it != h->record_index.end()) {
+    if (bytes > 0) h->records[it->second].algorithmic_bytes = bytes;
+    return it->second;
+  }
+  KernelRecord r;
+  r.name = name;
+  r.algorithmic_bytes = bytes;
+  h->records.push_back(r);
+  h->record_index[name] = static_cast<int>(h->records.size()) - 1;
+  return static_cast<int>(h->records.size()) - 1;
+}
+
+cudaEvent_t get_event(dba_handle* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct Scope {
+  dba_handle* h;
+  int rec;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Scope(dba_handle* hh, const char* name, double bytes = 0.0, int n_launch = 1) : h(hh) {
+    rec = record_id(h, name, bytes);
+    h->records[rec].launches += n_launch;
+    h->launches += n_launch;
+    if (h->stats_enabled) {
+      a = get_event(h);
+      b = get_event(h);
+      cudaEventRecord(a, h->st);
+    }
+  }
+  ~Scope() {
+    if (a) {
+      cudaEventRecord(b, h->st);
+      h->pending.push_back({rec, a, b});
+    }
+  }
+};
+
+void drain_events(dba_handle* h) {
+  for (auto& p : h->pending) {
+    cudaEventSynchronize(p.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    h->records[p.rec].total_ms += ms;
+    h->event_pool.push_back(p.a);
+    h->event_pool.push_back(p.b);
+  }
+  h->pending.clear();
+}
+
+// ---- collectives --------------------------------------------------------------------
+int allreduce(dba_handle* h, double* buf, size_t n, int op) {
+  if (h->world == 1 || n == 0) return DBA_OK;
+  int rc = nccl_api().AllReduce(buf, buf, n, kNcclFloat64, op, h->comm, h->st);
+  if (rc != 0) return h->fail(DBA_ERR_NCCL, "ncclAllReduce: %s", nccl_api().GetErrorString(rc));
+  return DBA_OK;
+}
+
+// The local scalars stay untouched (several fetches may happen between two writes of a slot);
+// the cross-rank combination goes to a second buffer that is what the host reads.
+int reduce_scalars_and_fetch(dba_handle* h) {
+  CU(h, cudaMemcpyAsync(h->d_scalars_red.p, h->W.scalars, S_TOTAL * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+  if (h->world > 1) {
+    int rc = nccl_api().AllReduce(h->W.scalars + 0, h->d_scalars_red.p + 0, 8, kNcclFloat64, kNcclSum, h->comm, h->st);
+    if (rc == 0)
+      rc = nccl_api().AllReduce(h->W.scalars + 8, h->d_scalars_red.p + 8, 4, kNcclFloat64, kNcclMax, h->comm, h->st);
+    if (rc != 0) return h->fail(DBA_ERR_NCCL, "ncclAllReduce: %s", nccl_api().GetErrorString(rc));
+  }
+  CU(h, cudaMemcpyAsync(h->h_scalars, h->d_scalars_red.p, S_TOTAL * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaStreamSynchronize(h->st));
+  return DBA_OK;
+}
+
+double bytes_per_obs_planes(const dba_handle* h, int planes) { return 16.0 * planes * static_cast<double>(h->n_obs); }
+
+// ---- LM building blocks ---------------------------------------------------------------
+void fill_ones(dba_handle* h, double* p, size_t n) {
+  std::vector<double> ones(n, 1.0);
+  cudaMemcpyAsync(p, ones.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->st);
+  cudaStreamSynchronize(h->st);
+}
+
+// Jacobian (+cost) at the current parameters.  first == true also establishes the Jacobi scales.
+int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
+  const DeviceProblem& D = h->D;
+  const ParamSet& P = h->P[h->cur];
+  const int nplanes = 4 + h->cb + (h->two && h->cb ? 6 : 0);
+  // read xy(16)+idx(8), write r + Jp + Jc planes
+  const double k1_bytes = (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs);
+  {
+    Scope s(h, "pose_rows");
+    launch_pose_rows(P, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
+  }
+  if (first) {
+    if (jacobi_scaling) {
+      {
+        Scope s(h, "jacobian", k1_bytes);
+        launch_jacobian(D, P, h->W, h->cb, h->two, /*unit_scale=*/1, nullptr, h->st);
+      }
+      {
+        Scope s(h, "point_prepare", bytes_per_obs_planes(h, 4));
+        launch_point_prepare(D, h->W, 1.0, 0.0, 0.0, /*mode=*/0, h->d_partA.p, h->st);
+      }
+      if (h->cb) {
+        {
+          Scope s(h, "camera_gather", 0.0, 2);
+          launch_camera_gather(D, h->W, 0, h->st);
+        }
+        int rc = allreduce(h, h->W.cam_acc, static_cast<size_t>(D.n_blocks) * h->cb * (h->cb + 3), kNcclSum);
+        if (rc != DBA_OK) return rc;
+        Scope s(h, "camera_scales");
+        launch_camera_scales(D, h->W, h->st);
+      }
+    } else {
+      fill_ones(h, h->W.sp, 3 * static_cast<size_t>(h->n_pts));
+      if (h->cb) fill_ones(h, h->W.sc, static_cast<size_t>(D.n_blocks) * h->cb);
+    }
+  }
+  {
+    Scope s(h, "jacobian", k1_bytes);
+    launch_jacobian(D, P, h->W, h->cb, h->two, /*unit_scale=*/0, h->d_partA.p, h->st);
+  }
+  {
+    Scope s(h, "reduce");
+    launch_reduce_sum(h->d_partA.p, cost_grid(D), 1, 0, h->W.scalars + S_COST, h->st);
+  }
+  CU(h, cudaGetLastError());
+  return DBA_OK;
+}
+
+// Schur front half for the given radius; leaves gradient norms / failure flags in the scalars.
+int prepare_step(dba_handle* h, double radius, const dba_solve_options& o) {
+  const DeviceProblem& D = h->D;
+  {
+    Scope s(h, "point_prepare", bytes_per_obs_planes(h, 4));
+    launch_point_prepare(D, h->W, radius, o.min_lm_diagonal, o.max_lm_diagonal, 1, h->d_partA.p, h->st);
+  }
+  {
+    Scope s(h, "reduce", 0.0, 3);
+    launch_reduce_sum(h->d_partA.p, D.n_tiles, 3, 0, h->W.scalars + S_GSQ_PT, h->st);
+    launch_reduce_max(h->d_partA.p, D.n_tiles, 3, 1, h->W.scalars + S_GMAX_PT, h->st);
+    launch_reduce_sum(h->d_partA.p, D.n_tiles, 3, 2, h->W.scalars + S_BAD_PT, h->st);
+  }
+  if (h->cb) {
+    {
+      // gather: Jc + Jp + r planes at sector granularity, plus C^-1 and t per observation
+      Scope s(h, "camera_gather", 0.0, 2);
+      launch_camera_gather(D, h->W, 1, h->st);
+    }
+    int rc = allreduce(h, h->W.cam_acc, static_cast<size_t>(D.n_blocks) * h->cb * (h->cb + 3), kNcclSum);
+    if (rc != DBA_OK) return rc;
+    {
+      Scope s(h, "camera_finalize");
+      launch_camera_finalize(D, h->W, radius, o.min_lm_diagonal, o.max_lm_diagonal, h->d_partB.p, h->st);
+    }
+    const int g = camera_finalize_grid(D);
+    Scope s(h, "reduce", 0.0, 3);
+    launch_reduce_sum(h->d_partB.p, g, 3, 0, h->W.scalars + S_GSQ_CAM, h->st);
+    launch_reduce_max(h->d_partB.p, g, 3, 1, h->W.scalars + S_GMAX_CAM, h->st);
+    launch_reduce_sum(h->d_partB.p, g, 3, 2, h->W.scalars + S_BAD_CAM, h->st);
+  } else {
+    CU(h, cudaMemsetAsync(h->W.scalars + S_GSQ_CAM, 0, 3 * sizeof(double), h->st));
+  }
+  CU(h, cudaGetLastError());
+  return DBA_OK;
+}
+
+// Block-Jacobi PCG on the implicit Schur complement; returns iterations run.
+int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
+  const DeviceProblem& D = h->D;
+  const int nplanes = 3 + h->cb + (h->two ? 6 : 0);
+  const double spmv_bytes = (8.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs);
+  {
+    Scope s(h, "pcg_init");
+    launch_pcg_init(D, h->W, h->st);
+  }
+  const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance;
+  const int max_it = std::max(0, o.pcg_max_iterations);
+  const int nvec = D.n_blocks * h->cb;
+  int issued = 0;
+  const int check_every = (o.pcg_rel_tolerance > 0.0) ? 8 : max_it;
+  *iters_out = 0;
+  while (issued < max_it) {
+    const int batch = std::min(check_every > 0 ? check_every : max_it, max_it - issued);
+    for (int i = 0; i < batch; ++i) {
+      {
+        Scope s(h, "schur_spmv", spmv_bytes);
+        launch_schur_spmv(D, h->W, h->st);
+      }
+      int rc = allreduce(h, h->W.q, nvec, kNcclSum);
+      if (rc != DBA_OK) return rc;
+      Scope s(h, "pcg_update");
+      launch_pcg_update(D, h->W, tol2, o.pcg_min_iterations, h->st);
+    }
+    issued += batch;
+    CU(h, cudaMemcpyAsync(h->h_pcg_state, h->W.pcg_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+    *iters_out = h->h_pcg_state[0];
+    if (h->h_pcg_state[1]) break;
+  }
+  if (max_it == 0) {
+    CU(h, cudaMemcpyAsync(h->h_pcg_state, h->W.pcg_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+  }
+  CU(h, cudaGetLastError());
+  return DBA_OK;
+}
+
+// step -> candidate parameters, model cost change, norms, candidate cost
+int apply_step_and_evaluate(dba_handle* h) {
+  const DeviceProblem& D = h->D;
+  const ParamSet& cur = h->P[h->cur];
+  const ParamSet& cand = h->P[1 - h->cur];
+  const int nplanes = 4 + h->cb + (h->two && h->cb ? 6 : 0);
+  {
+    Scope s(h, "back_substitute", (8.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs));
+    launch_back_substitute(D, h->W, h->d_partA.p, h->st);
+  }
+  {
+    Scope s(h, "reduce");
+    launch_reduce_sum(h->d_partA.p, D.n_tiles, 1, 0, h->W.scalars + S_MODEL, h->st);
+  }
+  const int gp = update_points_grid(D), gc = update_cameras_grid(D);
+  {
+    Scope s(h, "param_update", 0.0, 2);
+    launch_update_points(D, cur, cand, h->W, h->d_partA.p, h->st);
+    launch_update_cameras(D, cur, cand, h->W, h->d_partB.p, h->st);
+  }
+  {
+    Scope s(h, "reduce", 0.0, 4);
+    launch_reduce_sum(h->d_partA.p, gp, 2, 0, h->W.scalars + S_STEP_PT, h->st);
+    launch_reduce_sum(h->d_partA.p, gp, 2, 1, h->W.scalars + S_X_PT, h->st);
+    launch_reduce_sum(h->d_partB.p, gc, 2, 0, h->W.scalars + S_STEP_CAM, h->st);
+    launch_reduce_sum(h->d_partB.p, gc, 2, 1, h->W.scalars + S_X_CAM, h->st);
+  }
+  {
+    Scope s(h, "pose_rows");
+    launch_pose_rows(cand, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
+  }
+  {
+    Scope s(h, "cost", 24.0 * static_cast<double>(h->n_obs));
+    launch_cost(D, cand, h->d_partA.p, nullptr, h->st);
+  }
+  {
+    Scope s(h, "reduce");
+    launch_reduce_sum(h->d_partA.p, cost_grid(D), 1, 0, h->W.scalars + S_CAND, h->st);
+  }
+  CU(h, cudaGetLastError());
+  return DBA_OK;
+}
+
+void print_progress_header() {
+  std::printf(
+      "iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  ls_iter  iter_time  total_time\n");
+}
+
+}  // namespace
+
+// ======================================================================== C ABI
+extern "C" {
+
+int dba_abi_version(void) { return DBA_ABI_VERSION; }
+
+int dba_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return DBA_ERR_NO_DEVICE;
+  }
+  return n;
+}
+
+int dba_nccl_unique_id(void* out128) {
+  if (!out128) return DBA_ERR_INVALID_ARGUMENT;
+  if (!nccl_api().load()) return DBA_ERR_NCCL;
+  NcclUniqueId id;
+  if (nccl_api().GetUniqueId(&id) != 0) return DBA_ERR_NCCL;
+  std::memcpy(out128, &id, sizeof id);
+  return DBA_OK;
+}
+
+const char* dba_last_error(const dba_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int dba_create(dba_handle** out, const dba_config* cfg) {
+  if (!out || !cfg) {
+    g_create_error = "dba_create: null argument";
+    return DBA_ERR_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    g_create_error = "no CUDA device available: this engine has no CPU path";
+    return DBA_ERR_NO_DEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev || cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) {
+    g_create_error = "dba_create: bad device / rank / world_size";
+    return DBA_ERR_INVALID_ARGUMENT;
+  }
+  dba_handle* h = new dba_handle;
+  h->device = cfg->device;
+  h->rank = cfg->rank;
+  h->world = cfg->world_size;
+  h->verbose = cfg->verbose;
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), S_TOTAL * sizeof(double));
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&h->h_pcg_state), 4 * sizeof(int));
+  if (e != cudaSuccess) {
+    g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+    delete h;
+    return DBA_ERR_CUDA;
+  }
+  if (h->world > 1) {
+    if (!cfg->nccl_unique_id || !nccl_api().load()) {
+      g_create_error = "world_size > 1 needs NCCL (libnccl.so.2) and a unique id";
+      delete h;
+      return DBA_ERR_NCCL;
+    }
+    NcclUniqueId id;
+    std::memcpy(&id, cfg->nccl_unique_id, sizeof id);
+    int rc = nccl_api().CommInitRank(&h->comm, h->world, id, h->rank);
+    if (rc != 0) {
+      g_create_error = std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(rc);
+      delete h;
+      return DBA_ERR_NCCL;
+    }
+  }
+  *out = h;
+  return DBA_OK;
+}
+
+void dba_destroy(dba_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->st) cudaStreamSynchronize(h->st);
+  drain_events(h);
+  for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+  if (h->comm) nccl_api().CommDestroy(h->comm);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_pcg_state) cudaFreeHost(h->h_pcg_state);
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+}
+
+int dba_kernel_stats_enable(dba_handle* h, int32_t enable) {
+  if (!h) return DBA_ERR_INVALID_ARGUMENT;
+  h->stats_enabled = enable != 0;
+  return DBA_OK;
+}
+int dba_kernel_stats_reset(dba_handle* h) {
+  if (!h) return DBA_ERR_INVALID_ARGUMENT;
+  drain_events(h);
+  for (auto& r : h->records) {
+    r.launches = 0;
+    r.total_ms = 0.0;
+  }
+  return DBA_OK;
+}
+int dba_kernel_stats(dba_handle* h, dba_kernel_stat* out, int32_t capacity) {
+  if (!h || (!out && capacity > 0)) return DBA_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(h->device);
+  drain_events(h);
+  int n = 0;
+  for (const auto& r : h->records) {
+    if (n >= capacity) break;
+    std::snprintf(out[n].name, sizeof out[n].name, "%s", r.name.c_str());
+    out[n].launches = r.launches;
+    out[n].total_ms = r.total_ms;
+    out[n].algorithmic_bytes = r.algorithmic_bytes;
+    ++n;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------- problem upload
+int dba_problem_set(dba_handle* h, const dba_problem* p) {
+  if (!h || !p) return DBA_ERR_INVALID_ARGUMENT;
+  CU(h, cudaSetDevice(h->device));
+  h->have_problem = false;
+  if (p->n_obs < 0 || p->n_pts < 0 || p->n_ext < 0 || p->n_intr < 0)
+    return h->fail(DBA_ERR_INVALID_ARGUMENT, "negative size");
+  if (p->n_obs > 0 && (!p->obs_xy || !p->obs_pt || !p->obs_pose_a || !p->obs_intr))
+    return h->fail(DBA_ERR_INVALID_ARGUMENT, "null observation array");
+  if ((p->n_pts > 0 && !p->pts) || (p->n_ext > 0 && (!p->ext_rot || !p->ext_trans)) ||
+      (p->n_intr > 0 && (!p->intr_center || !p->intr_focal || !p->intr_dist || !p->intr_nf || !p->intr_nd)))
+    return h->fail(DBA_ERR_INVALID_ARGUMENT, "null parameter array");
+  if (p->n_obs >= (int64_t{1} << 30)) return h->fail(DBA_ERR_UNSUPPORTED, "more than 2^30 observations per handle");
+  const int64_t n = p->n_obs;
+  bool two = false;
+  for (int64_t i = 0; i < n; ++i) {
+    if (p->obs_pt[i] < 0 || p->obs_pt[i] >= p->n_pts) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_pt[%lld] out of range", (long long)i);
+    if (p->obs_pose_a[i] < 0 || p->obs_pose_a[i] >= p->n_ext) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_pose_a[%lld] out of range", (long long)i);
+    if (p->obs_intr[i] < 0 || p->obs_intr[i] >= p->n_intr) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_intr[%lld] out of range", (long long)i);
+    if (p->obs_pose_b) {
+      if (p->obs_pose_b[i] < -1 || p->obs_pose_b[i] >= p->n_ext) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_pose_b[%lld] out of range", (long long)i);
+      two |= p->obs_pose_b[i] >= 0;
+    }
+  }
+  for (int i = 0; i < p->n_intr; ++i) {
+    if (p->intr_nf[i] < 1 || p->intr_nf[i] > 2 || p->intr_nd[i] < 0 || p->intr_nd[i] > 2)
+      return h->fail(DBA_ERR_INVALID_ARGUMENT, "intrinsic %d: nf must be 1|2 and nd 0|1|2", i);
+  }
+  h->freeze = p->freeze_camera != 0;
+  h->free_intr = (!h->freeze && p->free_intrinsics) ? 1 : 0;
+  if (h->free_intr) {
+    if (two) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics with composed poses is not implemented");
+    if (p->n_ext != p->n_intr) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs one intrinsic per extrinsic");
+    for (int i = 0; i < p->n_intr; ++i)
+      if (p->intr_nf[i] != 1 || p->intr_nd[i] != 2) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs nf=1, nd=2");
+    for (int64_t i = 0; i < n; ++i)
+      if (p->obs_intr[i] != p->obs_pose_a[i]) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs obs_intr == obs_pose_a");
+  }
+  h->cb = h->freeze ? 0 : (h->free_intr ? 9 : 6);
+  h->two = two ? 1 : 0;
+  h->n_obs_global = n;
+  h->n_pts_global = p->n_pts;
+  h->n_ext = p->n_ext;
+  h->n_intr = p->n_intr;
+
+  // ---- observations per point, point range of this rank (contiguous, balanced by observations)
+  std::vector<int64_t> pt_count(static_cast<size_t>(p->n_pts) + 1, 0);
+  for (int64_t i = 0; i < n; ++i) pt_count[p->obs_pt[i] + 1]++;
+  for (int i = 0; i < p->n_pts; ++i) pt_count[i + 1] += pt_count[i];  // prefix: first obs of each point (global sorted)
+  int pt_lo = 0, pt_hi = p->n_pts;
+  if (h->world > 1) {
+    auto cut = [&](int r) -> int {
+      if (r <= 0) return 0;
+      if (r >= h->world) return p->n_pts;
+      const int64_t target = n * r / h->world;
+      return static_cast<int>(std::lower_bound(pt_count.begin(), pt_count.end(), target) - pt_count.begin());
+    };
+    pt_lo = std::min(cut(h->rank), p->n_pts);
+    pt_hi = std::min(cut(h->rank + 1), p->n_pts);
+    if (pt_hi < pt_lo) pt_hi = pt_lo;
+  }
+  h->pt_lo = pt_lo;
+  h->n_pts = pt_hi - pt_lo;
+  const int64_t obs_lo = pt_count[pt_lo], obs_hi = pt_count[pt_hi];
+  const int64_t nl = obs_hi - obs_lo;
+  h->n_obs = nl;
+
+  // ---- stable counting sort by point, views
+  h->perm.assign(nl, 0);
+  {
+    std::vector<int64_t> cursor(pt_count.begin() + pt_lo, pt_count.begin() + pt_hi);
+    for (int64_t i = 0; i < n; ++i) {
+      const int pt = p->obs_pt[i];
+      if (pt < pt_lo || pt >= pt_hi) continue;
+      h->perm[cursor[pt - pt_lo]++ - obs_lo] = i;
+    }
+  }
+  std::vector<ObsView> views;
+  std::vector<int2> obs_idx(nl);
+  std::vector<double2> obs_xy(nl);
+  {
+    std::map<std::tuple<int, int, int>, int> view_of;
+    for (int64_t k = 0; k < nl; ++k) {
+      const int64_t i = h->perm[k];
+      const int pb = p->obs_pose_b ? p->obs_pose_b[i] : -1;
+      const auto key = std::make_tuple(p->obs_pose_a[i], pb, p->obs_intr[i]);
+      auto it = view_of.find(key);
+      int vid;
+      if (it == view_of.end()) {
+        vid = static_cast<int>(views.size());
+        view_of.emplace(key, vid);
+        views.push_back(ObsView{p->obs_pose_a[i], pb, p->obs_intr[i], 0});
+      } else {
+        vid = it->second;
+      }
+      obs_idx[k] = make_int2(vid, p->obs_pt[i] - pt_lo);
+      obs_xy[k] = make_double2(p->obs_xy[2 * i], p->obs_xy[2 * i + 1]);
+    }
+  }
+  // ---- tiles of whole points
+  std::vector<int> pt_first(static_cast<size_t>(h->n_pts) + 1);
+  for (int i = 0; i <= h->n_pts; ++i) pt_first[i] = static_cast<int>(pt_count[pt_lo + i] - obs_lo);
+  std::vector<int> tile_obs{0}, tile_pt{0};
+  {
+    int cur_obs = 0;
+    for (int i = 0; i < h->n_pts; ++i) {
+      const int len = pt_first[i + 1] - pt_first[i];
+      if (len > kTile)
+        return h->fail(DBA_ERR_UNSUPPORTED, "point %d has %d observations; tracks longer than %d are not implemented",
+                       pt_lo + i, len, kTile);
+      if (cur_obs + len > kTile) {
+        tile_obs.push_back(pt_first[i]);
+        tile_pt.push_back(i);
+        cur_obs = 0;
+      }
+      cur_obs += len;
+    }
+    if (h->n_pts > 0) {
+      tile_obs.push_back(pt_first[h->n_pts]);
+      tile_pt.push_back(h->n_pts);
+    }
+  }
+  const int n_tiles = static_cast<int>(tile_obs.size()) - 1;
+  // ---- camera-sorted incidence, chunked
+  std::vector<int> cam_entries;
+  std::vector<int4> cam_chunks;
+  if (h->cb) {
+    std::vector<int64_t> first(static_cast<size_t>(p->n_ext) + 1, 0);
+    for (int64_t k = 0; k < nl; ++k) {
+      const ObsView& v = views[obs_idx[k].x];
+      first[v.pose_a + 1]++;
+      if (v.pose_b >= 0) first[v.pose_b + 1]++;
+    }
+    for (int i = 0; i < p->n_ext; ++i) first[i + 1] += first[i];
+    cam_entries.resize(first[p->n_ext]);
+    std::vector<int64_t> cursor(first.begin(), first.end() - 1);
+    for (int64_t k = 0; k < nl; ++k) {
+      const ObsView& v = views[obs_idx[k].x];
+      cam_entries[cursor[v.pose_a]++] = static_cast<int>(k * 2);
+      if (v.pose_b >= 0) cam_entries[cursor[v.pose_b]++] = static_cast<int>(k * 2 + 1);
+    }
+    const int kChunk = 1024;
+    for (int b = 0; b < p->n_ext; ++b)
+      for (int64_t e = first[b]; e < first[b + 1]; e += kChunk)
+        cam_chunks.push_back(make_int4(b, static_cast<int>(e), static_cast<int>(std::min<int64_t>(e + kChunk, first[b + 1])), 0));
+  }
+
+  // ---- device allocation + upload
+  const int64_t ld = ((nl + 63) / 64) * 64;
+  h->j_planes = 4 + h->cb + ((h->two && h->cb) ? 6 : 0);
+  CU(h, h->d_obs_xy.alloc(std::max<int64_t>(nl, 1)));
+  CU(h, h->d_obs_idx.alloc(std::max<int64_t>(nl, 1)));
+  CU(h, h->d_views.alloc(std::max<size_t>(views.size(), 1)));
+  CU(h, h->d_tile_obs.alloc(tile_obs.size()));
+  CU(h, h->d_tile_pt.alloc(tile_pt.size()));
+  CU(h, h->d_pt_first.alloc(pt_first.size()));
+  CU(h, h->d_cam_entries.alloc(std::max<size_t>(cam_entries.size(), 1)));
+  CU(h, h->d_cam_chunks.alloc(std::max<size_t>(cam_chunks.size(), 1)));
+  CU(h, h->d_J.alloc(std::max<int64_t>(ld, 64) * h->j_planes));
+  CU(h, h->d_ext_const.alloc(std::max(p->n_ext, 1)));
+  CU(h, h->d_center.alloc(2 * std::max(p->n_intr, 1)));
+  CU(h, h->d_nf.alloc(std::max(p->n_intr, 1)));
+  CU(h, h->d_nd.alloc(std::max(p->n_intr, 1)));
+  for (int s = 0; s < 3; ++s) {
+    CU(h, h->d_pts[s].alloc(3 * std::max(h->n_pts, 1)));
+    CU(h, h->d_rot[s].alloc(3 * std::max(p->n_ext, 1)));
+    CU(h, h->d_trans[s].alloc(3 * std::max(p->n_ext, 1)));
+    CU(h, h->d_focal[s].alloc(2 * std::max(p->n_intr, 1)));
+    CU(h, h->d_dist[s].alloc(2 * std::max(p->n_intr, 1)));
+  }
+  for (int s = 0; s < 2; ++s) {
+    CU(h, h->d_pose_rows[s].alloc(std::max(p->n_ext, 1)));
+    CU(h, h->d_intr_rows[s].alloc(std::max(p->n_intr, 1)));
+  }
+  const size_t nvec = static_cast<size_t>(p->n_ext) * std::max(h->cb, 1);
+  CU(h, h->d_sp.alloc(3 * std::max(h->n_pts, 1)));
+  CU(h, h->d_cinv.alloc(6 * static_cast<size_t>(std::max(h->n_pts, 1))));
+  CU(h, h->d_tp.alloc(3 * std::max(h->n_pts, 1)));
+  CU(h, h->d_dp.alloc(3 * std::max(h->n_pts, 1)));
+  CU(h, h->d_sc.alloc(std::max<size_t>(nvec, 1)));
+  CU(h, h->d_cam_acc.alloc(std::max<size_t>(nvec * (std::max(h->cb, 1) + 3), 1)));
+  CU(h, h->d_minv.alloc(std::max<size_t>(nvec * std::max(h->cb, 1), 1)));
+  CU(h, h->d_dc2.alloc(std::max<size_t>(nvec, 1)));
+  CU(h, h->d_x.alloc(std::max<size_t>(nvec, 1)));
+  CU(h, h->d_r.alloc(std::max<size_t>(nvec, 1)));
+  CU(h, h->d_z.alloc(std::max<size_t>(nvec, 1)));
+  CU(h, h->d_p.alloc(std::max<size_t>(nvec, 1)));
+  CU(h, h->d_q.alloc(std::max<size_t>(nvec, 1)));
+  const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles),
+                                          2 * static_cast<size_t>((3 * static_cast<int64_t>(h->n_pts) + 255) / 256),
+                                          size_t{64}}) + 64;
+  CU(h, h->d_partA.alloc(n_part));
+  CU(h, h->d_partB.alloc(3 * static_cast<size_t>((std::max(p->n_ext, p->n_intr) + 63) / 64) + 64));
+  CU(h, h->d_scalars.alloc(S_TOTAL));
+  CU(h, h->d_scalars_red.alloc(S_TOTAL));
+  CU(h, h->d_pcg_scal.alloc(4));
+  CU(h, h->d_pcg_state.alloc(4));
+  CU(h, cudaMemsetAsync(h->d_scalars.p, 0, S_TOTAL * sizeof(double), h->st));
+  CU(h, cudaMemsetAsync(h->d_x.p, 0, std::max<size_t>(nvec, 1) * sizeof(double), h->st));
+  CU(h, cudaMemsetAsync(h->d_pcg_state.p, 0, 4 * sizeof(int), h->st));
+
+  auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->st);
+  };
+  CU(h, up(h->d_obs_xy.p, obs_xy.data(), nl * sizeof(double2)));
+  CU(h, up(h->d_obs_idx.p, obs_idx.data(), nl * sizeof(int2)));
+  CU(h, up(h->d_views.p, views.data(), views.size() * sizeof(ObsView)));
+  CU(h, up(h->d_tile_obs.p, tile_obs.data(), tile_obs.size() * sizeof(int)));
+  CU(h, up(h->d_tile_pt.p, tile_pt.data(), tile_pt.size() * sizeof(int)));
+  CU(h, up(h->d_pt_first.p, pt_first.data(), pt_first.size() * sizeof(int)));
+  CU(h, up(h->d_cam_entries.p, cam_entries.data(), cam_entries.size() * sizeof(int)));
+  CU(h, up(h->d_cam_chunks.p, cam_chunks.data(), cam_chunks.size() * sizeof(int4)));
+  std::vector<uint8_t> ext_const(std::max(p->n_ext, 1), 0);
+  h->any_const = false;
+  if (p->ext_const)
+    for (int i = 0; i < p->n_ext; ++i) {
+      ext_const[i] = p->ext_const[i] ? 1 : 0;
+      h->any_const |= ext_const[i] != 0;
+    }
+  CU(h, up(h->d_ext_const.p, ext_const.data(), p->n_ext));
+  CU(h, up(h->d_center.p, p->intr_center, 2 * sizeof(double) * p->n_intr));
+  CU(h, up(h->d_nf.p, p->intr_nf, sizeof(int) * p->n_intr));
+  CU(h, up(h->d_nd.p, p->intr_nd, sizeof(int) * p->n_intr));
+  // slot 2 = pristine copy for dba_params_reset, slot 0 = current
+  CU(h, up(h->d_pts[2].p, p->pts + 3 * static_cast<size_t>(pt_lo), 3 * sizeof(double) * h->n_pts));
+  CU(h, up(h->d_rot[2].p, p->ext_rot, 3 * sizeof(double) * p->n_ext));
+  CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * p->n_ext));
+  CU(h, up(h->d_focal[2].p, p->intr_focal, 2 * sizeof(double) * p->n_intr));
+  CU(h, up(h->d_dist[2].p, p->intr_dist, 2 * sizeof(double) * p->n_intr));
+  CU(h, cudaStreamSynchronize(h->st));  // host staging vectors go out of scope below
+
+  DeviceProblem& D = h->D;
+  D.n_obs = nl;
+  D.ld = std::max<int64_t>(ld, 64);
+  D.n_pts = h->n_pts;
+  D.n_ext = p->n_ext;
+  D.n_intr = p->n_intr;
+  D.n_views = static_cast<int>(views.size());
+  D.n_tiles = n_tiles;
+  D.cb = h->cb;
+  D.two = h->two;
+  D.n_blocks = p->n_ext;
+  D.obs_xy = h->d_obs_xy.p;
+  D.obs_idx = h->d_obs_idx.p;
+  D.views = h->d_views.p;
+  D.tile_obs = h->d_tile_obs.p;
+  D.tile_pt = h->d_tile_pt.p;
+  D.pt_first = h->d_pt_first.p;
+  D.cam_entries = h->d_cam_entries.p;
+  D.cam_chunks = h->d_cam_chunks.p;
+  D.n_chunks = static_cast<int>(cam_chunks.size());
+  D.J = h->d_J.p;
+  for (int s = 0; s < 2; ++s) {
+    ParamSet& P = h->P[s];
+    P.pts = h->d_pts[s].p;
+    P.ext_rot = h->d_rot[s].p;
+    P.ext_trans = h->d_trans[s].p;
+    P.focal = h->d_focal[s].p;
+    P.dist = h->d_dist[s].p;
+    P.center = h->d_center.p;
+    P.nf = h->d_nf.p;
+    P.nd = h->d_nd.p;
+    P.pose_rows = h->d_pose_rows[s].p;
+    P.intr_rows = h->d_intr_rows[s].p;
+  }
+  WorkArrays& W = h->W;
+  W.sp = h->d_sp.p;
+  W.sc = h->d_sc.p;
+  W.cinv = h->d_cinv.p;
+  W.tp = h->d_tp.p;
+  W.gp = nullptr;
+  W.diag_p = nullptr;
+  W.dp = h->d_dp.p;
+  W.cam_acc = h->d_cam_acc.p;
+  W.minv = h->d_minv.p;
+  W.dc2 = h->d_dc2.p;
+  W.diag_c = nullptr;
+  W.x = h->d_x.p;
+  W.r = h->d_r.p;
+  W.z = h->d_z.p;
+  W.p = h->d_p.p;
+  W.q = h->d_q.p;
+  W.partials = h->d_partA.p;
+  W.scalars = h->d_scalars.p;
+  W.pcg_state = h->d_pcg_state.p;
+  W.pcg_scal = h->d_pcg_scal.p;
+  h->have_problem = true;
+  return dba_params_reset(h);
+}
+
+int dba_params_reset(dba_handle* h) {
+  if (!h) return DBA_ERR_INVALID_ARGUMENT;
+  if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
+  CU(h, cudaSetDevice(h->device));
+  h->cur = 0;
+  auto cp = [&](DevBuf<double>* b) -> cudaError_t {
+    if (b[2].n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(b[0].p, b[2].p, b[2].n * sizeof(double), cudaMemcpyDeviceToDevice, h->st);
+  };
+  CU(h, cp(h->d_pts));
+  CU(h, cp(h->d_rot));
+  CU(h, cp(h->d_trans));
+  CU(h, cp(h->d_focal));
+  CU(h, cp(h->d_dist));
+  CU(h, cudaStreamSynchronize(h->st));
+  return DBA_OK;
+}
+
+// --------------------------------------------------------------------------- eval
+int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, double* jac_pose_a, double* jac_pose_b,
+             double* jac_intr) {
+  if (!h) return DBA_ERR_INVALID_ARGUMENT;
+  if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
+  CU(h, cudaSetDevice(h->device));
+  const bool per_obs = residuals || jac_pt || jac_pose_a || jac_pose_b || jac_intr;
+  if (per_obs && h->world > 1)
+    return h->fail(DBA_ERR_UNSUPPORTED, "per-observation outputs need a single-GPU handle");
+  const DeviceProblem& D0 = h->D;
+  const ParamSet& P = h->P[h->cur];
+  const bool want_jac = jac_pt || jac_pose_a || jac_pose_b || jac_intr;
+  {
+    Scope s(h, "pose_rows");
+    launch_pose_rows(P, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
+  }
+  const int64_t nl = h->n_obs;
+  if (!want_jac) {
+    DevBuf<double> mse;
+    if (residuals) {
+      // residual values come from the Jacobian kernel's r plane (same code path as the solver)
+      DeviceProblem D = D0;
+      DevBuf<double2> tmp;
+      CU(h, tmp.alloc(D.ld * 4));
+      D.J = tmp.p;
+      {
+        Scope s(h, "jacobian");
+        launch_jacobian(D, P, h->W, 0, 0, 1, h->d_partA.p, h->st);
+      }
+      std::vector<double2> r(nl);
+      CU(h, cudaMemcpyAsync(r.data(), tmp.p, nl * sizeof(double2), cudaMemcpyDeviceToHost, h->st));
+      CU(h, cudaStreamSynchronize(h->st));
+      for (int64_t k = 0; k < nl; ++k) {
+        residuals[2 * h->perm[k]] = r[k].x;
+        residuals[2 * h->perm[k] + 1] = r[k].y;
+      }
+    } else {
+      Scope s(h, "cost", 24.0 * static_cast<double>(nl));
+      launch_cost(D0, P, h->d_partA.p, nullptr, h->st);
+    }
+  } else {
+    DeviceProblem D = D0;
+    const int cbs = 9, twos = h->two;
+    const int planes = 4 + cbs + (twos ? 6 : 0);
+    DevBuf<double2> tmp;
+    CU(h, tmp.alloc(D.ld * planes));
+    D.J = tmp.p;
+    {
+      Scope s(h, "jacobian");
+      launch_jacobian(D, P, h->W, cbs, twos, 1, h->d_partA.p, h->st);
+    }
+    std::vector<double2> host(static_cast<size_t>(D.ld) * planes);
+    CU(h, cudaMemcpyAsync(host.data(), tmp.p, host.size() * sizeof(double2), cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+    auto plane = [&](int pl, int64_t k) -> double2 { return host[static_cast<size_t>(pl) * D.ld + k]; };
+    for (int64_t k = 0; k < nl; ++k) {
+      const int64_t i = h->perm[k];
+      if (residuals) {
+        residuals[2 * i] = plane(kPlaneR, k).x;
+        residuals[2 * i + 1] = plane(kPlaneR, k).y;
+      }
+      for (int c = 0; c < 3; ++c) {
+        if (jac_pt) {
+          jac_pt[6 * i + c] = plane(kPlaneJp + c, k).x;
+          jac_pt[6 * i + 3 + c] = plane(kPlaneJp + c, k).y;
+        }
+        if (jac_intr) {
+          jac_intr[6 * i + c] = plane(kPlaneJA + 6 + c, k).x;
+          jac_intr[6 * i + 3 + c] = plane(kPlaneJA + 6 + c, k).y;
+        }
+      }
+      for (int c = 0; c < 6; ++c) {
+        if (jac_pose_a) {
+          jac_pose_a[12 * i + c] = plane(kPlaneJA + c, k).x;
+          jac_pose_a[12 * i + 6 + c] = plane(kPlaneJA + c, k).y;
+        }
+        if (jac_pose_b) {
+          jac_pose_b[12 * i + c] = twos ? plane(kPlaneJA + 9 + c, k).x : 0.0;
+          jac_pose_b[12 * i + 6 + c] = twos ? plane(kPlaneJA + 9 + c, k).y : 0.0;
+        }
+      }
+    }
+  }
+  if (cost) {
+    {
+      Scope s(h, "reduce");
+      launch_reduce_sum(h->d_partA.p, cost_grid(D0), 1, 0, h->W.scalars + S_COST, h->st);
+    }
+    int rc = reduce_scalars_and_fetch(h);
+    if (rc != DBA_OK) return rc;
+    *cost = 0.5 * h->h_scalars[S_COST];
+  }
+  CU(h, cudaGetLastError());
+  return DBA_OK;
+}
+
+int dba_filter_mse(dba_handle* h, double* mse) {
+  if (!h || !mse) return DBA_ERR_INVALID_ARGUMENT;
+  if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
+  if (h->world > 1) return h->fail(DBA_ERR_UNSUPPORTED, "per-observation outputs need a single-GPU handle");
+  CU(h, cudaSetDevice(h->device));
+  const ParamSet& P = h->P[h->cur];
+  DevBuf<double> d;
+  CU(h, d.alloc(std::max<int64_t>(h->n_obs, 1)));
+  {
+    Scope s(h, "pose_rows");
+    launch_pose_rows(P, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
+  }
+  {
+    Scope s(h, "cost", 24.0 * static_cast<double>(h->n_obs));
+    launch_cost(h->D, P, h->d_partA.p, d.p, h->st);
+  }
+  std::vector<double> host(h->n_obs);
+  CU(h, cudaMemcpyAsync(host.data(), d.p, h->n_obs * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaStreamSynchronize(h->st));
+  for (int64_t k = 0; k < h->n_obs; ++k) mse[h->perm[k]] = host[k];
+  return DBA_OK;
+}
+
+// --------------------------------------------------------------------------- solve
+void dba_solve_options_default(dba_solve_options* o) {
+  if (!o) return;
+  o->max_num_iterations = 50;
+  o->max_solver_time_in_seconds = 1e9;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-6;
+  o->gradient_tolerance = 1e-10;
+  o->parameter_tolerance = 1e-8;
+  o->jacobi_scaling = 1;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->linear_solver = DBA_LS_AUTO;
+  o->pcg_max_iterations = 500;
+  o->pcg_min_iterations = 0;
+  o->pcg_rel_tolerance = 1e-12;
+  o->dense_max_size = 768;
+  o->progress_to_stdout = 0;
+}
+
+int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
+  if (!h || !opt || !sum) return DBA_ERR_INVALID_ARGUMENT;
+  if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
+  CU(h, cudaSetDevice(h->device));
+  const dba_solve_options o = *opt;
+  dba_iteration* it_buf = sum->iterations;
+  const int it_cap = it_buf ? sum->iterations_capacity : 0;
+  std::memset(sum, 0, sizeof *sum);
+  sum->iterations = it_buf;
+  sum->iterations_capacity = it_cap;
+  sum->linear_solver_used = DBA_LS_PCG;
+  sum->reduced_system_size = h->n_ext * h->cb;
+  const int64_t launches0 = h->launches;
+  const double t_start = now_s();
+  cudaEvent_t ev0, ev1;
+  CU(h, cudaEventCreate(&ev0));
+  CU(h, cudaEventCreate(&ev1));
+  CU(h, cudaEventRecord(ev0, h->st));
+
+  int n_it = 0;
+  auto push = [&](const dba_iteration& it) {
+    if (n_it < it_cap) it_buf[n_it] = it;
+    ++n_it;
+  };
+  double x_cost = 0.0;
+  auto finish = [&](int termination, const char* msg) -> int {
+    cudaEventRecord(ev1, h->st);
+    cudaEventSynchronize(ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    sum->termination = termination;
+    sum->num_iterations = std::min(n_it, it_cap);
+    sum->final_cost = x_cost;
+    sum->total_time_in_seconds = now_s() - t_start;
+    sum->device_time_in_seconds = ms * 1e-3;
+    sum->kernel_launches = h->launches - launches0;
+    std::snprintf(sum->message, sizeof sum->message, "%s", msg);
+    return DBA_OK;
+  };
+
+  if (h->n_obs_global == 0 || (h->n_pts_global == 0)) return finish(DBA_CONVERGENCE, "Function tolerance reached. No non-constant parameter blocks found.");
+
+  int rc = evaluate_jacobian(h, /*first=*/true, o.jacobi_scaling != 0);
+  if (rc != DBA_OK) return rc;
+  sum->jacobian_evaluations += o.jacobi_scaling ? 2 : 1;
+  double radius = o.initial_trust_region_radius;
+  double decrease_factor = 2.0;
+  if ((rc = prepare_step(h, radius, o)) != DBA_OK) return rc;
+  if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
+  const double* S = h->h_scalars;
+  x_cost = 0.5 * S[S_COST];
+  sum->initial_cost = x_cost;
+  if (!std::isfinite(x_cost)) {
+    finish(DBA_FAILURE, "Initial residual and Jacobian evaluation failed.");
+    return h->fail(DBA_ERR_NUMERIC, "non-finite cost at the initial point");
+  }
+  dba_iteration it{};
+  it.iteration = 0;
+  it.cost = x_cost;
+  it.gradient_max_norm = std::max(S[S_GMAX_PT], S[S_GMAX_CAM]);
+  it.gradient_norm = std::sqrt(S[S_GSQ_PT] + S[S_GSQ_CAM]);
+  bool linear_failure = (S[S_BAD_PT] + S[S_BAD_CAM]) > 0.0;
+  int num_consecutive_invalid = 0;
+  double iter_start = t_start;
+  bool first_finalize = true;
+  if (o.progress_to_stdout && h->rank == 0) print_progress_header();
+
+  // FinalizeIterationAndCheckIfMinimizerCanContinue; returns 0 to continue, 1 when finished
+  auto finalize = [&]() -> int {
+    if (!first_finalize) {
+      if (it.step_is_successful)
+        sum->num_successful_steps++;
+      else
+        sum->num_unsuccessful_steps++;
+    }
+    first_finalize = false;
+    it.trust_region_radius = radius;
+    const double t = now_s();
+    it.iteration_time_in_seconds = t - iter_start;
+    push(it);
+    if (o.progress_to_stdout && h->rank == 0) {
+      std::printf("%4d % 8e   % 3.2e   % 3.2e  % 3.2e  % 3.2e % 3.2e     % 4d   % 3.2e   % 3.2e\n", it.iteration, it.cost,
+                  it.cost_change, it.gradient_max_norm, it.step_norm, it.relative_decrease, it.trust_region_radius,
+                  it.linear_solver_iterations, it.iteration_time_in_seconds, t - t_start);
+      std::fflush(stdout);
+    }
+    if (t - t_start >= o.max_solver_time_in_seconds) {
+      finish(DBA_NO_CONVERGENCE, "Maximum solver time reached.");
+      return 1;
+    }
+    if (it.iteration >= o.max_num_iterations) {
+      finish(DBA_NO_CONVERGENCE, "Maximum number of iterations reached.");
+      return 1;
+    }
+    if (it.gradient_max_norm <= o.gradient_tolerance) {
+      finish(DBA_CONVERGENCE, "Gradient tolerance reached.");
+      return 1;
+    }
+    if (radius <= o.min_trust_region_radius) {
+      finish(DBA_CONVERGENCE, "Minimum trust region radius reached.");
+      return 1;
+    }
+    return 0;
+  };
+
+  char msg[192];
+  while (finalize() == 0) {
+    iter_start = now_s();
+    const dba_iteration prev = it;
+    it = dba_iteration{};
+    it.iteration = prev.iteration + 1;
+
+    // ---- ComputeTrustRegionStep: Schur-complement solve on the device
+    int pcg_iters = 0;
+    bool step_valid = false;
+    double model_cost_change = 0.0;
+    if (!linear_failure) {
+      if (h->cb) {
+        if ((rc = pcg_solve(h, o, &pcg_iters)) != DBA_OK) return rc;
+        sum->pcg_iterations_total += pcg_iters;
+      }
+      if ((rc = apply_step_and_evaluate(h)) != DBA_OK) return rc;
+      sum->residual_evaluations++;
+      if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
+      model_cost_change = -S[S_MODEL];
+      step_valid = std::isfinite(model_cost_change) && model_cost_change > 0.0 &&
+                   std::isfinite(S[S_STEP_PT] + S[S_STEP_CAM]);
+    }
+    it.linear_solver_iterations = h->cb ? pcg_iters : 1;
+    it.model_cost_change = model_cost_change;
+    it.step_is_valid = step_valid;
+    if (!step_valid) {
+      // HandleInvalidStep
+      if (++num_consecutive_invalid >= o.max_num_consecutive_invalid_steps) {
+        std::snprintf(msg, sizeof msg,
+                      "Number of consecutive invalid steps more than "
+                      "Solver::Options::max_num_consecutive_invalid_steps: %d",
+                      o.max_num_consecutive_invalid_steps);
+        it.cost = x_cost;
+        it.trust_region_radius = radius;
+        push(it);
+        return finish(DBA_FAILURE, msg);
+      }
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      it.cost = x_cost;
+      it.gradient_max_norm = prev.gradient_max_norm;
+      it.gradient_norm = prev.gradient_norm;
+      if ((rc = prepare_step(h, radius, o)) != DBA_OK) return rc;
+      if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
+      linear_failure = (S[S_BAD_PT] + S[S_BAD_CAM]) > 0.0;
+      continue;
+    }
+    num_consecutive_invalid = 0;
+    double candidate_cost = 0.5 * S[S_CAND];
+    if (!std::isfinite(candidate_cost)) candidate_cost = std::numeric_limits<double>::max();
+    const double x_norm = std::sqrt(S[S_X_PT] + S[S_X_CAM]);
+    it.step_norm = std::sqrt(S[S_STEP_PT] + S[S_STEP_CAM]);
+    // ---- ParameterToleranceReached
+    const double step_size_tolerance = o.parameter_tolerance * (x_norm + o.parameter_tolerance);
+    if (it.step_norm <= step_size_tolerance) {
+      std::snprintf(msg, sizeof msg, "Parameter tolerance reached. Relative step_norm: %e <= %e.",
+                    it.step_norm / (x_norm + o.parameter_tolerance), o.parameter_tolerance);
+      it.cost = x_cost;
+      it.trust_region_radius = radius;
+      push(it);
+      return finish(DBA_CONVERGENCE, msg);
+    }
+    // ---- FunctionToleranceReached
+    it.cost_change = x_cost - candidate_cost;
+    if (std::fabs(it.cost_change) <= o.function_tolerance * x_cost) {
+      std::snprintf(msg, sizeof msg, "Function tolerance reached. |cost_change|/cost: %e <= %e",
+                    std::fabs(it.cost_change) / x_cost, o.function_tolerance);
+      it.cost = x_cost;
+      it.trust_region_radius = radius;
+      push(it);
+      return finish(DBA_CONVERGENCE, msg);
+    }
+    // ---- IsStepSuccessful
+    it.relative_decrease = candidate_cost >= std::numeric_limits<double>::max()
+                               ? std::numeric_limits<double>::lowest()
+                               : (x_cost - candidate_cost) / model_cost_change;
+    if (it.relative_decrease > o.min_relative_decrease) {
+      // HandleSuccessfulStep: the candidate becomes x; Jacobian at the new point
+      h->cur = 1 - h->cur;
+      if ((rc = evaluate_jacobian(h, false, o.jacobi_scaling != 0)) != DBA_OK) return rc;
+      sum->jacobian_evaluations++;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+      radius = std::min(o.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      if ((rc = prepare_step(h, radius, o)) != DBA_OK) return rc;
+      if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
+      x_cost = 0.5 * S[S_COST];
+      it.cost = x_cost;
+      it.gradient_max_norm = std::max(S[S_GMAX_PT], S[S_GMAX_CAM]);
+      it.gradient_norm = std::sqrt(S[S_GSQ_PT] + S[S_GSQ_CAM]);
+      it.step_is_successful = 1;
+    } else {
+      it.step_is_successful = 0;
+      it.cost = candidate_cost;
+      it.gradient_max_norm = prev.gradient_max_norm;
+      it.gradient_norm = prev.gradient_norm;
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      if ((rc = prepare_step(h, radius, o)) != DBA_OK) return rc;
+      if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
+    }
+    linear_failure = (S[S_BAD_PT] + S[S_BAD_CAM]) > 0.0;
+  }
+  return DBA_OK;
+}
+
+// ---------------------------------------------------------------------- params out
+int dba_params_get(dba_handle* h, double* pts, double* ext_rot, double* ext_trans, double* intr_focal,
+                   double* intr_dist) {
+  if (!h) return DBA_ERR_INVALID_ARGUMENT;
+  if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
+  CU(h, cudaSetDevice(h->device));
+  const int c = h->cur;
+  if (pts) {
+    if (h->world == 1) {
+      CU(h, cudaMemcpyAsync(pts, h->d_pts[c].p, 3 * sizeof(double) * h->n_pts, cudaMemcpyDeviceToHost, h->st));
+    } else {
+      // every rank returns the full array: zero-padded local slice, summed over ranks
+      const size_t total = 3 * static_cast<size_t>(h->n_pts_global);
+      CU(h, h->d_full_pts.alloc(std::max<size_t>(total, 1)));
+      CU(h, cudaMemsetAsync(h->d_full_pts.p, 0, total * sizeof(double), h->st));
+      CU(h, cudaMemcpyAsync(h->d_full_pts.p + 3 * static_cast<size_t>(h->pt_lo), h->d_pts[c].p,
+                            3 * sizeof(double) * h->n_pts, cudaMemcpyDeviceToDevice, h->st));
+      int rc = allreduce(h, h->d_full_pts.p, total, kNcclSum);
+      if (rc != DBA_OK) return rc;
+      CU(h, cudaMemcpyAsync(pts, h->d_full_pts.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    }
+  }
+  if (ext_rot) CU(h, cudaMemcpyAsync(ext_rot, h->d_rot[c].p, 3 * sizeof(double) * h->n_ext, cudaMemcpyDeviceToHost, h->st));
+  if (ext_trans) CU(h, cudaMemcpyAsync(ext_trans, h->d_trans[c].p, 3 * sizeof(double) * h->n_ext, cudaMemcpyDeviceToHost, h->st));
+  if (intr_focal) CU(h, cudaMemcpyAsync(intr_focal, h->d_focal[c].p, 2 * sizeof(double) * h->n_intr, cudaMemcpyDeviceToHost, h->st));
+  if (intr_dist) CU(h, cudaMemcpyAsync(intr_dist, h->d_dist[c].p, 2 * sizeof(double) * h->n_intr, cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaStreamSynchronize(h->st));
+  return DBA_OK;
+}
+
+int dba_fit_hemisphere(dba_handle* h, const double* centres, int32_t n, double centre_io[3], double* rho_io,
+                       const dba_solve_options* o, dba_summary* s) {
+  if (!h || !centre_io || !rho_io || !o || !s || n < 0 || (n > 0 && !centres)) return DBA_ERR_INVALID_ARGUMENT;
+  CU(h, cudaSetDevice(h->device));
+  std::string err;
+  int64_t launches = 0;
+  int rc = hemisphere_fit_device(centres, n, centre_io, rho_io, o, s, h->st, &err, &launches);
+  h->launches += launches;
+  if (rc != DBA_OK) return h->fail(rc, "%s", err.c_str());
+  return DBA_OK;
+}
+
+}  // extern "C"

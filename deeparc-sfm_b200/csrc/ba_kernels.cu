@@ -1,0 +1,973 @@
+// Hand-written sm_100a kernels of the bundle-adjustment hot path.  fp64 throughout; the path
+// is HBM-bound streaming + segmented reductions (no dense contraction, so no tensor cores).
+// Kernel <-> reference map (DESIGN.md has the byte models):
+//   k_pose_rows        per-extrinsic trig hoisting for rotatePoint (snavely_reprojection_error.hh:80-91)
+//   k_jacobian   (K1)  residual + analytic Jacobian of operator() (:93-118), replaces Ceres autodiff
+//   k_cost       (K2)  residual-only evaluation (trial point; filterPoint3d, DeepArcManager.cc:335-347)
+//   k_point_prepare, k_camera_gather, k_camera_finalize (K3)  Schur elimination front half
+//   k_schur_spmv (K5)  implicit Schur complement product, one fused pass over point tiles
+//   k_pcg_init / k_pcg_update (K6)  block-Jacobi PCG vector work, single CTA
+//   k_back_substitute (K7), k_param_update  point back-substitution, x + delta, norms
+#include <cstdio>
+
+#include "ba_kernels.cuh"
+
+namespace dba {
+
+namespace {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Sum over the CTA; result valid in thread 0.  `red` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_sum(v);
+  return v;
+}
+__device__ __forceinline__ double block_max(double v, double* red) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  v = (threadIdx.x < nw) ? red[threadIdx.x] : 0.0;
+  if (wid == 0) v = warp_max(v);
+  return v;
+}
+// Sum over the CTA, result broadcast to every thread.
+__device__ __forceinline__ double block_sum_all(double v, double* red) {
+  v = block_sum(v, red);
+  __syncthreads();
+  if (threadIdx.x == 0) red[0] = v;
+  __syncthreads();
+  v = red[0];
+  __syncthreads();
+  return v;
+}
+
+__device__ __forceinline__ double dot2(const double2 a, const double2 b) { return a.x * b.x + a.y * b.y; }
+
+// ------------------------------------------------------------------------- pose rows
+__global__ void k_pose_rows(ParamSet P, const uint8_t* __restrict__ ext_const, int freeze_all, int n_ext, int n_intr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_ext) {
+    const double free_flag = (freeze_all || (ext_const && ext_const[i])) ? 0.0 : 1.0;
+    make_pose_row(P.ext_rot + 3 * i, P.ext_trans + 3 * i, free_flag, P.pose_rows + i);
+  }
+  if (i < n_intr) {
+    IntrRow r;
+    const int nf = P.nf[i], nd = P.nd[i];
+    r.fx = P.focal[2 * i];
+    r.fy = (nf == 2) ? P.focal[2 * i + 1] : P.focal[2 * i];
+    r.cx = P.center[2 * i];
+    r.cy = P.center[2 * i + 1];
+    r.k0 = nd >= 1 ? P.dist[2 * i] : 0.0;
+    r.k1 = nd >= 2 ? P.dist[2 * i + 1] : 0.0;
+    r.nf = static_cast<double>(nf);
+    r.nd = static_cast<double>(nd);
+    P.intr_rows[i] = r;
+  }
+}
+
+// ------------------------------------------------------------------ forward transform
+struct Forward {
+  double mid[3];  // point after the (optional) first pose
+  double cam[3];  // camera-frame point
+};
+__device__ __forceinline__ void forward(const ParamSet& P, const ObsView& v, const double X[3], Forward& f) {
+  if (v.pose_b >= 0) {
+    transform(P.pose_rows[v.pose_b], X, f.mid);
+  } else {
+    f.mid[0] = X[0];
+    f.mid[1] = X[1];
+    f.mid[2] = X[2];
+  }
+  transform(P.pose_rows[v.pose_a], f.mid, f.cam);
+}
+
+// ------------------------------------------------------------------------ K1 jacobian
+// One thread per observation (point-sorted).  Reads 16 B (xy) + 8 B (indices) + L1/L2-resident
+// tables; writes (1 + 3 + CB [+6]) double2 planes.
+template <int CB, bool TWO>
+__global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, WorkArrays W, int unit_scale,
+                                                   double* __restrict__ partial_cost) {
+  __shared__ double red[32];
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  double c = 0.0;
+  if (o < D.n_obs) {
+    const double2 xy = D.obs_xy[o];
+    const int2 idx = D.obs_idx[o];
+    const ObsView v = D.views[idx.x];
+    const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
+    const double X[3] = {Xp[0], Xp[1], Xp[2]};
+    Forward f;
+    forward(P, v, X, f);
+    const IntrRow I = P.intr_rows[v.intr];
+    Projection pr;
+    project<true>(I, f.cam, xy.x, xy.y, pr);
+    c = pr.r0 * pr.r0 + pr.r1 * pr.r1;
+    double2* J = D.J + o;
+    const int64_t ld = D.ld;
+    J[kPlaneR * ld] = make_double2(pr.r0, pr.r1);
+
+    const PoseRow& A = P.pose_rows[v.pose_a];
+    double GA[2][3];  // d r / d mid
+    mul23_R(pr.G, A.R, GA);
+    double Jp[2][3];
+    const bool two = v.pose_b >= 0;
+    if (two) {
+      mul23_R(GA, P.pose_rows[v.pose_b].R, Jp);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Jp[i][k] = GA[i][k];
+    }
+    {
+      double s0 = 1.0, s1 = 1.0, s2 = 1.0;
+      if (!unit_scale) {
+        const double* sp = W.sp + 3 * static_cast<int64_t>(idx.y);
+        s0 = sp[0];
+        s1 = sp[1];
+        s2 = sp[2];
+      }
+      J[(kPlaneJp + 0) * ld] = make_double2(Jp[0][0] * s0, Jp[1][0] * s0);
+      J[(kPlaneJp + 1) * ld] = make_double2(Jp[0][1] * s1, Jp[1][1] * s1);
+      J[(kPlaneJp + 2) * ld] = make_double2(Jp[0][2] * s2, Jp[1][2] * s2);
+    }
+    if (CB >= 6) {
+      double Da[3][3], Jw[2][3];
+      rotation_derivative(A, f.mid, Da);
+      mul23_33(pr.G, Da, Jw);
+      double s[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s[k] = 1.0;
+      if (!unit_scale) {
+        const double* sc = W.sc + static_cast<int64_t>(v.pose_a) * CB;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) s[k] = sc[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s[k] *= A.free_;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        J[(kPlaneJA + k) * ld] = make_double2(Jw[0][k] * s[k], Jw[1][k] * s[k]);
+        J[(kPlaneJA + 3 + k) * ld] = make_double2(pr.G[0][k] * s[3 + k], pr.G[1][k] * s[3 + k]);
+      }
+      if (CB == 9) {
+        J[(kPlaneJA + 6) * ld] = make_double2(pr.df[0] * s[6], pr.df[1] * s[6]);
+        J[(kPlaneJA + 7) * ld] = make_double2(pr.dk0[0] * s[7], pr.dk0[1] * s[7]);
+        J[(kPlaneJA + 8) * ld] = make_double2(pr.dk1[0] * s[8], pr.dk1[1] * s[8]);
+      }
+      if (TWO) {
+        const int pb = kPlaneJA + CB;
+        if (two) {
+          const PoseRow& B = P.pose_rows[v.pose_b];
+          double Db[3][3], JwB[2][3];
+          rotation_derivative(B, X, Db);
+          mul23_33(GA, Db, JwB);
+          double sb[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+          if (!unit_scale) {
+            const double* sc = W.sc + static_cast<int64_t>(v.pose_b) * CB;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) sb[k] = sc[k] * B.free_;
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            J[(pb + k) * ld] = make_double2(JwB[0][k] * sb[k], JwB[1][k] * sb[k]);
+            J[(pb + 3 + k) * ld] = make_double2(GA[0][k] * sb[3 + k], GA[1][k] * sb[3 + k]);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = make_double2(0.0, 0.0);
+        }
+      }
+    }
+  }
+  c = block_sum(c, red);
+  if (threadIdx.x == 0 && partial_cost) partial_cost[blockIdx.x] = c;
+}
+
+// ---------------------------------------------------------------------------- K2 cost
+__global__ void __launch_bounds__(256) k_cost(DeviceProblem D, ParamSet P, double* __restrict__ partial_cost,
+                                               double* __restrict__ mse_out) {
+  __shared__ double red[32];
+  const int64_t o = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  double c = 0.0;
+  if (o < D.n_obs) {
+    const double2 xy = D.obs_xy[o];
+    const int2 idx = D.obs_idx[o];
+    const ObsView v = D.views[idx.x];
+    const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
+    const double X[3] = {Xp[0], Xp[1], Xp[2]};
+    Forward f;
+    forward(P, v, X, f);
+    Projection pr;
+    project<false>(P.intr_rows[v.intr], f.cam, xy.x, xy.y, pr);
+    c = pr.r0 * pr.r0 + pr.r1 * pr.r1;
+    if (mse_out) mse_out[o] = c / 2.0;
+  }
+  c = block_sum(c, red);
+  if (threadIdx.x == 0 && partial_cost) partial_cost[blockIdx.x] = c;
+}
+
+// --------------------------------------------------------------- K3 point-side prepare
+// One CTA per tile of whole points (<= 256 observations).  Per point: H = E^T E (6 unique),
+// g = E^T r; mode 0: Jacobi scale sp = 1/(1+sqrt(diag H)); mode 1: C = H + D^2, C^-1, t = C^-1 g
+// and the point part of the gradient norms.  Reads Jp + r planes only (64 B / observation).
+__global__ void __launch_bounds__(kTile) k_point_prepare(DeviceProblem D, WorkArrays W, double radius,
+                                                          double min_diag, double max_diag, int mode,
+                                                          double* __restrict__ partials) {
+  __shared__ double v[9][kTile];
+  __shared__ double red[32];
+  const int t = blockIdx.x;
+  const int obs0 = D.tile_obs[t], obs1 = D.tile_obs[t + 1];
+  const int pt0 = D.tile_pt[t], pt1 = D.tile_pt[t + 1];
+  const int tid = threadIdx.x;
+  const int o = obs0 + tid;
+  if (o < obs1) {
+    const double2* J = D.J + o;
+    const int64_t ld = D.ld;
+    const double2 r = J[kPlaneR * ld];
+    const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
+    v[0][tid] = dot2(e0, e0);
+    v[1][tid] = dot2(e0, e1);
+    v[2][tid] = dot2(e0, e2);
+    v[3][tid] = dot2(e1, e1);
+    v[4][tid] = dot2(e1, e2);
+    v[5][tid] = dot2(e2, e2);
+    v[6][tid] = dot2(e0, r);
+    v[7][tid] = dot2(e1, r);
+    v[8][tid] = dot2(e2, r);
+  }
+  __syncthreads();
+  double gsq = 0.0, gmax = 0.0, bad = 0.0;
+  const int pt = pt0 + tid;
+  if (pt < pt1) {
+    const int a = D.pt_first[pt] - obs0, b = D.pt_first[pt + 1] - obs0;
+    double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = a; i < b; ++i) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s[k] += v[k][i];
+    }
+    const int64_t p3 = 3 * static_cast<int64_t>(pt);
+    if (mode == 0) {
+      W.sp[p3 + 0] = 1.0 / (1.0 + sqrt(s[0]));
+      W.sp[p3 + 1] = 1.0 / (1.0 + sqrt(s[3]));
+      W.sp[p3 + 2] = 1.0 / (1.0 + sqrt(s[5]));
+    } else {
+      double C[6] = {s[0], s[1], s[2], s[3], s[4], s[5]};
+      C[0] += fmin(fmax(s[0], min_diag), max_diag) / radius;
+      C[3] += fmin(fmax(s[3], min_diag), max_diag) / radius;
+      C[5] += fmin(fmax(s[5], min_diag), max_diag) / radius;
+      double inv[6];
+      if (!inv_sym3(C, inv)) {
+        bad = 1.0;
+        inv[0] = inv[1] = inv[2] = inv[3] = inv[4] = inv[5] = 0.0;
+      }
+      double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ci[k] = inv[k];
+      W.tp[p3 + 0] = inv[0] * s[6] + inv[1] * s[7] + inv[2] * s[8];
+      W.tp[p3 + 1] = inv[1] * s[6] + inv[3] * s[7] + inv[4] * s[8];
+      W.tp[p3 + 2] = inv[2] * s[6] + inv[4] * s[7] + inv[5] * s[8];
+      // unscaled gradient = scaled gradient / scale
+      const double g0 = s[6] / W.sp[p3 + 0], g1 = s[7] / W.sp[p3 + 1], g2 = s[8] / W.sp[p3 + 2];
+      gsq = g0 * g0 + g1 * g1 + g2 * g2;
+      gmax = fmax(fabs(g0), fmax(fabs(g1), fabs(g2)));
+    }
+  }
+  if (mode == 1) {
+    gsq = block_sum(gsq, red);
+    gmax = block_max(gmax, red);
+    bad = block_sum(bad, red);
+    if (tid == 0) {
+      partials[3 * t + 0] = gsq;
+      partials[3 * t + 1] = gmax;
+      partials[3 * t + 2] = bad;
+    }
+  }
+}
+
+// ------------------------------------------------------------- K3 camera-side gather
+// Camera-sorted incidence list, chunked; one CTA per chunk.  Gathers the Jacobian planes
+// of the chunk's observations (16 B per plane per observation), accumulates in registers
+//   mode 0: diag(F^T F)                      -> Jacobi scales
+//   mode 1: B = F^T (I - E C^-1 E^T) F (upper), diag(F^T F), g = F^T r, rhs = -F^T (r - E t)
+// then reduces across the CTA and adds to the per-block accumulators (few atomics per CTA).
+template <int CB, int MODE>
+__global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArrays W) {
+  constexpr int NU = CB * (CB + 1) / 2;
+  constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
+  __shared__ double red[4][NACC];
+  const int4 ch = D.cam_chunks[blockIdx.x];
+  const int blk = ch.x;
+  double acc[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  const int64_t ld = D.ld;
+  for (int e = ch.y + threadIdx.x; e < ch.z; e += blockDim.x) {
+    const int ent = D.cam_entries[e];
+    const int o = ent >> 1;
+    const int slot = ent & 1;
+    const double2* J = D.J + o;
+    const int base = kPlaneJA + (slot ? D.cb : 0);
+    double2 F[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) F[k] = (slot && k >= 6) ? make_double2(0.0, 0.0) : J[(base + k) * ld];
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < CB; ++k) acc[k] += dot2(F[k], F[k]);
+    } else {
+      const double2 r = J[kPlaneR * ld];
+      const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
+      const int pt = D.obs_idx[o].y;
+      const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
+      const double* tp = W.tp + 3 * static_cast<int64_t>(pt);
+      const double c0 = ci[0], c1 = ci[1], c2 = ci[2], c3 = ci[3], c4 = ci[4], c5 = ci[5];
+      // M = E C^-1 (2x3), P = I - M E^T (2x2 symmetric)
+      const double m00 = e0.x * c0 + e1.x * c1 + e2.x * c2, m01 = e0.x * c1 + e1.x * c3 + e2.x * c4,
+                   m02 = e0.x * c2 + e1.x * c4 + e2.x * c5;
+      const double m10 = e0.y * c0 + e1.y * c1 + e2.y * c2, m11 = e0.y * c1 + e1.y * c3 + e2.y * c4,
+                   m12 = e0.y * c2 + e1.y * c4 + e2.y * c5;
+      const double p00 = 1.0 - (m00 * e0.x + m01 * e1.x + m02 * e2.x);
+      const double p01 = -(m00 * e0.y + m01 * e1.y + m02 * e2.y);
+      const double p11 = 1.0 - (m10 * e0.y + m11 * e1.y + m12 * e2.y);
+      // rr = r - E t
+      const double t0 = tp[0], t1 = tp[1], t2 = tp[2];
+      const double rr0 = r.x - (e0.x * t0 + e1.x * t1 + e2.x * t2);
+      const double rr1 = r.y - (e0.y * t0 + e1.y * t1 + e2.y * t2);
+      int u = 0;
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        // (P F)_i
+        const double pf0 = p00 * F[i].x + p01 * F[i].y;
+        const double pf1 = p01 * F[i].x + p11 * F[i].y;
+#pragma unroll
+        for (int j = i; j < CB; ++j) {
+          acc[u] += pf0 * F[j].x + pf1 * F[j].y;
+          ++u;
+        }
+        acc[NU + i] += dot2(F[i], F[i]);
+        acc[NU + CB + i] += dot2(F[i], r);
+        acc[NU + 2 * CB + i] -= F[i].x * rr0 + F[i].y * rr1;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = s;
+  }
+  __syncthreads();
+  const int nb = D.n_blocks;
+  const int cb = D.cb;  // accumulator layout uses the problem's block size (== CB)
+  for (int k = threadIdx.x; k < NACC; k += blockDim.x) {
+    const double s = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+    if (MODE == 0) {
+      atomicAdd(W.cam_acc + static_cast<int64_t>(nb) * cb * cb + static_cast<int64_t>(blk) * cb + k, s);
+    } else if (k < NU) {
+      // unpack upper-triangular index k -> (i, j)
+      int i = 0, rem = k;
+      while (rem >= CB - i) {
+        rem -= CB - i;
+        ++i;
+      }
+      const int j = i + rem;
+      double* Bm = W.cam_acc + static_cast<int64_t>(blk) * cb * cb;
+      atomicAdd(Bm + i * cb + j, s);
+      if (i != j) atomicAdd(Bm + j * cb + i, s);
+    } else {
+      const int which = (k - NU) / CB, i = (k - NU) % CB;
+      atomicAdd(W.cam_acc + static_cast<int64_t>(nb) * cb * cb + (static_cast<int64_t>(which) * nb + blk) * cb + i, s);
+    }
+  }
+}
+
+// Jacobi scales of the camera columns from diag(F^T F) (iteration 0 only).
+__global__ void k_camera_scales(DeviceProblem D, WorkArrays W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = D.n_blocks * D.cb;
+  if (i < n) {
+    const double d = W.cam_acc[static_cast<int64_t>(D.n_blocks) * D.cb * D.cb + i];
+    W.sc[i] = 1.0 / (1.0 + sqrt(d));
+  }
+}
+
+// One thread per camera block: D_c^2 = clamp(diag F^T F)/radius, M = B + D_c^2, M^-1 by
+// Cholesky, camera part of the gradient norms.
+template <int CB>
+__global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArrays W, double radius, double min_diag,
+                                                         double max_diag, double* __restrict__ partials) {
+  __shared__ double red[32];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nb = D.n_blocks;
+  double gsq = 0.0, gmax = 0.0, bad = 0.0;
+  if (b < nb) {
+    const double* Bm = W.cam_acc + static_cast<int64_t>(b) * CB * CB;
+    const double* diagF = W.cam_acc + static_cast<int64_t>(nb) * CB * CB + static_cast<int64_t>(b) * CB;
+    const double* gc = diagF + static_cast<int64_t>(nb) * CB;
+    double L[CB][CB];
+#pragma unroll
+    for (int i = 0; i < CB; ++i) {
+      const double d2 = fmin(fmax(diagF[i], min_diag), max_diag) / radius;
+      W.dc2[static_cast<int64_t>(b) * CB + i] = d2;
+#pragma unroll
+      for (int j = 0; j < CB; ++j) L[i][j] = Bm[i * CB + j] + (i == j ? d2 : 0.0);
+      const double g = gc[i] / W.sc[static_cast<int64_t>(b) * CB + i];
+      gsq += g * g;
+      gmax = fmax(gmax, fabs(g));
+    }
+    // in-place lower Cholesky
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < CB; ++j) {
+      double d = L[j][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+      if (!(d > 0.0)) {
+        ok = false;
+        d = 1.0;
+      }
+      d = sqrt(d);
+      L[j][j] = d;
+      const double id = 1.0 / d;
+#pragma unroll
+      for (int i = j + 1; i < CB; ++i) {
+        double s = L[i][j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+        L[i][j] = s * id;
+      }
+    }
+    if (!ok) bad = 1.0;
+    // M^-1 = L^-T L^-1, column by column
+    double* Mi = W.minv + static_cast<int64_t>(b) * CB * CB;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+      double y[CB];
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+        y[i] = s / L[i][i];
+      }
+#pragma unroll
+      for (int i = CB - 1; i >= 0; --i) {
+        double s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < CB; ++k) s -= L[k][i] * y[k];
+        y[i] = s / L[i][i];
+      }
+#pragma unroll
+      for (int i = 0; i < CB; ++i) Mi[i * CB + c] = ok ? y[i] : (i == c ? 1.0 : 0.0);
+    }
+  }
+  gsq = block_sum(gsq, red);
+  gmax = block_max(gmax, red);
+  bad = block_sum(bad, red);
+  if (threadIdx.x == 0) {
+    partials[3 * blockIdx.x + 0] = gsq;
+    partials[3 * blockIdx.x + 1] = gmax;
+    partials[3 * blockIdx.x + 2] = bad;
+  }
+}
+
+// --------------------------------------------------------------------------- K6 PCG
+// Single CTA (the camera-space vectors are a few 10^4 doubles).
+//   init:   x = 0, r = rhs, z = M^-1 r, p = z, rz = rz0 = r.z, q = 0
+__global__ void __launch_bounds__(1024) k_pcg_init(DeviceProblem D, WorkArrays W) {
+  __shared__ double red[32];
+  const int n = D.n_blocks * D.cb, cb = D.cb;
+  const double* rhs = W.cam_acc + static_cast<int64_t>(D.n_blocks) * cb * cb + 2 * static_cast<int64_t>(n);
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = i / cb, row = i - b * cb;
+    const double* Mi = W.minv + (static_cast<int64_t>(b) * cb + row) * cb;
+    double z = 0.0;
+    for (int k = 0; k < cb; ++k) z += Mi[k] * rhs[b * cb + k];
+    W.x[i] = 0.0;
+    W.r[i] = rhs[i];
+    W.z[i] = z;
+    W.p[i] = z;
+    W.q[i] = 0.0;
+    acc += rhs[i] * z;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    W.pcg_scal[0] = acc;
+    W.pcg_scal[1] = acc;
+    W.pcg_state[0] = 0;
+    W.pcg_state[1] = (acc > 0.0) ? 0 : 1;  // zero right-hand side: nothing to do
+  }
+}
+
+//   update: q += D_c^2 p; alpha = rz / p.q; x += alpha p; r -= alpha q; z = M^-1 r;
+//           beta = r.z / rz; p = z + beta p; q = 0; convergence flag.
+__global__ void __launch_bounds__(1024) k_pcg_update(DeviceProblem D, WorkArrays W, double tol2, int min_iter) {
+  __shared__ double red[32];
+  if (W.pcg_state[1]) return;  // converged earlier: keep x
+  const int n = D.n_blocks * D.cb, cb = D.cb;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double p = W.p[i];
+    const double q = W.q[i] + W.dc2[i] * p;
+    W.q[i] = q;
+    acc += p * q;
+  }
+  const double pq = block_sum_all(acc, red);
+  const double rz = W.pcg_scal[0];
+  if (!(pq > 0.0) || !isfinite(pq)) {  // breakdown: stop with the current x
+    if (threadIdx.x == 0) W.pcg_state[1] = 1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) W.q[i] = 0.0;
+    return;
+  }
+  const double alpha = rz / pq;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    W.x[i] += alpha * W.p[i];
+    W.r[i] -= alpha * W.q[i];
+  }
+  __syncthreads();
+  acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int b = i / cb, row = i - b * cb;
+    const double* Mi = W.minv + (static_cast<int64_t>(b) * cb + row) * cb;
+    double z = 0.0;
+    for (int k = 0; k < cb; ++k) z += Mi[k] * W.r[b * cb + k];
+    W.z[i] = z;
+    acc += W.r[i] * z;
+  }
+  const double rz_new = block_sum_all(acc, red);
+  const double beta = rz_new / rz;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    W.p[i] = W.z[i] + beta * W.p[i];
+    W.q[i] = 0.0;
+  }
+  if (threadIdx.x == 0) {
+    const int it = W.pcg_state[0] + 1;
+    W.pcg_state[0] = it;
+    W.pcg_scal[0] = rz_new;
+    if ((it >= min_iter && rz_new <= tol2 * W.pcg_scal[1]) || !(rz_new > 0.0)) W.pcg_state[1] = 1;
+  }
+}
+
+// ----------------------------------------------------------------- K5 implicit Schur
+// q += F^T (I - E C^-1 E^T) F p in ONE pass over point tiles:
+//   u_o = F_o p[blocks(o)]            (gather of p through L1/L2)
+//   y_i = C_i^-1 sum_{o in i} E_o^T u_o   (segmented reduction inside the tile, shared memory)
+//   w_o = u_o - E_o y_i ;  q[blocks(o)] += F_o^T w_o   (fp64 RED to L2)
+// Algorithmic HBM traffic: the Jacobian planes, 16*(3+CB[+6]) B per observation.
+template <int CB, bool TWO>
+__global__ void __launch_bounds__(kTile) k_schur_spmv(DeviceProblem D, WorkArrays W) {
+  if (W.pcg_state[1]) return;
+  __shared__ double v[3][kTile];
+  __shared__ double y[3][kTile];
+  const int t = blockIdx.x;
+  const int obs0 = D.tile_obs[t], obs1 = D.tile_obs[t + 1];
+  const int pt0 = D.tile_pt[t], pt1 = D.tile_pt[t + 1];
+  const int tid = threadIdx.x;
+  const int o = obs0 + tid;
+  const bool active = o < obs1;
+  double2 FA[CB];
+  double2 FB[TWO ? 6 : 1];
+  double2 e0, e1, e2;
+  double u0 = 0.0, u1 = 0.0;
+  int ba = 0, bb = -1, lp = 0;
+  if (active) {
+    const int2 idx = D.obs_idx[o];
+    const ObsView vw = D.views[idx.x];
+    ba = vw.pose_a;
+    bb = vw.pose_b;
+    lp = idx.y - pt0;
+    const double2* J = D.J + o;
+    const int64_t ld = D.ld;
+    e0 = J[(kPlaneJp + 0) * ld];
+    e1 = J[(kPlaneJp + 1) * ld];
+    e2 = J[(kPlaneJp + 2) * ld];
+    const double* pa = W.p + static_cast<int64_t>(ba) * CB;
+#pragma unroll
+    for (int k = 0; k < CB; ++k) {
+      FA[k] = J[(kPlaneJA + k) * ld];
+      const double pk = pa[k];
+      u0 += FA[k].x * pk;
+      u1 += FA[k].y * pk;
+    }
+    if (TWO) {
+      if (bb >= 0) {
+        const double* pb = W.p + static_cast<int64_t>(bb) * CB;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          FB[k] = J[(kPlaneJA + CB + k) * ld];
+          const double pk = pb[k];
+          u0 += FB[k].x * pk;
+          u1 += FB[k].y * pk;
+        }
+      }
+    }
+    v[0][tid] = e0.x * u0 + e0.y * u1;
+    v[1][tid] = e1.x * u0 + e1.y * u1;
+    v[2][tid] = e2.x * u0 + e2.y * u1;
+  }
+  __syncthreads();
+  const int pt = pt0 + tid;
+  if (pt < pt1) {
+    const int a = D.pt_first[pt] - obs0, b = D.pt_first[pt + 1] - obs0;
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = a; i < b; ++i) {
+      z0 += v[0][i];
+      z1 += v[1][i];
+      z2 += v[2][i];
+    }
+    const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
+    y[0][tid] = ci[0] * z0 + ci[1] * z1 + ci[2] * z2;
+    y[1][tid] = ci[1] * z0 + ci[3] * z1 + ci[4] * z2;
+    y[2][tid] = ci[2] * z0 + ci[4] * z1 + ci[5] * z2;
+  }
+  __syncthreads();
+  if (active) {
+    const double y0 = y[0][lp], y1 = y[1][lp], y2 = y[2][lp];
+    const double w0 = u0 - (e0.x * y0 + e1.x * y1 + e2.x * y2);
+    const double w1 = u1 - (e0.y * y0 + e1.y * y1 + e2.y * y2);
+    double* qa = W.q + static_cast<int64_t>(ba) * CB;
+#pragma unroll
+    for (int k = 0; k < CB; ++k) atomicAdd(qa + k, FA[k].x * w0 + FA[k].y * w1);
+    if (TWO) {
+      if (bb >= 0) {
+        double* qb = W.q + static_cast<int64_t>(bb) * CB;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(qb + k, FB[k].x * w0 + FB[k].y * w1);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------- K7 back-substitution
+// dp_i = -t_i - C_i^-1 sum_o E_o^T F_o x ;  partial of sum (J d).(r + J d / 2)
+template <int CB, bool TWO>
+__global__ void __launch_bounds__(kTile) k_back_substitute(DeviceProblem D, WorkArrays W,
+                                                            double* __restrict__ partial_model) {
+  __shared__ double v[3][kTile];
+  __shared__ double y[3][kTile];
+  __shared__ double red[32];
+  const int t = blockIdx.x;
+  const int obs0 = D.tile_obs[t], obs1 = D.tile_obs[t + 1];
+  const int pt0 = D.tile_pt[t], pt1 = D.tile_pt[t + 1];
+  const int tid = threadIdx.x;
+  const int o = obs0 + tid;
+  const bool active = o < obs1;
+  double2 e0, e1, e2, r;
+  double u0 = 0.0, u1 = 0.0;
+  int lp = 0;
+  if (active) {
+    const int2 idx = D.obs_idx[o];
+    lp = idx.y - pt0;
+    const double2* J = D.J + o;
+    const int64_t ld = D.ld;
+    r = J[kPlaneR * ld];
+    e0 = J[(kPlaneJp + 0) * ld];
+    e1 = J[(kPlaneJp + 1) * ld];
+    e2 = J[(kPlaneJp + 2) * ld];
+    if (CB > 0) {
+      const ObsView vw = D.views[idx.x];
+      const double* xa = W.x + static_cast<int64_t>(vw.pose_a) * CB;
+#pragma unroll
+      for (int k = 0; k < CB; ++k) {
+        const double2 F = J[(kPlaneJA + k) * ld];
+        u0 += F.x * xa[k];
+        u1 += F.y * xa[k];
+      }
+      if (TWO) {
+        if (vw.pose_b >= 0) {
+          const double* xb = W.x + static_cast<int64_t>(vw.pose_b) * CB;
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            const double2 F = J[(kPlaneJA + CB + k) * ld];
+            u0 += F.x * xb[k];
+            u1 += F.y * xb[k];
+          }
+        }
+      }
+    }
+    v[0][tid] = e0.x * u0 + e0.y * u1;
+    v[1][tid] = e1.x * u0 + e1.y * u1;
+    v[2][tid] = e2.x * u0 + e2.y * u1;
+  }
+  __syncthreads();
+  const int pt = pt0 + tid;
+  if (pt < pt1) {
+    const int a = D.pt_first[pt] - obs0, b = D.pt_first[pt + 1] - obs0;
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = a; i < b; ++i) {
+      z0 += v[0][i];
+      z1 += v[1][i];
+      z2 += v[2][i];
+    }
+    const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
+    const double* tp = W.tp + 3 * static_cast<int64_t>(pt);
+    const double d0 = -tp[0] - (ci[0] * z0 + ci[1] * z1 + ci[2] * z2);
+    const double d1 = -tp[1] - (ci[1] * z0 + ci[3] * z1 + ci[4] * z2);
+    const double d2 = -tp[2] - (ci[2] * z0 + ci[4] * z1 + ci[5] * z2);
+    double* dp = W.dp + 3 * static_cast<int64_t>(pt);
+    dp[0] = d0;
+    dp[1] = d1;
+    dp[2] = d2;
+    y[0][tid] = d0;
+    y[1][tid] = d1;
+    y[2][tid] = d2;
+  }
+  __syncthreads();
+  double m = 0.0;
+  if (active) {
+    const double y0 = y[0][lp], y1 = y[1][lp], y2 = y[2][lp];
+    const double jd0 = u0 + e0.x * y0 + e1.x * y1 + e2.x * y2;
+    const double jd1 = u1 + e0.y * y0 + e1.y * y1 + e2.y * y2;
+    m = jd0 * (r.x + 0.5 * jd0) + jd1 * (r.y + 0.5 * jd1);
+  }
+  m = block_sum(m, red);
+  if (tid == 0) partial_model[t] = m;
+}
+
+// ---------------------------------------------------------------------- param update
+// candidate = current + scale * step for points (thread per scalar); partial sums of
+// step^2 and x^2 (free parameters only, as Ceres' reduced program).
+__global__ void __launch_bounds__(256) k_update_points(int64_t n3, const double* __restrict__ cur,
+                                                        double* __restrict__ cand, const double* __restrict__ sp,
+                                                        const double* __restrict__ dp, double* __restrict__ partials) {
+  __shared__ double red[32];
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+  double ssq = 0.0, xsq = 0.0;
+  if (i < n3) {
+    const double x = cur[i];
+    const double d = sp[i] * dp[i];
+    cand[i] = x + d;
+    ssq = d * d;
+    xsq = x * x;
+  }
+  ssq = block_sum(ssq, red);
+  xsq = block_sum(xsq, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = ssq;
+    partials[2 * blockIdx.x + 1] = xsq;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_update_cameras(DeviceProblem D, ParamSet cur, ParamSet cand, WorkArrays W,
+                                                         double* __restrict__ partials) {
+  __shared__ double red[32];
+  const int b = blockIdx.x * 256 + threadIdx.x;
+  const int cb = D.cb;
+  double ssq = 0.0, xsq = 0.0;
+  if (b < D.n_ext) {
+    const double free_ = cur.pose_rows[b].free_;
+    for (int k = 0; k < 3; ++k) {
+      double d = 0.0, dt = 0.0;
+      if (cb >= 6) {
+        d = W.sc[b * cb + k] * W.x[b * cb + k] * free_;
+        dt = W.sc[b * cb + 3 + k] * W.x[b * cb + 3 + k] * free_;
+      }
+      const double w = cur.ext_rot[3 * b + k], t = cur.ext_trans[3 * b + k];
+      cand.ext_rot[3 * b + k] = w + d;
+      cand.ext_trans[3 * b + k] = t + dt;
+      ssq += d * d + dt * dt;
+      xsq += free_ * (w * w + t * t);
+    }
+  }
+  if (b < D.n_intr) {
+    double f0 = cur.focal[2 * b], f1 = cur.focal[2 * b + 1], k0 = cur.dist[2 * b], k1 = cur.dist[2 * b + 1];
+    if (cb == 9) {
+      const double df = W.sc[b * cb + 6] * W.x[b * cb + 6];
+      const double dk0 = W.sc[b * cb + 7] * W.x[b * cb + 7];
+      const double dk1 = W.sc[b * cb + 8] * W.x[b * cb + 8];
+      ssq += df * df + dk0 * dk0 + dk1 * dk1;
+      xsq += f0 * f0 + k0 * k0 + k1 * k1;
+      f0 += df;
+      k0 += dk0;
+      k1 += dk1;
+    }
+    cand.focal[2 * b] = f0;
+    cand.focal[2 * b + 1] = f1;
+    cand.dist[2 * b] = k0;
+    cand.dist[2 * b + 1] = k1;
+  }
+  ssq = block_sum(ssq, red);
+  xsq = block_sum(xsq, red);
+  if (threadIdx.x == 0) {
+    partials[2 * blockIdx.x] = ssq;
+    partials[2 * blockIdx.x + 1] = xsq;
+  }
+}
+
+// ------------------------------------------------------------------------ reductions
+// Deterministic single-CTA reductions of per-CTA partials.
+__global__ void __launch_bounds__(1024) k_reduce_sum(const double* __restrict__ in, int n, int stride, int offset,
+                                                      double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += in[static_cast<int64_t>(i) * stride + offset];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) *out = acc;
+}
+__global__ void __launch_bounds__(1024) k_reduce_max(const double* __restrict__ in, int n, int stride, int offset,
+                                                      double* __restrict__ out) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc = fmax(acc, in[static_cast<int64_t>(i) * stride + offset]);
+  acc = block_max(acc, red);
+  if (threadIdx.x == 0) *out = acc;
+}
+
+}  // namespace
+
+// ================================================================== launch wrappers
+int tile_grid(const DeviceProblem& D) { return D.n_tiles; }
+int cost_grid(const DeviceProblem& D) { return static_cast<int>((D.n_obs + 255) / 256); }
+
+void launch_pose_rows(const ParamSet& P, const uint8_t* ext_const, int freeze_all, int n_ext, int n_intr,
+                      cudaStream_t st) {
+  const int n = n_ext > n_intr ? n_ext : n_intr;
+  if (n <= 0) return;
+  k_pose_rows<<<(n + 127) / 128, 128, 0, st>>>(P, ext_const, freeze_all, n_ext, n_intr);
+}
+
+void launch_jacobian(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, int cb_store, int store_two,
+                     int unit_scale, double* partial_cost, cudaStream_t st) {
+  if (D.n_obs == 0) return;
+  const int grid = cost_grid(D);
+  if (cb_store == 0)
+    k_jacobian<0, false><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+  else if (cb_store == 6 && !store_two)
+    k_jacobian<6, false><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+  else if (cb_store == 6 && store_two)
+    k_jacobian<6, true><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+  else if (cb_store == 9 && !store_two)
+    k_jacobian<9, false><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+  else
+    k_jacobian<9, true><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+}
+
+void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost, double* mse_out, cudaStream_t st) {
+  if (D.n_obs == 0) return;
+  k_cost<<<cost_grid(D), 256, 0, st>>>(D, P, partial_cost, mse_out);
+}
+
+void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
+                          double max_diag, int mode, double* partials, cudaStream_t st) {
+  if (D.n_tiles == 0) return;
+  k_point_prepare<<<D.n_tiles, kTile, 0, st>>>(D, W, radius, min_diag, max_diag, mode, partials);
+}
+
+static size_t cam_acc_doubles(const DeviceProblem& D) {
+  return static_cast<size_t>(D.n_blocks) * D.cb * D.cb + 3 * static_cast<size_t>(D.n_blocks) * D.cb;
+}
+
+void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st) {
+  if (D.cb == 0) return;
+  cudaMemsetAsync(W.cam_acc, 0, cam_acc_doubles(D) * sizeof(double), st);
+  if (D.n_chunks == 0) return;
+  if (D.cb == 6) {
+    if (mode == 0)
+      k_camera_gather<6, 0><<<D.n_chunks, 128, 0, st>>>(D, W);
+    else
+      k_camera_gather<6, 1><<<D.n_chunks, 128, 0, st>>>(D, W);
+  } else {
+    if (mode == 0)
+      k_camera_gather<9, 0><<<D.n_chunks, 128, 0, st>>>(D, W);
+    else
+      k_camera_gather<9, 1><<<D.n_chunks, 128, 0, st>>>(D, W);
+  }
+}
+
+void launch_camera_scales(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  const int n = D.n_blocks * D.cb;
+  if (n == 0) return;
+  k_camera_scales<<<(n + 255) / 256, 256, 0, st>>>(D, W);
+}
+
+int camera_finalize_grid(const DeviceProblem& D) { return (D.n_blocks + 63) / 64; }
+
+void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
+                            double max_diag, double* partials, cudaStream_t st) {
+  if (D.cb == 0 || D.n_blocks == 0) return;
+  const int grid = camera_finalize_grid(D);
+  if (D.cb == 6)
+    k_camera_finalize<6><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+  else
+    k_camera_finalize<9><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+}
+
+void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  k_pcg_init<<<1, 1024, 0, st>>>(D, W);
+}
+
+void launch_schur_spmv(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  if (D.n_tiles == 0) return;
+  if (D.cb == 6 && !D.two)
+    k_schur_spmv<6, false><<<D.n_tiles, kTile, 0, st>>>(D, W);
+  else if (D.cb == 6)
+    k_schur_spmv<6, true><<<D.n_tiles, kTile, 0, st>>>(D, W);
+  else
+    k_schur_spmv<9, false><<<D.n_tiles, kTile, 0, st>>>(D, W);
+}
+
+void launch_pcg_update(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st) {
+  k_pcg_update<<<1, 1024, 0, st>>>(D, W, tol2, min_iter);
+}
+
+void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st) {
+  if (D.n_tiles == 0) return;
+  if (D.cb == 0)
+    k_back_substitute<0, false><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+  else if (D.cb == 6 && !D.two)
+    k_back_substitute<6, false><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+  else if (D.cb == 6)
+    k_back_substitute<6, true><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+  else
+    k_back_substitute<9, false><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+}
+
+int update_points_grid(const DeviceProblem& D) { return static_cast<int>((3 * static_cast<int64_t>(D.n_pts) + 255) / 256); }
+int update_cameras_grid(const DeviceProblem& D) {
+  const int n = D.n_ext > D.n_intr ? D.n_ext : D.n_intr;
+  return (n + 255) / 256;
+}
+
+void launch_update_points(const DeviceProblem& D, const ParamSet& cur, const ParamSet& cand, const WorkArrays& W,
+                          double* partials, cudaStream_t st) {
+  const int64_t n3 = 3 * static_cast<int64_t>(D.n_pts);
+  if (n3 == 0) return;
+  k_update_points<<<update_points_grid(D), 256, 0, st>>>(n3, cur.pts, cand.pts, W.sp, W.dp, partials);
+}
+
+void launch_update_cameras(const DeviceProblem& D, const ParamSet& cur, const ParamSet& cand, const WorkArrays& W,
+                           double* partials, cudaStream_t st) {
+  const int g = update_cameras_grid(D);
+  if (g == 0) return;
+  k_update_cameras<<<g, 256, 0, st>>>(D, cur, cand, W, partials);
+}
+
+void launch_reduce_sum(const double* partials, int n, int stride, int offset, double* out, cudaStream_t st) {
+  k_reduce_sum<<<1, 1024, 0, st>>>(partials, n, stride, offset, out);
+}
+void launch_reduce_max(const double* partials, int n, int stride, int offset, double* out, cudaStream_t st) {
+  k_reduce_max<<<1, 1024, 0, st>>>(partials, n, stride, offset, out);
+}
+
+}  // namespace dba

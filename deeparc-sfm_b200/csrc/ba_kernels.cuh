@@ -1,0 +1,140 @@
+// Launch interface of the bundle-adjustment kernels (sm_100a).  See DESIGN.md for the data
+// layout and the roofline of each kernel.
+//
+// Observation-ordered data is POINT-SORTED; every per-observation quantity is a "plane" of
+// double2 (= the two residual rows of one Jacobian column) with plane stride `ld`, so each
+// thread issues 16-byte loads and a warp touches 512 contiguous bytes per plane:
+//   plane 0            r            (r0, r1)
+//   plane 1..3         Jp[:,k]      d r / d point_k         (Jacobi-scaled)
+//   plane 4..4+CB-1    JA[:,k]      d r / d block A (pose a [+ f,k0,k1 when CB = 9])
+//   plane 4+CB..+5     JB[:,k]      d r / d block B (pose b), TWO only
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ba_math.cuh"
+
+namespace dba {
+
+constexpr int kTile = 256;       // observations per tile / threads per tile CTA
+constexpr int kPlaneR = 0;
+constexpr int kPlaneJp = 1;
+constexpr int kPlaneJA = 4;
+
+struct ObsView {
+  int pose_a, pose_b, intr, pad;  // 16 B
+};
+
+// Everything a kernel needs to find its data.  Plain pointers, passed by value.
+struct DeviceProblem {
+  int64_t n_obs;   // local (this rank) observations
+  int64_t ld;      // plane stride (double2 elements)
+  int n_pts;       // local points
+  int n_ext, n_intr, n_views, n_tiles;
+  int cb;          // camera block size: 0 (points only), 6, 9
+  int two;         // 1: observations may carry a second pose block
+  int n_blocks;    // camera blocks (== n_ext)
+  const double2* obs_xy;    // [n_obs]
+  const int2* obs_idx;      // [n_obs] (view, local point)
+  const ObsView* views;     // [n_views]
+  const int* tile_obs;      // [n_tiles + 1]
+  const int* tile_pt;       // [n_tiles + 1]
+  const int* pt_first;      // [n_pts + 1] first observation of each local point
+  // camera-sorted incidence (entries = obs * 2 + slot), chunked for the gather kernel
+  const int* cam_entries;   // [n_entries]
+  const int4* cam_chunks;   // [n_chunks] (block, first entry, last entry, 0)
+  int n_chunks;
+  double2* J;               // planes
+};
+
+struct ParamSet {
+  double* pts;        // [n_pts_local][3]
+  double* ext_rot;    // [n_ext][3]
+  double* ext_trans;  // [n_ext][3]
+  double* focal;      // [n_intr][2]
+  double* dist;       // [n_intr][2]
+  const double* center;  // [n_intr][2] (never optimised)
+  const int* nf;      // [n_intr]
+  const int* nd;      // [n_intr]
+  PoseRow* pose_rows; // [n_ext]   derived
+  IntrRow* intr_rows; // [n_intr]  derived
+};
+
+// per-point and per-camera work arrays
+struct WorkArrays {
+  double* sp;      // [n_pts][3] Jacobi scale of point columns
+  double* sc;      // [n_blocks][cb] Jacobi scale of camera columns
+  double* cinv;    // [n_pts][6]  (E^T E + D^2)^-1
+  double* tp;      // [n_pts][3]  C^-1 g_p
+  double* gp;      // [n_pts][3]  E^T r  (scaled gradient)
+  double* diag_p;  // [n_pts][3]  diag(E^T E) at the last accepted point (for D and for scaling)
+  double* dp;      // [n_pts][3]  point step (scaled space)
+  // camera accumulators, ONE contiguous buffer (single allreduce):
+  //   B [n_blocks][cb][cb] | diagF [n_blocks][cb] | gc [n_blocks][cb] | rhs [n_blocks][cb]
+  double* cam_acc;
+  double* minv;    // [n_blocks][cb][cb] inverse of the block-Jacobi preconditioner
+  double* dc2;     // [n_blocks][cb] D_c^2
+  double* diag_c;  // [n_blocks][cb] diag(F^T F) kept from the last accepted point
+  // PCG vectors [n_blocks * cb]
+  double *x, *r, *z, *p, *q;
+  double* partials;  // [n_partials] per-CTA partial sums (deterministic reductions)
+  double* scalars;   // [32] reduced scalars, copied to the host
+  int* pcg_state;    // [4] iter, done, -, -
+  double* pcg_scal;  // [4] rz, rz0, -, -
+};
+
+// scalar slots in WorkArrays::scalars
+enum ScalarSlot {
+  kSCost = 0,          // sum r^2 at x
+  kSCostCand = 1,      // sum r^2 at x + delta
+  kSGradMax = 2,       // max |g_unscaled|
+  kSGradSq = 3,        // sum g_unscaled^2
+  kSModel = 4,         // sum (J d).(r + J d / 2)
+  kSStepSq = 5,        // sum (s d)^2
+  kSXSq = 6,           // sum x^2 over free parameters
+  kSBadPoint = 7,      // count of non-SPD point blocks
+  kSColPt = 8,
+  kSCount = 16
+};
+
+// ---- launches (all asynchronous on `st`) ---------------------------------------------
+void launch_pose_rows(const ParamSet& P, const uint8_t* ext_const, int freeze_all, int n_ext, int n_intr,
+                      cudaStream_t st);
+// residuals + Jacobians at P.  cb_store in {0,6,9}; store_two: also block B planes.
+// unit_scale: ignore sp/sc and constancy masks (raw derivatives for dba_eval / column norms).
+// partial_cost: per-CTA sums of r^2, cost_grid(D) entries.
+void launch_jacobian(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, int cb_store, int store_two,
+                     int unit_scale, double* partial_cost, cudaStream_t st);
+// residual-only cost at P: per-CTA partial sums of r^2; optional per-observation mse.
+void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost, double* mse_out, cudaStream_t st);
+int cost_grid(const DeviceProblem& D);
+int tile_grid(const DeviceProblem& D);
+// per point: H = E^T E, g = E^T r.  mode 0: Jacobi scales sp.  mode 1: C = H + D^2, C^-1,
+// t = C^-1 g, partials[3*tile + {0,1,2}] = {sum g^2, max |g|, #non-SPD blocks}.
+void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
+                          double max_diag, int mode, double* partials, cudaStream_t st);
+// camera-sorted gather into W.cam_acc (zeroed here).  mode 0: diag F^T F only; mode 1: everything.
+void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st);
+void launch_camera_scales(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+// D_c^2, block-Jacobi inverse; partials[3*cta + {0,1,2}] as above for the camera side
+int camera_finalize_grid(const DeviceProblem& D);
+void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
+                            double max_diag, double* partials, cudaStream_t st);
+void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+// q += (F^T F - F^T E C^-1 E^T F) p   (implicit Schur complement, one fused pass)
+void launch_schur_spmv(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+void launch_pcg_update(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
+// dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
+void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st);
+// candidate = current + scale * step; partials[2*cta + {0,1}] = {sum step^2, sum x^2}
+int update_points_grid(const DeviceProblem& D);
+int update_cameras_grid(const DeviceProblem& D);
+void launch_update_points(const DeviceProblem& D, const ParamSet& cur, const ParamSet& cand, const WorkArrays& W,
+                          double* partials, cudaStream_t st);
+void launch_update_cameras(const DeviceProblem& D, const ParamSet& cur, const ParamSet& cand, const WorkArrays& W,
+                           double* partials, cudaStream_t st);
+// deterministic single-CTA reductions of strided partials
+void launch_reduce_sum(const double* partials, int n, int stride, int offset, double* out, cudaStream_t st);
+void launch_reduce_max(const double* partials, int n, int stride, int offset, double* out, cudaStream_t st);
+
+}  // namespace dba
