@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/s of the B200 bundle-adjustment engine on BASELINE.json's
+BAL-scale workload (configs[3]: 1.7k cameras, 1M points, 5M observations, 9-dof cameras).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload bal5m|arc1m|stress50m|small] [--pcg-iters 20]
+
+A "step" is ONE Levenberg-Marquardt iteration on the whole problem: Schur elimination for the
+current radius, `--pcg-iters` block-Jacobi PCG iterations on the implicit Schur complement,
+back-substitution, trial-cost evaluation, accept/reject and (when accepted) a fresh residual +
+Jacobian evaluation.  Tolerances are 0 so exactly K iterations run.
+
+  value   LM iterations/s, problem resident in HBM, CUDA events around iterations 1..K
+          (dba_summary.loop_device_time_in_seconds), max over ranks
+  e2e     the same metric through the C ABI with HOST buffers: dba_problem_set (host sort +
+          host->device copies) + dba_solve (K iterations incl. the initial evaluation) +
+          dba_params_get (device->host), wall clock around the three calls
+  roofline  dominant kernel (schur_spmv): algorithmic bytes / mean CUDA-event duration,
+          against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (oracle/, a restatement of the reference's Ceres path: the
+          reference itself needs Ceres, which is not installable) on the box's host cores
+
+`--impl reference` times that CPU path alone (see DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "lm_iters_per_sec"
+UNIT = "LM iterations/s"
+
+WORKLOADS = {
+    # name: (generator kwargs, description)
+    "bal5m": dict(kind="bal", n_cam=1700, n_pts=1_000_000, obs_per_point=5, window=50),
+    "stress50m": dict(kind="bal", n_cam=10_000, n_pts=10_000_000, obs_per_point=5, window=50),
+    "arc1m": dict(kind="rig", n_arc=10, n_ring=10, n_pts=100_000, obs_per_point=10),
+    "small": dict(kind="bal", n_cam=200, n_pts=50_000, obs_per_point=5, window=50),
+}
+
+
+def build_workload(name: str):
+    from deeparc_sfm_b200 import synthetic
+    kw = dict(WORKLOADS[name])
+    kind = kw.pop("kind")
+    if kind == "bal":
+        return synthetic.bal_like(**kw, name=name)
+    return synthetic.arc_rig(**kw, name=name)
+
+
+def describe(name: str, p, pcg_iters: int, n_gpus: int):
+    return {
+        "workload": f"{name}: synthetic {'BAL-scale' if p.n_ring == 0 else 'DeepArc arc rig'}, "
+                    f"{p.n_ext} extrinsics, {p.n_pts} points, {p.n_obs} observations",
+        "camera_block": "9-dof [w,t,f,k0,k1]" if p.free_intrinsics else ("2x6-dof composed poses" if (p.obs_pose_b >= 0).any() else "6-dof pose"),
+        "pcg_iterations_per_lm_iteration": pcg_iters,
+        "linear_solver": "implicit Schur complement + block-Jacobi PCG (fixed iterations, tolerance 0)",
+        "tolerances": "function/gradient/parameter = 0 (exactly K iterations)",
+        "cache": "inputs larger than L2: Jacobian planes %.0f MB per pass vs 126 MB L2" % (p.n_obs * 16 * 13 / 1e6),
+        "parallelism": f"points sharded over {n_gpus} GPU(s)" if n_gpus > 1 else "1 GPU",
+    }
+
+
+def solve_options(capi, steps: int, pcg_iters: int):
+    return capi.make_options(max_num_iterations=steps, function_tolerance=0.0, gradient_tolerance=0.0,
+                             parameter_tolerance=0.0, linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=0.0,
+                             pcg_max_iterations=pcg_iters, pcg_min_iterations=0, progress_to_stdout=0)
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = os.path.join(ROOT, "gpurun_out", f"clocks_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            os.makedirs(os.path.dirname(self.path), exist_ok=True)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()  # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                sm.append(float(f[0]))
+                out["sm_max_mhz"] = float(f[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------- CPU baseline
+def cpu_reference_run(p, steps: int, pcg_iters: int, budget_s: float, dense: bool = True):
+    """Times the CPU oracle (restatement of the reference's Ceres path) on this host."""
+    from deeparc_sfm_b200 import capi
+    from tests import oracle_lib
+    O = oracle_lib.Oracle()
+    cores = O.num_procs()
+    ls = capi.DBA_LS_DENSE if dense else capi.DBA_LS_PCG
+    opts = capi.make_options(max_num_iterations=steps, function_tolerance=0.0, gradient_tolerance=0.0,
+                             parameter_tolerance=0.0, linear_solver=ls, pcg_rel_tolerance=0.0,
+                             pcg_max_iterations=pcg_iters, max_solver_time_in_seconds=budget_s)
+    t0 = time.time()
+    s, _ = O.solve(p, opts, num_threads=cores)
+    wall = time.time() - t0
+    it_times = s.trace("iteration_time_in_seconds")
+    n_done = max(len(it_times) - 1, 0)
+    loop = float(np.sum(it_times[1:])) if n_done else float("nan")
+    return {"iters_per_sec": (n_done / loop) if n_done and loop > 0 else 0.0, "steps_done": n_done,
+            "loop_seconds": loop, "wall_seconds": wall, "cores": cores,
+            "linear_solver": "DENSE_SCHUR (exact, as the reference configures Ceres, sfm.cc:67)" if dense
+            else f"implicit Schur PCG, {pcg_iters} iterations",
+            "initial_cost": s.initial_cost, "final_cost": s.final_cost}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="bal5m", choices=list(WORKLOADS))
+    ap.add_argument("--pcg-iters", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=40.0, help="seconds of CPU LM iterations")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        p = build_workload(args.workload)
+        r = cpu_reference_run(p, steps=max(args.steps, 1), pcg_iters=args.pcg_iters, budget_s=args.cpu_budget)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["iters_per_sec"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps_done"], "warmup": 0, "ms_per_step": (1e3 / r["iters_per_sec"]) if r["iters_per_sec"] else None,
+            "higher_is_better": True, "scaling": "weak" if args.gpus > 1 else "n/a", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": describe(args.workload, p, args.pcg_iters, 1),
+            "cpu_baseline": {"value": r["iters_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "sample": f"{r['steps_done']} full LM iteration(s) of the same problem within a "
+                                       f"{args.cpu_budget:.0f}s budget (requested {args.steps}); {r['linear_solver']}; "
+                                       "oracle/ restatement of the reference's Ceres path (real Ceres not installable)"},
+            "e2e": {"value": r["iters_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ----------------------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    from deeparc_sfm_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        lib = capi.load_library()
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            import ctypes
+            raw = ctypes.create_string_buffer(128)
+            st = lib.dba_nccl_unique_id(raw)
+            if st != 0:
+                raise SystemExit(f"dba_nccl_unique_id failed: {st}")
+            buf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        buf = buf.cuda()
+        dist.broadcast(buf, 0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+
+    p = build_workload(args.workload)
+    eng = capi.Engine(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    eng.problem_set(p)
+    opts_w = solve_options(capi, max(args.warmup, 3), args.pcg_iters)
+    eng.solve(opts_w)  # warm-up steps (untimed)
+    eng.params_reset()
+
+    # ---- timed: exactly K LM iterations, device resident
+    opts = solve_options(capi, args.steps, args.pcg_iters)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    s = eng.solve(opts)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    steps_done = s.num_iterations - 1
+    loop_s = max_over_ranks(s.loop_device_time_in_seconds)
+    value = steps_done / loop_s if loop_s > 0 else 0.0
+    launches = int(s.kernel_launches)
+    accepted = int(s.num_successful_steps)
+
+    # ---- same run with per-kernel CUDA events (roofline of the dominant kernel)
+    eng.params_reset()
+    eng.kernel_stats_enable(True)
+    eng.kernel_stats_reset()
+    barrier()
+    s2 = eng.solve(opts)
+    barrier()
+    stats = {k["name"]: k for k in eng.kernel_stats()}
+    eng.kernel_stats_enable(False)
+    loop2_s = max_over_ranks(s2.loop_device_time_in_seconds)
+
+    # ---- end to end through the C ABI with host buffers
+    barrier()
+    t0 = time.perf_counter()
+    eng.problem_set(p)
+    s3 = eng.solve(opts)
+    out = eng.params_get()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    q = eng.problem.p
+    h2d = (q.obs_xy.nbytes + 4 * q.obs_pt.nbytes + q.pts.nbytes + q.ext_rot.nbytes + q.ext_trans.nbytes +
+           q.intr_center.nbytes + q.intr_focal.nbytes + q.intr_dist.nbytes)
+    d2h = sum(v.nbytes for v in out.values())
+    e2e_value = (s3.num_iterations - 1) / e2e_s
+
+    if rank != 0:
+        return 0
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    roof = None
+    if "spmv_point" in stats and stats["spmv_point"]["launches"] > 0:
+        ka, kb = stats["spmv_point"], stats["spmv_camera"]
+        ms_a, ms_b = ka["total_ms"] / ka["launches"], kb["total_ms"] / max(kb["launches"], 1)
+        cb = 9 if p.free_intrinsics else 6
+        planes = 3 + cb + (6 if (p.obs_pose_b >= 0).any() else 0)
+        # SURVEY.md 8(d) model of ONE implicit Schur product: read Jc + Jp planes + indices once
+        model_bytes = (8.0 + 16.0 * planes) * (p.n_obs / world)
+        achieved = model_bytes / ((ms_a + ms_b) * 1e-3) / 1e9
+        total_ms = sum(v["total_ms"] for v in stats.values())
+        roof = {"bound": "hbm", "kernel": "implicit Schur product = k_spmv_point + k_spmv_camera",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": model_bytes,
+                "model": "single-pass model of SURVEY 8(d), %d B/observation; the two phases together move %.0f B/observation" % (
+                    8 + 16 * planes, (ka["algorithmic_bytes"] + kb["algorithmic_bytes"]) / (p.n_obs / world)),
+                "mean_launch_ms": ms_a + ms_b, "launches": ka["launches"],
+                "phases": {"k_spmv_point": {"mean_ms": ms_a, "bytes": ka["algorithmic_bytes"],
+                                            "gbs": ka["algorithmic_bytes"] / (ms_a * 1e-3) / 1e9,
+                                            "frac": ka["algorithmic_bytes"] / (ms_a * 1e-3) / 1e9 / peak},
+                           "k_spmv_camera": {"mean_ms": ms_b, "bytes": kb["algorithmic_bytes"],
+                                             "gbs": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 if ms_b > 0 else None,
+                                             "frac": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 / peak if ms_b > 0 else None}},
+                "share_of_kernel_time": (ka["total_ms"] + kb["total_ms"]) / total_ms if total_ms > 0 else None}
+    kernels = {n: {"launches": v["launches"], "total_ms": round(v["total_ms"], 4),
+                   "gbs": (v["algorithmic_bytes"] * v["launches"] / (v["total_ms"] * 1e-3) / 1e9) if v["total_ms"] > 0 and v["algorithmic_bytes"] > 0 else None}
+               for n, v in stats.items()}
+    jac = stats.get("jacobian")
+    jac_obs_s = (p.n_obs / world * jac["launches"] / (jac["total_ms"] * 1e-3)) * world if jac and jac["total_ms"] > 0 else None
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(p, steps=1, pcg_iters=args.pcg_iters, budget_s=args.cpu_budget)
+        cpu = {"value": r["iters_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+               "sample": f"{r['steps_done']} full LM iteration of the same problem ({r['loop_seconds']:.1f}s), "
+                         f"{r['linear_solver']}; oracle/ restatement of the reference's Ceres path"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * loop_s / max(steps_done, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": describe(args.workload, p, args.pcg_iters, world),
+        "clocks": clocks, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(steps_done, 1),
+                                  "d2h_bytes_per_step": d2h / max(steps_done, 1), "seconds": e2e_s,
+                                  "includes": "dba_problem_set (host sort + H2D) + dba_solve + dba_params_get (D2H)"},
+        "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "jacobian_obs_per_sec": jac_obs_s, "accepted_steps": accepted, "final_cost": s.final_cost,
+        "initial_cost": s.initial_cost, "ms_per_step_with_event_timers": 1e3 * loop2_s / max(steps_done, 1),
+        "kernels": kernels,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

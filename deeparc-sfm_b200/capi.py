@@ -73,6 +73,7 @@ class DbaSummary(C.Structure):
                 ("num_unsuccessful_steps", C.c_int32), ("linear_solver_used", C.c_int32),
                 ("reduced_system_size", C.c_int32), ("initial_cost", C.c_double), ("final_cost", C.c_double),
                 ("total_time_in_seconds", C.c_double), ("device_time_in_seconds", C.c_double),
+                ("loop_device_time_in_seconds", C.c_double),
                 ("kernel_launches", C.c_int64), ("jacobian_evaluations", C.c_int64),
                 ("residual_evaluations", C.c_int64), ("pcg_iterations_total", C.c_int64),
                 ("message", C.c_char * 192), ("iterations", C.POINTER(DbaIteration)),

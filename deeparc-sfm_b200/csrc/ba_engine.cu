@@ -95,20 +95,23 @@ struct dba_handle {
   WorkArrays W{};
 
   // device storage
-  DevBuf<double2> d_obs_xy, d_J;
+  DevBuf<double2> d_obs_xy, d_J, d_FC;
+  DevBuf<int> d_ent_pos;
   DevBuf<int2> d_obs_idx;
   DevBuf<ObsView> d_views;
-  DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_nf, d_nd, d_pcg_state;
+  DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
+  DevBuf<unsigned int> d_counters;
   DevBuf<int4> d_cam_chunks;
   DevBuf<uint8_t> d_ext_const;
   DevBuf<double> d_center, d_pts[3], d_rot[3], d_trans[3], d_focal[3], d_dist[3];  // [2] = initial copy
   DevBuf<PoseRow> d_pose_rows[2];
   DevBuf<IntrRow> d_intr_rows[2];
   DevBuf<double> d_sp, d_sc, d_cinv, d_tp, d_dp, d_cam_acc, d_minv, d_dc2, d_x, d_r, d_z, d_p, d_q;
-  DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts;
+  DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts, d_chunk_q, d_vec_partials;
   double* h_scalars = nullptr;  // pinned
   int* h_pcg_state = nullptr;   // pinned
   size_t j_planes = 0;
+  int plane_w = 0;  // extra plane holding w of the two-phase Schur product
 
   // accounting
   int64_t launches = 0;
@@ -240,7 +243,9 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
   const ParamSet& P = h->P[h->cur];
   const int nplanes = 4 + h->cb + (h->two && h->cb ? 6 : 0);
   // read xy(16)+idx(8), write r + Jp + Jc planes
-  const double k1_bytes = (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs);
+  // (+ the camera-sorted copy of the camera-side columns, written once more)
+  const double k1_bytes = (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs) +
+                          (h->cb ? (4.0 + 16.0 * h->cb) * static_cast<double>(h->d_cam_entries.n) : 0.0);
   {
     Scope s(h, "pose_rows");
     launch_pose_rows(P, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
@@ -323,7 +328,9 @@ int prepare_step(dba_handle* h, double radius, const dba_solve_options& o) {
 int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   const DeviceProblem& D = h->D;
   const int nplanes = 3 + h->cb + (h->two ? 6 : 0);
-  const double spmv_bytes = (8.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs);
+  // phase A: indices (8) + Jp, Jc planes + the w plane written; phase B: entry (4) + Jc planes + w
+  const double point_bytes = (8.0 + 16.0 * nplanes + 16.0) * static_cast<double>(h->n_obs);
+  const double cam_bytes = (4.0 + 16.0 * h->cb + 16.0) * static_cast<double>(h->d_cam_entries.n);
   {
     Scope s(h, "pcg_init");
     launch_pcg_init(D, h->W, h->st);
@@ -338,13 +345,25 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
     const int batch = std::min(check_every > 0 ? check_every : max_it, max_it - issued);
     for (int i = 0; i < batch; ++i) {
       {
-        Scope s(h, "schur_spmv", spmv_bytes);
-        launch_schur_spmv(D, h->W, h->st);
+        Scope s(h, "spmv_point", point_bytes);
+        launch_spmv_point(D, h->W, h->plane_w, h->st);
       }
-      int rc = allreduce(h, h->W.q, nvec, kNcclSum);
-      if (rc != DBA_OK) return rc;
-      Scope s(h, "pcg_update");
-      launch_pcg_update(D, h->W, tol2, o.pcg_min_iterations, h->st);
+      {
+        Scope s(h, "spmv_camera", cam_bytes);
+        launch_spmv_camera(D, h->W, h->plane_w, h->st);
+      }
+      if (h->world > 1) {
+        {
+          Scope s(h, "pcg_vector");
+          launch_chunks_to_q(D, h->W, h->st);
+        }
+        int rc = allreduce(h, h->W.q, nvec, kNcclSum);
+        if (rc != DBA_OK) return rc;
+      }
+      Scope s(h, "pcg_vector", 0.0, 3);
+      launch_pcg_dot(D, h->W, h->world == 1, h->st);
+      launch_pcg_step(D, h->W, tol2, o.pcg_min_iterations, h->st);
+      launch_pcg_direction(D, h->W, h->st);
     }
     issued += batch;
     CU(h, cudaMemcpyAsync(h->h_pcg_state, h->W.pcg_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -654,6 +673,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   // ---- camera-sorted incidence, chunked
   std::vector<int> cam_entries;
   std::vector<int4> cam_chunks;
+  std::vector<int> cam_chunk_first(static_cast<size_t>(p->n_ext) + 1, 0);
+  std::vector<int> ent_pos;
   if (h->cb) {
     std::vector<int64_t> first(static_cast<size_t>(p->n_ext) + 1, 0);
     for (int64_t k = 0; k < nl; ++k) {
@@ -664,20 +685,29 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     for (int i = 0; i < p->n_ext; ++i) first[i + 1] += first[i];
     cam_entries.resize(first[p->n_ext]);
     std::vector<int64_t> cursor(first.begin(), first.end() - 1);
+    ent_pos.assign(2 * static_cast<size_t>(nl), -1);
     for (int64_t k = 0; k < nl; ++k) {
       const ObsView& v = views[obs_idx[k].x];
+      ent_pos[2 * k] = static_cast<int>(cursor[v.pose_a]);
       cam_entries[cursor[v.pose_a]++] = static_cast<int>(k * 2);
-      if (v.pose_b >= 0) cam_entries[cursor[v.pose_b]++] = static_cast<int>(k * 2 + 1);
+      if (v.pose_b >= 0) {
+        ent_pos[2 * k + 1] = static_cast<int>(cursor[v.pose_b]);
+        cam_entries[cursor[v.pose_b]++] = static_cast<int>(k * 2 + 1);
+      }
     }
     const int kChunk = 1024;
-    for (int b = 0; b < p->n_ext; ++b)
+    for (int b = 0; b < p->n_ext; ++b) {
+      cam_chunk_first[b] = static_cast<int>(cam_chunks.size());
       for (int64_t e = first[b]; e < first[b + 1]; e += kChunk)
         cam_chunks.push_back(make_int4(b, static_cast<int>(e), static_cast<int>(std::min<int64_t>(e + kChunk, first[b + 1])), 0));
+    }
+    cam_chunk_first[p->n_ext] = static_cast<int>(cam_chunks.size());
   }
 
   // ---- device allocation + upload
   const int64_t ld = ((nl + 63) / 64) * 64;
-  h->j_planes = 4 + h->cb + ((h->two && h->cb) ? 6 : 0);
+  h->plane_w = 4 + h->cb + ((h->two && h->cb) ? 6 : 0);
+  h->j_planes = h->plane_w + 1;
   CU(h, h->d_obs_xy.alloc(std::max<int64_t>(nl, 1)));
   CU(h, h->d_obs_idx.alloc(std::max<int64_t>(nl, 1)));
   CU(h, h->d_views.alloc(std::max<size_t>(views.size(), 1)));
@@ -686,6 +716,14 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, h->d_pt_first.alloc(pt_first.size()));
   CU(h, h->d_cam_entries.alloc(std::max<size_t>(cam_entries.size(), 1)));
   CU(h, h->d_cam_chunks.alloc(std::max<size_t>(cam_chunks.size(), 1)));
+  CU(h, h->d_cam_chunk_first.alloc(cam_chunk_first.size()));
+  const int64_t ldc = ((static_cast<int64_t>(cam_entries.size()) + 63) / 64) * 64;
+  CU(h, h->d_FC.alloc(std::max<int64_t>(ldc, 64) * std::max(h->cb, 1)));
+  CU(h, h->d_ent_pos.alloc(std::max<size_t>(ent_pos.size(), 2)));
+  CU(h, h->d_chunk_q.alloc(std::max<size_t>(cam_chunks.size() * std::max(h->cb, 1), 1)));
+  CU(h, h->d_vec_partials.alloc(static_cast<size_t>(p->n_ext) * std::max(h->cb, 1) / 128 + 64));
+  CU(h, h->d_counters.alloc(4));
+  CU(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * sizeof(unsigned int), h->st));
   CU(h, h->d_J.alloc(std::max<int64_t>(ld, 64) * h->j_planes));
   CU(h, h->d_ext_const.alloc(std::max(p->n_ext, 1)));
   CU(h, h->d_center.alloc(2 * std::max(p->n_intr, 1)));
@@ -723,7 +761,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, h->d_partB.alloc(3 * static_cast<size_t>((std::max(p->n_ext, p->n_intr) + 63) / 64) + 64));
   CU(h, h->d_scalars.alloc(S_TOTAL));
   CU(h, h->d_scalars_red.alloc(S_TOTAL));
-  CU(h, h->d_pcg_scal.alloc(4));
+  CU(h, h->d_pcg_scal.alloc(8));
   CU(h, h->d_pcg_state.alloc(4));
   CU(h, cudaMemsetAsync(h->d_scalars.p, 0, S_TOTAL * sizeof(double), h->st));
   CU(h, cudaMemsetAsync(h->d_x.p, 0, std::max<size_t>(nvec, 1) * sizeof(double), h->st));
@@ -741,6 +779,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_pt_first.p, pt_first.data(), pt_first.size() * sizeof(int)));
   CU(h, up(h->d_cam_entries.p, cam_entries.data(), cam_entries.size() * sizeof(int)));
   CU(h, up(h->d_cam_chunks.p, cam_chunks.data(), cam_chunks.size() * sizeof(int4)));
+  CU(h, up(h->d_cam_chunk_first.p, cam_chunk_first.data(), cam_chunk_first.size() * sizeof(int)));
+  CU(h, up(h->d_ent_pos.p, ent_pos.data(), ent_pos.size() * sizeof(int)));
   std::vector<uint8_t> ext_const(std::max(p->n_ext, 1), 0);
   h->any_const = false;
   if (p->ext_const)
@@ -779,8 +819,12 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.pt_first = h->d_pt_first.p;
   D.cam_entries = h->d_cam_entries.p;
   D.cam_chunks = h->d_cam_chunks.p;
+  D.cam_chunk_first = h->d_cam_chunk_first.p;
   D.n_chunks = static_cast<int>(cam_chunks.size());
   D.J = h->d_J.p;
+  D.FC = h->cb ? h->d_FC.p : nullptr;
+  D.ldc = std::max<int64_t>(ldc, 64);
+  D.ent_pos = h->d_ent_pos.p;
   for (int s = 0; s < 2; ++s) {
     ParamSet& P = h->P[s];
     P.pts = h->d_pts[s].p;
@@ -815,6 +859,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.scalars = h->d_scalars.p;
   W.pcg_state = h->d_pcg_state.p;
   W.pcg_scal = h->d_pcg_scal.p;
+  W.chunk_q = h->d_chunk_q.p;
+  W.vec_partials = h->d_vec_partials.p;
+  W.counters = h->d_counters.p;
   h->have_problem = true;
   return dba_params_reset(h);
 }
@@ -862,6 +909,7 @@ int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, dou
       DevBuf<double2> tmp;
       CU(h, tmp.alloc(D.ld * 4));
       D.J = tmp.p;
+      D.FC = nullptr;
       {
         Scope s(h, "jacobian");
         launch_jacobian(D, P, h->W, 0, 0, 1, h->d_partA.p, h->st);
@@ -884,6 +932,7 @@ int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, dou
     DevBuf<double2> tmp;
     CU(h, tmp.alloc(D.ld * planes));
     D.J = tmp.p;
+    D.FC = nullptr;
     {
       Scope s(h, "jacobian");
       launch_jacobian(D, P, h->W, cbs, twos, 1, h->d_partA.p, h->st);
@@ -994,10 +1043,12 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
   sum->reduced_system_size = h->n_ext * h->cb;
   const int64_t launches0 = h->launches;
   const double t_start = now_s();
-  cudaEvent_t ev0, ev1;
+  cudaEvent_t ev0, ev1, ev_loop;
   CU(h, cudaEventCreate(&ev0));
   CU(h, cudaEventCreate(&ev1));
+  CU(h, cudaEventCreate(&ev_loop));
   CU(h, cudaEventRecord(ev0, h->st));
+  bool loop_started = false;
 
   int n_it = 0;
   auto push = [&](const dba_iteration& it) {
@@ -1008,10 +1059,13 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
   auto finish = [&](int termination, const char* msg) -> int {
     cudaEventRecord(ev1, h->st);
     cudaEventSynchronize(ev1);
-    float ms = 0.f;
+    float ms = 0.f, ms_loop = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
+    if (loop_started) cudaEventElapsedTime(&ms_loop, ev_loop, ev1);
     cudaEventDestroy(ev0);
     cudaEventDestroy(ev1);
+    cudaEventDestroy(ev_loop);
+    sum->loop_device_time_in_seconds = ms_loop * 1e-3;
     sum->termination = termination;
     sum->num_iterations = std::min(n_it, it_cap);
     sum->final_cost = x_cost;
@@ -1089,6 +1143,10 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
 
   char msg[192];
   while (finalize() == 0) {
+    if (!loop_started) {
+      CU(h, cudaEventRecord(ev_loop, h->st));
+      loop_started = true;
+    }
     iter_start = now_s();
     const dba_iteration prev = it;
     it = dba_iteration{};

@@ -5,8 +5,8 @@
 //   k_jacobian   (K1)  residual + analytic Jacobian of operator() (:93-118), replaces Ceres autodiff
 //   k_cost       (K2)  residual-only evaluation (trial point; filterPoint3d, DeepArcManager.cc:335-347)
 //   k_point_prepare, k_camera_gather, k_camera_finalize (K3)  Schur elimination front half
-//   k_schur_spmv (K5)  implicit Schur complement product, one fused pass over point tiles
-//   k_pcg_init / k_pcg_update (K6)  block-Jacobi PCG vector work, single CTA
+//   k_spmv_point + k_spmv_camera (K5)  implicit Schur complement product, two atomic-free phases
+//   k_pcg_init / k_pcg_dot / k_pcg_step / k_pcg_direction (K6)  block-Jacobi PCG vector work
 //   k_back_substitute (K7), k_param_update  point back-substitution, x + delta, norms
 #include <cstdio>
 
@@ -165,15 +165,24 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
 #pragma unroll
         for (int k = 0; k < 6; ++k) s[k] *= A.free_;
       }
+      double2 FA[CB > 0 ? CB : 1];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        J[(kPlaneJA + k) * ld] = make_double2(Jw[0][k] * s[k], Jw[1][k] * s[k]);
-        J[(kPlaneJA + 3 + k) * ld] = make_double2(pr.G[0][k] * s[3 + k], pr.G[1][k] * s[3 + k]);
+        FA[k] = make_double2(Jw[0][k] * s[k], Jw[1][k] * s[k]);
+        FA[3 + k] = make_double2(pr.G[0][k] * s[3 + k], pr.G[1][k] * s[3 + k]);
       }
       if (CB == 9) {
-        J[(kPlaneJA + 6) * ld] = make_double2(pr.df[0] * s[6], pr.df[1] * s[6]);
-        J[(kPlaneJA + 7) * ld] = make_double2(pr.dk0[0] * s[7], pr.dk0[1] * s[7]);
-        J[(kPlaneJA + 8) * ld] = make_double2(pr.dk1[0] * s[8], pr.dk1[1] * s[8]);
+        FA[6] = make_double2(pr.df[0] * s[6], pr.df[1] * s[6]);
+        FA[7] = make_double2(pr.dk0[0] * s[7], pr.dk0[1] * s[7]);
+        FA[8] = make_double2(pr.dk1[0] * s[8], pr.dk1[1] * s[8]);
+      }
+#pragma unroll
+      for (int k = 0; k < CB; ++k) J[(kPlaneJA + k) * ld] = FA[k];
+      // camera-sorted copy (sequential stream for the camera-side kernels): 16-byte scatter
+      if (D.FC) {
+        double2* FCa = D.FC + D.ent_pos[2 * o];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) FCa[k * D.ldc] = FA[k];
       }
       if (TWO) {
         const int pb = kPlaneJA + CB;
@@ -188,10 +197,18 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
 #pragma unroll
             for (int k = 0; k < 6; ++k) sb[k] = sc[k] * B.free_;
           }
+          double2 FB[6];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            J[(pb + k) * ld] = make_double2(JwB[0][k] * sb[k], JwB[1][k] * sb[k]);
-            J[(pb + 3 + k) * ld] = make_double2(GA[0][k] * sb[3 + k], GA[1][k] * sb[3 + k]);
+            FB[k] = make_double2(JwB[0][k] * sb[k], JwB[1][k] * sb[k]);
+            FB[3 + k] = make_double2(GA[0][k] * sb[3 + k], GA[1][k] * sb[3 + k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = FB[k];
+          if (D.FC) {
+            double2* FCb = D.FC + D.ent_pos[2 * o + 1];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) FCb[k * D.ldc] = FB[k];
           }
         } else {
 #pragma unroll
@@ -327,10 +344,10 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
     const int o = ent >> 1;
     const int slot = ent & 1;
     const double2* J = D.J + o;
-    const int base = kPlaneJA + (slot ? D.cb : 0);
+    const double2* FCe = D.FC + e;
     double2 F[CB];
 #pragma unroll
-    for (int k = 0; k < CB; ++k) F[k] = (slot && k >= 6) ? make_double2(0.0, 0.0) : J[(base + k) * ld];
+    for (int k = 0; k < CB; ++k) F[k] = (slot && k >= 6) ? make_double2(0.0, 0.0) : FCe[k * D.ldc];
     if (MODE == 0) {
 #pragma unroll
       for (int k = 0; k < CB; ++k) acc[k] += dot2(F[k], F[k]);
@@ -491,92 +508,20 @@ __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArr
   }
 }
 
-// --------------------------------------------------------------------------- K6 PCG
-// Single CTA (the camera-space vectors are a few 10^4 doubles).
-//   init:   x = 0, r = rhs, z = M^-1 r, p = z, rz = rz0 = r.z, q = 0
-__global__ void __launch_bounds__(1024) k_pcg_init(DeviceProblem D, WorkArrays W) {
-  __shared__ double red[32];
-  const int n = D.n_blocks * D.cb, cb = D.cb;
-  const double* rhs = W.cam_acc + static_cast<int64_t>(D.n_blocks) * cb * cb + 2 * static_cast<int64_t>(n);
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = i / cb, row = i - b * cb;
-    const double* Mi = W.minv + (static_cast<int64_t>(b) * cb + row) * cb;
-    double z = 0.0;
-    for (int k = 0; k < cb; ++k) z += Mi[k] * rhs[b * cb + k];
-    W.x[i] = 0.0;
-    W.r[i] = rhs[i];
-    W.z[i] = z;
-    W.p[i] = z;
-    W.q[i] = 0.0;
-    acc += rhs[i] * z;
-  }
-  acc = block_sum(acc, red);
-  if (threadIdx.x == 0) {
-    W.pcg_scal[0] = acc;
-    W.pcg_scal[1] = acc;
-    W.pcg_state[0] = 0;
-    W.pcg_state[1] = (acc > 0.0) ? 0 : 1;  // zero right-hand side: nothing to do
-  }
-}
-
-//   update: q += D_c^2 p; alpha = rz / p.q; x += alpha p; r -= alpha q; z = M^-1 r;
-//           beta = r.z / rz; p = z + beta p; q = 0; convergence flag.
-__global__ void __launch_bounds__(1024) k_pcg_update(DeviceProblem D, WorkArrays W, double tol2, int min_iter) {
-  __shared__ double red[32];
-  if (W.pcg_state[1]) return;  // converged earlier: keep x
-  const int n = D.n_blocks * D.cb, cb = D.cb;
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const double p = W.p[i];
-    const double q = W.q[i] + W.dc2[i] * p;
-    W.q[i] = q;
-    acc += p * q;
-  }
-  const double pq = block_sum_all(acc, red);
-  const double rz = W.pcg_scal[0];
-  if (!(pq > 0.0) || !isfinite(pq)) {  // breakdown: stop with the current x
-    if (threadIdx.x == 0) W.pcg_state[1] = 1;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) W.q[i] = 0.0;
-    return;
-  }
-  const double alpha = rz / pq;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    W.x[i] += alpha * W.p[i];
-    W.r[i] -= alpha * W.q[i];
-  }
-  __syncthreads();
-  acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int b = i / cb, row = i - b * cb;
-    const double* Mi = W.minv + (static_cast<int64_t>(b) * cb + row) * cb;
-    double z = 0.0;
-    for (int k = 0; k < cb; ++k) z += Mi[k] * W.r[b * cb + k];
-    W.z[i] = z;
-    acc += W.r[i] * z;
-  }
-  const double rz_new = block_sum_all(acc, red);
-  const double beta = rz_new / rz;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    W.p[i] = W.z[i] + beta * W.p[i];
-    W.q[i] = 0.0;
-  }
-  if (threadIdx.x == 0) {
-    const int it = W.pcg_state[0] + 1;
-    W.pcg_state[0] = it;
-    W.pcg_scal[0] = rz_new;
-    if ((it >= min_iter && rz_new <= tol2 * W.pcg_scal[1]) || !(rz_new > 0.0)) W.pcg_state[1] = 1;
-  }
-}
-
 // ----------------------------------------------------------------- K5 implicit Schur
-// q += F^T (I - E C^-1 E^T) F p in ONE pass over point tiles:
-//   u_o = F_o p[blocks(o)]            (gather of p through L1/L2)
-//   y_i = C_i^-1 sum_{o in i} E_o^T u_o   (segmented reduction inside the tile, shared memory)
-//   w_o = u_o - E_o y_i ;  q[blocks(o)] += F_o^T w_o   (fp64 RED to L2)
-// Algorithmic HBM traffic: the Jacobian planes, 16*(3+CB[+6]) B per observation.
+// q = (F^T F + D_c^2 - F^T E C^-1 E^T F) p, atomic-free, in two phases:
+//  phase A (k_spmv_point, point-sorted tiles; reads Jc + Jp planes, writes one plane):
+//     u_o = F_o p[blocks(o)]                 (gather of p through L1/L2)
+//     y_i = C_i^-1 sum_{o in i} E_o^T u_o     (segmented reduction inside the tile, smem)
+//     w_o = u_o - E_o y_i                     -> plane W
+//  phase B (k_spmv_camera, camera-sorted incidence chunks; gathers Jc + W):
+//     q_j = sum_{o in j} F_o^T w_o            (register accumulation + CTA reduction,
+//                                              one partial vector per chunk, no atomics)
+// The chunk partials are summed in fixed order by the PCG vector kernel, so the product is
+// bit-reproducible.  fp64 RED to L2 (the first version of this kernel) serialises at ~150
+// cycles per cache line on B200 and ran 17x slower than this two-phase form.
 template <int CB, bool TWO>
-__global__ void __launch_bounds__(kTile) k_schur_spmv(DeviceProblem D, WorkArrays W) {
+__global__ void __launch_bounds__(kTile) k_spmv_point(DeviceProblem D, WorkArrays W, int plane_w) {
   if (W.pcg_state[1]) return;
   __shared__ double v[3][kTile];
   __shared__ double y[3][kTile];
@@ -586,39 +531,35 @@ __global__ void __launch_bounds__(kTile) k_schur_spmv(DeviceProblem D, WorkArray
   const int tid = threadIdx.x;
   const int o = obs0 + tid;
   const bool active = o < obs1;
-  double2 FA[CB];
-  double2 FB[TWO ? 6 : 1];
   double2 e0, e1, e2;
   double u0 = 0.0, u1 = 0.0;
-  int ba = 0, bb = -1, lp = 0;
+  int lp = 0;
+  const int64_t ld = D.ld;
   if (active) {
     const int2 idx = D.obs_idx[o];
     const ObsView vw = D.views[idx.x];
-    ba = vw.pose_a;
-    bb = vw.pose_b;
     lp = idx.y - pt0;
     const double2* J = D.J + o;
-    const int64_t ld = D.ld;
     e0 = J[(kPlaneJp + 0) * ld];
     e1 = J[(kPlaneJp + 1) * ld];
     e2 = J[(kPlaneJp + 2) * ld];
-    const double* pa = W.p + static_cast<int64_t>(ba) * CB;
+    const double* pa = W.p + static_cast<int64_t>(vw.pose_a) * CB;
 #pragma unroll
     for (int k = 0; k < CB; ++k) {
-      FA[k] = J[(kPlaneJA + k) * ld];
+      const double2 F = J[(kPlaneJA + k) * ld];
       const double pk = pa[k];
-      u0 += FA[k].x * pk;
-      u1 += FA[k].y * pk;
+      u0 += F.x * pk;
+      u1 += F.y * pk;
     }
     if (TWO) {
-      if (bb >= 0) {
-        const double* pb = W.p + static_cast<int64_t>(bb) * CB;
+      if (vw.pose_b >= 0) {
+        const double* pb = W.p + static_cast<int64_t>(vw.pose_b) * CB;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-          FB[k] = J[(kPlaneJA + CB + k) * ld];
+          const double2 F = J[(kPlaneJA + CB + k) * ld];
           const double pk = pb[k];
-          u0 += FB[k].x * pk;
-          u1 += FB[k].y * pk;
+          u0 += F.x * pk;
+          u1 += F.y * pk;
         }
       }
     }
@@ -646,17 +587,196 @@ __global__ void __launch_bounds__(kTile) k_schur_spmv(DeviceProblem D, WorkArray
     const double y0 = y[0][lp], y1 = y[1][lp], y2 = y[2][lp];
     const double w0 = u0 - (e0.x * y0 + e1.x * y1 + e2.x * y2);
     const double w1 = u1 - (e0.y * y0 + e1.y * y1 + e2.y * y2);
-    double* qa = W.q + static_cast<int64_t>(ba) * CB;
+    D.J[static_cast<int64_t>(plane_w) * ld + o] = make_double2(w0, w1);
+  }
+}
+
+template <int CB>
+__global__ void __launch_bounds__(128) k_spmv_camera(DeviceProblem D, WorkArrays W, int plane_w) {
+  if (W.pcg_state[1]) return;
+  __shared__ double red[4][CB];
+  const int4 ch = D.cam_chunks[blockIdx.x];
+  double acc[CB];
 #pragma unroll
-    for (int k = 0; k < CB; ++k) atomicAdd(qa + k, FA[k].x * w0 + FA[k].y * w1);
-    if (TWO) {
-      if (bb >= 0) {
-        double* qb = W.q + static_cast<int64_t>(bb) * CB;
+  for (int k = 0; k < CB; ++k) acc[k] = 0.0;
+  const int64_t ld = D.ld;
+  const double2* Wp = D.J + static_cast<int64_t>(plane_w) * ld;
+  for (int e = ch.y + threadIdx.x; e < ch.z; e += blockDim.x) {
+    const int ent = D.cam_entries[e];
+    const int o = ent >> 1;
+    const int slot = ent & 1;
+    const double2* FCe = D.FC + e;
+    const double2 w = Wp[o];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) atomicAdd(qb + k, FB[k].x * w0 + FB[k].y * w1);
+    for (int k = 0; k < CB; ++k) {
+      if (slot && k >= 6) break;
+      const double2 F = FCe[k * D.ldc];
+      acc[k] += F.x * w.x + F.y * w.y;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < CB; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < CB)
+    W.chunk_q[static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x] =
+        red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+// --------------------------------------------------------------------------- K6 PCG
+// Block-Jacobi PCG vector work, multi-CTA (one thread per unknown), deterministic: every
+// global scalar is a fixed-order sum of per-CTA partials done by the last CTA to finish
+// ("last block" pattern with a device counter), so no cooperative launch is needed.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  return is_last;
+}
+__device__ __forceinline__ double sum_partials(const volatile double* part, int n, double* red) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  return block_sum_all(acc, red);
+}
+
+// q_j from the chunk partials (or, after an allreduce, from W.q) plus D_c^2 p
+__device__ __forceinline__ double gather_q(const DeviceProblem& D, const WorkArrays& W, int i, int from_chunks) {
+  const int cb = D.cb;
+  double q;
+  if (from_chunks) {
+    const int b = i / cb, row = i - b * cb;
+    q = 0.0;
+    for (int c = D.cam_chunk_first[b]; c < D.cam_chunk_first[b + 1]; ++c) q += W.chunk_q[static_cast<int64_t>(c) * cb + row];
+  } else {
+    q = W.q[i];
+  }
+  return q;
+}
+
+// x = 0, r = rhs, z = M^-1 r, p = z, rz = rz0 = r.z
+__global__ void __launch_bounds__(256) k_pcg_init(DeviceProblem D, WorkArrays W) {
+  __shared__ double red[32];
+  const int n = D.n_blocks * D.cb, cb = D.cb;
+  const double* rhs = W.cam_acc + static_cast<int64_t>(D.n_blocks) * cb * cb + 2 * static_cast<int64_t>(n);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (i < n) {
+    const int b = i / cb, row = i - b * cb;
+    const double* Mi = W.minv + (static_cast<int64_t>(b) * cb + row) * cb;
+    double z = 0.0;
+    for (int k = 0; k < cb; ++k) z += Mi[k] * rhs[b * cb + k];
+    W.x[i] = 0.0;
+    W.r[i] = rhs[i];
+    W.z[i] = z;
+    W.p[i] = z;
+    acc = rhs[i] * z;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) W.vec_partials[blockIdx.x] = acc;
+  if (last_block_done(W.counters + 0)) {
+    const double rz = sum_partials(W.vec_partials, gridDim.x, red);
+    if (threadIdx.x == 0) {
+      W.pcg_scal[0] = rz;
+      W.pcg_scal[1] = rz;
+      W.pcg_state[0] = 0;
+      W.pcg_state[1] = (rz > 0.0) ? 0 : 1;  // zero right-hand side: nothing to do
+      W.counters[0] = 0;
+    }
+  }
+}
+
+// phase 1: q (+ D_c^2 p), partial p.q; the last CTA publishes p.q
+__global__ void __launch_bounds__(256) k_pcg_dot(DeviceProblem D, WorkArrays W, int from_chunks) {
+  if (W.pcg_state[1]) return;
+  __shared__ double red[32];
+  const int n = D.n_blocks * D.cb;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (i < n) {
+    const double p = W.p[i];
+    const double q = gather_q(D, W, i, from_chunks) + W.dc2[i] * p;
+    W.q[i] = q;
+    acc = p * q;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) W.vec_partials[blockIdx.x] = acc;
+  if (last_block_done(W.counters + 1)) {
+    const double pq = sum_partials(W.vec_partials, gridDim.x, red);
+    if (threadIdx.x == 0) {
+      W.pcg_scal[2] = pq;
+      W.counters[1] = 0;
+    }
+  }
+}
+
+// phase 2: alpha = rz / p.q; x += alpha p; r -= alpha q; z = M^-1 r; partial r.z; the last CTA
+// publishes rz_new, beta and the convergence flag.  One thread per unknown; a CTA owns whole
+// camera blocks and stages their new residual in shared memory for the block mat-vec.
+__global__ void __launch_bounds__(256) k_pcg_step(DeviceProblem D, WorkArrays W, double tol2, int min_iter) {
+  if (W.pcg_state[1]) return;
+  __shared__ double red[32];
+  __shared__ double rn[256];
+  const int cb = D.cb;
+  const int rows_per_cta = (256 / cb) * cb;
+  const int n = D.n_blocks * cb;
+  const int i = blockIdx.x * rows_per_cta + threadIdx.x;
+  const bool active = threadIdx.x < rows_per_cta && i < n;
+  const double pq = W.pcg_scal[2], rz = W.pcg_scal[0];
+  const bool breakdown = !(pq > 0.0) || !isfinite(pq);
+  double acc = 0.0;
+  if (!breakdown) {
+    const double alpha = rz / pq;
+    if (active) {
+      W.x[i] += alpha * W.p[i];
+      const double r = W.r[i] - alpha * W.q[i];
+      W.r[i] = r;
+      rn[threadIdx.x] = r;
+    }
+    __syncthreads();
+    if (active) {
+      const int lb = threadIdx.x / cb, row = threadIdx.x - lb * cb;
+      const double* Mi = W.minv + static_cast<int64_t>(i) * cb;  // row i of the block-diagonal inverse
+      double z = 0.0;
+      for (int k = 0; k < cb; ++k) z += Mi[k] * rn[lb * cb + k];
+      W.z[i] = z;
+      acc = rn[threadIdx.x] * z;
+      (void)row;
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) W.vec_partials[blockIdx.x] = acc;
+  if (last_block_done(W.counters + 2)) {
+    const double rz_new = sum_partials(W.vec_partials, gridDim.x, red);
+    if (threadIdx.x == 0) {
+      W.counters[2] = 0;
+      if (breakdown) {
+        W.pcg_state[1] = 1;  // keep the current x
+        W.pcg_scal[3] = 0.0;
+      } else {
+        const int it = W.pcg_state[0] + 1;
+        W.pcg_state[0] = it;
+        W.pcg_scal[3] = rz_new / rz;  // beta
+        W.pcg_scal[0] = rz_new;
+        if ((it >= min_iter && rz_new <= tol2 * W.pcg_scal[1]) || !(rz_new > 0.0)) W.pcg_state[1] = 1;
       }
     }
   }
+}
+
+// phase 3: p = z + beta p
+__global__ void __launch_bounds__(256) k_pcg_direction(DeviceProblem D, WorkArrays W) {
+  if (W.pcg_state[1]) return;
+  const int n = D.n_blocks * D.cb;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) W.p[i] = W.z[i] + W.pcg_scal[3] * W.p[i];
 }
 
 // ------------------------------------------------------------- K7 back-substitution
@@ -914,21 +1034,51 @@ void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double 
 }
 
 void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
-  k_pcg_init<<<1, 1024, 0, st>>>(D, W);
+  const int n = D.n_blocks * D.cb;
+  k_pcg_init<<<(n + 255) / 256, 256, 0, st>>>(D, W);
 }
 
-void launch_schur_spmv(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+void launch_spmv_point(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st) {
   if (D.n_tiles == 0) return;
   if (D.cb == 6 && !D.two)
-    k_schur_spmv<6, false><<<D.n_tiles, kTile, 0, st>>>(D, W);
+    k_spmv_point<6, false><<<D.n_tiles, kTile, 0, st>>>(D, W, plane_w);
   else if (D.cb == 6)
-    k_schur_spmv<6, true><<<D.n_tiles, kTile, 0, st>>>(D, W);
+    k_spmv_point<6, true><<<D.n_tiles, kTile, 0, st>>>(D, W, plane_w);
   else
-    k_schur_spmv<9, false><<<D.n_tiles, kTile, 0, st>>>(D, W);
+    k_spmv_point<9, false><<<D.n_tiles, kTile, 0, st>>>(D, W, plane_w);
 }
 
-void launch_pcg_update(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st) {
-  k_pcg_update<<<1, 1024, 0, st>>>(D, W, tol2, min_iter);
+void launch_spmv_camera(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st) {
+  if (D.n_chunks == 0) return;
+  if (D.cb == 6)
+    k_spmv_camera<6><<<D.n_chunks, 128, 0, st>>>(D, W, plane_w);
+  else
+    k_spmv_camera<9><<<D.n_chunks, 128, 0, st>>>(D, W, plane_w);
+}
+
+// sums the chunk partials of this rank into W.q (multi-GPU: input of the allreduce)
+__global__ void __launch_bounds__(256) k_chunks_to_q(DeviceProblem D, WorkArrays W) {
+  if (W.pcg_state[1]) return;
+  const int n = D.n_blocks * D.cb;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) W.q[i] = gather_q(D, W, i, 1);
+}
+void launch_chunks_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  const int n = D.n_blocks * D.cb;
+  k_chunks_to_q<<<(n + 255) / 256, 256, 0, st>>>(D, W);
+}
+
+void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int from_chunks, cudaStream_t st) {
+  const int n = D.n_blocks * D.cb;
+  k_pcg_dot<<<(n + 255) / 256, 256, 0, st>>>(D, W, from_chunks);
+}
+void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st) {
+  const int blocks_per_cta = 256 / D.cb;
+  k_pcg_step<<<(D.n_blocks + blocks_per_cta - 1) / blocks_per_cta, 256, 0, st>>>(D, W, tol2, min_iter);
+}
+void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  const int n = D.n_blocks * D.cb;
+  k_pcg_direction<<<(n + 255) / 256, 256, 0, st>>>(D, W);
 }
 
 void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st) {

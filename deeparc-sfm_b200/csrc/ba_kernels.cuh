@@ -43,8 +43,15 @@ struct DeviceProblem {
   // camera-sorted incidence (entries = obs * 2 + slot), chunked for the gather kernel
   const int* cam_entries;   // [n_entries]
   const int4* cam_chunks;   // [n_chunks] (block, first entry, last entry, 0)
+  const int* cam_chunk_first;  // [n_blocks + 1] first chunk of each camera block
   int n_chunks;
   double2* J;               // planes
+  // camera-sorted copy of the camera-side Jacobian columns: FC[k * ldc + e] = column k of the
+  // block of incidence entry e (written by the Jacobian kernel through ent_pos, read
+  // sequentially by the camera-side kernels).  NULL: do not write (dba_eval scratch runs).
+  double2* FC;
+  int64_t ldc;
+  const int* ent_pos;       // [n_obs][2] entry index of (obs, slot), -1 if the slot is unused
 };
 
 struct ParamSet {
@@ -80,7 +87,10 @@ struct WorkArrays {
   double* partials;  // [n_partials] per-CTA partial sums (deterministic reductions)
   double* scalars;   // [32] reduced scalars, copied to the host
   int* pcg_state;    // [4] iter, done, -, -
-  double* pcg_scal;  // [4] rz, rz0, -, -
+  double* pcg_scal;  // [4] rz, rz0, p.q, beta
+  double* chunk_q;   // [n_chunks][cb] per-chunk partial products of the camera phase
+  double* vec_partials;    // per-CTA partials of the PCG vector kernels
+  unsigned int* counters;  // [4] "last block" arrival counters
 };
 
 // scalar slots in WorkArrays::scalars
@@ -121,9 +131,16 @@ int camera_finalize_grid(const DeviceProblem& D);
 void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
                             double max_diag, double* partials, cudaStream_t st);
 void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
-// q += (F^T F - F^T E C^-1 E^T F) p   (implicit Schur complement, one fused pass)
-void launch_schur_spmv(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
-void launch_pcg_update(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
+// implicit Schur complement product, phase A (point tiles -> plane_w) and phase B (camera
+// chunks -> W.chunk_q)
+void launch_spmv_point(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st);
+void launch_spmv_camera(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st);
+void launch_chunks_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+// PCG vector phases: p.q (q from the chunk partials or from the allreduced W.q), the
+// x/r/z update with r.z, the new direction
+void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int from_chunks, cudaStream_t st);
+void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
+void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
 void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st);
 // candidate = current + scale * step; partials[2*cta + {0,1}] = {sum step^2, sum x^2}

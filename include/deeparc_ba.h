@@ -158,7 +158,9 @@ typedef struct dba_summary {
   double initial_cost;
   double final_cost;
   double total_time_in_seconds;      /* host wall clock around the LM loop              */
-  double device_time_in_seconds;     /* CUDA events around the LM loop                  */
+  double device_time_in_seconds;     /* CUDA events around the whole call               */
+  double loop_device_time_in_seconds;/* CUDA events around iterations >= 1 only (the
+                                        initial evaluation, iteration 0, excluded)      */
   int64_t kernel_launches;           /* kernels of this library launched by the call    */
   int64_t jacobian_evaluations;
   int64_t residual_evaluations;
