@@ -15,7 +15,7 @@ Jacobian evaluation.  Tolerances are 0 so exactly K iterations run.
   e2e     the same metric through the C ABI with HOST buffers: dba_problem_set (host sort +
           host->device copies) + dba_solve (K iterations incl. the initial evaluation) +
           dba_params_get (device->host), wall clock around the three calls
-  roofline  dominant kernel (schur_spmv): algorithmic bytes / mean CUDA-event duration,
+  roofline  dominant kernel (the implicit Schur product): model bytes / mean CUDA-event duration,
           against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the CPU oracle (oracle/, a restatement of the reference's Ceres path: the
           reference itself needs Ceres, which is not installable) on the box's host cores
@@ -282,8 +282,8 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     roof = None
-    if "spmv_point" in stats and stats["spmv_point"]["launches"] > 0:
-        ka, kb = stats["spmv_point"], stats["spmv_camera"]
+    if "spmv_tile" in stats and stats["spmv_tile"]["launches"] > 0:
+        ka, kb = stats["spmv_tile"], stats["partials_to_q"]
         ms_a, ms_b = ka["total_ms"] / ka["launches"], kb["total_ms"] / max(kb["launches"], 1)
         cb = 9 if p.free_intrinsics else 6
         planes = 3 + cb + (6 if (p.obs_pose_b >= 0).any() else 0)
@@ -291,16 +291,16 @@ def main():
         model_bytes = (8.0 + 16.0 * planes) * (p.n_obs / world)
         achieved = model_bytes / ((ms_a + ms_b) * 1e-3) / 1e9
         total_ms = sum(v["total_ms"] for v in stats.values())
-        roof = {"bound": "hbm", "kernel": "implicit Schur product = k_spmv_point + k_spmv_camera",
+        roof = {"bound": "hbm", "kernel": "implicit Schur product = k_spmv_tile + k_partials_to_q",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": model_bytes,
-                "model": "single-pass model of SURVEY 8(d), %d B/observation; the two phases together move %.0f B/observation" % (
+                "model": "single-pass model of SURVEY 8(d), %d B/observation; the two kernels together move %.0f B/observation" % (
                     8 + 16 * planes, (ka["algorithmic_bytes"] + kb["algorithmic_bytes"]) / (p.n_obs / world)),
                 "mean_launch_ms": ms_a + ms_b, "launches": ka["launches"],
-                "phases": {"k_spmv_point": {"mean_ms": ms_a, "bytes": ka["algorithmic_bytes"],
+                "phases": {"k_spmv_tile": {"mean_ms": ms_a, "bytes": ka["algorithmic_bytes"],
                                             "gbs": ka["algorithmic_bytes"] / (ms_a * 1e-3) / 1e9,
                                             "frac": ka["algorithmic_bytes"] / (ms_a * 1e-3) / 1e9 / peak},
-                           "k_spmv_camera": {"mean_ms": ms_b, "bytes": kb["algorithmic_bytes"],
+                           "k_partials_to_q": {"mean_ms": ms_b, "bytes": kb["algorithmic_bytes"],
                                              "gbs": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 if ms_b > 0 else None,
                                              "frac": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 / peak if ms_b > 0 else None}},
                 "share_of_kernel_time": (ka["total_ms"] + kb["total_ms"]) / total_ms if total_ms > 0 else None}

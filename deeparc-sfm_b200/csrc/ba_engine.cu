@@ -96,7 +96,11 @@ struct dba_handle {
 
   // device storage
   DevBuf<double2> d_obs_xy, d_J, d_FC;
-  DevBuf<int> d_ent_pos;
+  DevBuf<int> d_ent_pos, d_tile_part_first, d_part_item_first, d_cam_part_first, d_cam_part_idx;
+  DevBuf<unsigned short> d_items, d_obs_lp, d_part_first_rel;
+  DevBuf<TileMeta> d_tile_meta;
+  DevBuf<int2> d_obs_ab;
+  DevBuf<double> d_partials_q;
   DevBuf<int2> d_obs_idx;
   DevBuf<ObsView> d_views;
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
@@ -107,7 +111,7 @@ struct dba_handle {
   DevBuf<PoseRow> d_pose_rows[2];
   DevBuf<IntrRow> d_intr_rows[2];
   DevBuf<double> d_sp, d_sc, d_cinv, d_tp, d_dp, d_cam_acc, d_minv, d_dc2, d_x, d_r, d_z, d_p, d_q;
-  DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts, d_chunk_q, d_vec_partials;
+  DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts, d_vec_partials;
   double* h_scalars = nullptr;  // pinned
   int* h_pcg_state = nullptr;   // pinned
   size_t j_planes = 0;
@@ -328,9 +332,11 @@ int prepare_step(dba_handle* h, double radius, const dba_solve_options& o) {
 int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   const DeviceProblem& D = h->D;
   const int nplanes = 3 + h->cb + (h->two ? 6 : 0);
-  // phase A: indices (8) + Jp, Jc planes + the w plane written; phase B: entry (4) + Jc planes + w
-  const double point_bytes = (8.0 + 16.0 * nplanes + 16.0) * static_cast<double>(h->n_obs);
-  const double cam_bytes = (4.0 + 16.0 * h->cb + 16.0) * static_cast<double>(h->d_cam_entries.n);
+  // one pass over the planes (indices 8 B + Jp, Jc planes) + the tile partials written once
+  // and read once by the per-camera sum
+  const double tile_bytes = (8.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs) +
+                            8.0 * h->cb * static_cast<double>(D.n_partials);
+  const double part_bytes = (8.0 * h->cb + 4.0) * static_cast<double>(D.n_partials);
   {
     Scope s(h, "pcg_init");
     launch_pcg_init(D, h->W, h->st);
@@ -345,23 +351,19 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
     const int batch = std::min(check_every > 0 ? check_every : max_it, max_it - issued);
     for (int i = 0; i < batch; ++i) {
       {
-        Scope s(h, "spmv_point", point_bytes);
-        launch_spmv_point(D, h->W, h->plane_w, h->st);
+        Scope s(h, "spmv_tile", tile_bytes);
+        launch_spmv_tile(D, h->W, h->st);
       }
       {
-        Scope s(h, "spmv_camera", cam_bytes);
-        launch_spmv_camera(D, h->W, h->plane_w, h->st);
+        Scope s(h, "partials_to_q", part_bytes);
+        launch_partials_to_q(D, h->W, h->st);
       }
       if (h->world > 1) {
-        {
-          Scope s(h, "pcg_vector");
-          launch_chunks_to_q(D, h->W, h->st);
-        }
         int rc = allreduce(h, h->W.q, nvec, kNcclSum);
         if (rc != DBA_OK) return rc;
       }
       Scope s(h, "pcg_vector", 0.0, 3);
-      launch_pcg_dot(D, h->W, h->world == 1, h->st);
+      launch_pcg_dot(D, h->W, h->st);
       launch_pcg_step(D, h->W, tol2, o.pcg_min_iterations, h->st);
       launch_pcg_direction(D, h->W, h->st);
     }
@@ -704,10 +706,84 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     cam_chunk_first[p->n_ext] = static_cast<int>(cam_chunks.size());
   }
 
+  // ---- static tile-local camera incidence for the implicit Schur product
+  std::vector<int> tile_part_first(static_cast<size_t>(n_tiles) + 1, 0), part_item_first{0}, cam_part_first, cam_part_idx;
+  std::vector<unsigned short> items;
+  std::vector<int> part_block;
+  if (h->cb) {
+    std::vector<int> local_of(static_cast<size_t>(p->n_ext), -1), locals;
+    std::vector<std::vector<unsigned short>> lists;
+    items.reserve(cam_entries.size());
+    for (int t = 0; t < n_tiles; ++t) {
+      locals.clear();
+      size_t used = 0;
+      for (int k = tile_obs[t]; k < tile_obs[t + 1]; ++k) {
+        const ObsView& v = views[obs_idx[k].x];
+        const int lo = k - tile_obs[t];
+        for (int slot = 0; slot < 2; ++slot) {
+          const int blk = slot ? v.pose_b : v.pose_a;
+          if (blk < 0) continue;
+          int lc = local_of[blk];
+          if (lc < 0) {
+            lc = static_cast<int>(locals.size());
+            local_of[blk] = lc;
+            locals.push_back(blk);
+            if (lists.size() <= static_cast<size_t>(lc)) lists.emplace_back();
+            lists[lc].clear();
+            ++used;
+          }
+          lists[lc].push_back(static_cast<unsigned short>(lo | (slot << 15)));
+        }
+      }
+      for (size_t lc = 0; lc < locals.size(); ++lc) {
+        items.insert(items.end(), lists[lc].begin(), lists[lc].end());
+        part_item_first.push_back(static_cast<int>(items.size()));
+        part_block.push_back(locals[lc]);
+        local_of[locals[lc]] = -1;
+      }
+      tile_part_first[t + 1] = static_cast<int>(part_block.size());
+      (void)used;
+    }
+    const int n_part = static_cast<int>(part_block.size());
+    cam_part_first.assign(static_cast<size_t>(p->n_ext) + 1, 0);
+    for (int g = 0; g < n_part; ++g) cam_part_first[part_block[g] + 1]++;
+    for (int b = 0; b < p->n_ext; ++b) cam_part_first[b + 1] += cam_part_first[b];
+    cam_part_idx.resize(n_part);
+    std::vector<int> cur(cam_part_first.begin(), cam_part_first.end() - 1);
+    for (int g = 0; g < n_part; ++g) cam_part_idx[cur[part_block[g]]++] = g;
+  } else {
+    cam_part_first.assign(static_cast<size_t>(p->n_ext) + 1, 0);
+  }
+  const size_t n_partials = part_block.size();
+  // packed per-tile records and per-observation block indices for the tile kernels
+  std::vector<TileMeta> tile_meta(static_cast<size_t>(std::max(n_tiles, 1)));
+  std::vector<int2> obs_ab(static_cast<size_t>(std::max<int64_t>(nl, 1)));
+  std::vector<unsigned short> obs_lp(static_cast<size_t>(std::max<int64_t>(nl, 1)), 0);
+  std::vector<unsigned short> part_first_rel(n_partials + static_cast<size_t>(n_tiles) + 1, 0);
+  for (int t = 0; t < n_tiles; ++t) {
+    TileMeta& m = tile_meta[t];
+    m.obs0 = tile_obs[t];
+    m.n_obs = tile_obs[t + 1] - tile_obs[t];
+    m.pt0 = tile_pt[t];
+    m.n_pts = tile_pt[t + 1] - tile_pt[t];
+    m.g0 = tile_part_first[t];
+    m.n_parts = tile_part_first[t + 1] - tile_part_first[t];
+    m.item0 = h->cb ? part_item_first[m.g0] : 0;
+    m.n_items = h->cb ? part_item_first[m.g0 + m.n_parts] - m.item0 : 0;
+    if (h->cb)
+      for (int i = 0; i <= m.n_parts; ++i)
+        part_first_rel[static_cast<size_t>(m.g0) + t + i] = static_cast<unsigned short>(part_item_first[m.g0 + i] - m.item0);
+    for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) obs_lp[k] = static_cast<unsigned short>(obs_idx[k].y - m.pt0);
+  }
+  for (int64_t k = 0; k < nl; ++k) {
+    const ObsView& v = views[obs_idx[k].x];
+    obs_ab[k] = make_int2(v.pose_a, v.pose_b);
+  }
+
   // ---- device allocation + upload
   const int64_t ld = ((nl + 63) / 64) * 64;
   h->plane_w = 4 + h->cb + ((h->two && h->cb) ? 6 : 0);
-  h->j_planes = h->plane_w + 1;
+  h->j_planes = h->plane_w;
   CU(h, h->d_obs_xy.alloc(std::max<int64_t>(nl, 1)));
   CU(h, h->d_obs_idx.alloc(std::max<int64_t>(nl, 1)));
   CU(h, h->d_views.alloc(std::max<size_t>(views.size(), 1)));
@@ -720,7 +796,16 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   const int64_t ldc = ((static_cast<int64_t>(cam_entries.size()) + 63) / 64) * 64;
   CU(h, h->d_FC.alloc(std::max<int64_t>(ldc, 64) * std::max(h->cb, 1)));
   CU(h, h->d_ent_pos.alloc(std::max<size_t>(ent_pos.size(), 2)));
-  CU(h, h->d_chunk_q.alloc(std::max<size_t>(cam_chunks.size() * std::max(h->cb, 1), 1)));
+  CU(h, h->d_tile_part_first.alloc(tile_part_first.size()));
+  CU(h, h->d_tile_meta.alloc(tile_meta.size()));
+  CU(h, h->d_obs_ab.alloc(obs_ab.size()));
+  CU(h, h->d_obs_lp.alloc(obs_lp.size()));
+  CU(h, h->d_part_first_rel.alloc(part_first_rel.size()));
+  CU(h, h->d_part_item_first.alloc(part_item_first.size()));
+  CU(h, h->d_items.alloc(std::max<size_t>(items.size(), 1)));
+  CU(h, h->d_cam_part_first.alloc(cam_part_first.size()));
+  CU(h, h->d_cam_part_idx.alloc(std::max<size_t>(cam_part_idx.size(), 1)));
+  CU(h, h->d_partials_q.alloc(std::max<size_t>(n_partials * std::max(h->cb, 1), 1)));
   CU(h, h->d_vec_partials.alloc(static_cast<size_t>(p->n_ext) * std::max(h->cb, 1) / 128 + 64));
   CU(h, h->d_counters.alloc(4));
   CU(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * sizeof(unsigned int), h->st));
@@ -781,6 +866,15 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_cam_chunks.p, cam_chunks.data(), cam_chunks.size() * sizeof(int4)));
   CU(h, up(h->d_cam_chunk_first.p, cam_chunk_first.data(), cam_chunk_first.size() * sizeof(int)));
   CU(h, up(h->d_ent_pos.p, ent_pos.data(), ent_pos.size() * sizeof(int)));
+  CU(h, up(h->d_tile_part_first.p, tile_part_first.data(), tile_part_first.size() * sizeof(int)));
+  CU(h, up(h->d_tile_meta.p, tile_meta.data(), tile_meta.size() * sizeof(TileMeta)));
+  CU(h, up(h->d_obs_ab.p, obs_ab.data(), obs_ab.size() * sizeof(int2)));
+  CU(h, up(h->d_obs_lp.p, obs_lp.data(), obs_lp.size() * sizeof(unsigned short)));
+  CU(h, up(h->d_part_first_rel.p, part_first_rel.data(), part_first_rel.size() * sizeof(unsigned short)));
+  CU(h, up(h->d_part_item_first.p, part_item_first.data(), part_item_first.size() * sizeof(int)));
+  CU(h, up(h->d_items.p, items.data(), items.size() * sizeof(unsigned short)));
+  CU(h, up(h->d_cam_part_first.p, cam_part_first.data(), cam_part_first.size() * sizeof(int)));
+  CU(h, up(h->d_cam_part_idx.p, cam_part_idx.data(), cam_part_idx.size() * sizeof(int)));
   std::vector<uint8_t> ext_const(std::max(p->n_ext, 1), 0);
   h->any_const = false;
   if (p->ext_const)
@@ -825,6 +919,16 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.FC = h->cb ? h->d_FC.p : nullptr;
   D.ldc = std::max<int64_t>(ldc, 64);
   D.ent_pos = h->d_ent_pos.p;
+  D.tile_part_first = h->d_tile_part_first.p;
+  D.tile_meta = h->d_tile_meta.p;
+  D.obs_ab = h->d_obs_ab.p;
+  D.obs_lp = h->d_obs_lp.p;
+  D.part_first_rel = h->d_part_first_rel.p;
+  D.part_item_first = h->d_part_item_first.p;
+  D.items = h->d_items.p;
+  D.cam_part_first = h->d_cam_part_first.p;
+  D.cam_part_idx = h->d_cam_part_idx.p;
+  D.n_partials = static_cast<int>(n_partials);
   for (int s = 0; s < 2; ++s) {
     ParamSet& P = h->P[s];
     P.pts = h->d_pts[s].p;
@@ -859,7 +963,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.scalars = h->d_scalars.p;
   W.pcg_state = h->d_pcg_state.p;
   W.pcg_scal = h->d_pcg_scal.p;
-  W.chunk_q = h->d_chunk_q.p;
+  W.partials_q = h->d_partials_q.p;
   W.vec_partials = h->d_vec_partials.p;
   W.counters = h->d_counters.p;
   h->have_problem = true;

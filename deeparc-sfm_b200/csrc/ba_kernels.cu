@@ -5,7 +5,7 @@
 //   k_jacobian   (K1)  residual + analytic Jacobian of operator() (:93-118), replaces Ceres autodiff
 //   k_cost       (K2)  residual-only evaluation (trial point; filterPoint3d, DeepArcManager.cc:335-347)
 //   k_point_prepare, k_camera_gather, k_camera_finalize (K3)  Schur elimination front half
-//   k_spmv_point + k_spmv_camera (K5)  implicit Schur complement product, two atomic-free phases
+//   k_spmv_tile + k_partials_to_q (K5)  implicit Schur complement product, one pass, atomic-free
 //   k_pcg_init / k_pcg_dot / k_pcg_step / k_pcg_direction (K6)  block-Jacobi PCG vector work
 //   k_back_substitute (K7), k_param_update  point back-substitution, x + delta, norms
 #include <cstdio>
@@ -509,110 +509,198 @@ __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArr
 }
 
 // ----------------------------------------------------------------- K5 implicit Schur
-// q = (F^T F + D_c^2 - F^T E C^-1 E^T F) p, atomic-free, in two phases:
-//  phase A (k_spmv_point, point-sorted tiles; reads Jc + Jp planes, writes one plane):
+// q = (F^T F - F^T E C^-1 E^T F) p  (+ D_c^2 p, added by the PCG vector kernel), atomic-free:
+//  k_spmv_tile, ONE pass over the point-sorted Jacobian planes (point tiles of <= 256 obs):
 //     u_o = F_o p[blocks(o)]                 (gather of p through L1/L2)
 //     y_i = C_i^-1 sum_{o in i} E_o^T u_o     (segmented reduction inside the tile, smem)
-//     w_o = u_o - E_o y_i                     -> plane W
-//  phase B (k_spmv_camera, camera-sorted incidence chunks; gathers Jc + W):
-//     q_j = sum_{o in j} F_o^T w_o            (register accumulation + CTA reduction,
-//                                              one partial vector per chunk, no atomics)
-// The chunk partials are summed in fixed order by the PCG vector kernel, so the product is
-// bit-reproducible.  fp64 RED to L2 (the first version of this kernel) serialises at ~150
-// cycles per cache line on B200 and ran 17x slower than this two-phase form.
+//     w_o = u_o - E_o y_i ;  c_o = F_o^T w_o  (per observation, registers -> smem)
+//     tile-local reduce-by-camera of c_o through a STATIC per-tile incidence list (built once
+//     on upload): one partial vector per (tile, camera present in the tile)
+//  k_partials_to_q: per camera block, fixed-order sum of its partial vectors.
+// HBM traffic: the Jacobian planes once (16*(3+CB[+6]) + 8 B/obs) plus 2 * 8*CB B per partial;
+// with d observations per (tile, camera) pair that is 16*CB/d B/obs extra (d ~ 4.6 on the
+// banded bal5m problem, d = 1 in the worst case, where it equals a second pass over Jc).
+// History: fp64 RED to L2 serialises at ~150 cycles per cache line on B200 (3.65 ms per
+// product); a camera-sorted second pass over a copy of Jc took 0.33 ms.
+// --- TMA (cp.async.bulk) + mbarrier helpers: 1-D bulk copies global -> shared, sm_90+ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// Shared-memory plan of k_spmv_tile (dynamic): NP = 3 + CB (+6) planes of (kTile + 1) double2
+// (the +1 keeps the camera reduce, which reads 9 consecutive planes at one column, off a single
+// bank), then the static tile incidence.  The three Jp planes are recycled as (v, y) pairs and
+// the Jc planes as the per-observation contributions once their Jacobian column is consumed.
 template <int CB, bool TWO>
-__global__ void __launch_bounds__(kTile) k_spmv_point(DeviceProblem D, WorkArrays W, int plane_w) {
+struct SpmvSmem {
+  static constexpr int NP = 3 + CB + (TWO ? 6 : 0);
+  static constexpr int kStride = kTile + 1;
+  static constexpr int kMaxItems = TWO ? 2 * kTile : kTile;
+  static constexpr size_t kPlaneBytes = static_cast<size_t>(NP) * kStride * sizeof(double2);
+  static constexpr size_t kBytes = kPlaneBytes + sizeof(unsigned short) * (2 * kMaxItems + 2) + 16;
+};
+
+template <int CB, bool TWO>
+__global__ void __launch_bounds__(kTile) k_spmv_tile(DeviceProblem D, WorkArrays W) {
   if (W.pcg_state[1]) return;
-  __shared__ double v[3][kTile];
-  __shared__ double y[3][kTile];
+  using L = SpmvSmem<CB, TWO>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* sJ = reinterpret_cast<double2*>(smem_raw);  // [NP][kStride]; plane 0..2 = Jp, 3.. = Jc
+  unsigned short* s_items = reinterpret_cast<unsigned short*>(smem_raw + L::kPlaneBytes);
+  unsigned short* s_first = s_items + L::kMaxItems;
+  __shared__ __align__(8) uint64_t bar;
   const int t = blockIdx.x;
-  const int obs0 = D.tile_obs[t], obs1 = D.tile_obs[t + 1];
-  const int pt0 = D.tile_pt[t], pt1 = D.tile_pt[t + 1];
   const int tid = threadIdx.x;
+  const TileMeta tm = D.tile_meta[t];  // one 32-byte record: no dependent index chain
+  const int obs0 = tm.obs0, n_tile = tm.n_obs;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_proxy_async();
+    // one elected thread: arm the barrier with the byte count, then one bulk copy per plane
+    mbar_expect_tx(&bar, static_cast<uint32_t>(L::NP * n_tile * sizeof(double2)));
+    const double2* src = D.J + static_cast<int64_t>(kPlaneJp) * D.ld + obs0;
+#pragma unroll
+    for (int pl = 0; pl < L::NP; ++pl)
+      tma_load_1d(sJ + pl * L::kStride, src + static_cast<int64_t>(pl) * D.ld, static_cast<uint32_t>(n_tile * sizeof(double2)), &bar);
+  }
   const int o = obs0 + tid;
-  const bool active = o < obs1;
-  double2 e0, e1, e2;
-  double u0 = 0.0, u1 = 0.0;
+  const bool active = tid < n_tile;
+  // everything else the CTA needs is requested now, while the bulk copies are in flight:
+  // static tile incidence, block indices + p, and the per-point rows used after the first barrier
+  for (int i = tid; i < tm.n_items; i += kTile) s_items[i] = D.items[tm.item0 + i];
+  for (int i = tid; i <= tm.n_parts; i += kTile) s_first[i] = D.part_first_rel[tm.g0 + t + i];
+  int seg_a = 0, seg_b = 0;
+  double ci0 = 0.0, ci1 = 0.0, ci2 = 0.0, ci3 = 0.0, ci4 = 0.0, ci5 = 0.0;
+  const bool is_pt = tid < tm.n_pts;
+  if (is_pt) {
+    const int pt = tm.pt0 + tid;
+    seg_a = D.pt_first[pt] - obs0;
+    seg_b = D.pt_first[pt + 1] - obs0;
+    const double2* ci = reinterpret_cast<const double2*>(W.cinv + 6 * static_cast<int64_t>(pt));
+    const double2 c01 = ci[0], c23 = ci[1], c45 = ci[2];
+    ci0 = c01.x; ci1 = c01.y; ci2 = c23.x; ci3 = c23.y; ci4 = c45.x; ci5 = c45.y;
+  }
+  double pa[CB];
+  double pb[TWO ? 6 : 1];
   int lp = 0;
-  const int64_t ld = D.ld;
+  bool has_b = false;
   if (active) {
-    const int2 idx = D.obs_idx[o];
-    const ObsView vw = D.views[idx.x];
-    lp = idx.y - pt0;
-    const double2* J = D.J + o;
-    e0 = J[(kPlaneJp + 0) * ld];
-    e1 = J[(kPlaneJp + 1) * ld];
-    e2 = J[(kPlaneJp + 2) * ld];
-    const double* pa = W.p + static_cast<int64_t>(vw.pose_a) * CB;
+    const int2 ab = D.obs_ab[o];
+    lp = D.obs_lp[o];
+    const double* pap = W.p + static_cast<int64_t>(ab.x) * CB;
+#pragma unroll
+    for (int k = 0; k < CB; ++k) pa[k] = pap[k];
+    if (TWO) {
+      has_b = ab.y >= 0;
+      const double* pbp = W.p + static_cast<int64_t>(has_b ? ab.y : 0) * CB;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pb[k] = has_b ? pbp[k] : 0.0;
+    }
+  }
+  __syncthreads();  // barrier init visible to all waiters; tile incidence staged
+  while (!mbar_try_wait(&bar, 0)) {
+  }
+  double2 e0 = make_double2(0.0, 0.0), e1 = e0, e2 = e0;
+  double u0 = 0.0, u1 = 0.0;
+  if (active) {
+    e0 = sJ[0 * L::kStride + tid];
+    e1 = sJ[1 * L::kStride + tid];
+    e2 = sJ[2 * L::kStride + tid];
 #pragma unroll
     for (int k = 0; k < CB; ++k) {
-      const double2 F = J[(kPlaneJA + k) * ld];
-      const double pk = pa[k];
-      u0 += F.x * pk;
-      u1 += F.y * pk;
+      const double2 F = sJ[(3 + k) * L::kStride + tid];
+      u0 += F.x * pa[k];
+      u1 += F.y * pa[k];
     }
     if (TWO) {
-      if (vw.pose_b >= 0) {
-        const double* pb = W.p + static_cast<int64_t>(vw.pose_b) * CB;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const double2 F = J[(kPlaneJA + CB + k) * ld];
-          const double pk = pb[k];
-          u0 += F.x * pk;
-          u1 += F.y * pk;
-        }
+      for (int k = 0; k < 6; ++k) {
+        const double2 F = sJ[(3 + CB + k) * L::kStride + tid];
+        u0 += F.x * pb[k];
+        u1 += F.y * pb[k];
       }
     }
-    v[0][tid] = e0.x * u0 + e0.y * u1;
-    v[1][tid] = e1.x * u0 + e1.y * u1;
-    v[2][tid] = e2.x * u0 + e2.y * u1;
+    // v = E^T u into the .x halves of the (consumed) Jp slots of this thread
+    sJ[0 * L::kStride + tid].x = e0.x * u0 + e0.y * u1;
+    sJ[1 * L::kStride + tid].x = e1.x * u0 + e1.y * u1;
+    sJ[2 * L::kStride + tid].x = e2.x * u0 + e2.y * u1;
   }
   __syncthreads();
-  const int pt = pt0 + tid;
-  if (pt < pt1) {
-    const int a = D.pt_first[pt] - obs0, b = D.pt_first[pt + 1] - obs0;
+  if (is_pt) {
     double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = a; i < b; ++i) {
-      z0 += v[0][i];
-      z1 += v[1][i];
-      z2 += v[2][i];
+    for (int i = seg_a; i < seg_b; ++i) {
+      z0 += sJ[0 * L::kStride + i].x;
+      z1 += sJ[1 * L::kStride + i].x;
+      z2 += sJ[2 * L::kStride + i].x;
     }
-    const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
-    y[0][tid] = ci[0] * z0 + ci[1] * z1 + ci[2] * z2;
-    y[1][tid] = ci[1] * z0 + ci[3] * z1 + ci[4] * z2;
-    y[2][tid] = ci[2] * z0 + ci[4] * z1 + ci[5] * z2;
+    // y of local point `tid` into the .y halves (nobody reads .y before the next barrier)
+    sJ[0 * L::kStride + tid].y = ci0 * z0 + ci1 * z1 + ci2 * z2;
+    sJ[1 * L::kStride + tid].y = ci1 * z0 + ci3 * z1 + ci4 * z2;
+    sJ[2 * L::kStride + tid].y = ci2 * z0 + ci4 * z1 + ci5 * z2;
   }
   __syncthreads();
   if (active) {
-    const double y0 = y[0][lp], y1 = y[1][lp], y2 = y[2][lp];
+    const double y0 = sJ[0 * L::kStride + lp].y, y1 = sJ[1 * L::kStride + lp].y, y2 = sJ[2 * L::kStride + lp].y;
     const double w0 = u0 - (e0.x * y0 + e1.x * y1 + e2.x * y2);
     const double w1 = u1 - (e0.y * y0 + e1.y * y1 + e2.y * y2);
-    D.J[static_cast<int64_t>(plane_w) * ld + o] = make_double2(w0, w1);
+    // contribution c_k = F_k . w overwrites the .x half of the Jacobian slot it came from
+#pragma unroll
+    for (int k = 0; k < L::NP - 3; ++k) {
+      double2* slot = sJ + (3 + k) * L::kStride + tid;
+      const double2 F = *slot;
+      slot->x = F.x * w0 + F.y * w1;
+    }
+  }
+  __syncthreads();
+  // tile-local reduce-by-camera: partial g = g0 + local camera
+  const int n_work = tm.n_parts * CB;
+  for (int wk = tid; wk < n_work; wk += kTile) {
+    const int lc = wk / CB, k = wk - lc * CB;
+    const int i0 = s_first[lc], i1 = s_first[lc + 1];
+    double acc = 0.0;
+    for (int i = i0; i < i1; ++i) {
+      const unsigned int it = s_items[i];
+      const int lo = it & 0x7fffu;
+      const int row = TWO ? 3 + (it >> 15) * CB + k : 3 + k;  // slot-B items: planes 3+CB.. (CB == 6 there)
+      acc += sJ[row * L::kStride + lo].x;
+    }
+    W.partials_q[static_cast<int64_t>(tm.g0 + lc) * CB + k] = acc;
   }
 }
 
+// q_j = sum of the partial vectors of camera block j, in the fixed order of the static list.
 template <int CB>
-__global__ void __launch_bounds__(128) k_spmv_camera(DeviceProblem D, WorkArrays W, int plane_w) {
+__global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArrays W) {
   if (W.pcg_state[1]) return;
   __shared__ double red[4][CB];
-  const int4 ch = D.cam_chunks[blockIdx.x];
+  const int blk = blockIdx.x;
+  const int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
   double acc[CB];
 #pragma unroll
   for (int k = 0; k < CB; ++k) acc[k] = 0.0;
-  const int64_t ld = D.ld;
-  const double2* Wp = D.J + static_cast<int64_t>(plane_w) * ld;
-  for (int e = ch.y + threadIdx.x; e < ch.z; e += blockDim.x) {
-    const int ent = D.cam_entries[e];
-    const int o = ent >> 1;
-    const int slot = ent & 1;
-    const double2* FCe = D.FC + e;
-    const double2 w = Wp[o];
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    const double* pv = W.partials_q + static_cast<int64_t>(D.cam_part_idx[i]) * CB;
 #pragma unroll
-    for (int k = 0; k < CB; ++k) {
-      if (slot && k >= 6) break;
-      const double2 F = FCe[k * D.ldc];
-      acc[k] += F.x * w.x + F.y * w.y;
-    }
+    for (int k = 0; k < CB; ++k) acc[k] += pv[k];
   }
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -622,7 +710,7 @@ __global__ void __launch_bounds__(128) k_spmv_camera(DeviceProblem D, WorkArrays
   }
   __syncthreads();
   if (threadIdx.x < CB)
-    W.chunk_q[static_cast<int64_t>(blockIdx.x) * CB + threadIdx.x] =
+    W.q[static_cast<int64_t>(blk) * CB + threadIdx.x] =
         red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
 }
 
@@ -645,20 +733,6 @@ __device__ __forceinline__ double sum_partials(const volatile double* part, int 
   double acc = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
   return block_sum_all(acc, red);
-}
-
-// q_j from the chunk partials (or, after an allreduce, from W.q) plus D_c^2 p
-__device__ __forceinline__ double gather_q(const DeviceProblem& D, const WorkArrays& W, int i, int from_chunks) {
-  const int cb = D.cb;
-  double q;
-  if (from_chunks) {
-    const int b = i / cb, row = i - b * cb;
-    q = 0.0;
-    for (int c = D.cam_chunk_first[b]; c < D.cam_chunk_first[b + 1]; ++c) q += W.chunk_q[static_cast<int64_t>(c) * cb + row];
-  } else {
-    q = W.q[i];
-  }
-  return q;
 }
 
 // x = 0, r = rhs, z = M^-1 r, p = z, rz = rz0 = r.z
@@ -693,8 +767,8 @@ __global__ void __launch_bounds__(256) k_pcg_init(DeviceProblem D, WorkArrays W)
   }
 }
 
-// phase 1: q (+ D_c^2 p), partial p.q; the last CTA publishes p.q
-__global__ void __launch_bounds__(256) k_pcg_dot(DeviceProblem D, WorkArrays W, int from_chunks) {
+// phase 1: q += D_c^2 p, partial p.q; the last CTA publishes p.q
+__global__ void __launch_bounds__(256) k_pcg_dot(DeviceProblem D, WorkArrays W) {
   if (W.pcg_state[1]) return;
   __shared__ double red[32];
   const int n = D.n_blocks * D.cb;
@@ -702,7 +776,7 @@ __global__ void __launch_bounds__(256) k_pcg_dot(DeviceProblem D, WorkArrays W, 
   double acc = 0.0;
   if (i < n) {
     const double p = W.p[i];
-    const double q = gather_q(D, W, i, from_chunks) + W.dc2[i] * p;
+    const double q = W.q[i] + W.dc2[i] * p;
     W.q[i] = q;
     acc = p * q;
   }
@@ -1038,39 +1112,38 @@ void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t s
   k_pcg_init<<<(n + 255) / 256, 256, 0, st>>>(D, W);
 }
 
-void launch_spmv_point(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st) {
+template <int CB, bool TWO>
+static void launch_spmv_tile_t(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  static bool configured = false;
+  constexpr size_t smem = SpmvSmem<CB, TWO>::kBytes;
+  if (!configured) {
+    cudaFuncSetAttribute(k_spmv_tile<CB, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = true;
+  }
+  k_spmv_tile<CB, TWO><<<D.n_tiles, kTile, smem, st>>>(D, W);
+}
+
+void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
   if (D.n_tiles == 0) return;
   if (D.cb == 6 && !D.two)
-    k_spmv_point<6, false><<<D.n_tiles, kTile, 0, st>>>(D, W, plane_w);
+    launch_spmv_tile_t<6, false>(D, W, st);
   else if (D.cb == 6)
-    k_spmv_point<6, true><<<D.n_tiles, kTile, 0, st>>>(D, W, plane_w);
+    launch_spmv_tile_t<6, true>(D, W, st);
   else
-    k_spmv_point<9, false><<<D.n_tiles, kTile, 0, st>>>(D, W, plane_w);
+    launch_spmv_tile_t<9, false>(D, W, st);
 }
 
-void launch_spmv_camera(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st) {
-  if (D.n_chunks == 0) return;
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  if (D.n_blocks == 0) return;
   if (D.cb == 6)
-    k_spmv_camera<6><<<D.n_chunks, 128, 0, st>>>(D, W, plane_w);
+    k_partials_to_q<6><<<D.n_blocks, 128, 0, st>>>(D, W);
   else
-    k_spmv_camera<9><<<D.n_chunks, 128, 0, st>>>(D, W, plane_w);
+    k_partials_to_q<9><<<D.n_blocks, 128, 0, st>>>(D, W);
 }
 
-// sums the chunk partials of this rank into W.q (multi-GPU: input of the allreduce)
-__global__ void __launch_bounds__(256) k_chunks_to_q(DeviceProblem D, WorkArrays W) {
-  if (W.pcg_state[1]) return;
+void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
   const int n = D.n_blocks * D.cb;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) W.q[i] = gather_q(D, W, i, 1);
-}
-void launch_chunks_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
-  const int n = D.n_blocks * D.cb;
-  k_chunks_to_q<<<(n + 255) / 256, 256, 0, st>>>(D, W);
-}
-
-void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int from_chunks, cudaStream_t st) {
-  const int n = D.n_blocks * D.cb;
-  k_pcg_dot<<<(n + 255) / 256, 256, 0, st>>>(D, W, from_chunks);
+  k_pcg_dot<<<(n + 255) / 256, 256, 0, st>>>(D, W);
 }
 void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st) {
   const int blocks_per_cta = 256 / D.cb;

@@ -21,6 +21,14 @@ constexpr int kPlaneR = 0;
 constexpr int kPlaneJp = 1;
 constexpr int kPlaneJA = 4;
 
+// One record per point tile: everything a tile CTA needs to find its data (32 B, one load).
+struct alignas(16) TileMeta {
+  int obs0, n_obs;    // observations [obs0, obs0 + n_obs)
+  int pt0, n_pts;     // whole points [pt0, pt0 + n_pts)
+  int g0, n_parts;    // partials (tile, camera block) [g0, g0 + n_parts)
+  int item0, n_items; // incidence items of the tile, grouped by partial
+};
+
 struct ObsView {
   int pose_a, pose_b, intr, pad;  // 16 B
 };
@@ -45,6 +53,18 @@ struct DeviceProblem {
   const int4* cam_chunks;   // [n_chunks] (block, first entry, last entry, 0)
   const int* cam_chunk_first;  // [n_blocks + 1] first chunk of each camera block
   int n_chunks;
+  // static tile-local camera incidence for the implicit Schur product: one "partial" per
+  // (tile, camera block present in the tile)
+  const TileMeta* tile_meta;        // [n_tiles]
+  const int2* obs_ab;               // [n_obs] (block a, block b or -1) of each observation
+  const unsigned short* obs_lp;     // [n_obs] point index local to the tile
+  const unsigned short* part_first_rel;  // per tile t, n_parts + 1 item offsets relative to item0, at [g0 + t]
+  const int* tile_part_first;       // [n_tiles + 1] first partial of each tile
+  const int* part_item_first;       // [n_partials + 1] first item of each partial
+  const unsigned short* items;      // [n_entries] local observation | slot << 15, grouped by partial
+  const int* cam_part_first;        // [n_blocks + 1] camera block -> its partials
+  const int* cam_part_idx;          // [n_partials]
+  int n_partials;
   double2* J;               // planes
   // camera-sorted copy of the camera-side Jacobian columns: FC[k * ldc + e] = column k of the
   // block of incidence entry e (written by the Jacobian kernel through ent_pos, read
@@ -88,7 +108,7 @@ struct WorkArrays {
   double* scalars;   // [32] reduced scalars, copied to the host
   int* pcg_state;    // [4] iter, done, -, -
   double* pcg_scal;  // [4] rz, rz0, p.q, beta
-  double* chunk_q;   // [n_chunks][cb] per-chunk partial products of the camera phase
+  double* partials_q;  // [n_partials][cb] tile-local partial products of the implicit Schur product
   double* vec_partials;    // per-CTA partials of the PCG vector kernels
   unsigned int* counters;  // [4] "last block" arrival counters
 };
@@ -131,14 +151,12 @@ int camera_finalize_grid(const DeviceProblem& D);
 void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
                             double max_diag, double* partials, cudaStream_t st);
 void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
-// implicit Schur complement product, phase A (point tiles -> plane_w) and phase B (camera
-// chunks -> W.chunk_q)
-void launch_spmv_point(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st);
-void launch_spmv_camera(const DeviceProblem& D, const WorkArrays& W, int plane_w, cudaStream_t st);
-void launch_chunks_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
-// PCG vector phases: p.q (q from the chunk partials or from the allreduced W.q), the
-// x/r/z update with r.z, the new direction
-void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int from_chunks, cudaStream_t st);
+// implicit Schur complement product: one pass over point tiles -> W.partials_q, then the
+// per-camera fixed-order sum -> W.q
+void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+// PCG vector phases: q += D_c^2 p and p.q; the x/r/z update with r.z; the new direction
+void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
 void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
