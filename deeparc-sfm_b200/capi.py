@@ -189,6 +189,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.dba_abi_version.restype = C.c_int
     lib.dba_device_count.restype = C.c_int
     lib.dba_nccl_unique_id.argtypes = [C.c_void_p]
+    lib.dba_shard_plan.argtypes = [C.POINTER(DbaProblem), C.c_int32, _ip, C.POINTER(C.c_int64)]
     lib.dba_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(DbaConfig)]
     lib.dba_destroy.argtypes = [C.c_void_p]
     lib.dba_destroy.restype = None
@@ -210,6 +211,19 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     if path == LIB_PATH:
         _lib = lib
     return lib
+
+
+def shard_plan(p: Problem, world_size: int):
+    """Host-only: (pt_begin[world+1], obs_count[world]) of the point sharding (no GPU needed)."""
+    lib = load_library()
+    m = ProblemMarshal(p)
+    pt_begin = np.zeros(world_size + 1, np.int32)
+    obs_count = np.zeros(world_size, np.int64)
+    st = lib.dba_shard_plan(C.byref(m.struct), world_size, pt_begin.ctypes.data_as(_ip),
+                            obs_count.ctypes.data_as(C.POINTER(C.c_int64)))
+    if st != DBA_OK:
+        raise EngineError(st, "dba_shard_plan")
+    return pt_begin, obs_count
 
 
 def _ptr(a: Optional[np.ndarray]):

@@ -549,6 +549,29 @@ int dba_kernel_stats(dba_handle* h, dba_kernel_stat* out, int32_t capacity) {
   return n;
 }
 
+// ------------------------------------------------------------------- sharding plan
+int dba_shard_plan(const dba_problem* p, int32_t world_size, int32_t* pt_begin, int64_t* obs_count) {
+  if (!p || world_size < 1 || !pt_begin || p->n_obs < 0 || p->n_pts < 0 || (p->n_obs > 0 && !p->obs_pt))
+    return DBA_ERR_INVALID_ARGUMENT;
+  std::vector<int64_t> first(static_cast<size_t>(p->n_pts) + 1, 0);
+  for (int64_t i = 0; i < p->n_obs; ++i) {
+    if (p->obs_pt[i] < 0 || p->obs_pt[i] >= p->n_pts) return DBA_ERR_INVALID_ARGUMENT;
+    first[p->obs_pt[i] + 1]++;
+  }
+  for (int i = 0; i < p->n_pts; ++i) first[i + 1] += first[i];
+  pt_begin[0] = 0;
+  for (int r = 1; r < world_size; ++r) {
+    const int64_t target = p->n_obs * r / world_size;
+    int cut = static_cast<int>(std::lower_bound(first.begin(), first.end(), target) - first.begin());
+    cut = std::min(cut, p->n_pts);
+    pt_begin[r] = std::max(cut, pt_begin[r - 1]);
+  }
+  pt_begin[world_size] = p->n_pts;
+  if (obs_count)
+    for (int r = 0; r < world_size; ++r) obs_count[r] = first[pt_begin[r + 1]] - first[pt_begin[r]];
+  return DBA_OK;
+}
+
 // ------------------------------------------------------------------- problem upload
 int dba_problem_set(dba_handle* h, const dba_problem* p) {
   if (!h || !p) return DBA_ERR_INVALID_ARGUMENT;
@@ -600,15 +623,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   for (int i = 0; i < p->n_pts; ++i) pt_count[i + 1] += pt_count[i];  // prefix: first obs of each point (global sorted)
   int pt_lo = 0, pt_hi = p->n_pts;
   if (h->world > 1) {
-    auto cut = [&](int r) -> int {
-      if (r <= 0) return 0;
-      if (r >= h->world) return p->n_pts;
-      const int64_t target = n * r / h->world;
-      return static_cast<int>(std::lower_bound(pt_count.begin(), pt_count.end(), target) - pt_count.begin());
-    };
-    pt_lo = std::min(cut(h->rank), p->n_pts);
-    pt_hi = std::min(cut(h->rank + 1), p->n_pts);
-    if (pt_hi < pt_lo) pt_hi = pt_lo;
+    std::vector<int32_t> plan(static_cast<size_t>(h->world) + 1);
+    dba_shard_plan(p, h->world, plan.data(), nullptr);
+    pt_lo = plan[h->rank];
+    pt_hi = plan[h->rank + 1];
   }
   h->pt_lo = pt_lo;
   h->n_pts = pt_hi - pt_lo;

@@ -116,29 +116,15 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
     const ObsView v = D.views[idx.x];
     const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
     const double X[3] = {Xp[0], Xp[1], Xp[2]};
-    Forward f;
-    forward(P, v, X, f);
-    const IntrRow I = P.intr_rows[v.intr];
-    Projection pr;
-    project<true>(I, f.cam, xy.x, xy.y, pr);
-    c = pr.r0 * pr.r0 + pr.r1 * pr.r1;
+    const PoseRow& A = P.pose_rows[v.pose_a];
+    const bool two = v.pose_b >= 0;
+    const PoseRow* B = two ? P.pose_rows + v.pose_b : nullptr;
+    ObsJacobian j;
+    observation_jacobian(A, B, P.intr_rows[v.intr], X, xy.x, xy.y, CB > 0, j);
+    c = j.r0 * j.r0 + j.r1 * j.r1;
     double2* J = D.J + o;
     const int64_t ld = D.ld;
-    J[kPlaneR * ld] = make_double2(pr.r0, pr.r1);
-
-    const PoseRow& A = P.pose_rows[v.pose_a];
-    double GA[2][3];  // d r / d mid
-    mul23_R(pr.G, A.R, GA);
-    double Jp[2][3];
-    const bool two = v.pose_b >= 0;
-    if (two) {
-      mul23_R(GA, P.pose_rows[v.pose_b].R, Jp);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) Jp[i][k] = GA[i][k];
-    }
+    J[kPlaneR * ld] = make_double2(j.r0, j.r1);
     {
       double s0 = 1.0, s1 = 1.0, s2 = 1.0;
       if (!unit_scale) {
@@ -147,14 +133,11 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
         s1 = sp[1];
         s2 = sp[2];
       }
-      J[(kPlaneJp + 0) * ld] = make_double2(Jp[0][0] * s0, Jp[1][0] * s0);
-      J[(kPlaneJp + 1) * ld] = make_double2(Jp[0][1] * s1, Jp[1][1] * s1);
-      J[(kPlaneJp + 2) * ld] = make_double2(Jp[0][2] * s2, Jp[1][2] * s2);
+      J[(kPlaneJp + 0) * ld] = make_double2(j.Jp[0][0] * s0, j.Jp[1][0] * s0);
+      J[(kPlaneJp + 1) * ld] = make_double2(j.Jp[0][1] * s1, j.Jp[1][1] * s1);
+      J[(kPlaneJp + 2) * ld] = make_double2(j.Jp[0][2] * s2, j.Jp[1][2] * s2);
     }
     if (CB >= 6) {
-      double Da[3][3], Jw[2][3];
-      rotation_derivative(A, f.mid, Da);
-      mul23_33(pr.G, Da, Jw);
       double s[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) s[k] = 1.0;
@@ -163,18 +146,18 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
 #pragma unroll
         for (int k = 0; k < CB; ++k) s[k] = sc[k];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) s[k] *= A.free_;
+        for (int k = 0; k < 6; ++k) s[k] *= A.free_;  // constant pose: its six columns vanish
       }
       double2 FA[CB > 0 ? CB : 1];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        FA[k] = make_double2(Jw[0][k] * s[k], Jw[1][k] * s[k]);
-        FA[3 + k] = make_double2(pr.G[0][k] * s[3 + k], pr.G[1][k] * s[3 + k]);
+        FA[k] = make_double2(j.JwA[0][k] * s[k], j.JwA[1][k] * s[k]);
+        FA[3 + k] = make_double2(j.JtA[0][k] * s[3 + k], j.JtA[1][k] * s[3 + k]);
       }
       if (CB == 9) {
-        FA[6] = make_double2(pr.df[0] * s[6], pr.df[1] * s[6]);
-        FA[7] = make_double2(pr.dk0[0] * s[7], pr.dk0[1] * s[7]);
-        FA[8] = make_double2(pr.dk1[0] * s[8], pr.dk1[1] * s[8]);
+        FA[6] = make_double2(j.df[0] * s[6], j.df[1] * s[6]);
+        FA[7] = make_double2(j.dk0[0] * s[7], j.dk0[1] * s[7]);
+        FA[8] = make_double2(j.dk1[0] * s[8], j.dk1[1] * s[8]);
       }
 #pragma unroll
       for (int k = 0; k < CB; ++k) J[(kPlaneJA + k) * ld] = FA[k];
@@ -187,21 +170,17 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
       if (TWO) {
         const int pb = kPlaneJA + CB;
         if (two) {
-          const PoseRow& B = P.pose_rows[v.pose_b];
-          double Db[3][3], JwB[2][3];
-          rotation_derivative(B, X, Db);
-          mul23_33(GA, Db, JwB);
           double sb[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
           if (!unit_scale) {
             const double* sc = W.sc + static_cast<int64_t>(v.pose_b) * CB;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) sb[k] = sc[k] * B.free_;
+            for (int k = 0; k < 6; ++k) sb[k] = sc[k] * B->free_;
           }
           double2 FB[6];
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            FB[k] = make_double2(JwB[0][k] * sb[k], JwB[1][k] * sb[k]);
-            FB[3 + k] = make_double2(GA[0][k] * sb[3 + k], GA[1][k] * sb[3 + k]);
+            FB[k] = make_double2(j.JwB[0][k] * sb[k], j.JwB[1][k] * sb[k]);
+            FB[3 + k] = make_double2(j.JtB[0][k] * sb[3 + k], j.JtB[1][k] * sb[3 + k]);
           }
 #pragma unroll
           for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = FB[k];

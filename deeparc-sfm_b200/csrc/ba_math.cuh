@@ -83,14 +83,14 @@ __host__ __device__ inline void make_pose_row(const double* w, const double* t, 
 }
 
 // out = R X + t
-__device__ __forceinline__ void transform(const PoseRow& P, const double X[3], double out[3]) {
+__host__ __device__ __forceinline__ void transform(const PoseRow& P, const double X[3], double out[3]) {
   out[0] = P.R[0] * X[0] + P.R[1] * X[1] + P.R[2] * X[2] + P.t[0];
   out[1] = P.R[3] * X[0] + P.R[4] * X[1] + P.R[5] * X[2] + P.t[1];
   out[2] = P.R[6] * X[0] + P.R[7] * X[1] + P.R[8] * X[2] + P.t[2];
 }
 
 // D[r][k] = d (R X)_r / d omega_k
-__device__ __forceinline__ void rotation_derivative(const PoseRow& P, const double X[3], double D[3][3]) {
+__host__ __device__ __forceinline__ void rotation_derivative(const PoseRow& P, const double X[3], double D[3][3]) {
   const double wx = P.w[0], wy = P.w[1], wz = P.w[2];
   // c1 = w x X, c2 = w x c1
   const double c1x = wy * X[2] - wz * X[1], c1y = wz * X[0] - wx * X[2], c1z = wx * X[1] - wy * X[0];
@@ -121,7 +121,7 @@ struct Projection {
 // projectPoint (snavely_reprojection_error.hh:38-78): no sign flip, fy = nf==2 ? f[1] : f[0],
 // distortion 1 + r2 (k0 + k1 r2) with unused coefficients stored as exact zeros.
 template <bool WITH_JAC>
-__device__ __forceinline__ void project(const IntrRow& I, const double p[3], double ox, double oy, Projection& out) {
+__host__ __device__ __forceinline__ void project(const IntrRow& I, const double p[3], double ox, double oy, Projection& out) {
   const double u = p[0] / p[2];
   const double v = p[1] / p[2];
   const double rr = u * u + v * v;
@@ -152,18 +152,81 @@ __device__ __forceinline__ void project(const IntrRow& I, const double p[3], dou
 }
 
 // C(2x3) = A(2x3) * B(3x3), B given as B[r][c]
-__device__ __forceinline__ void mul23_33(const double A[2][3], const double B[3][3], double C[2][3]) {
+__host__ __device__ __forceinline__ void mul23_33(const double A[2][3], const double B[3][3], double C[2][3]) {
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * B[0][j] + A[i][1] * B[1][j] + A[i][2] * B[2][j];
 }
 // C(2x3) = A(2x3) * R, R row-major 9
-__device__ __forceinline__ void mul23_R(const double A[2][3], const double* R, double C[2][3]) {
+__host__ __device__ __forceinline__ void mul23_R(const double A[2][3], const double* R, double C[2][3]) {
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) C[i][j] = A[i][0] * R[j] + A[i][1] * R[3 + j] + A[i][2] * R[6 + j];
+}
+
+// Everything the Jacobian kernel stores for one observation, UNSCALED:
+//   r, Jp = d r/d X, JA = d r/d (w_a, t_a [, f, k0, k1]), JB = d r/d (w_b, t_b) (two-pose only).
+struct ObsJacobian {
+  double r0, r1;
+  double Jp[2][3];
+  double JwA[2][3], JtA[2][3];
+  double JwB[2][3], JtB[2][3];
+  double df[2], dk0[2], dk1[2];
+};
+
+// p = R_a (R_b X + t_b) + t_a (B != nullptr) or p = R_a X + t_a; chain rule through project():
+//   d r/d t_a = G;  d r/d w_a = G D(w_a; mid);  d r/d mid = G R_a =: GA
+//   d r/d t_b = GA; d r/d w_b = GA D(w_b; X);   d r/d X = GA R_b   (or GA when there is no B)
+__host__ __device__ __forceinline__ void observation_jacobian(const PoseRow& A, const PoseRow* B, const IntrRow& I,
+                                                              const double X[3], double ox, double oy, bool want_cam,
+                                                              ObsJacobian& out) {
+  double mid[3], cam[3];
+  if (B) {
+    transform(*B, X, mid);
+  } else {
+    mid[0] = X[0];
+    mid[1] = X[1];
+    mid[2] = X[2];
+  }
+  transform(A, mid, cam);
+  Projection pr;
+  project<true>(I, cam, ox, oy, pr);
+  out.r0 = pr.r0;
+  out.r1 = pr.r1;
+  double GA[2][3];
+  mul23_R(pr.G, A.R, GA);
+  if (B) {
+    mul23_R(GA, B->R, out.Jp);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) out.Jp[i][k] = GA[i][k];
+  }
+  if (!want_cam) return;
+  double D[3][3];
+  rotation_derivative(A, mid, D);
+  mul23_33(pr.G, D, out.JwA);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out.JtA[i][k] = pr.G[i][k];
+  out.df[0] = pr.df[0];
+  out.df[1] = pr.df[1];
+  out.dk0[0] = pr.dk0[0];
+  out.dk0[1] = pr.dk0[1];
+  out.dk1[0] = pr.dk1[0];
+  out.dk1[1] = pr.dk1[1];
+  if (B) {
+    rotation_derivative(*B, X, D);
+    mul23_33(GA, D, out.JwB);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) out.JtB[i][k] = GA[i][k];
+  }
 }
 
 // inverse of a symmetric positive definite 3x3 given by its 6 unique entries

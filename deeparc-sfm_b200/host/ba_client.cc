@@ -1,0 +1,158 @@
+// See ba_client.hh.
+#include "ba_client.hh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace deeparc {
+
+dba_problem FlatProblem::view() const {
+  dba_problem p;
+  std::memset(&p, 0, sizeof p);
+  p.n_obs = static_cast<int64_t>(obs_pt.size());
+  p.n_pts = static_cast<int32_t>(point_of.size());
+  p.n_ext = static_cast<int32_t>(ext_of.size());
+  p.n_intr = static_cast<int32_t>(intr_of.size());
+  p.obs_xy = obs_xy.data();
+  p.obs_pt = obs_pt.data();
+  p.obs_pose_a = obs_pose_a.data();
+  p.obs_pose_b = obs_pose_b.data();
+  p.obs_intr = obs_intr.data();
+  p.pts = pts.data();
+  p.ext_rot = ext_rot.data();
+  p.ext_trans = ext_trans.data();
+  p.intr_center = intr_center.data();
+  p.intr_focal = intr_focal.data();
+  p.intr_dist = intr_dist.data();
+  p.intr_nf = intr_nf.data();
+  p.intr_nd = intr_nd.data();
+  p.ext_const = ext_const.data();
+  p.freeze_camera = freeze_camera;
+  p.free_intrinsics = 0;  // principal point, focal, distortion stay constant (sfm.cc:60-62)
+  return p;
+}
+
+void flatten(DeepArcManager& m, bool freeze_camera, FlatProblem* out) {
+  FlatProblem& f = *out;
+  f = FlatProblem();
+  f.freeze_camera = freeze_camera ? 1 : 0;
+  std::vector<ParameterBlock*>& blocks = *m.parameters();
+  std::vector<Point3d*>& points = *m.point3ds();
+  std::vector<Extrinsic*>& exts = *m.extrinsics();
+  std::vector<Intrinsic*>& intrs = *m.intrinsics();
+  std::unordered_map<const Point3d*, int> pt_index;
+  std::unordered_map<const Extrinsic*, int> ext_index;
+  std::unordered_map<const Intrinsic*, int> intr_index;
+  pt_index.reserve(points.size() * 2);
+  f.point_of = points;
+  f.pts.resize(3 * points.size());
+  for (size_t i = 0; i < points.size(); ++i) {
+    pt_index[points[i]] = static_cast<int>(i);
+    for (int k = 0; k < 3; ++k) f.pts[3 * i + k] = points[i]->position()[k];
+  }
+  f.ext_of = exts;
+  f.ext_rot.resize(3 * exts.size());
+  f.ext_trans.resize(3 * exts.size());
+  f.ext_const.assign(exts.size(), 0);
+  for (size_t i = 0; i < exts.size(); ++i) {
+    ext_index[exts[i]] = static_cast<int>(i);
+    for (int k = 0; k < 3; ++k) {
+      f.ext_rot[3 * i + k] = exts[i]->rotation()[k];
+      f.ext_trans[3 * i + k] = exts[i]->translation()[k];
+    }
+  }
+  f.intr_of = intrs;
+  f.intr_center.resize(2 * intrs.size());
+  f.intr_focal.assign(2 * intrs.size(), 0.0);
+  f.intr_dist.assign(2 * intrs.size(), 0.0);
+  f.intr_nf.resize(intrs.size());
+  f.intr_nd.resize(intrs.size());
+  for (size_t i = 0; i < intrs.size(); ++i) {
+    intr_index[intrs[i]] = static_cast<int>(i);
+    f.intr_center[2 * i] = intrs[i]->center()[0];
+    f.intr_center[2 * i + 1] = intrs[i]->center()[1];
+    f.intr_nf[i] = intrs[i]->focal_size();
+    f.intr_nd[i] = intrs[i]->distrotion_size();
+    for (int k = 0; k < 2; ++k) {
+      if (k < intrs[i]->focal_size()) f.intr_focal[2 * i + k] = intrs[i]->focal()[k];
+      if (k < intrs[i]->distrotion_size()) f.intr_dist[2 * i + k] = intrs[i]->distrotion()[k];
+    }
+  }
+  const size_t n = blocks.size();
+  f.obs_xy.resize(2 * n);
+  f.obs_pt.resize(n);
+  f.obs_pose_a.resize(n);
+  f.obs_pose_b.resize(n);
+  f.obs_intr.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    ParameterBlock* b = blocks[i];
+    f.obs_xy[2 * i] = b->point2d()->x();
+    f.obs_xy[2 * i + 1] = b->point2d()->y();
+    f.obs_pt[i] = pt_index.at(b->point3d());
+    f.obs_intr[i] = intr_index.at(b->intrinsic());
+    // the poses behind params[4],[5] (and [6],[7]) exactly as ParameterBlock::get() picks them
+    Extrinsic *pa, *pb = nullptr;
+    if (!b->share_extrinsic())
+      pa = b->extrinsic();
+    else if (b->pos_ring() == 0)
+      pa = b->arc();
+    else if (b->pos_arc() == 0)
+      pa = b->ring();
+    else {
+      pa = b->arc();
+      pb = b->ring();
+    }
+    f.obs_pose_a[i] = ext_index.at(pa);
+    f.obs_pose_b[i] = pb ? ext_index.at(pb) : -1;
+    // gauge: blocks at (arc 0, ring 0) pin params[4],[5] (sfm.cc:50-53)
+    if (b->pos_arc() == 0 && b->pos_ring() == 0) f.ext_const[f.obs_pose_a[i]] = 1;
+  }
+}
+
+void scatter(const FlatProblem& f, const std::vector<double>& pts, const std::vector<double>& ext_rot,
+             const std::vector<double>& ext_trans) {
+  for (size_t i = 0; i < f.point_of.size(); ++i)
+    for (int k = 0; k < 3; ++k) f.point_of[i]->position()[k] = pts[3 * i + k];
+  for (size_t i = 0; i < f.ext_of.size(); ++i) {
+    f.ext_of[i]->rotation(&ext_rot[3 * i]);
+    f.ext_of[i]->translation(ext_trans[3 * i], ext_trans[3 * i + 1], ext_trans[3 * i + 2]);
+  }
+}
+
+namespace {
+dba_handle* g_engine = nullptr;
+}
+
+dba_handle* engine() {
+  if (g_engine) return g_engine;
+  dba_config cfg;
+  std::memset(&cfg, 0, sizeof cfg);
+  const char* dev = std::getenv("DEEPARC_DEVICE");
+  cfg.device = dev ? std::atoi(dev) : 0;
+  cfg.rank = 0;
+  cfg.world_size = 1;
+  const int st = dba_create(&g_engine, &cfg);
+  if (st != DBA_OK) {
+    const std::string msg = std::string("deeparc: cannot create the GPU engine: ") + dba_last_error(nullptr);
+    g_engine = nullptr;
+    throw std::runtime_error(msg);
+  }
+  return g_engine;
+}
+
+void engine_release() {
+  if (g_engine) dba_destroy(g_engine);
+  g_engine = nullptr;
+}
+
+void check(int status, const char* what) {
+  if (status == DBA_OK) return;
+  throw std::runtime_error(std::string(what) + " failed (" + std::to_string(status) + "): " +
+                           (g_engine ? dba_last_error(g_engine) : dba_last_error(nullptr)));
+}
+
+}  // namespace deeparc

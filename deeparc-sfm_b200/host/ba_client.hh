@@ -1,0 +1,56 @@
+// C++ binding of the C ABI (include/deeparc_ba.h) for the host mirror: the gather from the
+// AoS pointer graph into the flat SoA image (by POINTER IDENTITY — Point3d ids go stale after
+// filterPoint3d, reference DeepArcManager.cc:368-378), the scatter-back that emulates Ceres
+// optimising in place through the raw double* (reference sfm.cc:47-48), and a process-wide
+// engine handle.  This is the only place where the host code talks to CUDA, and it does so
+// exclusively through the C ABI.
+#ifndef DEEPARC_B200_BA_CLIENT_HH_
+#define DEEPARC_B200_BA_CLIENT_HH_
+
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/deeparc_ba.h"
+#include "DeepArcManager.hh"
+
+namespace deeparc {
+
+struct FlatProblem {
+  std::vector<double> obs_xy, pts, ext_rot, ext_trans, intr_center, intr_focal, intr_dist;
+  std::vector<int32_t> obs_pt, obs_pose_a, obs_pose_b, obs_intr, intr_nf, intr_nd;
+  std::vector<uint8_t> ext_const;
+  std::vector<Point3d*> point_of;      // flat point index -> object
+  std::vector<Extrinsic*> ext_of;
+  std::vector<Intrinsic*> intr_of;
+  int freeze_camera = 0;
+  dba_problem view() const;
+};
+
+// Problem construction of solve() (reference sfm.cc:36-65): one observation per
+// ParameterBlock, parameter blocks from ParameterBlock::get(), the gauge rule (:50-53) as
+// ext_const, freeze_camera (:54-57); intrinsics stay constant as shipped (:60-62).
+void flatten(DeepArcManager& manager, bool freeze_camera, FlatProblem* out);
+
+// Writes optimised values back into Point3d::position(), Extrinsic::rotation()/translation().
+void scatter(const FlatProblem& flat, const std::vector<double>& pts, const std::vector<double>& ext_rot,
+             const std::vector<double>& ext_trans);
+
+// Process-wide engine (device DEEPARC_DEVICE, default 0).  Throws std::runtime_error if the
+// engine cannot be created (no GPU => no solve; there is no CPU fallback).
+dba_handle* engine();
+void engine_release();
+void check(int status, const char* what);
+
+}  // namespace deeparc
+
+// Drop-in for the reference's solve() (sfm.cc:31-75).
+void solve(DeepArcManager& deeparcManager, int max_iteration = 1000, int max_second = 3600,
+           bool freeze_camera = false);
+
+// Last summary of solve() / of the hemisphere fit, for drivers that want more than stdout.
+const dba_summary& last_solve_summary();
+const std::vector<dba_iteration>& last_solve_iterations();
+
+#endif  // DEEPARC_B200_BA_CLIENT_HH_

@@ -1,0 +1,67 @@
+// solve(): drop-in for the reference's solve() (reference src/sfm.cc:31-75).  Same signature
+// and defaults; instead of building a ceres::Problem and calling ceres::Solve it gathers the
+// scene into the flat SoA image, runs the GPU Levenberg-Marquardt engine through the C ABI and
+// scatters the result back into the objects the raw double* of ParameterBlock::get() point at —
+// which is what Ceres' in-place optimisation leaves behind for filterPoint3d / write / writePly.
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <vector>
+
+#include "ba_client.hh"
+
+namespace {
+dba_summary g_summary;
+std::vector<dba_iteration> g_iterations;
+
+void print_full_report(const dba_summary& s, const deeparc::FlatProblem& f, bool freeze) {
+  std::printf("\nSolver Summary (deeparc B200 engine)\n\n");
+  std::printf("Observations       %12zu\nPoints             %12zu\nExtrinsics         %12zu\nIntrinsics         %12zu (constant)\n",
+              f.obs_pt.size(), f.point_of.size(), f.ext_of.size(), f.intr_of.size());
+  std::printf("Camera parameters  %12s\n", freeze ? "constant" : "6 per free extrinsic");
+  std::printf("Linear solver      %s, reduced system %d\n",
+              s.linear_solver_used == DBA_LS_DENSE ? "explicit Schur + dense Cholesky" : "implicit Schur + block-Jacobi PCG",
+              s.reduced_system_size);
+  std::printf("\nCost:\nInitial          %30e\nFinal            %30e\nChange           %30e\n\n", s.initial_cost,
+              s.final_cost, s.initial_cost - s.final_cost);
+  std::printf("Minimizer iterations %d\nSuccessful steps     %d\nUnsuccessful steps   %d\n\n", s.num_iterations,
+              s.num_successful_steps, s.num_unsuccessful_steps);
+  std::printf("Time (in seconds):\n  Device LM loop   %12.6f\n  Total            %12.6f\nKernel launches    %lld\n\n",
+              s.device_time_in_seconds, s.total_time_in_seconds, static_cast<long long>(s.kernel_launches));
+  std::printf("Termination: %s (%s)\n",
+              s.termination == DBA_CONVERGENCE ? "CONVERGENCE" : (s.termination == DBA_NO_CONVERGENCE ? "NO_CONVERGENCE" : "FAILURE"),
+              s.message);
+}
+}  // namespace
+
+const dba_summary& last_solve_summary() { return g_summary; }
+const std::vector<dba_iteration>& last_solve_iterations() { return g_iterations; }
+
+void solve(DeepArcManager& deeparcManager, int max_iteration, int max_second, bool freeze_camera) {
+  deeparc::FlatProblem flat;
+  deeparc::flatten(deeparcManager, freeze_camera, &flat);  // sfm.cc:36-65
+  dba_handle* h = deeparc::engine();
+  dba_problem view = flat.view();
+  deeparc::check(dba_problem_set(h, &view), "dba_problem_set");
+
+  dba_solve_options options;
+  dba_solve_options_default(&options);            // Ceres defaults (not overridden at sfm.cc:66-71)
+  options.linear_solver = DBA_LS_AUTO;            // sfm.cc:67 DENSE_SCHUR -> exact where it fits
+  options.progress_to_stdout = 1;                 // sfm.cc:68
+  options.max_num_iterations = max_iteration;     // sfm.cc:69
+  options.max_solver_time_in_seconds = max_second;  // sfm.cc:71
+  options.pcg_rel_tolerance = 1e-13;              // drive the inexact solve to the exact step
+  options.pcg_max_iterations = 4000;
+  // (sfm.cc:70 num_threads has no meaning here)
+  g_iterations.assign(static_cast<size_t>(max_iteration) + 2, dba_iteration());
+  std::memset(&g_summary, 0, sizeof g_summary);
+  g_summary.iterations = g_iterations.data();
+  g_summary.iterations_capacity = static_cast<int32_t>(g_iterations.size());
+  deeparc::check(dba_solve(h, &options, &g_summary), "dba_solve");  // sfm.cc:73
+  g_iterations.resize(static_cast<size_t>(g_summary.num_iterations));
+
+  std::vector<double> pts(flat.pts.size()), rot(flat.ext_rot.size()), trans(flat.ext_trans.size());
+  deeparc::check(dba_params_get(h, pts.data(), rot.data(), trans.data(), nullptr, nullptr), "dba_params_get");
+  deeparc::scatter(flat, pts, rot, trans);
+  print_full_report(g_summary, flat, freeze_camera);  // sfm.cc:74
+}

@@ -187,6 +187,12 @@ int dba_device_count(void);
 /* Rank 0 fills 128 bytes that every rank then passes in dba_config.nccl_unique_id. */
 int dba_nccl_unique_id(void* out128);
 
+/* Host-only helper (no GPU needed): the point range each rank of a world_size-rank job owns,
+ * contiguous in point index and balanced by observation count.  pt_begin has world_size + 1
+ * entries (rank r owns points [pt_begin[r], pt_begin[r+1])), obs_count world_size entries.
+ * dba_problem_set uses exactly this plan.                                                  */
+int dba_shard_plan(const dba_problem* p, int32_t world_size, int32_t* pt_begin, int64_t* obs_count);
+
 int dba_create(dba_handle** out, const dba_config* cfg);
 void dba_destroy(dba_handle* h);
 const char* dba_last_error(const dba_handle* h); /* h may be NULL: last create error     */

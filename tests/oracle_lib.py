@@ -122,72 +122,55 @@ class Oracle:
         return out
 
 
-class Reference:
-    """The reference's own DeepArcManager / solve() / functors behind a C bridge."""
+class _ManagerApi:
+    """Manager-level C entry points shared by the reference bridge (prefix ``ref_``) and the
+    product's C++ host mirror (prefix ``dam_``)."""
 
-    def __init__(self, path: str = REF_PATH):
-        self.lib = C.CDLL(path)
-        L = self.lib
-        L.ref_eval.argtypes = [C.POINTER(capi.DbaProblem), _dp, _dp, _dp, _dp, _dp, _dp]
-        L.ref_set_overrides.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
-        L.ref_set_overrides.restype = None
-        L.ref_last_summary.argtypes = [C.POINTER(capi.DbaSummary)]
-        L.ref_last_summary.restype = None
-        L.ref_fit_hemisphere.argtypes = [_dp, C.c_int, _dp, _dp, C.POINTER(capi.DbaSummary)]
-        L.ref_manager_read.argtypes = [C.c_char_p]
-        L.ref_manager_read.restype = C.c_void_p
-        L.ref_manager_free.argtypes = [C.c_void_p]
-        L.ref_manager_free.restype = None
-        L.ref_manager_is_shared.argtypes = [C.c_void_p]
-        L.ref_manager_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int64)] + [C.POINTER(C.c_int)] * 5
-        L.ref_manager_counts.restype = None
-        L.ref_manager_export.argtypes = [C.c_void_p, _dp, _ip, _ip, _ip, _ip, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _bp]
-        L.ref_manager_solve.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
-        L.ref_manager_solve.restype = None
-        L.ref_manager_filter.argtypes = [C.c_void_p, C.c_double, _dp, C.c_double]
-        L.ref_manager_filter.restype = None
-        L.ref_manager_write.argtypes = [C.c_void_p, C.c_char_p]
-        L.ref_manager_write.restype = None
-        L.ref_manager_write_ply.argtypes = [C.c_void_p, C.c_char_p]
-        L.ref_manager_write_ply.restype = None
-        L.ref_manager_camera_centers.argtypes = [C.c_void_p, _dp, C.c_int]
-        self.set_overrides(quiet=1)
+    def _bind_manager(self, L, prefix):
+        self._pfx = prefix
+        f = lambda name: getattr(L, prefix + name)
+        f("manager_read").argtypes = [C.c_char_p]
+        f("manager_read").restype = C.c_void_p
+        f("manager_free").argtypes = [C.c_void_p]
+        f("manager_free").restype = None
+        f("manager_is_shared").argtypes = [C.c_void_p]
+        f("manager_counts").argtypes = [C.c_void_p, C.POINTER(C.c_int64)] + [C.POINTER(C.c_int)] * 5
+        f("manager_counts").restype = None
+        f("manager_export").argtypes = [C.c_void_p, _dp, _ip, _ip, _ip, _ip, _dp, _ip, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _bp]
+        f("manager_solve").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        f("manager_filter").argtypes = [C.c_void_p, C.c_double, _dp, C.c_double]
+        f("manager_write").argtypes = [C.c_void_p, C.c_char_p]
+        f("manager_write").restype = None
+        f("manager_write_ply").argtypes = [C.c_void_p, C.c_char_p]
+        f("manager_write_ply").restype = None
+        f("manager_camera_centers").argtypes = [C.c_void_p, _dp, C.c_int]
+        f("last_summary").argtypes = [C.POINTER(capi.DbaSummary)]
+        f("last_summary").restype = None
 
-    def set_overrides(self, quiet=-1, num_threads=-1, max_num_iterations=-1, function_tolerance=-1.0,
-                      gradient_tolerance=-1.0, parameter_tolerance=-1.0):
-        self.lib.ref_set_overrides(quiet, num_threads, max_num_iterations, function_tolerance, gradient_tolerance,
-                                   parameter_tolerance)
-
-    def eval(self, p: Problem, residuals=True, jacobians=False):
-        return _eval_common(self.lib.ref_eval, p, residuals, jacobians)
+    def _f(self, name):
+        return getattr(self.lib, self._pfx + name)
 
     def last_summary(self, capacity=1024):
         s = capi.Summary(capacity)
-        self.lib.ref_last_summary(C.byref(s.struct))
+        self._f("last_summary")(C.byref(s.struct))
         return s
 
-    def fit_hemisphere(self, centres, centre0=(0.0, 0.0, 0.0), rho0=1.0):
-        centres = np.ascontiguousarray(centres, dtype=np.float64)
-        c = np.array(centre0, dtype=np.float64)
-        rho = C.c_double(rho0)
-        s = capi.Summary(1024)
-        self.lib.ref_fit_hemisphere(_ptr(centres), centres.shape[0], _ptr(c), C.byref(rho), C.byref(s.struct))
-        return c, rho.value, s
-
-    # manager ------------------------------------------------------------------------
     def read(self, path: str):
-        h = self.lib.ref_manager_read(path.encode())
+        h = self._f("manager_read")(path.encode())
         if not h:
-            raise IOError(f"reference DeepArcManager::read failed for {path}")
+            raise IOError(f"DeepArcManager::read failed for {path}")
         return h
 
     def free(self, h):
-        self.lib.ref_manager_free(h)
+        self._f("manager_free")(h)
+
+    def is_shared(self, h) -> bool:
+        return bool(self._f("manager_is_shared")(h))
 
     def counts(self, h):
         n_obs = C.c_int64()
         v = [C.c_int() for _ in range(5)]
-        self.lib.ref_manager_counts(h, C.byref(n_obs), *[C.byref(x) for x in v])
+        self._f("manager_counts")(h, C.byref(n_obs), *[C.byref(x) for x in v])
         return {"n_obs": n_obs.value, "n_pts": v[0].value, "n_ext": v[1].value, "n_intr": v[2].value,
                 "n_arc": v[3].value, "n_ring": v[4].value}
 
@@ -201,28 +184,74 @@ class Reference:
                     intr_nd=np.zeros(ni, np.int32), ext_const=np.zeros(ne, np.uint8), n_arc=c["n_arc"], n_ring=c["n_ring"])
         p.pts_rgb = np.zeros((npt, 3), np.int32)
         ip = lambda a: a.ctypes.data_as(_ip)
-        self.lib.ref_manager_export(h, _ptr(p.obs_xy), ip(p.obs_pt), ip(p.obs_pose_a), ip(p.obs_pose_b), ip(p.obs_intr),
-                                    _ptr(p.pts), ip(p.pts_rgb), _ptr(p.ext_rot), _ptr(p.ext_trans), _ptr(p.intr_center),
-                                    _ptr(p.intr_focal), _ptr(p.intr_dist), ip(p.intr_nf), ip(p.intr_nd),
-                                    p.ext_const.ctypes.data_as(_bp))
+        self._f("manager_export")(h, _ptr(p.obs_xy), ip(p.obs_pt), ip(p.obs_pose_a), ip(p.obs_pose_b), ip(p.obs_intr),
+                                  _ptr(p.pts), ip(p.pts_rgb), _ptr(p.ext_rot), _ptr(p.ext_trans), _ptr(p.intr_center),
+                                  _ptr(p.intr_focal), _ptr(p.intr_dist), ip(p.intr_nf), ip(p.intr_nd),
+                                  p.ext_const.ctypes.data_as(_bp))
         return p
 
     def solve(self, h, max_iteration=100, max_second=3600, freeze_camera=False):
-        self.lib.ref_manager_solve(h, max_iteration, max_second, int(freeze_camera))
+        self._f("manager_solve")(h, max_iteration, max_second, int(freeze_camera))
         return self.last_summary()
 
     def filter(self, h, error_boundary, centre, radius):
         centre = np.ascontiguousarray(centre, dtype=np.float64)
-        self.lib.ref_manager_filter(h, error_boundary, _ptr(centre), radius)
+        self._f("manager_filter")(h, error_boundary, _ptr(centre), radius)
 
     def write(self, h, path):
-        self.lib.ref_manager_write(h, path.encode())
+        self._f("manager_write")(h, path.encode())
 
     def write_ply(self, h, path):
-        self.lib.ref_manager_write_ply(h, path.encode())
+        self._f("manager_write_ply")(h, path.encode())
 
     def camera_centers(self, h):
-        n = self.lib.ref_manager_camera_centers(h, None, 0)
+        n = self._f("manager_camera_centers")(h, None, 0)
         out = np.zeros((max(n, 1), 3))
-        self.lib.ref_manager_camera_centers(h, _ptr(out), n)
+        self._f("manager_camera_centers")(h, _ptr(out), n)
         return out[:n]
+
+
+class Reference(_ManagerApi):
+    """The reference's own DeepArcManager / solve() / functors behind a C bridge (oracle/_ref)."""
+
+    def __init__(self, path: str = REF_PATH):
+        self.lib = C.CDLL(path)
+        L = self.lib
+        self._bind_manager(L, "ref_")
+        L.ref_eval.argtypes = [C.POINTER(capi.DbaProblem), _dp, _dp, _dp, _dp, _dp, _dp]
+        L.ref_set_overrides.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+        L.ref_set_overrides.restype = None
+        L.ref_fit_hemisphere.argtypes = [_dp, C.c_int, _dp, _dp, C.POINTER(capi.DbaSummary)]
+        self.set_overrides(quiet=1)
+
+    def set_overrides(self, quiet=-1, num_threads=-1, max_num_iterations=-1, function_tolerance=-1.0,
+                      gradient_tolerance=-1.0, parameter_tolerance=-1.0):
+        self.lib.ref_set_overrides(quiet, num_threads, max_num_iterations, function_tolerance, gradient_tolerance,
+                                   parameter_tolerance)
+
+    def eval(self, p: Problem, residuals=True, jacobians=False):
+        return _eval_common(self.lib.ref_eval, p, residuals, jacobians)
+
+    def fit_hemisphere(self, centres, centre0=(0.0, 0.0, 0.0), rho0=1.0):
+        centres = np.ascontiguousarray(centres, dtype=np.float64)
+        c = np.array(centre0, dtype=np.float64)
+        rho = C.c_double(rho0)
+        s = capi.Summary(1024)
+        self.lib.ref_fit_hemisphere(_ptr(centres), centres.shape[0], _ptr(c), C.byref(rho), C.byref(s.struct))
+        return c, rho.value, s
+
+
+HOST_PATH = os.path.join(ROOT, "deeparc-sfm_b200", "lib", "libdeeparc_host.so")
+
+
+class HostMirror(_ManagerApi):
+    """The product's C++ mirror of the reference host surface (deeparc-sfm_b200/host)."""
+
+    def __init__(self, path: str = HOST_PATH):
+        capi.load_library()  # libdeeparc_ba.so first (RTLD_GLOBAL)
+        self.lib = C.CDLL(path)
+        self._bind_manager(self.lib, "dam_")
+        self.lib.dam_last_error.restype = C.c_char_p
+
+    def last_error(self) -> str:
+        return self.lib.dam_last_error().decode()

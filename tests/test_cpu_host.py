@@ -1,0 +1,226 @@
+"""CPU tests (no GPU) of the boundary and the host side: the C ABI library loads and exports
+every symbol include/deeparc_ba.h declares, fails loudly without a device, the C++ mirror of the
+reference's DeepArcManager reads / writes exactly what the reference's own code does, and the
+multi-GPU sharding plan is consistent across ranks (world_size-2 gloo)."""
+import filecmp
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from deeparc_sfm_b200 import capi, synthetic
+from tests import oracle_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _no_gpu():
+    return capi.load_library().dba_device_count() <= 0
+
+
+# ----------------------------------------------------------------------------------- ABI
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "deeparc_ba.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(dba_[a-z_0-9]+)\s*\(", header)))
+    assert len(declared) >= 17, declared
+    lib = capi.load_library()
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+    assert lib.dba_abi_version() == 1
+
+
+def test_struct_layouts_match_header_sizes():
+    # sizes computed by the C compiler from the header, compared with the ctypes mirrors
+    src = '#include <stdio.h>\n#include "deeparc_ba.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(dba_config), sizeof(dba_problem), sizeof(dba_solve_options), sizeof(dba_iteration), sizeof(dba_summary), sizeof(dba_kernel_stat));return 0;}'
+    d = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(d, exist_ok=True)
+    c = os.path.join(d, "abi_sizes.c")
+    open(c, "w").write(src)
+    exe = os.path.join(d, "abi_sizes")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+    sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    import ctypes as C
+    mine = [C.sizeof(t) for t in (capi.DbaConfig, capi.DbaProblem, capi.DbaSolveOptions, capi.DbaIteration,
+                                  capi.DbaSummary, capi.DbaKernelStat)]
+    assert sizes == mine, (sizes, mine)
+
+
+def test_default_options_match_python_mirror():
+    lib = capi.load_library()
+    o = capi.DbaSolveOptions()
+    lib.dba_solve_options_default(o)
+    ref = capi.default_options_struct()
+    for name, _ in capi.DbaSolveOptions._fields_:
+        assert getattr(o, name) == getattr(ref, name), name
+
+
+def test_no_cpu_fallback_without_device():
+    if not _no_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.EngineError) as e:
+        capi.Engine(device=0)
+    assert e.value.status == capi.DBA_ERR_NO_DEVICE
+    assert "no CPU path" in str(e.value)
+
+
+def test_sfm_driver_fails_loudly_without_device(tmp_path):
+    if not _no_gpu():
+        pytest.skip("a GPU is present")
+    p = synthetic.arc_rig(n_arc=2, n_ring=3, n_pts=20, obs_per_point=4)
+    f = str(tmp_path / "in.deeparc")
+    synthetic.write_deeparc(p, f)
+    exe = os.path.join(ROOT, "deeparc-sfm_b200", "bin", "sfm")
+    r = subprocess.run([exe, "--input", f, "--output", str(tmp_path / "out.deeparc"), "--ply-init", str(tmp_path / "i.ply"),
+                        "--ply-adjust", str(tmp_path / "a_"), "--ply-clear", str(tmp_path / "c.ply")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "cannot create the GPU engine" in r.stderr
+
+
+def test_sfm_driver_missing_input_reports_like_reference(tmp_path):
+    exe = os.path.join(ROOT, "deeparc-sfm_b200", "bin", "sfm")
+    r = subprocess.run([exe, "--input", str(tmp_path / "nope.deeparc")], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "Cannot read" in r.stdout and "Cannot read input file" in r.stderr  # DeepArcManager.cc:28-31
+
+
+# ---------------------------------------------------------------------- host mirror vs ref
+CASES = [("rig_aa", dict(kind="rig", fmt=3)), ("rig_matrix", dict(kind="rig", fmt=9)), ("rig_quat", dict(kind="rig", fmt=4)),
+         ("plain", dict(kind="bal", fmt=3))]
+
+
+def _make(kind):
+    if kind == "rig":
+        return synthetic.arc_rig(n_arc=3, n_ring=4, n_pts=120, obs_per_point=6, seed=51)
+    return synthetic.bal_like(n_cam=12, n_pts=100, window=6, seed=52, free_intrinsics=0)
+
+
+@pytest.mark.parametrize("name,cfg", CASES)
+def test_host_mirror_reads_and_writes_like_the_reference(reference, tmp_path, name, cfg):
+    H = oracle_lib.HostMirror()
+    p = _make(cfg["kind"])
+    f = str(tmp_path / (name + ".deeparc"))
+    synthetic.write_deeparc(p, f, rotation_format=cfg["fmt"], center_override=(923.5, 1223.5))
+    hr, hh = reference.read(f), H.read(f)
+    assert reference.counts(hr) == H.counts(hh)
+    assert reference.is_shared(hr) == H.is_shared(hh)
+    a, b = reference.export(hr), H.export(hh)
+    for k in ("obs_xy", "obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "pts", "ext_rot", "ext_trans", "intr_center",
+              "intr_focal", "intr_dist", "intr_nf", "intr_nd", "ext_const", "pts_rgb"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(b.intr_center[0], [923.0, 1223.0])  # Intrinsic::center(int,int) truncation
+    reference.write(hr, f + ".ref"), H.write(hh, f + ".host")
+    assert filecmp.cmp(f + ".ref", f + ".host", shallow=False)
+    reference.write_ply(hr, f + ".ref.ply"), H.write_ply(hh, f + ".host.ply")
+    assert filecmp.cmp(f + ".ref.ply", f + ".host.ply", shallow=False)
+    assert np.array_equal(reference.camera_centers(hr), H.camera_centers(hh))
+    reference.free(hr), H.free(hh)
+
+
+def test_host_mirror_standalone_roundtrip(tmp_path):
+    """Without the reference build: read -> write -> read reproduces the scene to the 6 decimals
+    of the text format; ids, modes and the gauge mask survive."""
+    H = oracle_lib.HostMirror()
+    p = synthetic.arc_rig(n_arc=3, n_ring=3, n_pts=80, obs_per_point=5, seed=53)
+    f = str(tmp_path / "a.deeparc")
+    synthetic.write_deeparc(p, f)
+    h = H.read(f)
+    a = H.export(h)
+    for k in ("obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "ext_const"):
+        assert np.array_equal(getattr(a, k), getattr(p, k)), k
+    assert np.array_equal(a.pts, p.pts) and np.array_equal(a.ext_rot, p.ext_rot)
+    H.write(h, f + ".out")
+    h2 = H.read(f + ".out")
+    b = H.export(h2)
+    assert np.array_equal(a.obs_pose_a, b.obs_pose_a) and np.array_equal(a.obs_pose_b, b.obs_pose_b)
+    np.testing.assert_allclose(b.pts, a.pts, atol=5.1e-7)
+    np.testing.assert_allclose(b.ext_trans, a.ext_trans, atol=5.1e-7)
+    text = synthetic.read_deeparc_text(f + ".out")
+    assert text["version"] == 0.01 and all(len(r) == 3 for _, r in text["ext"])
+    H.free(h), H.free(h2)
+
+
+def test_host_mirror_bad_point_id_raises_out_of_range(tmp_path):
+    H = oracle_lib.HostMirror()
+    p = synthetic.arc_rig(n_arc=2, n_ring=2, n_pts=10, obs_per_point=3, seed=54)
+    p.obs_pt = p.obs_pt.copy()
+    p.obs_pt[0] = 999
+    f = str(tmp_path / "bad.deeparc")
+    synthetic.write_deeparc(p, f)
+    with pytest.raises(IOError):
+        H.read(f)
+    assert "vector" in H.last_error() or "range" in H.last_error()
+
+
+# ------------------------------------------------------------------------- sharding plan
+def test_shard_plan_covers_and_balances():
+    p = synthetic.bal_like(n_cam=40, n_pts=5000, window=10, seed=61)
+    for world in (1, 2, 3, 8):
+        pt_begin, obs_count = capi.shard_plan(p, world)
+        assert pt_begin[0] == 0 and pt_begin[-1] == p.n_pts and np.all(np.diff(pt_begin) >= 0)
+        assert obs_count.sum() == p.n_obs
+        assert obs_count.max() - obs_count.min() <= 2 * 5  # within a couple of tracks
+    # ragged: empty problem and a single huge track
+    e = synthetic.bal_like(n_cam=3, n_pts=4, obs_per_point=3, window=3, seed=62)
+    e.obs_pt = np.zeros_like(e.obs_pt)
+    pt_begin, obs_count = capi.shard_plan(e, 4)
+    assert obs_count.sum() == e.n_obs and pt_begin[-1] == e.n_pts
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["REPO_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from deeparc_sfm_b200 import capi, synthetic
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+p = synthetic.bal_like(n_cam=30, n_pts=2000, window=10, seed=63)      # every rank builds the full problem
+pt_begin, obs_count = capi.shard_plan(p, world)
+lo, hi = int(pt_begin[rank]), int(pt_begin[rank + 1])
+mine = (p.obs_pt >= lo) & (p.obs_pt < hi)
+assert int(mine.sum()) == int(obs_count[rank])
+# every observation is owned by exactly one rank
+owned = torch.from_numpy(mine.astype(np.int64)); dist.all_reduce(owned); assert bool((owned == 1).all())
+# a camera-space vector (observations per camera) summed over shards == the global one: the
+# collective the engine runs (allreduce of per-camera accumulators), with gloo standing in for NCCL
+local = torch.from_numpy(np.bincount(p.obs_pose_a[mine], minlength=p.n_ext).astype(np.float64))
+dist.all_reduce(local)
+assert np.array_equal(local.numpy(), np.bincount(p.obs_pose_a, minlength=p.n_ext).astype(np.float64))
+# scalar reductions (cost): sum of shard partials == global
+from tests import oracle_lib
+res = oracle_lib.Oracle().eval(p)["residuals"]
+part = torch.tensor([0.5 * float((res[mine] ** 2).sum())], dtype=torch.float64); dist.all_reduce(part)
+assert abs(part.item() - 0.5 * float((res ** 2).sum())) <= 1e-12 * part.item()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_shard_plan_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, REPO_ROOT=ROOT, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
+
+
+# ---------------------------------------------------------------------------- generators
+def test_generators_follow_the_reference_aliasing_rules():
+    p = synthetic.arc_rig(n_arc=4, n_ring=5, n_pts=300, obs_per_point=9, seed=71)
+    arc, ring = p.obs_col0, p.obs_col1
+    A = p.n_arc
+    ring_slot = np.where(ring == 0, 0, ring + A - 1)
+    assert np.array_equal(p.obs_intr, arc)
+    assert np.array_equal(p.obs_pose_a, np.where((arc == 0) & (ring != 0), ring_slot, arc))
+    assert np.array_equal(p.obs_pose_b, np.where((arc != 0) & (ring != 0), ring_slot, -1))
+    assert p.ext_const[0] == 1 and p.ext_const[1:].sum() == 0
+    assert p.n_ext == A + p.n_ring - 1
+    r = synthetic.project(p, pts=p.truth["pts"], ext_rot=p.truth["ext_rot"], ext_trans=p.truth["ext_trans"]) - p.obs_xy
+    assert 0.3 < r.std() < 0.7  # 0.5 px observation noise around the ground truth
