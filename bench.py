@@ -190,6 +190,7 @@ def main():
         return 0
 
     # ----------------------------------------------------------------------------- our arm
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from deeparc_sfm_b200 import capi
@@ -273,6 +274,10 @@ def main():
     d2h = sum(v.nbytes for v in out.values())
     e2e_value = (s3.num_iterations - 1) / e2e_s
 
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 

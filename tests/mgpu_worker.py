@@ -24,16 +24,15 @@ if rank == 0:
 dist.broadcast(buf, 0)
 uid = bytes(buf.cpu().numpy().tobytes())
 
+eng = capi.Engine(device=local, rank=rank, world_size=world, nccl_unique_id=uid)  # one communicator per unique id
 for name, p in (("bal", synthetic.bal_like(n_cam=60, n_pts=6000, window=12, seed=91)),
                 ("rig", synthetic.arc_rig(n_arc=4, n_ring=5, n_pts=3000, obs_per_point=8, seed=92))):
     opts = capi.make_options(max_num_iterations=5, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
                              linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=1e-13, pcg_max_iterations=3000)
-    eng = capi.Engine(device=local, rank=rank, world_size=world, nccl_unique_id=uid)
     eng.problem_set(p)
     c0 = eng.eval(residuals=False)["cost"]
     s = eng.solve(opts)
     x = eng.params_get()
-    eng.close()
     if rank == 0:
         one = capi.Engine(device=local)
         one.problem_set(p)
@@ -48,6 +47,7 @@ for name, p in (("bal", synthetic.bal_like(n_cam=60, n_pts=6000, window=12, seed
             assert np.max(np.abs(x[k] - x1[k])) <= 1e-8 * max(np.max(np.abs(x1[k])), 1e-300), (name, k)
         print(name, "sharded == single:", s.final_cost, s1.final_cost, flush=True)
     dist.barrier()
+eng.close()
 if rank == 0:
     print("MGPU OK", flush=True)
 dist.destroy_process_group()
