@@ -7,6 +7,8 @@
 // parity tests compare against).  All O(n_obs)/O(n_pts) work runs in the kernels of
 // ba_kernels.cu; the host only sequences launches and reads ~20 scalars per LM iteration.
 // There is no CPU fallback: any CUDA failure is reported through the status code.
+#include <omp.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -75,6 +77,7 @@ struct DevBuf {
 
 }  // namespace
 
+struct dba_upload_state;
 struct dba_handle {
   int device = 0, rank = 0, world = 1, verbose = 0;
   cudaStream_t st = nullptr;
@@ -101,8 +104,7 @@ struct dba_handle {
   DevBuf<TileMeta> d_tile_meta;
   DevBuf<int2> d_obs_ab;
   DevBuf<double> d_partials_q;
-  DevBuf<int2> d_obs_idx;
-  DevBuf<ObsView> d_views;
+  DevBuf<int2> d_obs_ip;
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
   DevBuf<unsigned int> d_counters;
   DevBuf<int4> d_cam_chunks;
@@ -114,6 +116,8 @@ struct dba_handle {
   DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts, d_vec_partials;
   double* h_scalars = nullptr;  // pinned
   int* h_pcg_state = nullptr;   // pinned
+  struct dba_upload_state* upload = nullptr;  // pinned staging arena (grow-only)
+  int64_t n_cam_entries = 0;
   size_t j_planes = 0;
   int plane_w = 0;  // extra plane holding w of the two-phase Schur product
 
@@ -146,6 +150,49 @@ struct dba_handle {
     if (e__ != cudaSuccess)                                                                           \
       return (h)->fail(DBA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+
+// ---- upload helpers: grow-only pinned staging arena, grow-only device buffers
+struct PinnedArena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  cudaError_t reserve(size_t bytes) {
+    used = 0;
+    if (bytes <= cap) return cudaSuccess;
+    if (base) cudaFreeHost(base);
+    base = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&base), bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  template <typename T>
+  T* take(size_t n) {
+    used = (used + 255) & ~size_t{255};
+    T* p = reinterpret_cast<T*>(base + used);
+    used += n * sizeof(T);
+    return p;
+  }
+  ~PinnedArena() {
+    if (base) cudaFreeHost(base);
+  }
+};
+struct dba_upload_state {
+  PinnedArena arena;
+};
+
+namespace {
+PinnedArena& arena_of(dba_handle* h) {
+  if (!h->upload) h->upload = new dba_upload_state;
+  return h->upload->arena;
+}
+template <typename T>
+cudaError_t ensure(DevBuf<T>& b, size_t count) {
+  if (count < 1) count = 1;
+  if (b.p && b.n >= count) return cudaSuccess;
+  return b.alloc(count);
+}
+inline size_t pad256(size_t bytes) { return (bytes + 255) & ~size_t{255}; }
+}  // namespace
 
 namespace {
 
@@ -249,7 +296,7 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
   // read xy(16)+idx(8), write r + Jp + Jc planes
   // (+ the camera-sorted copy of the camera-side columns, written once more)
   const double k1_bytes = (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs) +
-                          (h->cb ? (4.0 + 16.0 * h->cb) * static_cast<double>(h->d_cam_entries.n) : 0.0);
+                          (h->cb ? (4.0 + 16.0 * h->cb) * static_cast<double>(h->n_cam_entries) : 0.0);
   {
     Scope s(h, "pose_rows");
     launch_pose_rows(P, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
@@ -513,6 +560,7 @@ void dba_destroy(dba_handle* h) {
   drain_events(h);
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
   if (h->comm) nccl_api().CommDestroy(h->comm);
+  delete h->upload;
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_pcg_state) cudaFreeHost(h->h_pcg_state);
   if (h->st) cudaStreamDestroy(h->st);
@@ -573,6 +621,8 @@ int dba_shard_plan(const dba_problem* p, int32_t world_size, int32_t* pt_begin, 
 }
 
 // ------------------------------------------------------------------- problem upload
+// Host side of the upload: every O(n_obs) step is a parallel pass (OpenMP over the host cores)
+// writing straight into the pinned staging arena, copied with a handful of large async memcpys.
 int dba_problem_set(dba_handle* h, const dba_problem* p) {
   if (!h || !p) return DBA_ERR_INVALID_ARGUMENT;
   CU(h, cudaSetDevice(h->device));
@@ -586,57 +636,82 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     return h->fail(DBA_ERR_INVALID_ARGUMENT, "null parameter array");
   if (p->n_obs >= (int64_t{1} << 30)) return h->fail(DBA_ERR_UNSUPPORTED, "more than 2^30 observations per handle");
   const int64_t n = p->n_obs;
-  bool two = false;
+  const int n_ext = p->n_ext, n_intr = p->n_intr;
+
+  // ---- pass 1 (parallel): validation, two-pose detection, sortedness
+  int64_t bad_index = -1;
+  int two = 0, sorted = 1, intr_is_pose = 1;
+#pragma omp parallel for schedule(static) reduction(max : bad_index, two) reduction(min : sorted, intr_is_pose)
   for (int64_t i = 0; i < n; ++i) {
-    if (p->obs_pt[i] < 0 || p->obs_pt[i] >= p->n_pts) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_pt[%lld] out of range", (long long)i);
-    if (p->obs_pose_a[i] < 0 || p->obs_pose_a[i] >= p->n_ext) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_pose_a[%lld] out of range", (long long)i);
-    if (p->obs_intr[i] < 0 || p->obs_intr[i] >= p->n_intr) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_intr[%lld] out of range", (long long)i);
-    if (p->obs_pose_b) {
-      if (p->obs_pose_b[i] < -1 || p->obs_pose_b[i] >= p->n_ext) return h->fail(DBA_ERR_INVALID_ARGUMENT, "obs_pose_b[%lld] out of range", (long long)i);
-      two |= p->obs_pose_b[i] >= 0;
-    }
+    const int pt = p->obs_pt[i], a = p->obs_pose_a[i], in = p->obs_intr[i];
+    const int b = p->obs_pose_b ? p->obs_pose_b[i] : -1;
+    if (pt < 0 || pt >= p->n_pts || a < 0 || a >= n_ext || in < 0 || in >= n_intr || b < -1 || b >= n_ext) bad_index = std::max(bad_index, i);
+    if (b >= 0) two = 1;
+    if (i > 0 && p->obs_pt[i - 1] > pt) sorted = 0;
+    if (in != a) intr_is_pose = 0;
   }
-  for (int i = 0; i < p->n_intr; ++i) {
+  if (bad_index >= 0) return h->fail(DBA_ERR_INVALID_ARGUMENT, "observation %lld: index out of range", (long long)bad_index);
+  for (int i = 0; i < n_intr; ++i)
     if (p->intr_nf[i] < 1 || p->intr_nf[i] > 2 || p->intr_nd[i] < 0 || p->intr_nd[i] > 2)
       return h->fail(DBA_ERR_INVALID_ARGUMENT, "intrinsic %d: nf must be 1|2 and nd 0|1|2", i);
-  }
   h->freeze = p->freeze_camera != 0;
   h->free_intr = (!h->freeze && p->free_intrinsics) ? 1 : 0;
   if (h->free_intr) {
     if (two) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics with composed poses is not implemented");
-    if (p->n_ext != p->n_intr) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs one intrinsic per extrinsic");
-    for (int i = 0; i < p->n_intr; ++i)
+    if (n_ext != n_intr) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs one intrinsic per extrinsic");
+    for (int i = 0; i < n_intr; ++i)
       if (p->intr_nf[i] != 1 || p->intr_nd[i] != 2) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs nf=1, nd=2");
-    for (int64_t i = 0; i < n; ++i)
-      if (p->obs_intr[i] != p->obs_pose_a[i]) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs obs_intr == obs_pose_a");
+    if (!intr_is_pose) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs obs_intr == obs_pose_a");
   }
   h->cb = h->freeze ? 0 : (h->free_intr ? 9 : 6);
-  h->two = two ? 1 : 0;
+  h->two = two;
   h->n_obs_global = n;
   h->n_pts_global = p->n_pts;
-  h->n_ext = p->n_ext;
-  h->n_intr = p->n_intr;
+  h->n_ext = n_ext;
+  h->n_intr = n_intr;
+  const int cb = h->cb;
 
-  // ---- observations per point, point range of this rank (contiguous, balanced by observations)
+  // ---- observations per point (global), shard of this rank
   std::vector<int64_t> pt_count(static_cast<size_t>(p->n_pts) + 1, 0);
-  for (int64_t i = 0; i < n; ++i) pt_count[p->obs_pt[i] + 1]++;
-  for (int i = 0; i < p->n_pts; ++i) pt_count[i + 1] += pt_count[i];  // prefix: first obs of each point (global sorted)
+  if (sorted) {
+    // run boundaries of a sorted key array: first[pt] = first position with key >= pt
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i <= n; ++i) {
+      const int lo = i == 0 ? 0 : p->obs_pt[i - 1] + 1;
+      const int hi = i == n ? p->n_pts : p->obs_pt[i];
+      for (int q = lo; q <= hi; ++q) pt_count[q] = i;
+    }
+  } else {
+    for (int64_t i = 0; i < n; ++i) pt_count[p->obs_pt[i] + 1]++;
+    for (int i = 0; i < p->n_pts; ++i) pt_count[i + 1] += pt_count[i];
+  }
   int pt_lo = 0, pt_hi = p->n_pts;
   if (h->world > 1) {
-    std::vector<int32_t> plan(static_cast<size_t>(h->world) + 1);
-    dba_shard_plan(p, h->world, plan.data(), nullptr);
-    pt_lo = plan[h->rank];
-    pt_hi = plan[h->rank + 1];
+    // same rule as dba_shard_plan
+    auto cut = [&](int r) -> int {
+      if (r <= 0) return 0;
+      if (r >= h->world) return p->n_pts;
+      const int64_t target = n * r / h->world;
+      return std::min(static_cast<int>(std::lower_bound(pt_count.begin(), pt_count.end(), target) - pt_count.begin()), p->n_pts);
+    };
+    pt_lo = cut(h->rank);
+    for (int r = 1; r < h->rank; ++r) pt_lo = std::max(pt_lo, cut(r));
+    pt_hi = std::max(cut(h->rank + 1), pt_lo);
+    if (h->rank + 1 == h->world) pt_hi = p->n_pts;
   }
   h->pt_lo = pt_lo;
   h->n_pts = pt_hi - pt_lo;
+  const int n_pts = h->n_pts;
   const int64_t obs_lo = pt_count[pt_lo], obs_hi = pt_count[pt_hi];
   const int64_t nl = obs_hi - obs_lo;
   h->n_obs = nl;
 
-  // ---- stable counting sort by point, views
-  h->perm.assign(nl, 0);
-  {
+  // ---- permutation (local sorted position -> caller's index)
+  h->perm.resize(static_cast<size_t>(nl));
+  if (sorted) {
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < nl; ++k) h->perm[k] = obs_lo + k;
+  } else {
     std::vector<int64_t> cursor(pt_count.begin() + pt_lo, pt_count.begin() + pt_hi);
     for (int64_t i = 0; i < n; ++i) {
       const int pt = p->obs_pt[i];
@@ -644,228 +719,318 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
       h->perm[cursor[pt - pt_lo]++ - obs_lo] = i;
     }
   }
-  std::vector<ObsView> views;
-  std::vector<int2> obs_idx(nl);
-  std::vector<double2> obs_xy(nl);
+  const int64_t* perm = h->perm.data();
+
+  // ---- tiles of whole points (greedy, serial: O(n_pts))
+  std::vector<TileMeta> tile_meta;
+  tile_meta.reserve(static_cast<size_t>(nl / 200 + 16));
   {
-    std::map<std::tuple<int, int, int>, int> view_of;
-    for (int64_t k = 0; k < nl; ++k) {
-      const int64_t i = h->perm[k];
-      const int pb = p->obs_pose_b ? p->obs_pose_b[i] : -1;
-      const auto key = std::make_tuple(p->obs_pose_a[i], pb, p->obs_intr[i]);
-      auto it = view_of.find(key);
-      int vid;
-      if (it == view_of.end()) {
-        vid = static_cast<int>(views.size());
-        view_of.emplace(key, vid);
-        views.push_back(ObsView{p->obs_pose_a[i], pb, p->obs_intr[i], 0});
-      } else {
-        vid = it->second;
-      }
-      obs_idx[k] = make_int2(vid, p->obs_pt[i] - pt_lo);
-      obs_xy[k] = make_double2(p->obs_xy[2 * i], p->obs_xy[2 * i + 1]);
-    }
-  }
-  // ---- tiles of whole points
-  std::vector<int> pt_first(static_cast<size_t>(h->n_pts) + 1);
-  for (int i = 0; i <= h->n_pts; ++i) pt_first[i] = static_cast<int>(pt_count[pt_lo + i] - obs_lo);
-  std::vector<int> tile_obs{0}, tile_pt{0};
-  {
-    int cur_obs = 0;
-    for (int i = 0; i < h->n_pts; ++i) {
-      const int len = pt_first[i + 1] - pt_first[i];
+    int cur_obs = 0, t_pt0 = 0;
+    for (int i = 0; i < n_pts; ++i) {
+      const int len = static_cast<int>(pt_count[pt_lo + i + 1] - pt_count[pt_lo + i]);
       if (len > kTile)
         return h->fail(DBA_ERR_UNSUPPORTED, "point %d has %d observations; tracks longer than %d are not implemented",
                        pt_lo + i, len, kTile);
       if (cur_obs + len > kTile) {
-        tile_obs.push_back(pt_first[i]);
-        tile_pt.push_back(i);
+        TileMeta m{};
+        m.obs0 = static_cast<int>(pt_count[pt_lo + t_pt0] - obs_lo);
+        m.n_obs = cur_obs;
+        m.pt0 = t_pt0;
+        m.n_pts = i - t_pt0;
+        tile_meta.push_back(m);
+        t_pt0 = i;
         cur_obs = 0;
       }
       cur_obs += len;
     }
-    if (h->n_pts > 0) {
-      tile_obs.push_back(pt_first[h->n_pts]);
-      tile_pt.push_back(h->n_pts);
+    if (n_pts > t_pt0) {
+      TileMeta m{};
+      m.obs0 = static_cast<int>(pt_count[pt_lo + t_pt0] - obs_lo);
+      m.n_obs = cur_obs;
+      m.pt0 = t_pt0;
+      m.n_pts = n_pts - t_pt0;
+      tile_meta.push_back(m);
     }
   }
-  const int n_tiles = static_cast<int>(tile_obs.size()) - 1;
-  // ---- camera-sorted incidence, chunked
-  std::vector<int> cam_entries;
-  std::vector<int4> cam_chunks;
-  std::vector<int> cam_chunk_first(static_cast<size_t>(p->n_ext) + 1, 0);
-  std::vector<int> ent_pos;
-  if (h->cb) {
-    std::vector<int64_t> first(static_cast<size_t>(p->n_ext) + 1, 0);
-    for (int64_t k = 0; k < nl; ++k) {
-      const ObsView& v = views[obs_idx[k].x];
-      first[v.pose_a + 1]++;
-      if (v.pose_b >= 0) first[v.pose_b + 1]++;
-    }
-    for (int i = 0; i < p->n_ext; ++i) first[i + 1] += first[i];
-    cam_entries.resize(first[p->n_ext]);
-    std::vector<int64_t> cursor(first.begin(), first.end() - 1);
-    ent_pos.assign(2 * static_cast<size_t>(nl), -1);
-    for (int64_t k = 0; k < nl; ++k) {
-      const ObsView& v = views[obs_idx[k].x];
-      ent_pos[2 * k] = static_cast<int>(cursor[v.pose_a]);
-      cam_entries[cursor[v.pose_a]++] = static_cast<int>(k * 2);
-      if (v.pose_b >= 0) {
-        ent_pos[2 * k + 1] = static_cast<int>(cursor[v.pose_b]);
-        cam_entries[cursor[v.pose_b]++] = static_cast<int>(k * 2 + 1);
+  const int n_tiles = static_cast<int>(tile_meta.size());
+
+  // ---- sizes of everything that goes through the pinned arena
+  const int64_t ld = std::max<int64_t>(((nl + 63) / 64) * 64, 64);
+  const int64_t n_ent_max = cb ? 2 * nl : 0;
+  size_t arena_bytes = 0;
+  auto want = [&](size_t bytes) { arena_bytes += pad256(bytes) + 256; };
+  want(nl * sizeof(double2));          // obs_xy
+  want(nl * sizeof(int2));             // obs_ip
+  want(nl * sizeof(int2));             // obs_ab
+  want(nl * sizeof(unsigned short));   // obs_lp
+  want((n_pts + 1) * sizeof(int));     // pt_first
+  want(n_tiles * sizeof(TileMeta));
+  want((n_tiles + 1) * sizeof(int) * 3);
+  want(n_ent_max * sizeof(int));       // cam_entries
+  want(2 * nl * sizeof(int));          // ent_pos
+  want(n_ent_max * sizeof(unsigned short));  // items
+  want((n_ent_max + n_tiles + 1) * sizeof(unsigned short));  // part_first_rel
+  want((n_ent_max + 1) * sizeof(int));  // part_item_first
+  want(n_ent_max * sizeof(int));        // cam_part_idx
+  want((n_ent_max / 1024 + n_ext + 2) * sizeof(int4));  // cam_chunks
+  want((n_ext + 1) * sizeof(int) * 3);
+  PinnedArena& A = arena_of(h);
+  CU(h, cudaStreamSynchronize(h->st));  // the arena may still feed copies of a previous call
+  CU(h, A.reserve(arena_bytes));
+
+  // ---- per-observation arrays (parallel)
+  double2* s_xy = A.take<double2>(nl);
+  int2* s_ip = A.take<int2>(nl);
+  int2* s_ab = A.take<int2>(nl);
+  unsigned short* s_lp = A.take<unsigned short>(nl);
+  int* s_pt_first = A.take<int>(static_cast<size_t>(n_pts) + 1);
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nl; ++k) {
+    const int64_t i = perm[k];
+    s_xy[k] = make_double2(p->obs_xy[2 * i], p->obs_xy[2 * i + 1]);
+    s_ip[k] = make_int2(p->obs_intr[i], p->obs_pt[i] - pt_lo);
+    s_ab[k] = make_int2(p->obs_pose_a[i], p->obs_pose_b ? p->obs_pose_b[i] : -1);
+  }
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i <= n_pts; ++i) s_pt_first[i] = static_cast<int>(pt_count[pt_lo + i] - obs_lo);
+
+  // ---- camera-sorted incidence: stable parallel counting sort of (obs, slot) entries by block
+  int* s_cam_entries = A.take<int>(static_cast<size_t>(n_ent_max));
+  int* s_ent_pos = A.take<int>(2 * static_cast<size_t>(nl));
+  int4* s_cam_chunks = nullptr;
+  int* s_cam_chunk_first = A.take<int>(static_cast<size_t>(n_ext) + 1);
+  int64_t n_entries = 0;
+  int n_chunks = 0;
+  const int kChunk = 1024;
+  if (cb) {
+    const int nthreads = std::max(1, omp_get_max_threads());
+    std::vector<std::vector<int>> hist(nthreads, std::vector<int>(static_cast<size_t>(n_ext) + 1, 0));
+#pragma omp parallel num_threads(nthreads)
+    {
+      const int t = omp_get_thread_num();
+      const int64_t k0 = nl * t / nthreads, k1 = nl * (t + 1) / nthreads;
+      std::vector<int>& hc = hist[t];
+      for (int64_t k = k0; k < k1; ++k) {
+        hc[s_ab[k].x]++;
+        if (s_ab[k].y >= 0) hc[s_ab[k].y]++;
       }
     }
-    const int kChunk = 1024;
-    for (int b = 0; b < p->n_ext; ++b) {
-      cam_chunk_first[b] = static_cast<int>(cam_chunks.size());
-      for (int64_t e = first[b]; e < first[b + 1]; e += kChunk)
-        cam_chunks.push_back(make_int4(b, static_cast<int>(e), static_cast<int>(std::min<int64_t>(e + kChunk, first[b + 1])), 0));
+    // offsets: for block b, thread t starts at first[b] + sum_{t' < t} hist[t'][b]
+    std::vector<int64_t> first(static_cast<size_t>(n_ext) + 1, 0);
+    for (int b = 0; b < n_ext; ++b) {
+      int64_t tot = 0;
+      for (int t = 0; t < nthreads; ++t) {
+        const int c = hist[t][b];
+        hist[t][b] = static_cast<int>(tot);
+        tot += c;
+      }
+      first[b + 1] = first[b] + tot;
     }
-    cam_chunk_first[p->n_ext] = static_cast<int>(cam_chunks.size());
-  }
-
-  // ---- static tile-local camera incidence for the implicit Schur product
-  std::vector<int> tile_part_first(static_cast<size_t>(n_tiles) + 1, 0), part_item_first{0}, cam_part_first, cam_part_idx;
-  std::vector<unsigned short> items;
-  std::vector<int> part_block;
-  if (h->cb) {
-    std::vector<int> local_of(static_cast<size_t>(p->n_ext), -1), locals;
-    std::vector<std::vector<unsigned short>> lists;
-    items.reserve(cam_entries.size());
-    for (int t = 0; t < n_tiles; ++t) {
-      locals.clear();
-      size_t used = 0;
-      for (int k = tile_obs[t]; k < tile_obs[t + 1]; ++k) {
-        const ObsView& v = views[obs_idx[k].x];
-        const int lo = k - tile_obs[t];
-        for (int slot = 0; slot < 2; ++slot) {
-          const int blk = slot ? v.pose_b : v.pose_a;
-          if (blk < 0) continue;
-          int lc = local_of[blk];
-          if (lc < 0) {
-            lc = static_cast<int>(locals.size());
-            local_of[blk] = lc;
-            locals.push_back(blk);
-            if (lists.size() <= static_cast<size_t>(lc)) lists.emplace_back();
-            lists[lc].clear();
-            ++used;
-          }
-          lists[lc].push_back(static_cast<unsigned short>(lo | (slot << 15)));
+    n_entries = first[n_ext];
+#pragma omp parallel num_threads(nthreads)
+    {
+      const int t = omp_get_thread_num();
+      const int64_t k0 = nl * t / nthreads, k1 = nl * (t + 1) / nthreads;
+      std::vector<int>& hc = hist[t];
+      for (int64_t k = k0; k < k1; ++k) {
+        const int a = s_ab[k].x, b = s_ab[k].y;
+        const int64_t pa = first[a] + hc[a]++;
+        s_cam_entries[pa] = static_cast<int>(2 * k);
+        s_ent_pos[2 * k] = static_cast<int>(pa);
+        if (b >= 0) {
+          const int64_t pb = first[b] + hc[b]++;
+          s_cam_entries[pb] = static_cast<int>(2 * k + 1);
+          s_ent_pos[2 * k + 1] = static_cast<int>(pb);
+        } else {
+          s_ent_pos[2 * k + 1] = -1;
         }
       }
-      for (size_t lc = 0; lc < locals.size(); ++lc) {
-        items.insert(items.end(), lists[lc].begin(), lists[lc].end());
-        part_item_first.push_back(static_cast<int>(items.size()));
-        part_block.push_back(locals[lc]);
-        local_of[locals[lc]] = -1;
-      }
-      tile_part_first[t + 1] = static_cast<int>(part_block.size());
-      (void)used;
     }
-    const int n_part = static_cast<int>(part_block.size());
-    cam_part_first.assign(static_cast<size_t>(p->n_ext) + 1, 0);
-    for (int g = 0; g < n_part; ++g) cam_part_first[part_block[g] + 1]++;
-    for (int b = 0; b < p->n_ext; ++b) cam_part_first[b + 1] += cam_part_first[b];
-    cam_part_idx.resize(n_part);
-    std::vector<int> cur(cam_part_first.begin(), cam_part_first.end() - 1);
-    for (int g = 0; g < n_part; ++g) cam_part_idx[cur[part_block[g]]++] = g;
+    for (int b = 0; b < n_ext; ++b) n_chunks += static_cast<int>((first[b + 1] - first[b] + kChunk - 1) / kChunk);
+    s_cam_chunks = A.take<int4>(static_cast<size_t>(std::max(n_chunks, 1)));
+    int c = 0;
+    for (int b = 0; b < n_ext; ++b) {
+      s_cam_chunk_first[b] = c;
+      for (int64_t e = first[b]; e < first[b + 1]; e += kChunk)
+        s_cam_chunks[c++] = make_int4(b, static_cast<int>(e), static_cast<int>(std::min<int64_t>(e + kChunk, first[b + 1])), 0);
+    }
+    s_cam_chunk_first[n_ext] = c;
   } else {
-    cam_part_first.assign(static_cast<size_t>(p->n_ext) + 1, 0);
-  }
-  const size_t n_partials = part_block.size();
-  // packed per-tile records and per-observation block indices for the tile kernels
-  std::vector<TileMeta> tile_meta(static_cast<size_t>(std::max(n_tiles, 1)));
-  std::vector<int2> obs_ab(static_cast<size_t>(std::max<int64_t>(nl, 1)));
-  std::vector<unsigned short> obs_lp(static_cast<size_t>(std::max<int64_t>(nl, 1)), 0);
-  std::vector<unsigned short> part_first_rel(n_partials + static_cast<size_t>(n_tiles) + 1, 0);
-  for (int t = 0; t < n_tiles; ++t) {
-    TileMeta& m = tile_meta[t];
-    m.obs0 = tile_obs[t];
-    m.n_obs = tile_obs[t + 1] - tile_obs[t];
-    m.pt0 = tile_pt[t];
-    m.n_pts = tile_pt[t + 1] - tile_pt[t];
-    m.g0 = tile_part_first[t];
-    m.n_parts = tile_part_first[t + 1] - tile_part_first[t];
-    m.item0 = h->cb ? part_item_first[m.g0] : 0;
-    m.n_items = h->cb ? part_item_first[m.g0 + m.n_parts] - m.item0 : 0;
-    if (h->cb)
-      for (int i = 0; i <= m.n_parts; ++i)
-        part_first_rel[static_cast<size_t>(m.g0) + t + i] = static_cast<unsigned short>(part_item_first[m.g0 + i] - m.item0);
-    for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) obs_lp[k] = static_cast<unsigned short>(obs_idx[k].y - m.pt0);
-  }
-  for (int64_t k = 0; k < nl; ++k) {
-    const ObsView& v = views[obs_idx[k].x];
-    obs_ab[k] = make_int2(v.pose_a, v.pose_b);
+    for (int b = 0; b <= n_ext; ++b) s_cam_chunk_first[b] = 0;
+    s_cam_chunks = A.take<int4>(1);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < 2 * nl; ++k) s_ent_pos[k] = -1;
   }
 
-  // ---- device allocation + upload
-  const int64_t ld = ((nl + 63) / 64) * 64;
-  h->plane_w = 4 + h->cb + ((h->two && h->cb) ? 6 : 0);
+  // ---- static tile-local camera incidence (parallel over tiles, two passes)
+  unsigned short* s_items = A.take<unsigned short>(static_cast<size_t>(std::max<int64_t>(n_entries, 1)));
+  unsigned short* s_part_first_rel = A.take<unsigned short>(static_cast<size_t>(n_entries + n_tiles + 1));
+  int* s_tile_part_first = A.take<int>(static_cast<size_t>(n_tiles) + 1);
+  int* s_cam_part_first = A.take<int>(static_cast<size_t>(n_ext) + 1);
+  int* s_cam_part_idx = nullptr;
+  int n_partials = 0;
+  std::vector<int> part_block;
+  {
+    // pass A: distinct blocks and items per tile
+    std::vector<int> tile_np(static_cast<size_t>(n_tiles) + 1, 0), tile_ni(static_cast<size_t>(n_tiles) + 1, 0);
+    if (cb) {
+#pragma omp parallel
+      {
+        std::vector<int> seen(static_cast<size_t>(n_ext), -1);
+#pragma omp for schedule(static)
+        for (int t = 0; t < n_tiles; ++t) {
+          const TileMeta& m = tile_meta[t];
+          int np = 0, ni = 0;
+          for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) {
+            const int a = s_ab[k].x, b = s_ab[k].y;
+            if (seen[a] != t) { seen[a] = t; ++np; }
+            ++ni;
+            if (b >= 0) {
+              if (seen[b] != t) { seen[b] = t; ++np; }
+              ++ni;
+            }
+          }
+          tile_np[t + 1] = np;
+          tile_ni[t + 1] = ni;
+        }
+      }
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      tile_np[t + 1] += tile_np[t];
+      tile_ni[t + 1] += tile_ni[t];
+    }
+    n_partials = tile_np[n_tiles];
+    part_block.resize(static_cast<size_t>(n_partials));
+    for (int t = 0; t <= n_tiles; ++t) s_tile_part_first[t] = tile_np[t];
+    // pass B: fill (items grouped by local block, in order of first appearance)
+#pragma omp parallel
+    {
+      std::vector<int> local_of(static_cast<size_t>(n_ext), -1), locals, count, start;
+#pragma omp for schedule(static)
+      for (int t = 0; t < n_tiles; ++t) {
+        TileMeta& m = tile_meta[t];
+        m.g0 = tile_np[t];
+        m.n_parts = tile_np[t + 1] - tile_np[t];
+        m.item0 = tile_ni[t];
+        m.n_items = tile_ni[t + 1] - tile_ni[t];
+        for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) s_lp[k] = static_cast<unsigned short>(s_ip[k].y - m.pt0);
+        if (!cb) continue;
+        locals.clear();
+        count.clear();
+        for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) {
+          for (int slot = 0; slot < 2; ++slot) {
+            const int blk = slot ? s_ab[k].y : s_ab[k].x;
+            if (blk < 0) continue;
+            int lc = local_of[blk];
+            if (lc < 0) {
+              lc = static_cast<int>(locals.size());
+              local_of[blk] = lc;
+              locals.push_back(blk);
+              count.push_back(0);
+            }
+            count[lc]++;
+          }
+        }
+        start.assign(locals.size() + 1, 0);
+        for (size_t lc = 0; lc < locals.size(); ++lc) start[lc + 1] = start[lc] + count[lc];
+        unsigned short* rel = s_part_first_rel + m.g0 + t;
+        for (size_t lc = 0; lc <= locals.size(); ++lc) rel[lc] = static_cast<unsigned short>(start[lc]);
+        for (size_t lc = 0; lc < locals.size(); ++lc) part_block[m.g0 + lc] = locals[lc];
+        for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) {
+          const int lo = k - m.obs0;
+          for (int slot = 0; slot < 2; ++slot) {
+            const int blk = slot ? s_ab[k].y : s_ab[k].x;
+            if (blk < 0) continue;
+            const int lc = local_of[blk];
+            s_items[m.item0 + start[lc]++] = static_cast<unsigned short>(lo | (slot << 15));
+          }
+        }
+        for (int blk : locals) local_of[blk] = -1;
+      }
+    }
+    // partials grouped by camera block (serial counting sort: O(n_partials))
+    for (int b = 0; b <= n_ext; ++b) s_cam_part_first[b] = 0;
+    for (int g = 0; g < n_partials; ++g) s_cam_part_first[part_block[g] + 1]++;
+    for (int b = 0; b < n_ext; ++b) s_cam_part_first[b + 1] += s_cam_part_first[b];
+    s_cam_part_idx = A.take<int>(static_cast<size_t>(std::max(n_partials, 1)));
+    std::vector<int> cur(s_cam_part_first, s_cam_part_first + n_ext);
+    for (int g = 0; g < n_partials; ++g) s_cam_part_idx[cur[part_block[g]]++] = g;
+  }
+  TileMeta* s_tile_meta = A.take<TileMeta>(static_cast<size_t>(std::max(n_tiles, 1)));
+  if (n_tiles) std::memcpy(s_tile_meta, tile_meta.data(), sizeof(TileMeta) * n_tiles);
+  int* s_tile_obs = A.take<int>(static_cast<size_t>(n_tiles) + 1);
+  int* s_tile_pt = A.take<int>(static_cast<size_t>(n_tiles) + 1);
+  for (int t = 0; t < n_tiles; ++t) {
+    s_tile_obs[t] = tile_meta[t].obs0;
+    s_tile_pt[t] = tile_meta[t].pt0;
+  }
+  s_tile_obs[n_tiles] = static_cast<int>(nl);
+  s_tile_pt[n_tiles] = n_pts;
+
+  // ---- device buffers (kept across calls, grow only)
+  h->plane_w = 4 + cb + ((two && cb) ? 6 : 0);
   h->j_planes = h->plane_w;
-  CU(h, h->d_obs_xy.alloc(std::max<int64_t>(nl, 1)));
-  CU(h, h->d_obs_idx.alloc(std::max<int64_t>(nl, 1)));
-  CU(h, h->d_views.alloc(std::max<size_t>(views.size(), 1)));
-  CU(h, h->d_tile_obs.alloc(tile_obs.size()));
-  CU(h, h->d_tile_pt.alloc(tile_pt.size()));
-  CU(h, h->d_pt_first.alloc(pt_first.size()));
-  CU(h, h->d_cam_entries.alloc(std::max<size_t>(cam_entries.size(), 1)));
-  CU(h, h->d_cam_chunks.alloc(std::max<size_t>(cam_chunks.size(), 1)));
-  CU(h, h->d_cam_chunk_first.alloc(cam_chunk_first.size()));
-  const int64_t ldc = ((static_cast<int64_t>(cam_entries.size()) + 63) / 64) * 64;
-  CU(h, h->d_FC.alloc(std::max<int64_t>(ldc, 64) * std::max(h->cb, 1)));
-  CU(h, h->d_ent_pos.alloc(std::max<size_t>(ent_pos.size(), 2)));
-  CU(h, h->d_tile_part_first.alloc(tile_part_first.size()));
-  CU(h, h->d_tile_meta.alloc(tile_meta.size()));
-  CU(h, h->d_obs_ab.alloc(obs_ab.size()));
-  CU(h, h->d_obs_lp.alloc(obs_lp.size()));
-  CU(h, h->d_part_first_rel.alloc(part_first_rel.size()));
-  CU(h, h->d_part_item_first.alloc(part_item_first.size()));
-  CU(h, h->d_items.alloc(std::max<size_t>(items.size(), 1)));
-  CU(h, h->d_cam_part_first.alloc(cam_part_first.size()));
-  CU(h, h->d_cam_part_idx.alloc(std::max<size_t>(cam_part_idx.size(), 1)));
-  CU(h, h->d_partials_q.alloc(std::max<size_t>(n_partials * std::max(h->cb, 1), 1)));
-  CU(h, h->d_vec_partials.alloc(static_cast<size_t>(p->n_ext) * std::max(h->cb, 1) / 128 + 64));
-  CU(h, h->d_counters.alloc(4));
-  CU(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * sizeof(unsigned int), h->st));
-  CU(h, h->d_J.alloc(std::max<int64_t>(ld, 64) * h->j_planes));
-  CU(h, h->d_ext_const.alloc(std::max(p->n_ext, 1)));
-  CU(h, h->d_center.alloc(2 * std::max(p->n_intr, 1)));
-  CU(h, h->d_nf.alloc(std::max(p->n_intr, 1)));
-  CU(h, h->d_nd.alloc(std::max(p->n_intr, 1)));
+  const int64_t ldc = std::max<int64_t>(((n_entries + 63) / 64) * 64, 64);
+  CU(h, ensure(h->d_obs_xy, nl));
+  CU(h, ensure(h->d_obs_ip, nl));
+  CU(h, ensure(h->d_obs_ab, nl));
+  CU(h, ensure(h->d_obs_lp, nl));
+  CU(h, ensure(h->d_tile_obs, n_tiles + 1));
+  CU(h, ensure(h->d_tile_pt, n_tiles + 1));
+  CU(h, ensure(h->d_pt_first, n_pts + 1));
+  CU(h, ensure(h->d_cam_entries, n_entries));
+  CU(h, ensure(h->d_cam_chunks, n_chunks));
+  CU(h, ensure(h->d_cam_chunk_first, n_ext + 1));
+  CU(h, ensure(h->d_FC, ldc * std::max(cb, 1)));
+  CU(h, ensure(h->d_ent_pos, 2 * nl));
+  CU(h, ensure(h->d_tile_part_first, n_tiles + 1));
+  CU(h, ensure(h->d_tile_meta, n_tiles));
+  CU(h, ensure(h->d_part_first_rel, n_entries + n_tiles + 1));
+  CU(h, ensure(h->d_items, n_entries));
+  CU(h, ensure(h->d_cam_part_first, n_ext + 1));
+  CU(h, ensure(h->d_cam_part_idx, n_partials));
+  CU(h, ensure(h->d_partials_q, static_cast<size_t>(n_partials) * std::max(cb, 1)));
+  CU(h, ensure(h->d_J, ld * h->j_planes));
+  CU(h, ensure(h->d_ext_const, n_ext));
+  CU(h, ensure(h->d_center, 2 * n_intr));
+  CU(h, ensure(h->d_nf, n_intr));
+  CU(h, ensure(h->d_nd, n_intr));
   for (int s = 0; s < 3; ++s) {
-    CU(h, h->d_pts[s].alloc(3 * std::max(h->n_pts, 1)));
-    CU(h, h->d_rot[s].alloc(3 * std::max(p->n_ext, 1)));
-    CU(h, h->d_trans[s].alloc(3 * std::max(p->n_ext, 1)));
-    CU(h, h->d_focal[s].alloc(2 * std::max(p->n_intr, 1)));
-    CU(h, h->d_dist[s].alloc(2 * std::max(p->n_intr, 1)));
+    CU(h, ensure(h->d_pts[s], 3 * static_cast<size_t>(n_pts)));
+    CU(h, ensure(h->d_rot[s], 3 * n_ext));
+    CU(h, ensure(h->d_trans[s], 3 * n_ext));
+    CU(h, ensure(h->d_focal[s], 2 * n_intr));
+    CU(h, ensure(h->d_dist[s], 2 * n_intr));
   }
   for (int s = 0; s < 2; ++s) {
-    CU(h, h->d_pose_rows[s].alloc(std::max(p->n_ext, 1)));
-    CU(h, h->d_intr_rows[s].alloc(std::max(p->n_intr, 1)));
+    CU(h, ensure(h->d_pose_rows[s], n_ext));
+    CU(h, ensure(h->d_intr_rows[s], n_intr));
   }
-  const size_t nvec = static_cast<size_t>(p->n_ext) * std::max(h->cb, 1);
-  CU(h, h->d_sp.alloc(3 * std::max(h->n_pts, 1)));
-  CU(h, h->d_cinv.alloc(6 * static_cast<size_t>(std::max(h->n_pts, 1))));
-  CU(h, h->d_tp.alloc(3 * std::max(h->n_pts, 1)));
-  CU(h, h->d_dp.alloc(3 * std::max(h->n_pts, 1)));
-  CU(h, h->d_sc.alloc(std::max<size_t>(nvec, 1)));
-  CU(h, h->d_cam_acc.alloc(std::max<size_t>(nvec * (std::max(h->cb, 1) + 3), 1)));
-  CU(h, h->d_minv.alloc(std::max<size_t>(nvec * std::max(h->cb, 1), 1)));
-  CU(h, h->d_dc2.alloc(std::max<size_t>(nvec, 1)));
-  CU(h, h->d_x.alloc(std::max<size_t>(nvec, 1)));
-  CU(h, h->d_r.alloc(std::max<size_t>(nvec, 1)));
-  CU(h, h->d_z.alloc(std::max<size_t>(nvec, 1)));
-  CU(h, h->d_p.alloc(std::max<size_t>(nvec, 1)));
-  CU(h, h->d_q.alloc(std::max<size_t>(nvec, 1)));
+  const size_t nvec = static_cast<size_t>(n_ext) * std::max(cb, 1);
+  CU(h, ensure(h->d_sp, 3 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_cinv, 6 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_tp, 3 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_dp, 3 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_sc, nvec));
+  CU(h, ensure(h->d_cam_acc, nvec * (std::max(cb, 1) + 3)));
+  CU(h, ensure(h->d_minv, nvec * std::max(cb, 1)));
+  CU(h, ensure(h->d_dc2, nvec));
+  CU(h, ensure(h->d_x, nvec));
+  CU(h, ensure(h->d_r, nvec));
+  CU(h, ensure(h->d_z, nvec));
+  CU(h, ensure(h->d_p, nvec));
+  CU(h, ensure(h->d_q, nvec));
+  CU(h, ensure(h->d_vec_partials, nvec / 128 + 64));
+  CU(h, ensure(h->d_counters, 4));
   const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles),
-                                          2 * static_cast<size_t>((3 * static_cast<int64_t>(h->n_pts) + 255) / 256),
-                                          size_t{64}}) + 64;
-  CU(h, h->d_partA.alloc(n_part));
-  CU(h, h->d_partB.alloc(3 * static_cast<size_t>((std::max(p->n_ext, p->n_intr) + 63) / 64) + 64));
-  CU(h, h->d_scalars.alloc(S_TOTAL));
-  CU(h, h->d_scalars_red.alloc(S_TOTAL));
-  CU(h, h->d_pcg_scal.alloc(8));
-  CU(h, h->d_pcg_state.alloc(4));
+                                          2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256), size_t{64}}) + 64;
+  CU(h, ensure(h->d_partA, n_part));
+  CU(h, ensure(h->d_partB, 3 * static_cast<size_t>((std::max(n_ext, n_intr) + 63) / 64) + 64));
+  CU(h, ensure(h->d_scalars, S_TOTAL));
+  CU(h, ensure(h->d_scalars_red, S_TOTAL));
+  CU(h, ensure(h->d_pcg_scal, 8));
+  CU(h, ensure(h->d_pcg_state, 4));
+  CU(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * sizeof(unsigned int), h->st));
   CU(h, cudaMemsetAsync(h->d_scalars.p, 0, S_TOTAL * sizeof(double), h->st));
   CU(h, cudaMemsetAsync(h->d_x.p, 0, std::max<size_t>(nvec, 1) * sizeof(double), h->st));
   CU(h, cudaMemsetAsync(h->d_pcg_state.p, 0, 4 * sizeof(int), h->st));
@@ -874,79 +1039,76 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     if (bytes == 0) return cudaSuccess;
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->st);
   };
-  CU(h, up(h->d_obs_xy.p, obs_xy.data(), nl * sizeof(double2)));
-  CU(h, up(h->d_obs_idx.p, obs_idx.data(), nl * sizeof(int2)));
-  CU(h, up(h->d_views.p, views.data(), views.size() * sizeof(ObsView)));
-  CU(h, up(h->d_tile_obs.p, tile_obs.data(), tile_obs.size() * sizeof(int)));
-  CU(h, up(h->d_tile_pt.p, tile_pt.data(), tile_pt.size() * sizeof(int)));
-  CU(h, up(h->d_pt_first.p, pt_first.data(), pt_first.size() * sizeof(int)));
-  CU(h, up(h->d_cam_entries.p, cam_entries.data(), cam_entries.size() * sizeof(int)));
-  CU(h, up(h->d_cam_chunks.p, cam_chunks.data(), cam_chunks.size() * sizeof(int4)));
-  CU(h, up(h->d_cam_chunk_first.p, cam_chunk_first.data(), cam_chunk_first.size() * sizeof(int)));
-  CU(h, up(h->d_ent_pos.p, ent_pos.data(), ent_pos.size() * sizeof(int)));
-  CU(h, up(h->d_tile_part_first.p, tile_part_first.data(), tile_part_first.size() * sizeof(int)));
-  CU(h, up(h->d_tile_meta.p, tile_meta.data(), tile_meta.size() * sizeof(TileMeta)));
-  CU(h, up(h->d_obs_ab.p, obs_ab.data(), obs_ab.size() * sizeof(int2)));
-  CU(h, up(h->d_obs_lp.p, obs_lp.data(), obs_lp.size() * sizeof(unsigned short)));
-  CU(h, up(h->d_part_first_rel.p, part_first_rel.data(), part_first_rel.size() * sizeof(unsigned short)));
-  CU(h, up(h->d_part_item_first.p, part_item_first.data(), part_item_first.size() * sizeof(int)));
-  CU(h, up(h->d_items.p, items.data(), items.size() * sizeof(unsigned short)));
-  CU(h, up(h->d_cam_part_first.p, cam_part_first.data(), cam_part_first.size() * sizeof(int)));
-  CU(h, up(h->d_cam_part_idx.p, cam_part_idx.data(), cam_part_idx.size() * sizeof(int)));
-  std::vector<uint8_t> ext_const(std::max(p->n_ext, 1), 0);
+  CU(h, up(h->d_obs_xy.p, s_xy, nl * sizeof(double2)));
+  CU(h, up(h->d_obs_ip.p, s_ip, nl * sizeof(int2)));
+  CU(h, up(h->d_obs_ab.p, s_ab, nl * sizeof(int2)));
+  CU(h, up(h->d_obs_lp.p, s_lp, nl * sizeof(unsigned short)));
+  CU(h, up(h->d_tile_obs.p, s_tile_obs, (n_tiles + 1) * sizeof(int)));
+  CU(h, up(h->d_tile_pt.p, s_tile_pt, (n_tiles + 1) * sizeof(int)));
+  CU(h, up(h->d_pt_first.p, s_pt_first, (static_cast<size_t>(n_pts) + 1) * sizeof(int)));
+  CU(h, up(h->d_cam_entries.p, s_cam_entries, n_entries * sizeof(int)));
+  CU(h, up(h->d_cam_chunks.p, s_cam_chunks, n_chunks * sizeof(int4)));
+  CU(h, up(h->d_cam_chunk_first.p, s_cam_chunk_first, (n_ext + 1) * sizeof(int)));
+  CU(h, up(h->d_ent_pos.p, s_ent_pos, 2 * nl * sizeof(int)));
+  CU(h, up(h->d_tile_part_first.p, s_tile_part_first, (n_tiles + 1) * sizeof(int)));
+  CU(h, up(h->d_tile_meta.p, s_tile_meta, n_tiles * sizeof(TileMeta)));
+  CU(h, up(h->d_part_first_rel.p, s_part_first_rel, (n_entries + n_tiles + 1) * sizeof(unsigned short)));
+  CU(h, up(h->d_items.p, s_items, n_entries * sizeof(unsigned short)));
+  CU(h, up(h->d_cam_part_first.p, s_cam_part_first, (n_ext + 1) * sizeof(int)));
+  CU(h, up(h->d_cam_part_idx.p, s_cam_part_idx, n_partials * sizeof(int)));
+  std::vector<uint8_t> ext_const(std::max(n_ext, 1), 0);
   h->any_const = false;
   if (p->ext_const)
-    for (int i = 0; i < p->n_ext; ++i) {
+    for (int i = 0; i < n_ext; ++i) {
       ext_const[i] = p->ext_const[i] ? 1 : 0;
       h->any_const |= ext_const[i] != 0;
     }
-  CU(h, up(h->d_ext_const.p, ext_const.data(), p->n_ext));
-  CU(h, up(h->d_center.p, p->intr_center, 2 * sizeof(double) * p->n_intr));
-  CU(h, up(h->d_nf.p, p->intr_nf, sizeof(int) * p->n_intr));
-  CU(h, up(h->d_nd.p, p->intr_nd, sizeof(int) * p->n_intr));
+  CU(h, up(h->d_ext_const.p, ext_const.data(), n_ext));
+  CU(h, up(h->d_center.p, p->intr_center, 2 * sizeof(double) * n_intr));
+  CU(h, up(h->d_nf.p, p->intr_nf, sizeof(int) * n_intr));
+  CU(h, up(h->d_nd.p, p->intr_nd, sizeof(int) * n_intr));
   // slot 2 = pristine copy for dba_params_reset, slot 0 = current
-  CU(h, up(h->d_pts[2].p, p->pts + 3 * static_cast<size_t>(pt_lo), 3 * sizeof(double) * h->n_pts));
-  CU(h, up(h->d_rot[2].p, p->ext_rot, 3 * sizeof(double) * p->n_ext));
-  CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * p->n_ext));
-  CU(h, up(h->d_focal[2].p, p->intr_focal, 2 * sizeof(double) * p->n_intr));
-  CU(h, up(h->d_dist[2].p, p->intr_dist, 2 * sizeof(double) * p->n_intr));
-  CU(h, cudaStreamSynchronize(h->st));  // host staging vectors go out of scope below
+  CU(h, up(h->d_pts[2].p, p->pts + 3 * static_cast<size_t>(pt_lo), 3 * sizeof(double) * n_pts));
+  CU(h, up(h->d_rot[2].p, p->ext_rot, 3 * sizeof(double) * n_ext));
+  CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * n_ext));
+  CU(h, up(h->d_focal[2].p, p->intr_focal, 2 * sizeof(double) * n_intr));
+  CU(h, up(h->d_dist[2].p, p->intr_dist, 2 * sizeof(double) * n_intr));
+  CU(h, cudaStreamSynchronize(h->st));  // caller buffers and local staging may go away now
+  h->n_cam_entries = n_entries;
 
   DeviceProblem& D = h->D;
   D.n_obs = nl;
-  D.ld = std::max<int64_t>(ld, 64);
-  D.n_pts = h->n_pts;
-  D.n_ext = p->n_ext;
-  D.n_intr = p->n_intr;
-  D.n_views = static_cast<int>(views.size());
+  D.ld = ld;
+  D.n_pts = n_pts;
+  D.n_ext = n_ext;
+  D.n_intr = n_intr;
   D.n_tiles = n_tiles;
-  D.cb = h->cb;
-  D.two = h->two;
-  D.n_blocks = p->n_ext;
+  D.cb = cb;
+  D.two = two;
+  D.n_blocks = n_ext;
   D.obs_xy = h->d_obs_xy.p;
-  D.obs_idx = h->d_obs_idx.p;
-  D.views = h->d_views.p;
+  D.obs_ip = h->d_obs_ip.p;
   D.tile_obs = h->d_tile_obs.p;
   D.tile_pt = h->d_tile_pt.p;
   D.pt_first = h->d_pt_first.p;
   D.cam_entries = h->d_cam_entries.p;
   D.cam_chunks = h->d_cam_chunks.p;
   D.cam_chunk_first = h->d_cam_chunk_first.p;
-  D.n_chunks = static_cast<int>(cam_chunks.size());
+  D.n_chunks = n_chunks;
   D.J = h->d_J.p;
-  D.FC = h->cb ? h->d_FC.p : nullptr;
-  D.ldc = std::max<int64_t>(ldc, 64);
+  D.FC = cb ? h->d_FC.p : nullptr;
+  D.ldc = ldc;
   D.ent_pos = h->d_ent_pos.p;
   D.tile_part_first = h->d_tile_part_first.p;
   D.tile_meta = h->d_tile_meta.p;
   D.obs_ab = h->d_obs_ab.p;
   D.obs_lp = h->d_obs_lp.p;
   D.part_first_rel = h->d_part_first_rel.p;
-  D.part_item_first = h->d_part_item_first.p;
+  D.part_item_first = nullptr;
   D.items = h->d_items.p;
   D.cam_part_first = h->d_cam_part_first.p;
   D.cam_part_idx = h->d_cam_part_idx.p;
-  D.n_partials = static_cast<int>(n_partials);
+  D.n_partials = n_partials;
   for (int s = 0; s < 2; ++s) {
     ParamSet& P = h->P[s];
     P.pts = h->d_pts[s].p;
@@ -993,15 +1155,15 @@ int dba_params_reset(dba_handle* h) {
   if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
   CU(h, cudaSetDevice(h->device));
   h->cur = 0;
-  auto cp = [&](DevBuf<double>* b) -> cudaError_t {
-    if (b[2].n == 0) return cudaSuccess;
-    return cudaMemcpyAsync(b[0].p, b[2].p, b[2].n * sizeof(double), cudaMemcpyDeviceToDevice, h->st);
+  auto cp = [&](DevBuf<double>* b, size_t count) -> cudaError_t {
+    if (count == 0) return cudaSuccess;
+    return cudaMemcpyAsync(b[0].p, b[2].p, count * sizeof(double), cudaMemcpyDeviceToDevice, h->st);
   };
-  CU(h, cp(h->d_pts));
-  CU(h, cp(h->d_rot));
-  CU(h, cp(h->d_trans));
-  CU(h, cp(h->d_focal));
-  CU(h, cp(h->d_dist));
+  CU(h, cp(h->d_pts, 3 * static_cast<size_t>(h->n_pts)));
+  CU(h, cp(h->d_rot, 3 * static_cast<size_t>(h->n_ext)));
+  CU(h, cp(h->d_trans, 3 * static_cast<size_t>(h->n_ext)));
+  CU(h, cp(h->d_focal, 2 * static_cast<size_t>(h->n_intr)));
+  CU(h, cp(h->d_dist, 2 * static_cast<size_t>(h->n_intr)));
   CU(h, cudaStreamSynchronize(h->st));
   return DBA_OK;
 }

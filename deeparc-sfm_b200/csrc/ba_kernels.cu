@@ -90,15 +90,15 @@ struct Forward {
   double mid[3];  // point after the (optional) first pose
   double cam[3];  // camera-frame point
 };
-__device__ __forceinline__ void forward(const ParamSet& P, const ObsView& v, const double X[3], Forward& f) {
-  if (v.pose_b >= 0) {
-    transform(P.pose_rows[v.pose_b], X, f.mid);
+__device__ __forceinline__ void forward(const ParamSet& P, const int2 ab, const double X[3], Forward& f) {
+  if (ab.y >= 0) {
+    transform(P.pose_rows[ab.y], X, f.mid);
   } else {
     f.mid[0] = X[0];
     f.mid[1] = X[1];
     f.mid[2] = X[2];
   }
-  transform(P.pose_rows[v.pose_a], f.mid, f.cam);
+  transform(P.pose_rows[ab.x], f.mid, f.cam);
 }
 
 // ------------------------------------------------------------------------ K1 jacobian
@@ -112,15 +112,16 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
   double c = 0.0;
   if (o < D.n_obs) {
     const double2 xy = D.obs_xy[o];
-    const int2 idx = D.obs_idx[o];
-    const ObsView v = D.views[idx.x];
+    const int2 idx = D.obs_ip[o];  // (intrinsic, local point)
+    const int2 ab = D.obs_ab[o];   // (block a, block b or -1)
+    struct { int pose_a, pose_b; } v = {ab.x, ab.y};
     const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
     const double X[3] = {Xp[0], Xp[1], Xp[2]};
     const PoseRow& A = P.pose_rows[v.pose_a];
     const bool two = v.pose_b >= 0;
     const PoseRow* B = two ? P.pose_rows + v.pose_b : nullptr;
     ObsJacobian j;
-    observation_jacobian(A, B, P.intr_rows[v.intr], X, xy.x, xy.y, CB > 0, j);
+    observation_jacobian(A, B, P.intr_rows[idx.x], X, xy.x, xy.y, CB > 0, j);
     c = j.r0 * j.r0 + j.r1 * j.r1;
     double2* J = D.J + o;
     const int64_t ld = D.ld;
@@ -208,14 +209,13 @@ __global__ void __launch_bounds__(256) k_cost(DeviceProblem D, ParamSet P, doubl
   double c = 0.0;
   if (o < D.n_obs) {
     const double2 xy = D.obs_xy[o];
-    const int2 idx = D.obs_idx[o];
-    const ObsView v = D.views[idx.x];
+    const int2 idx = D.obs_ip[o];
     const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
     const double X[3] = {Xp[0], Xp[1], Xp[2]};
     Forward f;
-    forward(P, v, X, f);
+    forward(P, D.obs_ab[o], X, f);
     Projection pr;
-    project<false>(P.intr_rows[v.intr], f.cam, xy.x, xy.y, pr);
+    project<false>(P.intr_rows[idx.x], f.cam, xy.x, xy.y, pr);
     c = pr.r0 * pr.r0 + pr.r1 * pr.r1;
     if (mse_out) mse_out[o] = c / 2.0;
   }
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
     } else {
       const double2 r = J[kPlaneR * ld];
       const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
-      const int pt = D.obs_idx[o].y;
+      const int pt = D.obs_ip[o].y;
       const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
       const double* tp = W.tp + 3 * static_cast<int64_t>(pt);
       const double c0 = ci[0], c1 = ci[1], c2 = ci[2], c3 = ci[3], c4 = ci[4], c5 = ci[5];
@@ -850,8 +850,7 @@ __global__ void __launch_bounds__(kTile) k_back_substitute(DeviceProblem D, Work
   double u0 = 0.0, u1 = 0.0;
   int lp = 0;
   if (active) {
-    const int2 idx = D.obs_idx[o];
-    lp = idx.y - pt0;
+    lp = D.obs_ip[o].y - pt0;
     const double2* J = D.J + o;
     const int64_t ld = D.ld;
     r = J[kPlaneR * ld];
@@ -859,7 +858,8 @@ __global__ void __launch_bounds__(kTile) k_back_substitute(DeviceProblem D, Work
     e1 = J[(kPlaneJp + 1) * ld];
     e2 = J[(kPlaneJp + 2) * ld];
     if (CB > 0) {
-      const ObsView vw = D.views[idx.x];
+      const int2 ab = D.obs_ab[o];
+      struct { int pose_a, pose_b; } vw = {ab.x, ab.y};
       const double* xa = W.x + static_cast<int64_t>(vw.pose_a) * CB;
 #pragma unroll
       for (int k = 0; k < CB; ++k) {

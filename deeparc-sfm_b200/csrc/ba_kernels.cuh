@@ -29,22 +29,17 @@ struct alignas(16) TileMeta {
   int item0, n_items; // incidence items of the tile, grouped by partial
 };
 
-struct ObsView {
-  int pose_a, pose_b, intr, pad;  // 16 B
-};
-
 // Everything a kernel needs to find its data.  Plain pointers, passed by value.
 struct DeviceProblem {
   int64_t n_obs;   // local (this rank) observations
   int64_t ld;      // plane stride (double2 elements)
   int n_pts;       // local points
-  int n_ext, n_intr, n_views, n_tiles;
+  int n_ext, n_intr, n_tiles;
   int cb;          // camera block size: 0 (points only), 6, 9
   int two;         // 1: observations may carry a second pose block
   int n_blocks;    // camera blocks (== n_ext)
   const double2* obs_xy;    // [n_obs]
-  const int2* obs_idx;      // [n_obs] (view, local point)
-  const ObsView* views;     // [n_views]
+  const int2* obs_ip;       // [n_obs] (intrinsic, local point)
   const int* tile_obs;      // [n_tiles + 1]
   const int* tile_pt;       // [n_tiles + 1]
   const int* pt_first;      // [n_pts + 1] first observation of each local point
