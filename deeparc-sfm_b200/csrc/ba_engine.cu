@@ -98,8 +98,8 @@ struct dba_handle {
   WorkArrays W{};
 
   // device storage
-  DevBuf<double2> d_obs_xy, d_J, d_FC;
-  DevBuf<int> d_ent_pos, d_tile_part_first, d_part_item_first, d_cam_part_first, d_cam_part_idx;
+  DevBuf<double2> d_obs_xy, d_J;
+  DevBuf<int> d_tile_part_first, d_part_item_first, d_cam_part_first, d_cam_part_idx;
   DevBuf<unsigned short> d_items, d_obs_lp, d_part_first_rel;
   DevBuf<TileMeta> d_tile_meta;
   DevBuf<int2> d_obs_ab;
@@ -294,9 +294,7 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
   const ParamSet& P = h->P[h->cur];
   const int nplanes = 4 + h->cb + (h->two && h->cb ? 6 : 0);
   // read xy(16)+idx(8), write r + Jp + Jc planes
-  // (+ the camera-sorted copy of the camera-side columns, written once more)
-  const double k1_bytes = (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs) +
-                          (h->cb ? (4.0 + 16.0 * h->cb) * static_cast<double>(h->n_cam_entries) : 0.0);
+  const double k1_bytes = (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs);
   {
     Scope s(h, "pose_rows");
     launch_pose_rows(P, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
@@ -767,7 +765,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   want(n_tiles * sizeof(TileMeta));
   want((n_tiles + 1) * sizeof(int) * 3);
   want(n_ent_max * sizeof(int));       // cam_entries
-  want(2 * nl * sizeof(int));          // ent_pos
   want(n_ent_max * sizeof(unsigned short));  // items
   want((n_ent_max + n_tiles + 1) * sizeof(unsigned short));  // part_first_rel
   want((n_ent_max + 1) * sizeof(int));  // part_item_first
@@ -796,7 +793,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
 
   // ---- camera-sorted incidence: stable parallel counting sort of (obs, slot) entries by block
   int* s_cam_entries = A.take<int>(static_cast<size_t>(n_ent_max));
-  int* s_ent_pos = A.take<int>(2 * static_cast<size_t>(nl));
   int4* s_cam_chunks = nullptr;
   int* s_cam_chunk_first = A.take<int>(static_cast<size_t>(n_ext) + 1);
   int64_t n_entries = 0;
@@ -836,13 +832,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
         const int a = s_ab[k].x, b = s_ab[k].y;
         const int64_t pa = first[a] + hc[a]++;
         s_cam_entries[pa] = static_cast<int>(2 * k);
-        s_ent_pos[2 * k] = static_cast<int>(pa);
         if (b >= 0) {
           const int64_t pb = first[b] + hc[b]++;
           s_cam_entries[pb] = static_cast<int>(2 * k + 1);
-          s_ent_pos[2 * k + 1] = static_cast<int>(pb);
-        } else {
-          s_ent_pos[2 * k + 1] = -1;
         }
       }
     }
@@ -858,8 +850,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   } else {
     for (int b = 0; b <= n_ext; ++b) s_cam_chunk_first[b] = 0;
     s_cam_chunks = A.take<int4>(1);
-#pragma omp parallel for schedule(static)
-    for (int64_t k = 0; k < 2 * nl; ++k) s_ent_pos[k] = -1;
   }
 
   // ---- static tile-local camera incidence (parallel over tiles, two passes)
@@ -970,7 +960,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   // ---- device buffers (kept across calls, grow only)
   h->plane_w = 4 + cb + ((two && cb) ? 6 : 0);
   h->j_planes = h->plane_w;
-  const int64_t ldc = std::max<int64_t>(((n_entries + 63) / 64) * 64, 64);
   CU(h, ensure(h->d_obs_xy, nl));
   CU(h, ensure(h->d_obs_ip, nl));
   CU(h, ensure(h->d_obs_ab, nl));
@@ -981,8 +970,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_cam_entries, n_entries));
   CU(h, ensure(h->d_cam_chunks, n_chunks));
   CU(h, ensure(h->d_cam_chunk_first, n_ext + 1));
-  CU(h, ensure(h->d_FC, ldc * std::max(cb, 1)));
-  CU(h, ensure(h->d_ent_pos, 2 * nl));
   CU(h, ensure(h->d_tile_part_first, n_tiles + 1));
   CU(h, ensure(h->d_tile_meta, n_tiles));
   CU(h, ensure(h->d_part_first_rel, n_entries + n_tiles + 1));
@@ -1049,7 +1036,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_cam_entries.p, s_cam_entries, n_entries * sizeof(int)));
   CU(h, up(h->d_cam_chunks.p, s_cam_chunks, n_chunks * sizeof(int4)));
   CU(h, up(h->d_cam_chunk_first.p, s_cam_chunk_first, (n_ext + 1) * sizeof(int)));
-  CU(h, up(h->d_ent_pos.p, s_ent_pos, 2 * nl * sizeof(int)));
   CU(h, up(h->d_tile_part_first.p, s_tile_part_first, (n_tiles + 1) * sizeof(int)));
   CU(h, up(h->d_tile_meta.p, s_tile_meta, n_tiles * sizeof(TileMeta)));
   CU(h, up(h->d_part_first_rel.p, s_part_first_rel, (n_entries + n_tiles + 1) * sizeof(unsigned short)));
@@ -1096,9 +1082,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.cam_chunk_first = h->d_cam_chunk_first.p;
   D.n_chunks = n_chunks;
   D.J = h->d_J.p;
-  D.FC = cb ? h->d_FC.p : nullptr;
-  D.ldc = ldc;
-  D.ent_pos = h->d_ent_pos.p;
   D.tile_part_first = h->d_tile_part_first.p;
   D.tile_meta = h->d_tile_meta.p;
   D.obs_ab = h->d_obs_ab.p;
@@ -1193,7 +1176,6 @@ int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, dou
       DevBuf<double2> tmp;
       CU(h, tmp.alloc(D.ld * 4));
       D.J = tmp.p;
-      D.FC = nullptr;
       {
         Scope s(h, "jacobian");
         launch_jacobian(D, P, h->W, 0, 0, 1, h->d_partA.p, h->st);
@@ -1216,7 +1198,6 @@ int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, dou
     DevBuf<double2> tmp;
     CU(h, tmp.alloc(D.ld * planes));
     D.J = tmp.p;
-    D.FC = nullptr;
     {
       Scope s(h, "jacobian");
       launch_jacobian(D, P, h->W, cbs, twos, 1, h->d_partA.p, h->st);

@@ -8,7 +8,9 @@
 //   k_spmv_tile + k_partials_to_q (K5)  implicit Schur complement product, one pass, atomic-free
 //   k_pcg_init / k_pcg_dot / k_pcg_step / k_pcg_direction (K6)  block-Jacobi PCG vector work
 //   k_back_substitute (K7), k_param_update  point back-substitution, x + delta, norms
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ba_kernels.cuh"
 
@@ -162,12 +164,6 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
       }
 #pragma unroll
       for (int k = 0; k < CB; ++k) J[(kPlaneJA + k) * ld] = FA[k];
-      // camera-sorted copy (sequential stream for the camera-side kernels): 16-byte scatter
-      if (D.FC) {
-        double2* FCa = D.FC + D.ent_pos[2 * o];
-#pragma unroll
-        for (int k = 0; k < CB; ++k) FCa[k * D.ldc] = FA[k];
-      }
       if (TWO) {
         const int pb = kPlaneJA + CB;
         if (two) {
@@ -185,11 +181,6 @@ __global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, W
           }
 #pragma unroll
           for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = FB[k];
-          if (D.FC) {
-            double2* FCb = D.FC + D.ent_pos[2 * o + 1];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) FCb[k * D.ldc] = FB[k];
-          }
         } else {
 #pragma unroll
           for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = make_double2(0.0, 0.0);
@@ -323,10 +314,10 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
     const int o = ent >> 1;
     const int slot = ent & 1;
     const double2* J = D.J + o;
-    const double2* FCe = D.FC + e;
+    const int base = kPlaneJA + (slot ? D.cb : 0);
     double2 F[CB];
 #pragma unroll
-    for (int k = 0; k < CB; ++k) F[k] = (slot && k >= 6) ? make_double2(0.0, 0.0) : FCe[k * D.ldc];
+    for (int k = 0; k < CB; ++k) F[k] = (slot && k >= 6) ? make_double2(0.0, 0.0) : J[(base + k) * ld];
     if (MODE == 0) {
 #pragma unroll
       for (int k = 0; k < CB; ++k) acc[k] += dot2(F[k], F[k]);
@@ -539,7 +530,7 @@ struct SpmvSmem {
 };
 
 template <int CB, bool TWO>
-__global__ void __launch_bounds__(kTile) k_spmv_tile(DeviceProblem D, WorkArrays W) {
+__global__ void __launch_bounds__(kTile, 4) k_spmv_tile(DeviceProblem D, WorkArrays W) {
   if (W.pcg_state[1]) return;
   using L = SpmvSmem<CB, TWO>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -650,19 +641,26 @@ __global__ void __launch_bounds__(kTile) k_spmv_tile(DeviceProblem D, WorkArrays
     }
   }
   __syncthreads();
-  // tile-local reduce-by-camera: partial g = g0 + local camera
-  const int n_work = tm.n_parts * CB;
+  // tile-local reduce-by-camera: partial g = g0 + local camera; one work item = (camera, 3 columns),
+  // so the incidence list of a camera is walked CB/3 times instead of CB times
+  constexpr int KG = CB / 3;
+  const int n_work = tm.n_parts * KG;
   for (int wk = tid; wk < n_work; wk += kTile) {
-    const int lc = wk / CB, k = wk - lc * CB;
+    const int lc = wk / KG, k0 = (wk - lc * KG) * 3;
     const int i0 = s_first[lc], i1 = s_first[lc + 1];
-    double acc = 0.0;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     for (int i = i0; i < i1; ++i) {
       const unsigned int it = s_items[i];
       const int lo = it & 0x7fffu;
-      const int row = TWO ? 3 + (it >> 15) * CB + k : 3 + k;  // slot-B items: planes 3+CB.. (CB == 6 there)
-      acc += sJ[row * L::kStride + lo].x;
+      const int row = TWO ? 3 + (it >> 15) * CB + k0 : 3 + k0;  // slot-B items: planes 3+CB.. (CB == 6 there)
+      a0 += sJ[row * L::kStride + lo].x;
+      a1 += sJ[(row + 1) * L::kStride + lo].x;
+      a2 += sJ[(row + 2) * L::kStride + lo].x;
     }
-    W.partials_q[static_cast<int64_t>(tm.g0 + lc) * CB + k] = acc;
+    double* out = W.partials_q + static_cast<int64_t>(tm.g0 + lc) * CB + k0;
+    out[0] = a0;
+    out[1] = a1;
+    out[2] = a2;
   }
 }
 

@@ -61,12 +61,6 @@ struct DeviceProblem {
   const int* cam_part_idx;          // [n_partials]
   int n_partials;
   double2* J;               // planes
-  // camera-sorted copy of the camera-side Jacobian columns: FC[k * ldc + e] = column k of the
-  // block of incidence entry e (written by the Jacobian kernel through ent_pos, read
-  // sequentially by the camera-side kernels).  NULL: do not write (dba_eval scratch runs).
-  double2* FC;
-  int64_t ldc;
-  const int* ent_pos;       // [n_obs][2] entry index of (obs, slot), -1 if the slot is unused
 };
 
 struct ParamSet {
