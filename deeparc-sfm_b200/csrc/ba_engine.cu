@@ -401,14 +401,14 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
       }
       {
         Scope s(h, "partials_to_q", part_bytes);
-        launch_partials_to_q(D, h->W, h->st);
+        launch_partials_to_q(D, h->W, h->world == 1, h->st);
       }
       if (h->world > 1) {
         int rc = allreduce(h, h->W.q, nvec, kNcclSum);
         if (rc != DBA_OK) return rc;
       }
-      Scope s(h, "pcg_vector", 0.0, 3);
-      launch_pcg_dot(D, h->W, h->st);
+      Scope s(h, "pcg_vector", 0.0, h->world > 1 ? 3 : 2);
+      if (h->world > 1) launch_pcg_dot(D, h->W, h->st);
       launch_pcg_step(D, h->W, tol2, o.pcg_min_iterations, h->st);
       launch_pcg_direction(D, h->W, h->st);
     }
@@ -1007,7 +1007,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_z, nvec));
   CU(h, ensure(h->d_p, nvec));
   CU(h, ensure(h->d_q, nvec));
-  CU(h, ensure(h->d_vec_partials, nvec / 128 + 64));
+  CU(h, ensure(h->d_vec_partials, nvec / 128 + static_cast<size_t>(n_ext) + 64));  // k_partials_to_q: one partial per block
   CU(h, ensure(h->d_counters, 4));
   const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles),
                                           2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256), size_t{64}}) + 64;

@@ -63,6 +63,24 @@ __device__ __forceinline__ double block_sum_all(double v, double* red) {
   return v;
 }
 
+// "last block" pattern: deterministic grid-wide scalars without a cooperative launch
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(counter, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  return is_last;
+}
+__device__ __forceinline__ double sum_partials(const volatile double* part, int n, double* red) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+  return block_sum_all(acc, red);
+}
+
 __device__ __forceinline__ double dot2(const double2 a, const double2 b) { return a.x * b.x + a.y * b.y; }
 
 // ------------------------------------------------------------------------- pose rows
@@ -665,10 +683,13 @@ __global__ void __launch_bounds__(kTile, 4) k_spmv_tile(DeviceProblem D, WorkArr
 }
 
 // q_j = sum of the partial vectors of camera block j, in the fixed order of the static list.
+// fuse_dot (single GPU): also q += D_c^2 p and the p.q partial of this block; the last CTA
+// publishes p.q, so k_pcg_dot is not launched.
 template <int CB>
-__global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArrays W) {
+__global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArrays W, int fuse_dot) {
   if (W.pcg_state[1]) return;
   __shared__ double red[4][CB];
+  __shared__ double red2[32];
   const int blk = blockIdx.x;
   const int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
   double acc[CB];
@@ -686,32 +707,33 @@ __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArra
     if (lane == 0) red[wid][k] = s;
   }
   __syncthreads();
-  if (threadIdx.x < CB)
-    W.q[static_cast<int64_t>(blk) * CB + threadIdx.x] =
-        red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+  double pq = 0.0;
+  if (threadIdx.x < CB) {
+    const int64_t i = static_cast<int64_t>(blk) * CB + threadIdx.x;
+    double q = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    if (fuse_dot) {
+      const double p = W.p[i];
+      q += W.dc2[i] * p;
+      pq = p * q;
+    }
+    W.q[i] = q;
+  }
+  if (!fuse_dot) return;
+  if (threadIdx.x < 32) pq = warp_sum(pq);
+  if (threadIdx.x == 0) W.vec_partials[blockIdx.x] = pq;
+  if (last_block_done(W.counters + 1)) {
+    const double tot = sum_partials(W.vec_partials, gridDim.x, red2);
+    if (threadIdx.x == 0) {
+      W.pcg_scal[2] = tot;
+      W.counters[1] = 0;
+    }
+  }
 }
 
 // --------------------------------------------------------------------------- K6 PCG
 // Block-Jacobi PCG vector work, multi-CTA (one thread per unknown), deterministic: every
 // global scalar is a fixed-order sum of per-CTA partials done by the last CTA to finish
 // ("last block" pattern with a device counter), so no cooperative launch is needed.
-__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(counter, 1u);
-    is_last = (prev == gridDim.x - 1);
-  }
-  __syncthreads();
-  return is_last;
-}
-__device__ __forceinline__ double sum_partials(const volatile double* part, int n, double* red) {
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
-  return block_sum_all(acc, red);
-}
-
 // x = 0, r = rhs, z = M^-1 r, p = z, rz = rz0 = r.z
 __global__ void __launch_bounds__(256) k_pcg_init(DeviceProblem D, WorkArrays W) {
   __shared__ double red[32];
@@ -1110,12 +1132,12 @@ void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t 
     launch_spmv_tile_t<9, false>(D, W, st);
 }
 
-void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, cudaStream_t st) {
   if (D.n_blocks == 0) return;
   if (D.cb == 6)
-    k_partials_to_q<6><<<D.n_blocks, 128, 0, st>>>(D, W);
+    k_partials_to_q<6><<<D.n_blocks, 128, 0, st>>>(D, W, fuse_dot);
   else
-    k_partials_to_q<9><<<D.n_blocks, 128, 0, st>>>(D, W);
+    k_partials_to_q<9><<<D.n_blocks, 128, 0, st>>>(D, W, fuse_dot);
 }
 
 void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {

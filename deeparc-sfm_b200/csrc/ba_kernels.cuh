@@ -143,7 +143,7 @@ void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t s
 // implicit Schur complement product: one pass over point tiles -> W.partials_q, then the
 // per-camera fixed-order sum -> W.q
 void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
-void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, cudaStream_t st);
 // PCG vector phases: q += D_c^2 p and p.q; the x/r/z update with r.z; the new direction
 void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
