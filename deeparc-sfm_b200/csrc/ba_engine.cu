@@ -720,16 +720,23 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   const int64_t* perm = h->perm.data();
 
   // ---- tiles of whole points (greedy, serial: O(n_pts))
+  // tile capacity: 256 unless some point has a longer track (then 512 / 1024; two-pose
+  // problems stop at 512 because a 1024-observation two-pose tile exceeds shared memory)
+  int64_t max_track = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_track)
+  for (int i = 0; i < p->n_pts; ++i) max_track = std::max(max_track, pt_count[i + 1] - pt_count[i]);
+  const int tile_cap_max = (two && !h->freeze) ? 512 : kMaxTile;
+  if (max_track > tile_cap_max)
+    return h->fail(DBA_ERR_UNSUPPORTED, "a point has %lld observations; tracks longer than %d are not implemented",
+                   (long long)max_track, tile_cap_max);
+  const int tile_cap = max_track <= 256 ? 256 : (max_track <= 512 ? 512 : 1024);
   std::vector<TileMeta> tile_meta;
   tile_meta.reserve(static_cast<size_t>(nl / 200 + 16));
   {
     int cur_obs = 0, t_pt0 = 0;
     for (int i = 0; i < n_pts; ++i) {
       const int len = static_cast<int>(pt_count[pt_lo + i + 1] - pt_count[pt_lo + i]);
-      if (len > kTile)
-        return h->fail(DBA_ERR_UNSUPPORTED, "point %d has %d observations; tracks longer than %d are not implemented",
-                       pt_lo + i, len, kTile);
-      if (cur_obs + len > kTile) {
+      if (cur_obs + len > tile_cap) {
         TileMeta m{};
         m.obs0 = static_cast<int>(pt_count[pt_lo + t_pt0] - obs_lo);
         m.n_obs = cur_obs;
@@ -1009,7 +1016,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_q, nvec));
   CU(h, ensure(h->d_vec_partials, nvec / 128 + static_cast<size_t>(n_ext) + 64));  // k_partials_to_q: one partial per block
   CU(h, ensure(h->d_counters, 4));
-  const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles),
+  const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles) + 3,
                                           2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256), size_t{64}}) + 64;
   CU(h, ensure(h->d_partA, n_part));
   CU(h, ensure(h->d_partB, 3 * static_cast<size_t>((std::max(n_ext, n_intr) + 63) / 64) + 64));
@@ -1069,6 +1076,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.n_ext = n_ext;
   D.n_intr = n_intr;
   D.n_tiles = n_tiles;
+  D.tile = tile_cap;
   D.cb = cb;
   D.two = two;
   D.n_blocks = n_ext;

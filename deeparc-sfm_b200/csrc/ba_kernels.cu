@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "ba_kernels.cuh"
 
@@ -236,10 +237,12 @@ __global__ void __launch_bounds__(256) k_cost(DeviceProblem D, ParamSet P, doubl
 // One CTA per tile of whole points (<= 256 observations).  Per point: H = E^T E (6 unique),
 // g = E^T r; mode 0: Jacobi scale sp = 1/(1+sqrt(diag H)); mode 1: C = H + D^2, C^-1, t = C^-1 g
 // and the point part of the gradient norms.  Reads Jp + r planes only (64 B / observation).
-__global__ void __launch_bounds__(kTile) k_point_prepare(DeviceProblem D, WorkArrays W, double radius,
+template <int T>
+__global__ void __launch_bounds__(T) k_point_prepare(DeviceProblem D, WorkArrays W, double radius,
                                                           double min_diag, double max_diag, int mode,
                                                           double* __restrict__ partials) {
-  __shared__ double v[9][kTile];
+  extern __shared__ __align__(16) unsigned char smem_pp[];
+  double(*v)[T] = reinterpret_cast<double(*)[T]>(smem_pp);  // [9][T]
   __shared__ double red[32];
   const int t = blockIdx.x;
   const int obs0 = D.tile_obs[t], obs1 = D.tile_obs[t + 1];
@@ -538,19 +541,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // (the +1 keeps the camera reduce, which reads 9 consecutive planes at one column, off a single
 // bank), then the static tile incidence.  The three Jp planes are recycled as (v, y) pairs and
 // the Jc planes as the per-observation contributions once their Jacobian column is consumed.
-template <int CB, bool TWO>
+template <int CB, bool TWO, int T>
 struct SpmvSmem {
   static constexpr int NP = 3 + CB + (TWO ? 6 : 0);
-  static constexpr int kStride = kTile + 1;
-  static constexpr int kMaxItems = TWO ? 2 * kTile : kTile;
+  static constexpr int kStride = T + 1;
+  static constexpr int kMaxItems = TWO ? 2 * T : T;
   static constexpr size_t kPlaneBytes = static_cast<size_t>(NP) * kStride * sizeof(double2);
   static constexpr size_t kBytes = kPlaneBytes + sizeof(unsigned short) * (2 * kMaxItems + 2) + 16;
 };
 
-template <int CB, bool TWO>
-__global__ void __launch_bounds__(kTile, 4) k_spmv_tile(DeviceProblem D, WorkArrays W) {
+template <int CB, bool TWO, int T>
+__global__ void __launch_bounds__(T, 1024 / T) k_spmv_tile(DeviceProblem D, WorkArrays W) {
   if (W.pcg_state[1]) return;
-  using L = SpmvSmem<CB, TWO>;
+  constexpr int kTile = T;  // tile capacity == threads per CTA
+  using L = SpmvSmem<CB, TWO, T>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double2* sJ = reinterpret_cast<double2*>(smem_raw);  // [NP][kStride]; plane 0..2 = Jp, 3.. = Jc
   unsigned short* s_items = reinterpret_cast<unsigned short*>(smem_raw + L::kPlaneBytes);
@@ -854,11 +858,12 @@ __global__ void __launch_bounds__(256) k_pcg_direction(DeviceProblem D, WorkArra
 
 // ------------------------------------------------------------- K7 back-substitution
 // dp_i = -t_i - C_i^-1 sum_o E_o^T F_o x ;  partial of sum (J d).(r + J d / 2)
-template <int CB, bool TWO>
-__global__ void __launch_bounds__(kTile) k_back_substitute(DeviceProblem D, WorkArrays W,
+template <int CB, bool TWO, int T>
+__global__ void __launch_bounds__(T) k_back_substitute(DeviceProblem D, WorkArrays W,
                                                             double* __restrict__ partial_model) {
-  __shared__ double v[3][kTile];
-  __shared__ double y[3][kTile];
+  extern __shared__ __align__(16) unsigned char smem_bs[];
+  double(*v)[T] = reinterpret_cast<double(*)[T]>(smem_bs);  // [3][T]
+  double(*y)[T] = v + 3;                                     // [3][T]
   __shared__ double red[32];
   const int t = blockIdx.x;
   const int obs0 = D.tile_obs[t], obs1 = D.tile_obs[t + 1];
@@ -1064,7 +1069,19 @@ void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost
 void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
                           double max_diag, int mode, double* partials, cudaStream_t st) {
   if (D.n_tiles == 0) return;
-  k_point_prepare<<<D.n_tiles, kTile, 0, st>>>(D, W, radius, min_diag, max_diag, mode, partials);
+  auto go = [&](auto tag) {
+    constexpr int T = decltype(tag)::value;
+    constexpr size_t smem = 9 * T * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(k_point_prepare<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      configured = true;
+    }
+    k_point_prepare<T><<<D.n_tiles, T, smem, st>>>(D, W, radius, min_diag, max_diag, mode, partials);
+  };
+  if (D.tile == 256) go(std::integral_constant<int, 256>());
+  else if (D.tile == 512) go(std::integral_constant<int, 512>());
+  else go(std::integral_constant<int, 1024>());
 }
 
 static size_t cam_acc_doubles(const DeviceProblem& D) {
@@ -1111,15 +1128,22 @@ void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t s
   k_pcg_init<<<(n + 255) / 256, 256, 0, st>>>(D, W);
 }
 
-template <int CB, bool TWO>
-static void launch_spmv_tile_t(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+template <int CB, bool TWO, int T>
+static void launch_spmv_tile_tt(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
   static bool configured = false;
-  constexpr size_t smem = SpmvSmem<CB, TWO>::kBytes;
+  constexpr size_t smem = SpmvSmem<CB, TWO, T>::kBytes;
+  static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
   if (!configured) {
-    cudaFuncSetAttribute(k_spmv_tile<CB, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaFuncSetAttribute(k_spmv_tile<CB, TWO, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = true;
   }
-  k_spmv_tile<CB, TWO><<<D.n_tiles, kTile, smem, st>>>(D, W);
+  k_spmv_tile<CB, TWO, T><<<D.n_tiles, T, smem, st>>>(D, W);
+}
+template <int CB, bool TWO>
+static void launch_spmv_tile_t(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  if (D.tile == 256) launch_spmv_tile_tt<CB, TWO, 256>(D, W, st);
+  else if (D.tile == 512) launch_spmv_tile_tt<CB, TWO, 512>(D, W, st);
+  else if constexpr (!TWO) launch_spmv_tile_tt<CB, TWO, 1024>(D, W, st);  // two-pose tiles of 1024 exceed 227 KB
 }
 
 void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
@@ -1153,16 +1177,33 @@ void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStrea
   k_pcg_direction<<<(n + 255) / 256, 256, 0, st>>>(D, W);
 }
 
+template <int CB, bool TWO>
+static void launch_back_substitute_t(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st) {
+  auto go = [&](auto tag) {
+    constexpr int T = decltype(tag)::value;
+    constexpr size_t smem = 6 * T * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+      cudaFuncSetAttribute(k_back_substitute<CB, TWO, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      configured = true;
+    }
+    k_back_substitute<CB, TWO, T><<<D.n_tiles, T, smem, st>>>(D, W, partial_model);
+  };
+  if (D.tile == 256) go(std::integral_constant<int, 256>());
+  else if (D.tile == 512) go(std::integral_constant<int, 512>());
+  else go(std::integral_constant<int, 1024>());
+}
+
 void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st) {
   if (D.n_tiles == 0) return;
   if (D.cb == 0)
-    k_back_substitute<0, false><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+    launch_back_substitute_t<0, false>(D, W, partial_model, st);
   else if (D.cb == 6 && !D.two)
-    k_back_substitute<6, false><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+    launch_back_substitute_t<6, false>(D, W, partial_model, st);
   else if (D.cb == 6)
-    k_back_substitute<6, true><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+    launch_back_substitute_t<6, true>(D, W, partial_model, st);
   else
-    k_back_substitute<9, false><<<D.n_tiles, kTile, 0, st>>>(D, W, partial_model);
+    launch_back_substitute_t<9, false>(D, W, partial_model, st);
 }
 
 int update_points_grid(const DeviceProblem& D) { return static_cast<int>((3 * static_cast<int64_t>(D.n_pts) + 255) / 256); }

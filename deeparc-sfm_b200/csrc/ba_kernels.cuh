@@ -16,7 +16,9 @@
 
 namespace dba {
 
-constexpr int kTile = 256;       // observations per tile / threads per tile CTA
+constexpr int kTile = 256;       // default tile capacity (observations per tile == threads per tile CTA);
+                                 // 512 / 1024 are selected when a point has a longer track
+constexpr int kMaxTile = 1024;
 constexpr int kPlaneR = 0;
 constexpr int kPlaneJp = 1;
 constexpr int kPlaneJA = 4;
@@ -35,6 +37,7 @@ struct DeviceProblem {
   int64_t ld;      // plane stride (double2 elements)
   int n_pts;       // local points
   int n_ext, n_intr, n_tiles;
+  int tile;        // tile capacity actually used: 256, 512 or 1024
   int cb;          // camera block size: 0 (points only), 6, 9
   int two;         // 1: observations may carry a second pose block
   int n_blocks;    // camera blocks (== n_ext)

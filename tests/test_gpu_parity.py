@@ -145,6 +145,27 @@ def test_lm_bal_9dof_matches_oracle(engine, oracle):
     _compare_solve(engine, oracle, PROBLEMS["bal"], n_iter=6)
 
 
+@pytest.mark.parametrize("kind", ["rig_512", "bal_1024"])
+def test_long_tracks_match_oracle(engine, oracle, kind):
+    """Points seen by more than 256 cameras select the 512- / 1024-observation tile kernels."""
+    if kind == "rig_512":
+        p = synthetic.arc_rig(n_arc=6, n_ring=60, n_pts=40, obs_per_point=300, seed=17)
+    else:
+        p = synthetic.bal_like(n_cam=800, n_pts=24, obs_per_point=700, window=800, seed=18, free_intrinsics=0)
+    engine.problem_set(p)
+    g = engine.eval(residuals=True, jacobians=False)
+    o = oracle.eval(p, residuals=True, jacobians=False)
+    _check_residuals(g["residuals"], o["residuals"], p.obs_xy)
+    _compare_solve(engine, oracle, p, n_iter=3)
+
+
+def test_track_longer_than_supported_is_rejected(engine):
+    p = synthetic.bal_like(n_cam=1200, n_pts=3, obs_per_point=1100, window=1200, seed=19, free_intrinsics=0)
+    with pytest.raises(capi.EngineError) as e:
+        engine.problem_set(p)
+    assert e.value.status == capi.DBA_ERR_UNSUPPORTED
+
+
 def test_lm_default_tolerances_converge_like_oracle(engine, oracle):
     """As the driver calls it: 100 iterations max, Ceres default tolerances."""
     p = PROBLEMS["rig"]
