@@ -103,7 +103,8 @@ struct dba_handle {
   DevBuf<unsigned short> d_items, d_obs_lp, d_part_first_rel;
   DevBuf<TileMeta> d_tile_meta;
   DevBuf<int2> d_obs_ab;
-  DevBuf<double> d_partials_q;
+  DevBuf<double> d_partials_q, d_q_split;
+  int q_split = 1;  // slices of the per-camera partial sum (few camera blocks => long lists)
   DevBuf<int2> d_obs_ip;
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
   DevBuf<unsigned int> d_counters;
@@ -391,6 +392,7 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   const int nvec = D.n_blocks * h->cb;
   int issued = 0;
   const int check_every = (o.pcg_rel_tolerance > 0.0) ? 8 : max_it;
+  const int fused = (h->world == 1 && h->q_split == 1) ? 1 : 0;  // q sum + D^2 p + p.q in one kernel
   *iters_out = 0;
   while (issued < max_it) {
     const int batch = std::min(check_every > 0 ? check_every : max_it, max_it - issued);
@@ -401,14 +403,18 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
       }
       {
         Scope s(h, "partials_to_q", part_bytes);
-        launch_partials_to_q(D, h->W, h->world == 1, h->st);
+        launch_partials_to_q(D, h->W, fused, h->q_split, h->st);
       }
       if (h->world > 1) {
+        if (h->q_split > 1) {  // fold the slices before the allreduce
+          Scope s(h, "pcg_vector");
+          launch_fold_q(D, h->W, h->q_split, h->st);
+        }
         int rc = allreduce(h, h->W.q, nvec, kNcclSum);
         if (rc != DBA_OK) return rc;
       }
-      Scope s(h, "pcg_vector", 0.0, h->world > 1 ? 3 : 2);
-      if (h->world > 1) launch_pcg_dot(D, h->W, h->st);
+      Scope s(h, "pcg_vector", 0.0, fused ? 2 : 3);
+      if (!fused) launch_pcg_dot(D, h->W, h->world > 1 ? 1 : h->q_split, h->st);
       launch_pcg_step(D, h->W, tol2, o.pcg_min_iterations, h->st);
       launch_pcg_direction(D, h->W, h->st);
     }
@@ -1014,6 +1020,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_z, nvec));
   CU(h, ensure(h->d_p, nvec));
   CU(h, ensure(h->d_q, nvec));
+  h->q_split = (n_ext >= 296 || !cb) ? 1 : std::min(32, (592 + std::max(n_ext, 1) - 1) / std::max(n_ext, 1));
+  CU(h, ensure(h->d_q_split, nvec * static_cast<size_t>(h->q_split)));
   CU(h, ensure(h->d_vec_partials, nvec / 128 + static_cast<size_t>(n_ext) + 64));  // k_partials_to_q: one partial per block
   CU(h, ensure(h->d_counters, 4));
   const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles) + 3,
@@ -1135,6 +1143,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.pcg_state = h->d_pcg_state.p;
   W.pcg_scal = h->d_pcg_scal.p;
   W.partials_q = h->d_partials_q.p;
+  W.q_split = h->d_q_split.p;
   W.vec_partials = h->d_vec_partials.p;
   W.counters = h->d_counters.p;
   h->have_problem = true;

@@ -689,13 +689,20 @@ __global__ void __launch_bounds__(T, 1024 / T) k_spmv_tile(DeviceProblem D, Work
 // q_j = sum of the partial vectors of camera block j, in the fixed order of the static list.
 // fuse_dot (single GPU): also q += D_c^2 p and the p.q partial of this block; the last CTA
 // publishes p.q, so k_pcg_dot is not launched.
+// n_split > 1 (few camera blocks, long partial lists): blockIdx.y owns one slice of the list and
+// writes W.q_split[slice]; k_pcg_dot adds the slices in order.
 template <int CB>
-__global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArrays W, int fuse_dot) {
+__global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArrays W, int fuse_dot, int n_split) {
   if (W.pcg_state[1]) return;
   __shared__ double red[4][CB];
   __shared__ double red2[32];
   const int blk = blockIdx.x;
-  const int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
+  int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
+  if (n_split > 1) {
+    const int len = i1 - i0, per = (len + n_split - 1) / n_split;
+    i0 = min(i0 + static_cast<int>(blockIdx.y) * per, i1);
+    i1 = min(i0 + per, i1);
+  }
   double acc[CB];
 #pragma unroll
   for (int k = 0; k < CB; ++k) acc[k] = 0.0;
@@ -720,7 +727,10 @@ __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArra
       q += W.dc2[i] * p;
       pq = p * q;
     }
-    W.q[i] = q;
+    if (n_split > 1)
+      W.q_split[static_cast<int64_t>(blockIdx.y) * D.n_blocks * CB + i] = q;
+    else
+      W.q[i] = q;
   }
   if (!fuse_dot) return;
   if (threadIdx.x < 32) pq = warp_sum(pq);
@@ -770,8 +780,8 @@ __global__ void __launch_bounds__(256) k_pcg_init(DeviceProblem D, WorkArrays W)
   }
 }
 
-// phase 1: q += D_c^2 p, partial p.q; the last CTA publishes p.q
-__global__ void __launch_bounds__(256) k_pcg_dot(DeviceProblem D, WorkArrays W) {
+// phase 1: q (= sum of the slices when n_split > 1) += D_c^2 p, partial p.q; the last CTA publishes p.q
+__global__ void __launch_bounds__(256) k_pcg_dot(DeviceProblem D, WorkArrays W, int n_split) {
   if (W.pcg_state[1]) return;
   __shared__ double red[32];
   const int n = D.n_blocks * D.cb;
@@ -779,7 +789,14 @@ __global__ void __launch_bounds__(256) k_pcg_dot(DeviceProblem D, WorkArrays W) 
   double acc = 0.0;
   if (i < n) {
     const double p = W.p[i];
-    const double q = W.q[i] + W.dc2[i] * p;
+    double q;
+    if (n_split > 1) {
+      q = 0.0;
+      for (int sl = 0; sl < n_split; ++sl) q += W.q_split[static_cast<int64_t>(sl) * n + i];
+    } else {
+      q = W.q[i];
+    }
+    q += W.dc2[i] * p;
     W.q[i] = q;
     acc = p * q;
   }
@@ -1156,17 +1173,35 @@ void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t 
     launch_spmv_tile_t<9, false>(D, W, st);
 }
 
-void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, cudaStream_t st) {
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, int n_split, cudaStream_t st) {
   if (D.n_blocks == 0) return;
+  const dim3 grid(D.n_blocks, n_split > 1 ? n_split : 1);
+  if (n_split > 1) fuse_dot = 0;
   if (D.cb == 6)
-    k_partials_to_q<6><<<D.n_blocks, 128, 0, st>>>(D, W, fuse_dot);
+    k_partials_to_q<6><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
   else
-    k_partials_to_q<9><<<D.n_blocks, 128, 0, st>>>(D, W, fuse_dot);
+    k_partials_to_q<9><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
 }
 
-void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+// q = sum of the slices (multi-GPU with n_split > 1: input of the allreduce)
+__global__ void __launch_bounds__(256) k_fold_q(DeviceProblem D, WorkArrays W, int n_split) {
+  if (W.pcg_state[1]) return;
   const int n = D.n_blocks * D.cb;
-  k_pcg_dot<<<(n + 255) / 256, 256, 0, st>>>(D, W);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double q = 0.0;
+    for (int sl = 0; sl < n_split; ++sl) q += W.q_split[static_cast<int64_t>(sl) * n + i];
+    W.q[i] = q;
+  }
+}
+void launch_fold_q(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st) {
+  const int n = D.n_blocks * D.cb;
+  k_fold_q<<<(n + 255) / 256, 256, 0, st>>>(D, W, n_split);
+}
+
+void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st) {
+  const int n = D.n_blocks * D.cb;
+  k_pcg_dot<<<(n + 255) / 256, 256, 0, st>>>(D, W, n_split);
 }
 void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st) {
   const int blocks_per_cta = 256 / D.cb;

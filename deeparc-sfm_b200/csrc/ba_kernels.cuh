@@ -100,6 +100,7 @@ struct WorkArrays {
   double* scalars;   // [32] reduced scalars, copied to the host
   int* pcg_state;    // [4] iter, done, -, -
   double* pcg_scal;  // [4] rz, rz0, p.q, beta
+  double* q_split;     // [n_split][n_blocks * cb] slices of q when the per-camera sum is split
   double* partials_q;  // [n_partials][cb] tile-local partial products of the implicit Schur product
   double* vec_partials;    // per-CTA partials of the PCG vector kernels
   unsigned int* counters;  // [4] "last block" arrival counters
@@ -146,9 +147,10 @@ void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t s
 // implicit Schur complement product: one pass over point tiles -> W.partials_q, then the
 // per-camera fixed-order sum -> W.q
 void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
-void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, cudaStream_t st);
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, int n_split, cudaStream_t st);
 // PCG vector phases: q += D_c^2 p and p.q; the x/r/z update with r.z; the new direction
-void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+void launch_fold_q(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st);
+void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st);
 void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
 void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
