@@ -735,7 +735,11 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   if (max_track > tile_cap_max)
     return h->fail(DBA_ERR_UNSUPPORTED, "a point has %lld observations; tracks longer than %d are not implemented",
                    (long long)max_track, tile_cap_max);
-  const int tile_cap = max_track <= 256 ? 256 : (max_track <= 512 ? 512 : 1024);
+  int tile_cap = max_track <= 256 ? 256 : (max_track <= 512 ? 512 : 1024);
+  if (const char* env = std::getenv("DBA_TILE")) {  // tuning knob: force a larger tile capacity
+    const int forced = std::atoi(env);
+    if ((forced == 512 || forced == 1024) && forced >= tile_cap && forced <= tile_cap_max) tile_cap = forced;
+  }
   std::vector<TileMeta> tile_meta;
   tile_meta.reserve(static_cast<size_t>(nl / 200 + 16));
   {

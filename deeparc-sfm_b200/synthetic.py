@@ -118,29 +118,39 @@ def matrix_to_angle_axis(R: np.ndarray) -> np.ndarray:
     return v * scale[..., None]
 
 
-def project(p: Problem, pts=None, ext_rot=None, ext_trans=None) -> np.ndarray:
+def project(p: Problem, pts=None, ext_rot=None, ext_trans=None, chunk: int = 2_000_000) -> np.ndarray:
     """Predicted pixels of every observation (numpy restatement of the forward model used
-    ONLY to synthesise observations; the parity oracle lives in oracle/)."""
+    ONLY to synthesise observations; the parity oracle lives in oracle/).  Chunked so that the
+    50M-observation workload does not materialise per-observation rotation matrices at once."""
     pts = p.pts if pts is None else pts
     ext_rot = p.ext_rot if ext_rot is None else ext_rot
     ext_trans = p.ext_trans if ext_trans is None else ext_trans
-    X = pts[p.obs_pt]
     R = rodrigues(ext_rot)
-    has_b = p.obs_pose_b >= 0
-    b = np.where(has_b, p.obs_pose_b, 0)
-    Xb = np.einsum("nij,nj->ni", R[b], X) + ext_trans[b]
-    X = np.where(has_b[:, None], Xb, X)
-    cam = np.einsum("nij,nj->ni", R[p.obs_pose_a], X) + ext_trans[p.obs_pose_a]
-    u = cam[:, 0] / cam[:, 2]
-    v = cam[:, 1] / cam[:, 2]
-    it = p.obs_intr
-    fx = p.intr_focal[it, 0]
-    fy = np.where(p.intr_nf[it] == 2, p.intr_focal[it, 1], p.intr_focal[it, 0])
-    rr = u * u + v * v
-    k0 = np.where(p.intr_nd[it] >= 1, p.intr_dist[it, 0], 0.0)
-    k1 = np.where(p.intr_nd[it] >= 2, p.intr_dist[it, 1], 0.0)
-    d = 1.0 + rr * (k0 + k1 * rr)
-    return np.stack([fx * d * u + p.intr_center[it, 0], fy * d * v + p.intr_center[it, 1]], axis=-1)
+    n = p.obs_pt.shape[0]
+    out = np.empty((n, 2))
+    any_b = bool((p.obs_pose_b >= 0).any())
+    for lo in range(0, n, chunk):
+        sl = slice(lo, min(lo + chunk, n))
+        X = pts[p.obs_pt[sl]]
+        if any_b:
+            has_b = p.obs_pose_b[sl] >= 0
+            b = np.where(has_b, p.obs_pose_b[sl], 0)
+            Xb = np.einsum("nij,nj->ni", R[b], X) + ext_trans[b]
+            X = np.where(has_b[:, None], Xb, X)
+        a = p.obs_pose_a[sl]
+        cam = np.einsum("nij,nj->ni", R[a], X) + ext_trans[a]
+        u = cam[:, 0] / cam[:, 2]
+        v = cam[:, 1] / cam[:, 2]
+        it = p.obs_intr[sl]
+        fx = p.intr_focal[it, 0]
+        fy = np.where(p.intr_nf[it] == 2, p.intr_focal[it, 1], p.intr_focal[it, 0])
+        rr = u * u + v * v
+        k0 = np.where(p.intr_nd[it] >= 1, p.intr_dist[it, 0], 0.0)
+        k1 = np.where(p.intr_nd[it] >= 2, p.intr_dist[it, 1], 0.0)
+        d = 1.0 + rr * (k0 + k1 * rr)
+        out[sl, 0] = fx * d * u + p.intr_center[it, 0]
+        out[sl, 1] = fy * d * v + p.intr_center[it, 1]
+    return out
 
 
 def _rng(seed: int, stream: int) -> np.random.Generator:
@@ -255,7 +265,15 @@ def bal_like(n_cam: int = 1700, n_pts: int = 1_000_000, obs_per_point: int = 5, 
         start = g.permutation(start)
     centre_x = 0.1 * (start + window / 2.0)
     pts = np.stack([centre_x + g.uniform(-1.5, 1.5, n_pts), g.uniform(-1.5, 1.5, n_pts), g.uniform(6.0, 10.0, n_pts)], axis=1)
-    offs = np.argsort(g.random((n_pts, window)), axis=1)[:, :k]
+    if n_pts * window <= 60_000_000:
+        offs = np.argsort(g.random((n_pts, window)), axis=1)[:, :k]
+    else:
+        # large problems: k distinct offsets per point from a random base and a stride coprime
+        # to the window (O(n_pts * k) memory instead of O(n_pts * window))
+        strides = np.array([s_ for s_ in range(1, window) if np.gcd(s_, window) == 1], dtype=np.int64)
+        base = g.integers(0, window, n_pts)
+        stride = strides[g.integers(0, len(strides), n_pts)]
+        offs = (base[:, None] + stride[:, None] * np.arange(k)[None, :]) % window
     cams = np.sort(start[:, None] + offs, axis=1).astype(np.int32).reshape(-1)
     obs_pt = np.repeat(np.arange(n_pts, dtype=np.int32), k)
 
