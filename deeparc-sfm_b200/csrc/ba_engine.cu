@@ -105,6 +105,12 @@ struct dba_handle {
   DevBuf<int2> d_obs_ab;
   DevBuf<double> d_partials_q, d_q_split;
   int q_split = 1;  // slices of the per-camera partial sum (few camera blocks => long lists)
+  // matrix-free implicit Schur product (default); DBA_SPMV=planes selects the product that reads
+  // the materialised Jacobian planes (kept for A/B measurements)
+  int mf = 1;
+  DevBuf<int> d_mf_cols, d_part_dst;
+  DevBuf<unsigned short> d_items_mf;
+  DevBuf<double> d_mf_rows, d_mf_T;
   DevBuf<int2> d_obs_ip;
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
   DevBuf<unsigned int> d_counters;
@@ -333,6 +339,10 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
     Scope s(h, "reduce");
     launch_reduce_sum(h->d_partA.p, cost_grid(D), 1, 0, h->W.scalars + S_COST, h->st);
   }
+  if (h->mf && h->cb) {
+    Scope s(h, "mf_rows");
+    launch_mf_rows(D, P, h->W, h->st);
+  }
   CU(h, cudaGetLastError());
   return DBA_OK;
 }
@@ -382,10 +392,17 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   // and read once by the per-camera sum
   const double tile_bytes = (8.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs) +
                             8.0 * h->cb * static_cast<double>(D.n_partials);
-  const double part_bytes = (8.0 * h->cb + 4.0) * static_cast<double>(D.n_partials);
+  const double part_bytes = 8.0 * h->cb * static_cast<double>(D.n_partials);
+  // matrix-free product: column indices + per-point X, sp, C^-1, segment bounds + partials written once
+  const double mf_bytes = (h->cb == 9 ? 8.0 : 16.0) * static_cast<double>(D.n_tiles) * D.tile + 100.0 * static_cast<double>(h->n_pts) +
+                          (8.0 * h->cb + 4.0) * static_cast<double>(D.n_partials);
   {
     Scope s(h, "pcg_init");
     launch_pcg_init(D, h->W, h->st);
+  }
+  if (h->mf) {
+    Scope s(h, "pcg_vector");
+    launch_mf_direction(D, h->W, /*init=*/1, h->st);
   }
   const double tol2 = o.pcg_rel_tolerance * o.pcg_rel_tolerance;
   const int max_it = std::max(0, o.pcg_max_iterations);
@@ -397,13 +414,16 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   while (issued < max_it) {
     const int batch = std::min(check_every > 0 ? check_every : max_it, max_it - issued);
     for (int i = 0; i < batch; ++i) {
-      {
+      if (h->mf) {
+        Scope s(h, "spmv_mf", mf_bytes);
+        launch_spmv_mf(D, h->P[h->cur], h->W, h->st);
+      } else {
         Scope s(h, "spmv_tile", tile_bytes);
         launch_spmv_tile(D, h->W, h->st);
       }
       {
         Scope s(h, "partials_to_q", part_bytes);
-        launch_partials_to_q(D, h->W, fused, h->q_split, h->st);
+        launch_partials_to_q(D, h->W, fused, h->q_split, h->mf, h->st);
       }
       if (h->world > 1) {
         if (h->q_split > 1) {  // fold the slices before the allreduce
@@ -416,7 +436,10 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
       Scope s(h, "pcg_vector", 0.0, fused ? 2 : 3);
       if (!fused) launch_pcg_dot(D, h->W, h->world > 1 ? 1 : h->q_split, h->st);
       launch_pcg_step(D, h->W, tol2, o.pcg_min_iterations, h->st);
-      launch_pcg_direction(D, h->W, h->st);
+      if (h->mf)
+        launch_mf_direction(D, h->W, /*init=*/0, h->st);
+      else
+        launch_pcg_direction(D, h->W, h->st);
     }
     issued += batch;
     CU(h, cudaMemcpyAsync(h->h_pcg_state, h->W.pcg_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -786,6 +809,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   want((n_ent_max + n_tiles + 1) * sizeof(unsigned short));  // part_first_rel
   want((n_ent_max + 1) * sizeof(int));  // part_item_first
   want(n_ent_max * sizeof(int));        // cam_part_idx
+  want(n_ent_max * sizeof(int));        // part_dst
+  want(cb ? (static_cast<size_t>(n_tiles) * tile_cap) * sizeof(int4) : 0);  // mf_cols (padded per tile)
+  want((two && cb) ? n_ent_max * sizeof(unsigned short) : 0);  // items_mf
   want((n_ent_max / 1024 + n_ext + 2) * sizeof(int4));  // cam_chunks
   want((n_ext + 1) * sizeof(int) * 3);
   PinnedArena& A = arena_of(h);
@@ -875,6 +901,11 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   int* s_tile_part_first = A.take<int>(static_cast<size_t>(n_tiles) + 1);
   int* s_cam_part_first = A.take<int>(static_cast<size_t>(n_ext) + 1);
   int* s_cam_part_idx = nullptr;
+  int* s_part_dst = nullptr;
+  const int mf_w = cb == 9 ? 2 : 4;  // ints per column record
+  const size_t n_cols = cb ? static_cast<size_t>(n_tiles) * tile_cap : 0;  // padded: tile t owns [t * tile_cap, (t + 1) * tile_cap)
+  int* s_mf_cols = A.take<int>(std::max<size_t>(n_cols * mf_w, 1));
+  unsigned short* s_items_mf = A.take<unsigned short>((two && cb) ? static_cast<size_t>(std::max<int64_t>(n_entries, 1)) : 1);
   int n_partials = 0;
   std::vector<int> part_block;
   {
@@ -912,7 +943,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     // pass B: fill (items grouped by local block, in order of first appearance)
 #pragma omp parallel
     {
-      std::vector<int> local_of(static_cast<size_t>(n_ext), -1), locals, count, start;
+      std::vector<int> local_of(static_cast<size_t>(n_ext), -1), locals, count, start, col_of;
 #pragma omp for schedule(static)
       for (int t = 0; t < n_tiles; ++t) {
         TileMeta& m = tile_meta[t];
@@ -953,6 +984,36 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
           }
         }
         for (int blk : locals) local_of[blk] = -1;
+        // columns of the matrix-free product: the tile's observations in camera-block order
+        // (slot-0 items in item order; every observation has exactly one)
+        col_of.assign(static_cast<size_t>(m.n_obs), 0);
+        int col = 0;
+        for (int i = 0; i < m.n_items; ++i) {
+          const unsigned short it = s_items[m.item0 + i];
+          if (it >> 15) continue;
+          const int lo = it & 0x7fff, k = m.obs0 + lo;
+          col_of[lo] = col;
+          int* rec = s_mf_cols + (static_cast<size_t>(t) * tile_cap + col) * mf_w;
+          const int lplo = static_cast<int>((static_cast<unsigned int>(s_lp[k]) << 16) | static_cast<unsigned int>(lo));
+          rec[0] = s_ab[k].x;
+          if (mf_w == 2) {
+            rec[1] = lplo;
+          } else {
+            rec[1] = s_ab[k].y;
+            rec[2] = lplo;
+            rec[3] = s_ip[k].x;
+          }
+          ++col;
+        }
+        for (; col < tile_cap; ++col) {
+          int* rec = s_mf_cols + (static_cast<size_t>(t) * tile_cap + col) * mf_w;
+          for (int w = 0; w < mf_w; ++w) rec[w] = w == 0 ? -1 : 0;
+        }
+        if (two)
+          for (int i = 0; i < m.n_items; ++i) {
+            const unsigned short it = s_items[m.item0 + i];
+            s_items_mf[m.item0 + i] = static_cast<unsigned short>(col_of[it & 0x7fff] | (it & 0x8000));
+          }
       }
     }
     // partials grouped by camera block (serial counting sort: O(n_partials))
@@ -961,7 +1022,12 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     for (int b = 0; b < n_ext; ++b) s_cam_part_first[b + 1] += s_cam_part_first[b];
     s_cam_part_idx = A.take<int>(static_cast<size_t>(std::max(n_partials, 1)));
     std::vector<int> cur(s_cam_part_first, s_cam_part_first + n_ext);
-    for (int g = 0; g < n_partials; ++g) s_cam_part_idx[cur[part_block[g]]++] = g;
+    s_part_dst = A.take<int>(static_cast<size_t>(std::max(n_partials, 1)));
+    for (int g = 0; g < n_partials; ++g) {
+      const int pos = cur[part_block[g]]++;
+      s_cam_part_idx[pos] = g;
+      s_part_dst[g] = pos;
+    }
   }
   TileMeta* s_tile_meta = A.take<TileMeta>(static_cast<size_t>(std::max(n_tiles, 1)));
   if (n_tiles) std::memcpy(s_tile_meta, tile_meta.data(), sizeof(TileMeta) * n_tiles);
@@ -993,6 +1059,15 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_items, n_entries));
   CU(h, ensure(h->d_cam_part_first, n_ext + 1));
   CU(h, ensure(h->d_cam_part_idx, n_partials));
+  CU(h, ensure(h->d_part_dst, n_partials));
+  CU(h, ensure(h->d_mf_cols, std::max<size_t>(n_cols * mf_w, 1)));
+  CU(h, ensure(h->d_items_mf, (two && cb) ? n_entries : 1));
+  CU(h, ensure(h->d_mf_rows, static_cast<size_t>(n_ext) * mf_row_len(cb)));
+  CU(h, ensure(h->d_mf_T, static_cast<size_t>(n_ext) * (9 + cb)));
+  {
+    const char* env = std::getenv("DBA_SPMV");
+    h->mf = !(env && std::strcmp(env, "planes") == 0);
+  }
   CU(h, ensure(h->d_partials_q, static_cast<size_t>(n_partials) * std::max(cb, 1)));
   CU(h, ensure(h->d_J, ld * h->j_planes));
   CU(h, ensure(h->d_ext_const, n_ext));
@@ -1061,6 +1136,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_items.p, s_items, n_entries * sizeof(unsigned short)));
   CU(h, up(h->d_cam_part_first.p, s_cam_part_first, (n_ext + 1) * sizeof(int)));
   CU(h, up(h->d_cam_part_idx.p, s_cam_part_idx, n_partials * sizeof(int)));
+  CU(h, up(h->d_part_dst.p, s_part_dst, n_partials * sizeof(int)));
+  if (cb) CU(h, up(h->d_mf_cols.p, s_mf_cols, n_cols * mf_w * sizeof(int)));
+  if (two && cb) CU(h, up(h->d_items_mf.p, s_items_mf, n_entries * sizeof(unsigned short)));
   std::vector<uint8_t> ext_const(std::max(n_ext, 1), 0);
   h->any_const = false;
   if (p->ext_const)
@@ -1112,6 +1190,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.cam_part_first = h->d_cam_part_first.p;
   D.cam_part_idx = h->d_cam_part_idx.p;
   D.n_partials = n_partials;
+  D.mf_cols = h->d_mf_cols.p;
+  D.items_mf = h->d_items_mf.p;
+  D.part_dst = h->d_part_dst.p;
   for (int s = 0; s < 2; ++s) {
     ParamSet& P = h->P[s];
     P.pts = h->d_pts[s].p;
@@ -1148,6 +1229,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.pcg_scal = h->d_pcg_scal.p;
   W.partials_q = h->d_partials_q.p;
   W.q_split = h->d_q_split.p;
+  W.mf_rows = h->d_mf_rows.p;
+  W.mf_T = h->d_mf_T.p;
   W.vec_partials = h->d_vec_partials.p;
   W.counters = h->d_counters.p;
   h->have_problem = true;

@@ -679,22 +679,25 @@ __global__ void __launch_bounds__(T, 1024 / T) k_spmv_tile(DeviceProblem D, Work
       a1 += sJ[(row + 1) * L::kStride + lo].x;
       a2 += sJ[(row + 2) * L::kStride + lo].x;
     }
-    double* out = W.partials_q + static_cast<int64_t>(tm.g0 + lc) * CB + k0;
+    double* out = W.partials_q + static_cast<int64_t>(D.part_dst[tm.g0 + lc]) * CB + k0;
     out[0] = a0;
     out[1] = a1;
     out[2] = a2;
   }
 }
 
-// q_j = sum of the partial vectors of camera block j, in the fixed order of the static list.
+// q_j = sum of the partial vectors of camera block j, in the fixed order of the static list
+// (the tile kernels write partial g to row part_dst[g], so a camera's partials are contiguous).
+// MF: the partials are in geometric coordinates; q = T^T (sum) = sc * free * (J_l^T . , . , .).
 // fuse_dot (single GPU): also q += D_c^2 p and the p.q partial of this block; the last CTA
 // publishes p.q, so k_pcg_dot is not launched.
 // n_split > 1 (few camera blocks, long partial lists): blockIdx.y owns one slice of the list and
 // writes W.q_split[slice]; k_pcg_dot adds the slices in order.
-template <int CB>
+template <int CB, bool MF>
 __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArrays W, int fuse_dot, int n_split) {
   if (W.pcg_state[1]) return;
   __shared__ double red[4][CB];
+  __shared__ double qg[CB];
   __shared__ double red2[32];
   const int blk = blockIdx.x;
   int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
@@ -707,7 +710,7 @@ __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArra
 #pragma unroll
   for (int k = 0; k < CB; ++k) acc[k] = 0.0;
   for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    const double* pv = W.partials_q + static_cast<int64_t>(D.cam_part_idx[i]) * CB;
+    const double* pv = W.partials_q + static_cast<int64_t>(i) * CB;
 #pragma unroll
     for (int k = 0; k < CB; ++k) acc[k] += pv[k];
   }
@@ -718,10 +721,22 @@ __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArra
     if (lane == 0) red[wid][k] = s;
   }
   __syncthreads();
+  if (MF) {
+    if (threadIdx.x < CB) qg[threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    __syncthreads();
+  }
   double pq = 0.0;
   if (threadIdx.x < CB) {
     const int64_t i = static_cast<int64_t>(blk) * CB + threadIdx.x;
-    double q = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    double q;
+    if (MF) {
+      const double* Tm = W.mf_T + static_cast<int64_t>(blk) * (9 + CB);
+      const int k = threadIdx.x;
+      q = (k < 3) ? Tm[k] * qg[0] + Tm[3 + k] * qg[1] + Tm[6 + k] * qg[2] : qg[k];  // (J_l^T q)_k
+      q *= Tm[9 + k];
+    } else {
+      q = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    }
     if (fuse_dot) {
       const double p = W.p[i];
       q += W.dc2[i] * p;
@@ -742,6 +757,357 @@ __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArra
       W.counters[1] = 0;
     }
   }
+}
+
+// ------------------------------------------------ K5' matrix-free implicit Schur product
+// Same operator as k_spmv_tile, but the Jacobian is RECOMPUTED per observation from the camera
+// row and the point instead of being read (~130 fp64 operations against 200 B):
+// the kernel reads 8-16 B of indices per observation, X / C^-1 per point and L1-resident camera
+// rows, so it leaves the HBM roofline of the materialised product behind.
+// Geometric coordinates: with q = R X (rotated point), G = d r / d p_cam (2x3),
+//   F p = G (a x q + p~_t) + (d r/d f, k0, k1) p~_fk,   a = p~_w = J_l(w) (sc * free * p)_w
+//   F^T w = T^T [q x g, g, (d r/d f,k0,k1)^T w],        g = G^T w
+// (d(R(w) X) = (J_l dw) x (R X) is exact; in Ceres' small-angle branch, 0 < |w|^2 <= eps, it differs
+// from -[X]x dw by |w| <= 1.5e-8 relative — inside the product only, never in residuals or gradient.)
+// Threads of a tile map to observations in camera-block order (static `mf_cols`), so the
+// reduce-by-camera runs over contiguous columns and a warp's row loads hit few distinct rows.
+template <int N>
+__device__ __forceinline__ void load_row(const double* __restrict__ row, double (&r)[N]) {
+  const double2* p = reinterpret_cast<const double2*>(row);
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const double2 v = __ldg(p + i);
+    r[2 * i] = v.x;
+    r[2 * i + 1] = v.y;
+  }
+}
+
+// G = d r / d p_cam for projectPoint (snavely_reprojection_error.hh:38-78); also u, v, r^2, d
+__device__ __forceinline__ void project_G(double fx, double fy, double k0, double k1, const double c[3], double G[2][3],
+                                          double& uu, double& vv, double& rr, double& d) {
+  // reciprocal by MUFU seed + two Newton steps (~1 ulp; the product does not need IEEE division)
+  double iz;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(iz) : "d"(c[2]));
+  iz = iz * (2.0 - c[2] * iz);
+  iz = iz * (2.0 - c[2] * iz);
+  uu = c[0] * iz;
+  vv = c[1] * iz;
+  rr = uu * uu + vv * vv;
+  const double kk = k0 + k1 * rr;
+  d = 1.0 + rr * kk;
+  const double kap = kk + k1 * rr;
+  const double uv2 = 2.0 * uu * vv * kap;
+  const double r0u = fx * (d + 2.0 * uu * uu * kap), r0v = fx * uv2;
+  const double r1u = fy * uv2, r1v = fy * (d + 2.0 * vv * vv * kap);
+  G[0][0] = r0u * iz;
+  G[0][1] = r0v * iz;
+  G[0][2] = -(r0u * uu + r0v * vv) * iz;
+  G[1][0] = r1u * iz;
+  G[1][1] = r1v * iz;
+  G[1][2] = -(r1u * uu + r1v * vv) * iz;
+}
+
+template <int CB, bool TWO, int T>
+struct MfSmem {
+  static constexpr int NC = CB + (TWO ? 6 : 0);
+  static constexpr int S = T + 1;
+  static constexpr int kMaxParts = TWO ? 2 * T : T;
+  static constexpr size_t kDoubles = 6 * T + static_cast<size_t>(NC) * S;
+  static constexpr size_t kBytes = kDoubles * sizeof(double) + sizeof(unsigned short) * (kMaxParts + 2 + (TWO ? 2 * T : 0)) + 16;
+};
+
+template <int CB, bool TWO, int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays W, const double* __restrict__ pts,
+                                                      const IntrRow* __restrict__ intr_rows) {
+  if (W.pcg_state[1]) return;
+  using L = MfSmem<CB, TWO, T>;
+  constexpr int NC = L::NC, S = L::S, ROW = mf_row_len(CB), SEL = ROW - 2;
+  extern __shared__ __align__(16) unsigned char smem_mf[];
+  double* sX = reinterpret_cast<double*>(smem_mf);  // [6][T]: X, sp of the tile's points; rows 0..2 become y
+  double* sC = sX + 6 * T;                          // [NC][S] contributions; rows 0..2 first hold v = E^T u
+  unsigned short* s_first = reinterpret_cast<unsigned short*>(sC + NC * S);
+  unsigned short* s_items = s_first + L::kMaxParts + 2;
+  const int t = blockIdx.x, tid = threadIdx.x;
+  // ---- phase 0: this thread's column (padded per-tile layout: no dependence on the tile record)
+  // and, as soon as it arrives, its camera rows; meanwhile stage the tile's points and incidence
+  int blk_a = -1, blk_b = -1, intr = 0;
+  unsigned int lplo = 0;
+  if (CB == 9) {
+    const int2 c = reinterpret_cast<const int2*>(D.mf_cols)[static_cast<int64_t>(t) * T + tid];
+    blk_a = c.x;
+    lplo = static_cast<unsigned int>(c.y);
+  } else {
+    const int4 c = reinterpret_cast<const int4*>(D.mf_cols)[static_cast<int64_t>(t) * T + tid];
+    blk_a = c.x;
+    blk_b = c.y;
+    lplo = static_cast<unsigned int>(c.z);
+    intr = c.w;
+  }
+  const TileMeta tm = D.tile_meta[t];
+  const int obs0 = tm.obs0;
+  const bool active = blk_a >= 0;
+  const bool has_b = TWO && blk_b >= 0;
+  double ra[ROW];
+  double rb[TWO ? ROW : 2];
+  double fx = 0.0, fy = 0.0, k0 = 0.0, k1 = 0.0;
+  if (active) {
+    load_row<ROW>(W.mf_rows + static_cast<int64_t>(blk_a) * ROW, ra);
+    if constexpr (TWO) {
+      if (has_b) load_row<ROW>(W.mf_rows + static_cast<int64_t>(blk_b) * ROW, rb);
+    }
+    if (CB != 9) {
+      const double2* ir = reinterpret_cast<const double2*>(intr_rows + intr);
+      const double2 f2 = __ldg(ir), k2 = __ldg(ir + 2);
+      fx = f2.x; fy = f2.y; k0 = k2.x; k1 = k2.y;
+    }
+  }
+  const bool is_pt = tid < tm.n_pts;
+  int seg_a = 0, seg_b = 0;
+  double ci0 = 0.0, ci1 = 0.0, ci2 = 0.0, ci3 = 0.0, ci4 = 0.0, ci5 = 0.0;
+  if (is_pt) {
+    const int64_t pt = tm.pt0 + tid;
+    const double* Xp = pts + 3 * pt;
+    const double* sp = W.sp + 3 * pt;
+    sX[0 * T + tid] = Xp[0];
+    sX[1 * T + tid] = Xp[1];
+    sX[2 * T + tid] = Xp[2];
+    sX[3 * T + tid] = sp[0];
+    sX[4 * T + tid] = sp[1];
+    sX[5 * T + tid] = sp[2];
+    seg_a = D.pt_first[pt] - obs0;
+    seg_b = D.pt_first[pt + 1] - obs0;
+    const double2* ci = reinterpret_cast<const double2*>(W.cinv + 6 * pt);
+    const double2 c01 = ci[0], c23 = ci[1], c45 = ci[2];
+    ci0 = c01.x; ci1 = c01.y; ci2 = c23.x; ci3 = c23.y; ci4 = c45.x; ci5 = c45.y;
+  }
+  for (int i = tid; i <= tm.n_parts; i += T) s_first[i] = D.part_first_rel[tm.g0 + t + i];
+  if (TWO)
+    for (int i = tid; i < tm.n_items; i += T) s_items[i] = D.items_mf[tm.item0 + i];
+  constexpr int KG = CB / 3;
+  const int n_work = tm.n_parts * KG;
+  int dst0 = 0;  // destination row of this thread's first reduce item, fetched early
+  if (tid < n_work) dst0 = D.part_dst[tm.g0 + tid / KG];
+  __syncthreads();
+  // ---- phase 1: geometry of this observation, u = F p, v = E^T u
+  // (xa, xb: the vector the rotation derivative crosses with: R X, or X itself in Ceres' small-angle branch)
+  const int lp = lplo >> 16, lo = lplo & 0xffffu;
+  double G[2][3], E[2][3], GA[2][3];
+  double xa[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0};
+  double u0 = 0.0, u1 = 0.0, uu = 0.0, vv = 0.0, rr = 0.0, dd = 0.0, ff = 0.0;
+  if (active) {
+    const double X[3] = {sX[0 * T + lp], sX[1 * T + lp], sX[2 * T + lp]};
+    const double s3[3] = {sX[3 * T + lp], sX[4 * T + lp], sX[5 * T + lp]};
+    double mid[3] = {X[0], X[1], X[2]};
+    double dmid[3] = {0.0, 0.0, 0.0};
+    if constexpr (TWO) {
+      if (has_b) {
+        double qb[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) qb[k] = rb[3 * k] * X[0] + rb[3 * k + 1] * X[1] + rb[3 * k + 2] * X[2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          mid[k] = qb[k] + rb[9 + k];
+          xb[k] = X[k] + rb[SEL] * (qb[k] - X[k]);
+        }
+        dmid[0] = rb[13] * xb[2] - rb[14] * xb[1] + rb[15];
+        dmid[1] = rb[14] * xb[0] - rb[12] * xb[2] + rb[16];
+        dmid[2] = rb[12] * xb[1] - rb[13] * xb[0] + rb[17];
+      }
+    }
+    double qa[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) qa[k] = ra[3 * k] * mid[0] + ra[3 * k + 1] * mid[1] + ra[3 * k + 2] * mid[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xa[k] = mid[k] + ra[SEL] * (qa[k] - mid[k]);
+    const double cam[3] = {qa[0] + ra[9], qa[1] + ra[10], qa[2] + ra[11]};
+    if (CB == 9) {
+      fx = fy = ra[12];
+      k0 = ra[13];
+      k1 = ra[14];
+    }
+    ff = fx;
+    project_G(fx, fy, k0, k1, cam, G, uu, vv, rr, dd);
+    constexpr int PO = CB == 9 ? 15 : 12;  // p~ offset in the row
+    double dc[3];
+    dc[0] = ra[PO + 1] * xa[2] - ra[PO + 2] * xa[1] + ra[PO + 3];
+    dc[1] = ra[PO + 2] * xa[0] - ra[PO + 0] * xa[2] + ra[PO + 4];
+    dc[2] = ra[PO + 0] * xa[1] - ra[PO + 1] * xa[0] + ra[PO + 5];
+    if (TWO) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) dc[k] += ra[3 * k] * dmid[0] + ra[3 * k + 1] * dmid[1] + ra[3 * k + 2] * dmid[2];
+    }
+    u0 = G[0][0] * dc[0] + G[0][1] * dc[1] + G[0][2] * dc[2];
+    u1 = G[1][0] * dc[0] + G[1][1] * dc[1] + G[1][2] * dc[2];
+    if (CB == 9) {
+      const double sI = dd * ra[21] + ff * rr * (ra[22] + rr * ra[23]);
+      u0 += uu * sI;
+      u1 += vv * sI;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) GA[i][j] = G[i][0] * ra[j] + G[i][1] * ra[3 + j] + G[i][2] * ra[6 + j];
+    if (TWO && has_b) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) E[i][j] = (GA[i][0] * rb[j] + GA[i][1] * rb[3 + j] + GA[i][2] * rb[6 + j]) * s3[j];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) E[i][j] = GA[i][j] * s3[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sC[j * S + lo] = E[0][j] * u0 + E[1][j] * u1;
+  }
+  __syncthreads();
+  // ---- phase 2: y = C^-1 sum_{o in point} v_o
+  if (is_pt) {
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = seg_a; i < seg_b; ++i) {
+      z0 += sC[0 * S + i];
+      z1 += sC[1 * S + i];
+      z2 += sC[2 * S + i];
+    }
+    sX[0 * T + tid] = ci0 * z0 + ci1 * z1 + ci2 * z2;
+    sX[1 * T + tid] = ci1 * z0 + ci3 * z1 + ci4 * z2;
+    sX[2 * T + tid] = ci2 * z0 + ci4 * z1 + ci5 * z2;
+  }
+  __syncthreads();
+  // ---- phase 3: w = u - E y, contributions F^T w in geometric coordinates
+  if (active) {
+    const double y0 = sX[0 * T + lp], y1 = sX[1 * T + lp], y2 = sX[2 * T + lp];
+    const double w0 = u0 - (E[0][0] * y0 + E[0][1] * y1 + E[0][2] * y2);
+    const double w1 = u1 - (E[1][0] * y0 + E[1][1] * y1 + E[1][2] * y2);
+    const double g0 = G[0][0] * w0 + G[1][0] * w1, g1 = G[0][1] * w0 + G[1][1] * w1, g2 = G[0][2] * w0 + G[1][2] * w1;
+    sC[0 * S + tid] = xa[1] * g2 - xa[2] * g1;
+    sC[1 * S + tid] = xa[2] * g0 - xa[0] * g2;
+    sC[2 * S + tid] = xa[0] * g1 - xa[1] * g0;
+    sC[3 * S + tid] = g0;
+    sC[4 * S + tid] = g1;
+    sC[5 * S + tid] = g2;
+    if (CB == 9) {
+      const double sw = uu * w0 + vv * w1;
+      const double ck0 = ff * rr * sw;
+      sC[6 * S + tid] = dd * sw;
+      sC[7 * S + tid] = ck0;
+      sC[8 * S + tid] = rr * ck0;
+    }
+    if (TWO) {
+      double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+      if (has_b) {
+        h0 = GA[0][0] * w0 + GA[1][0] * w1;
+        h1 = GA[0][1] * w0 + GA[1][1] * w1;
+        h2 = GA[0][2] * w0 + GA[1][2] * w1;
+      }
+      sC[(CB + 0) * S + tid] = xb[1] * h2 - xb[2] * h1;
+      sC[(CB + 1) * S + tid] = xb[2] * h0 - xb[0] * h2;
+      sC[(CB + 2) * S + tid] = xb[0] * h1 - xb[1] * h0;
+      sC[(CB + 3) * S + tid] = h0;
+      sC[(CB + 4) * S + tid] = h1;
+      sC[(CB + 5) * S + tid] = h2;
+    }
+  }
+  __syncthreads();
+  // ---- phase 4: tile-local reduce-by-camera over contiguous columns; one work item = (partial, 3 rows)
+  for (int wk = tid; wk < n_work; wk += T) {
+    const int lc = wk / KG, k0 = (wk - lc * KG) * 3;
+    const int i0 = s_first[lc], i1 = s_first[lc + 1];
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int i = i0; i < i1; ++i) {
+      int col = i, row = k0;
+      if (TWO) {
+        const unsigned int it = s_items[i];
+        col = it & 0x7fffu;
+        row = (it >> 15) * CB + k0;
+      }
+      a0 += sC[row * S + col];
+      a1 += sC[(row + 1) * S + col];
+      a2 += sC[(row + 2) * S + col];
+    }
+    const int dst = wk == tid ? dst0 : D.part_dst[tm.g0 + lc];
+    double* out = W.partials_q + static_cast<int64_t>(dst) * CB + k0;
+    out[0] = a0;
+    out[1] = a1;
+    out[2] = a2;
+  }
+}
+
+// Static part of the camera rows and the transform T, one thread per camera block; runs after
+// every Jacobian evaluation (parameters and Jacobi scales are fixed until the next one).
+template <int CB>
+__global__ void __launch_bounds__(128) k_mf_rows(DeviceProblem D, ParamSet P, WorkArrays W) {
+  constexpr int ROW = mf_row_len(CB);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= D.n_blocks) return;
+  const PoseRow pr = P.pose_rows[b];
+  double* row = W.mf_rows + static_cast<int64_t>(b) * ROW;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) row[k] = pr.R[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) row[9 + k] = pr.t[k];
+  if (CB == 9) {
+    const IntrRow ir = P.intr_rows[b];
+    row[12] = ir.fx;
+    row[13] = ir.k0;
+    row[14] = ir.k1;
+  }
+  // J_l = I + b [w]x + c [w]x^2, c = (theta - sin)/theta^3 (series near 0); identity in the small-angle branch
+  const double wx = pr.w[0], wy = pr.w[1], wz = pr.w[2];
+  const double th2 = wx * wx + wy * wy + wz * wz;
+  double bc = pr.b, cc;
+  row[ROW - 2] = (th2 > DBL_EPSILON) ? 1.0 : 0.0;  // 0: Ceres' small-angle branch, derivative -[X]x
+  row[ROW - 1] = 0.0;
+  if (!(th2 > DBL_EPSILON)) {
+    bc = 0.0;
+    cc = 0.0;
+  } else if (th2 < 1e-2) {
+    cc = 1.0 / 6.0 + th2 * (-1.0 / 120.0 + th2 * (1.0 / 5040.0 + th2 * (-1.0 / 362880.0 + th2 * (1.0 / 39916800.0))));
+  } else {
+    cc = (1.0 - pr.a) / th2;
+  }
+  double* Tm = W.mf_T + static_cast<int64_t>(b) * (9 + CB);
+  Tm[0] = 1.0 + cc * (wx * wx - th2);
+  Tm[1] = -bc * wz + cc * wx * wy;
+  Tm[2] = bc * wy + cc * wx * wz;
+  Tm[3] = bc * wz + cc * wx * wy;
+  Tm[4] = 1.0 + cc * (wy * wy - th2);
+  Tm[5] = -bc * wx + cc * wy * wz;
+  Tm[6] = -bc * wy + cc * wx * wz;
+  Tm[7] = bc * wx + cc * wy * wz;
+  Tm[8] = 1.0 + cc * (wz * wz - th2);
+#pragma unroll
+  for (int k = 0; k < CB; ++k) Tm[9 + k] = W.sc[static_cast<int64_t>(b) * CB + k] * (k < 6 ? pr.free_ : 1.0);
+}
+
+// PCG phase 3 of the matrix-free path, one thread per camera block: p = z + beta p (init: p as
+// left by k_pcg_init), then p~ = T p into the camera row.
+template <int CB>
+__global__ void __launch_bounds__(128) k_mf_direction(DeviceProblem D, WorkArrays W, int init) {
+  if (W.pcg_state[1]) return;
+  constexpr int ROW = mf_row_len(CB), PO = CB == 9 ? 15 : 12;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= D.n_blocks) return;
+  const double beta = init ? 0.0 : W.pcg_scal[3];
+  const double* Tm = W.mf_T + static_cast<int64_t>(b) * (9 + CB);
+  double ps[CB];
+#pragma unroll
+  for (int k = 0; k < CB; ++k) {
+    const int64_t i = static_cast<int64_t>(b) * CB + k;
+    double p = W.p[i];
+    if (!init) {
+      p = W.z[i] + beta * p;
+      W.p[i] = p;
+    }
+    ps[k] = p * Tm[9 + k];
+  }
+  double* row = W.mf_rows + static_cast<int64_t>(b) * ROW + PO;
+  row[0] = Tm[0] * ps[0] + Tm[1] * ps[1] + Tm[2] * ps[2];
+  row[1] = Tm[3] * ps[0] + Tm[4] * ps[1] + Tm[5] * ps[2];
+  row[2] = Tm[6] * ps[0] + Tm[7] * ps[1] + Tm[8] * ps[2];
+#pragma unroll
+  for (int k = 3; k < CB; ++k) row[k] = ps[k];
 }
 
 // --------------------------------------------------------------------------- K6 PCG
@@ -1173,14 +1539,76 @@ void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t 
     launch_spmv_tile_t<9, false>(D, W, st);
 }
 
-void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, int n_split, cudaStream_t st) {
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, int n_split, int mf, cudaStream_t st) {
   if (D.n_blocks == 0) return;
   const dim3 grid(D.n_blocks, n_split > 1 ? n_split : 1);
   if (n_split > 1) fuse_dot = 0;
-  if (D.cb == 6)
-    k_partials_to_q<6><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
+  if (D.cb == 6) {
+    if (mf) k_partials_to_q<6, true><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
+    else k_partials_to_q<6, false><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
+  } else {
+    if (mf) k_partials_to_q<9, true><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
+    else k_partials_to_q<9, false><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
+  }
+}
+
+void launch_mf_rows(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
+  if (D.cb == 0 || D.n_blocks == 0) return;
+  const int grid = (D.n_blocks + 127) / 128;
+  if (D.cb == 6) k_mf_rows<6><<<grid, 128, 0, st>>>(D, P, W);
+  else k_mf_rows<9><<<grid, 128, 0, st>>>(D, P, W);
+}
+
+void launch_mf_direction(const DeviceProblem& D, const WorkArrays& W, int init, cudaStream_t st) {
+  if (D.cb == 0 || D.n_blocks == 0) return;
+  const int grid = (D.n_blocks + 127) / 128;
+  if (D.cb == 6) k_mf_direction<6><<<grid, 128, 0, st>>>(D, W, init);
+  else k_mf_direction<9><<<grid, 128, 0, st>>>(D, W, init);
+}
+
+template <int CB, bool TWO, int T, int MINB>
+static void launch_spmv_mf_tt(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
+  static bool configured = false;
+  constexpr size_t smem = MfSmem<CB, TWO, T>::kBytes;
+  static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
+  if (!configured) {
+    cudaFuncSetAttribute(k_spmv_mf<CB, TWO, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    configured = true;
+  }
+  k_spmv_mf<CB, TWO, T, MINB><<<D.n_tiles, T, smem, st>>>(D, W, P.pts, P.intr_rows);
+}
+// resident CTAs per SM requested from the register allocator for 256-thread tiles (tuning knob DBA_MF_MINB)
+static int mf_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("DBA_MF_MINB");
+    v = e ? std::atoi(e) : 3;
+    if (v < 2 || v > 4) v = 3;
+  }
+  return v;
+}
+template <int CB, bool TWO>
+static void launch_spmv_mf_t(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
+  if (D.tile == 256) {
+    const int mb = mf_minb();
+    if (mb == 2) launch_spmv_mf_tt<CB, TWO, 256, 2>(D, P, W, st);
+    else if (mb == 3) launch_spmv_mf_tt<CB, TWO, 256, 3>(D, P, W, st);
+    else launch_spmv_mf_tt<CB, TWO, 256, 4>(D, P, W, st);
+  } else if (D.tile == 512) {
+    launch_spmv_mf_tt<CB, TWO, 512, 1>(D, P, W, st);
+  } else if constexpr (!TWO) {
+    launch_spmv_mf_tt<CB, TWO, 1024, 1>(D, P, W, st);
+  }
+}
+
+void launch_spmv_mf(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
+  if (D.n_tiles == 0) return;
+  if (D.cb == 6 && !D.two)
+    launch_spmv_mf_t<6, false>(D, P, W, st);
+  else if (D.cb == 6)
+    launch_spmv_mf_t<6, true>(D, P, W, st);
   else
-    k_partials_to_q<9><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
+    launch_spmv_mf_t<9, false>(D, P, W, st);
 }
 
 // q = sum of the slices (multi-GPU with n_split > 1: input of the allreduce)

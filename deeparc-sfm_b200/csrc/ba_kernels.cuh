@@ -64,7 +64,17 @@ struct DeviceProblem {
   const int* cam_part_idx;          // [n_partials]
   int n_partials;
   double2* J;               // planes
+  // matrix-free implicit Schur product (k_spmv_mf): observations of a tile re-ordered by camera
+  // block ("columns"), so a warp touches few distinct camera rows and the reduce-by-camera runs
+  // over contiguous columns
+  const void* mf_cols;              // [n_tiles][tile] (padded, block a = -1) per column: CB = 9: int2 (block a, lp << 16 | lo);
+                                    //   else int4 (block a, block b or -1, lp << 16 | lo, intrinsic);
+                                    //   lo = point-sorted position in the tile, lp = tile-local point
+  const unsigned short* items_mf;   // two-pose problems: `items` with lo replaced by the column
+  const int* part_dst;              // [n_partials] row of partial g in the camera-grouped partial buffer
 };
+
+__host__ __device__ constexpr int mf_row_len(int cb) { return cb == 9 ? 26 : 20; }
 
 struct ParamSet {
   double* pts;        // [n_pts_local][3]
@@ -102,6 +112,13 @@ struct WorkArrays {
   double* pcg_scal;  // [4] rz, rz0, p.q, beta
   double* q_split;     // [n_split][n_blocks * cb] slices of q when the per-camera sum is split
   double* partials_q;  // [n_partials][cb] tile-local partial products of the implicit Schur product
+  // matrix-free product: one row per camera block, rebuilt after every Jacobian evaluation
+  //   CB = 6: R[9] t[3] p~[6] sel 0      CB = 9: R[9] t[3] f k0 k1 p~[9] sel 0
+  //   (sel = 0 in Ceres' small-angle branch of AngleAxisRotatePoint, else 1)
+  // p~ = T p is the PCG direction in "geometric" coordinates, T = blockdiag(J_l(w), I, I) diag(sc * free)
+  // (J_l = left Jacobian of SO(3): d(R X) = (J_l dw) x (R X)); rewritten every PCG iteration
+  double* mf_rows;   // [n_blocks][mf_row_len(cb)]
+  double* mf_T;      // [n_blocks][9 + cb]  J_l row-major, then sc * free
   double* vec_partials;    // per-CTA partials of the PCG vector kernels
   unsigned int* counters;  // [4] "last block" arrival counters
 };
@@ -147,7 +164,11 @@ void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t s
 // implicit Schur complement product: one pass over point tiles -> W.partials_q, then the
 // per-camera fixed-order sum -> W.q
 void launch_spmv_tile(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
-void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, int n_split, cudaStream_t st);
+void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_dot, int n_split, int mf, cudaStream_t st);
+// matrix-free variant: camera rows (static part) after a Jacobian evaluation; p (+)= ..., p~ = T p; the product
+void launch_mf_rows(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st);
+void launch_mf_direction(const DeviceProblem& D, const WorkArrays& W, int init, cudaStream_t st);
+void launch_spmv_mf(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st);
 // PCG vector phases: q += D_c^2 p and p.q; the x/r/z update with r.z; the new direction
 void launch_fold_q(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st);
 void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st);

@@ -145,6 +145,32 @@ def test_lm_bal_9dof_matches_oracle(engine, oracle):
     _compare_solve(engine, oracle, PROBLEMS["bal"], n_iter=6)
 
 
+@pytest.mark.parametrize("name", ["rig", "bal", "plain", "nf2_nd2", "small_angle"])
+def test_matrix_free_product_matches_plane_product(engine, name, monkeypatch):
+    """The default implicit Schur product recomputes the Jacobian per observation (k_spmv_mf);
+    DBA_SPMV=planes selects the product that reads the materialised Jacobian planes.  Same
+    operator up to rounding: fixed-iteration PCG traces agree far inside the parity budget."""
+    p = PROBLEMS[name]
+    kw = dict(max_num_iterations=4, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+              linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=0.0, pcg_max_iterations=12)
+    runs = {}
+    for mode in ("planes", "mf"):
+        if mode == "planes":
+            monkeypatch.setenv("DBA_SPMV", "planes")
+        else:
+            monkeypatch.delenv("DBA_SPMV", raising=False)
+        engine.problem_set(p)
+        s = engine.solve(capi.make_options(**kw))
+        runs[mode] = (s, engine.params_get())
+    sa, xa = runs["planes"]
+    sb, xb = runs["mf"]
+    assert np.array_equal(sa.trace("step_is_successful"), sb.trace("step_is_successful"))
+    np.testing.assert_allclose(sb.trace("cost"), sa.trace("cost"), rtol=1e-9)
+    for k in ("pts", "ext_rot", "ext_trans", "intr_focal", "intr_dist"):
+        scale = max(np.max(np.abs(xa[k])), 1e-300)
+        assert np.max(np.abs(xa[k] - xb[k])) <= 1e-8 * scale, k
+
+
 @pytest.mark.parametrize("kind", ["rig_512", "bal_1024"])
 def test_long_tracks_match_oracle(engine, oracle, kind):
     """Points seen by more than 256 cameras select the 512- / 1024-observation tile kernels."""
