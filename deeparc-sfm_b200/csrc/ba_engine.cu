@@ -108,8 +108,7 @@ struct dba_handle {
   // matrix-free implicit Schur product (default); DBA_SPMV=planes selects the product that reads
   // the materialised Jacobian planes (kept for A/B measurements)
   int mf = 1;
-  DevBuf<int> d_mf_cols, d_part_dst;
-  DevBuf<unsigned short> d_items_mf;
+  DevBuf<int> d_mf_cols, d_part_dst, d_items_mf, d_part_first;
   DevBuf<double> d_mf_rows, d_mf_T;
   DevBuf<int2> d_obs_ip;
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
@@ -769,7 +768,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     int cur_obs = 0, t_pt0 = 0;
     for (int i = 0; i < n_pts; ++i) {
       const int len = static_cast<int>(pt_count[pt_lo + i + 1] - pt_count[pt_lo + i]);
-      if (cur_obs + len > tile_cap) {
+      if (cur_obs + len > tile_cap || i - t_pt0 >= max_tile_points(tile_cap)) {  // whole points, <= tile_cap observations, <= max_tile_points
         TileMeta m{};
         m.obs0 = static_cast<int>(pt_count[pt_lo + t_pt0] - obs_lo);
         m.n_obs = cur_obs;
@@ -811,7 +810,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   want(n_ent_max * sizeof(int));        // cam_part_idx
   want(n_ent_max * sizeof(int));        // part_dst
   want(cb ? (static_cast<size_t>(n_tiles) * tile_cap) * sizeof(int4) : 0);  // mf_cols (padded per tile)
-  want((two && cb) ? n_ent_max * sizeof(unsigned short) : 0);  // items_mf
+  want((two && cb) ? n_ent_max * sizeof(int) : 0);  // items_mf
+  want((n_ent_max + n_tiles + 1) * sizeof(int));    // part_first
   want((n_ent_max / 1024 + n_ext + 2) * sizeof(int4));  // cam_chunks
   want((n_ext + 1) * sizeof(int) * 3);
   PinnedArena& A = arena_of(h);
@@ -905,7 +905,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   const int mf_w = cb == 9 ? 2 : 4;  // ints per column record
   const size_t n_cols = cb ? static_cast<size_t>(n_tiles) * tile_cap : 0;  // padded: tile t owns [t * tile_cap, (t + 1) * tile_cap)
   int* s_mf_cols = A.take<int>(std::max<size_t>(n_cols * mf_w, 1));
-  unsigned short* s_items_mf = A.take<unsigned short>((two && cb) ? static_cast<size_t>(std::max<int64_t>(n_entries, 1)) : 1);
+  int* s_items_mf = A.take<int>((two && cb) ? static_cast<size_t>(std::max<int64_t>(n_entries, 1)) : 1);
+  int* s_part_first = A.take<int>(static_cast<size_t>(n_entries + n_tiles + 1));
   int n_partials = 0;
   std::vector<int> part_block;
   {
@@ -972,7 +973,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
         start.assign(locals.size() + 1, 0);
         for (size_t lc = 0; lc < locals.size(); ++lc) start[lc + 1] = start[lc] + count[lc];
         unsigned short* rel = s_part_first_rel + m.g0 + t;
-        for (size_t lc = 0; lc <= locals.size(); ++lc) rel[lc] = static_cast<unsigned short>(start[lc]);
+        for (size_t lc = 0; lc <= locals.size(); ++lc) {
+          rel[lc] = static_cast<unsigned short>(start[lc]);
+          s_part_first[m.g0 + t + lc] = start[lc];
+        }
         for (size_t lc = 0; lc < locals.size(); ++lc) part_block[m.g0 + lc] = locals[lc];
         for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) {
           const int lo = k - m.obs0;
@@ -1012,7 +1016,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
         if (two)
           for (int i = 0; i < m.n_items; ++i) {
             const unsigned short it = s_items[m.item0 + i];
-            s_items_mf[m.item0 + i] = static_cast<unsigned short>(col_of[it & 0x7fff] | (it & 0x8000));
+            s_items_mf[m.item0 + i] = col_of[it & 0x7fff] | (it & 0x8000);
           }
       }
     }
@@ -1062,6 +1066,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_part_dst, n_partials));
   CU(h, ensure(h->d_mf_cols, std::max<size_t>(n_cols * mf_w, 1)));
   CU(h, ensure(h->d_items_mf, (two && cb) ? n_entries : 1));
+  CU(h, ensure(h->d_part_first, n_entries + n_tiles + 1));
   CU(h, ensure(h->d_mf_rows, static_cast<size_t>(n_ext) * mf_row_len(cb)));
   CU(h, ensure(h->d_mf_T, static_cast<size_t>(n_ext) * (9 + cb)));
   {
@@ -1138,7 +1143,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_cam_part_idx.p, s_cam_part_idx, n_partials * sizeof(int)));
   CU(h, up(h->d_part_dst.p, s_part_dst, n_partials * sizeof(int)));
   if (cb) CU(h, up(h->d_mf_cols.p, s_mf_cols, n_cols * mf_w * sizeof(int)));
-  if (two && cb) CU(h, up(h->d_items_mf.p, s_items_mf, n_entries * sizeof(unsigned short)));
+  if (two && cb) CU(h, up(h->d_items_mf.p, s_items_mf, n_entries * sizeof(int)));
+  if (cb) CU(h, up(h->d_part_first.p, s_part_first, (n_entries + n_tiles + 1) * sizeof(int)));
   std::vector<uint8_t> ext_const(std::max(n_ext, 1), 0);
   h->any_const = false;
   if (p->ext_const)
@@ -1193,6 +1199,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.mf_cols = h->d_mf_cols.p;
   D.items_mf = h->d_items_mf.p;
   D.part_dst = h->d_part_dst.p;
+  D.part_first = h->d_part_first.p;
   for (int s = 0; s < 2; ++s) {
     ParamSet& P = h->P[s];
     P.pts = h->d_pts[s].p;

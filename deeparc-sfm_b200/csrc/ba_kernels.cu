@@ -807,230 +807,301 @@ __device__ __forceinline__ void project_G(double fx, double fy, double k0, doubl
   G[1][2] = -(r1u * uu + r1v * vv) * iz;
 }
 
+// cp.async (LDGSTS) helpers: per-thread 4/8/16-byte asynchronous copies global -> shared
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Shared-memory plan of k_spmv_mf.  Two stage buffers (tile k computes while tile k+1 lands):
+//   cols [T] column records | ptd [12][PS] X, sp, C^-1 of the tile's points (<= kMaxTilePoints by construction)
+//   | seg [PM+1] first observation of each point | first [MP+1] partial -> first column/item
+//   | dst [MP] partial -> row of the partial buffer | items [2T] (two-pose only)
+// and, single: sY [3][PS] per-point y', sV [3][S] v = E^T u in point-sorted order, sC [NC][S]
+// contributions in column order.
 template <int CB, bool TWO, int T>
 struct MfSmem {
   static constexpr int NC = CB + (TWO ? 6 : 0);
   static constexpr int S = T + 1;
-  static constexpr int kMaxParts = TWO ? 2 * T : T;
-  static constexpr size_t kDoubles = 6 * T + static_cast<size_t>(NC) * S;
-  static constexpr size_t kBytes = kDoubles * sizeof(double) + sizeof(unsigned short) * (kMaxParts + 2 + (TWO ? 2 * T : 0)) + 16;
+  static constexpr int PM = max_tile_points(T);  // points per tile (upload guarantees it)
+  static constexpr int PS = PM + 1;
+  static constexpr int MP = TWO ? 2 * T : T;  // partials per tile
+  static constexpr int kColBytes = CB == 9 ? 8 : 16;
+  static constexpr size_t oCols = 0;
+  static constexpr size_t oPtd = oCols + static_cast<size_t>(T) * kColBytes;
+  static constexpr size_t oSeg = oPtd + 12 * PS * sizeof(double);
+  static constexpr size_t oFirst = oSeg + ((PM + 1 + 3) / 4) * 4 * sizeof(int);
+  static constexpr size_t oDst = oFirst + ((MP + 1 + 3) / 4) * 4 * sizeof(int);
+  static constexpr size_t oItems = oDst + static_cast<size_t>(MP) * sizeof(int);
+  static constexpr size_t kStage = ((oItems + (TWO ? 2 * T * sizeof(int) : 0)) + 15) / 16 * 16;
+  static constexpr size_t oY = 2 * kStage;                       // [3][PS] y' = sp * C^-1 (sp * sum v) per point
+  static constexpr size_t oV = oY + 3 * PS * sizeof(double);
+  static constexpr size_t oC = oV + 3 * S * sizeof(double);
+  static constexpr size_t kBytes = oC + static_cast<size_t>(NC) * S * sizeof(double);
 };
 
+// Persistent CTAs (grid = resident CTAs), each walking tiles blockIdx.x, += gridDim.x.  Everything a
+// tile needs from HBM is fetched one tile ahead with cp.async into the other stage buffer, so the
+// only exposed latency per tile is the L1/L2-resident camera-row load.
 template <int CB, bool TWO, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays W, const double* __restrict__ pts,
                                                       const IntrRow* __restrict__ intr_rows) {
   if (W.pcg_state[1]) return;
   using L = MfSmem<CB, TWO, T>;
-  constexpr int NC = L::NC, S = L::S, ROW = mf_row_len(CB), SEL = ROW - 2;
+  constexpr int S = L::S, PS = L::PS, ROW = mf_row_len(CB), SEL = ROW - 2, KG = CB / 3;
   extern __shared__ __align__(16) unsigned char smem_mf[];
-  double* sX = reinterpret_cast<double*>(smem_mf);  // [6][T]: X, sp of the tile's points; rows 0..2 become y
-  double* sC = sX + 6 * T;                          // [NC][S] contributions; rows 0..2 first hold v = E^T u
-  unsigned short* s_first = reinterpret_cast<unsigned short*>(sC + NC * S);
-  unsigned short* s_items = s_first + L::kMaxParts + 2;
-  const int t = blockIdx.x, tid = threadIdx.x;
-  // ---- phase 0: this thread's column (padded per-tile layout: no dependence on the tile record)
-  // and, as soon as it arrives, its camera rows; meanwhile stage the tile's points and incidence
-  int blk_a = -1, blk_b = -1, intr = 0;
-  unsigned int lplo = 0;
-  if (CB == 9) {
-    const int2 c = reinterpret_cast<const int2*>(D.mf_cols)[static_cast<int64_t>(t) * T + tid];
-    blk_a = c.x;
-    lplo = static_cast<unsigned int>(c.y);
-  } else {
-    const int4 c = reinterpret_cast<const int4*>(D.mf_cols)[static_cast<int64_t>(t) * T + tid];
-    blk_a = c.x;
-    blk_b = c.y;
-    lplo = static_cast<unsigned int>(c.z);
-    intr = c.w;
-  }
-  const TileMeta tm = D.tile_meta[t];
-  const int obs0 = tm.obs0;
-  const bool active = blk_a >= 0;
-  const bool has_b = TWO && blk_b >= 0;
-  double ra[ROW];
-  double rb[TWO ? ROW : 2];
-  double fx = 0.0, fy = 0.0, k0 = 0.0, k1 = 0.0;
-  if (active) {
-    load_row<ROW>(W.mf_rows + static_cast<int64_t>(blk_a) * ROW, ra);
-    if constexpr (TWO) {
-      if (has_b) load_row<ROW>(W.mf_rows + static_cast<int64_t>(blk_b) * ROW, rb);
-    }
-    if (CB != 9) {
-      const double2* ir = reinterpret_cast<const double2*>(intr_rows + intr);
-      const double2 f2 = __ldg(ir), k2 = __ldg(ir + 2);
-      fx = f2.x; fy = f2.y; k0 = k2.x; k1 = k2.y;
-    }
-  }
-  const bool is_pt = tid < tm.n_pts;
-  int seg_a = 0, seg_b = 0;
-  double ci0 = 0.0, ci1 = 0.0, ci2 = 0.0, ci3 = 0.0, ci4 = 0.0, ci5 = 0.0;
-  if (is_pt) {
-    const int64_t pt = tm.pt0 + tid;
-    const double* Xp = pts + 3 * pt;
-    const double* sp = W.sp + 3 * pt;
-    sX[0 * T + tid] = Xp[0];
-    sX[1 * T + tid] = Xp[1];
-    sX[2 * T + tid] = Xp[2];
-    sX[3 * T + tid] = sp[0];
-    sX[4 * T + tid] = sp[1];
-    sX[5 * T + tid] = sp[2];
-    seg_a = D.pt_first[pt] - obs0;
-    seg_b = D.pt_first[pt + 1] - obs0;
-    const double2* ci = reinterpret_cast<const double2*>(W.cinv + 6 * pt);
-    const double2 c01 = ci[0], c23 = ci[1], c45 = ci[2];
-    ci0 = c01.x; ci1 = c01.y; ci2 = c23.x; ci3 = c23.y; ci4 = c45.x; ci5 = c45.y;
-  }
-  for (int i = tid; i <= tm.n_parts; i += T) s_first[i] = D.part_first_rel[tm.g0 + t + i];
-  if (TWO)
-    for (int i = tid; i < tm.n_items; i += T) s_items[i] = D.items_mf[tm.item0 + i];
-  constexpr int KG = CB / 3;
-  const int n_work = tm.n_parts * KG;
-  int dst0 = 0;  // destination row of this thread's first reduce item, fetched early
-  if (tid < n_work) dst0 = D.part_dst[tm.g0 + tid / KG];
-  __syncthreads();
-  // ---- phase 1: geometry of this observation, u = F p, v = E^T u
-  // (xa, xb: the vector the rotation derivative crosses with: R X, or X itself in Ceres' small-angle branch)
-  const int lp = lplo >> 16, lo = lplo & 0xffffu;
-  double G[2][3], E[2][3], GA[2][3];
-  double xa[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0};
-  double u0 = 0.0, u1 = 0.0, uu = 0.0, vv = 0.0, rr = 0.0, dd = 0.0, ff = 0.0;
-  if (active) {
-    const double X[3] = {sX[0 * T + lp], sX[1 * T + lp], sX[2 * T + lp]};
-    const double s3[3] = {sX[3 * T + lp], sX[4 * T + lp], sX[5 * T + lp]};
-    double mid[3] = {X[0], X[1], X[2]};
-    double dmid[3] = {0.0, 0.0, 0.0};
-    if constexpr (TWO) {
-      if (has_b) {
-        double qb[3];
+  double* sY = reinterpret_cast<double*>(smem_mf + L::oY);
+  double* sV = reinterpret_cast<double*>(smem_mf + L::oV);
+  double* sC = reinterpret_cast<double*>(smem_mf + L::oC);
+  const int tid = threadIdx.x;
+
+  // stage `buf` <- tile t (record m): every thread issues its share of the copies
+  auto issue = [&](int buf, int t, const TileMeta& m) {
+    unsigned char* st = smem_mf + buf * L::kStage;
+    if (CB == 9)
+      cp_async8(st + L::oCols + tid * 8, reinterpret_cast<const int2*>(D.mf_cols) + static_cast<int64_t>(t) * T + tid);
+    else
+      cp_async16(st + L::oCols + tid * 16, reinterpret_cast<const int4*>(D.mf_cols) + static_cast<int64_t>(t) * T + tid);
+    double* ptd = reinterpret_cast<double*>(st + L::oPtd);
+    int* seg = reinterpret_cast<int*>(st + L::oSeg);
+    if (tid < m.n_pts) {
+      const int64_t pt = m.pt0 + tid;
+      const double* Xp = pts + 3 * pt;
+      const double* sp = W.sp + 3 * pt;
+      const double* ci = W.cinv + 6 * pt;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) qb[k] = rb[3 * k] * X[0] + rb[3 * k + 1] * X[1] + rb[3 * k + 2] * X[2];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          mid[k] = qb[k] + rb[9 + k];
-          xb[k] = X[k] + rb[SEL] * (qb[k] - X[k]);
-        }
-        dmid[0] = rb[13] * xb[2] - rb[14] * xb[1] + rb[15];
-        dmid[1] = rb[14] * xb[0] - rb[12] * xb[2] + rb[16];
-        dmid[2] = rb[12] * xb[1] - rb[13] * xb[0] + rb[17];
+      for (int k = 0; k < 3; ++k) {
+        cp_async8(ptd + k * PS + tid, Xp + k);
+        cp_async8(ptd + (3 + k) * PS + tid, sp + k);
       }
-    }
-    double qa[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) qa[k] = ra[3 * k] * mid[0] + ra[3 * k + 1] * mid[1] + ra[3 * k + 2] * mid[2];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) xa[k] = mid[k] + ra[SEL] * (qa[k] - mid[k]);
-    const double cam[3] = {qa[0] + ra[9], qa[1] + ra[10], qa[2] + ra[11]};
-    if (CB == 9) {
-      fx = fy = ra[12];
-      k0 = ra[13];
-      k1 = ra[14];
+      for (int k = 0; k < 6; ++k) cp_async8(ptd + (6 + k) * PS + tid, ci + k);
     }
-    ff = fx;
-    project_G(fx, fy, k0, k1, cam, G, uu, vv, rr, dd);
-    constexpr int PO = CB == 9 ? 15 : 12;  // p~ offset in the row
-    double dc[3];
-    dc[0] = ra[PO + 1] * xa[2] - ra[PO + 2] * xa[1] + ra[PO + 3];
-    dc[1] = ra[PO + 2] * xa[0] - ra[PO + 0] * xa[2] + ra[PO + 4];
-    dc[2] = ra[PO + 0] * xa[1] - ra[PO + 1] * xa[0] + ra[PO + 5];
+    if (tid <= m.n_pts) cp_async4(seg + tid, D.pt_first + m.pt0 + tid);
+    int* first = reinterpret_cast<int*>(st + L::oFirst);
+    int* dst = reinterpret_cast<int*>(st + L::oDst);
+    for (int i = tid; i <= m.n_parts; i += T) cp_async4(first + i, D.part_first + m.g0 + t + i);
+    for (int i = tid; i < m.n_parts; i += T) cp_async4(dst + i, D.part_dst + m.g0 + i);
     if (TWO) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) dc[k] += ra[3 * k] * dmid[0] + ra[3 * k + 1] * dmid[1] + ra[3 * k + 2] * dmid[2];
+      int* items = reinterpret_cast<int*>(st + L::oItems);
+      for (int i = tid; i < m.n_items; i += T) cp_async4(items + i, D.items_mf + m.item0 + i);
     }
-    u0 = G[0][0] * dc[0] + G[0][1] * dc[1] + G[0][2] * dc[2];
-    u1 = G[1][0] * dc[0] + G[1][1] * dc[1] + G[1][2] * dc[2];
+  };
+
+  int t = blockIdx.x;
+  if (t >= D.n_tiles) return;
+  TileMeta tm = D.tile_meta[t];
+  issue(0, t, tm);
+  cp_async_commit();
+  int t_next = t + gridDim.x;
+  TileMeta tm_next = tm;
+  if (t_next < D.n_tiles) tm_next = D.tile_meta[t_next];
+
+  for (int k = 0;; ++k) {
+    const int buf = k & 1;
+    cp_async_wait_all();
+    __syncthreads();  // [A] tile k landed for every thread; everyone is done with tile k-1
+    const bool more = t_next < D.n_tiles;
+    if (more) issue(buf ^ 1, t_next, tm_next);
+    cp_async_commit();
+    const TileMeta tm_after = (t_next + static_cast<int>(gridDim.x) < D.n_tiles) ? D.tile_meta[t_next + gridDim.x] : tm_next;
+
+    unsigned char* st = smem_mf + buf * L::kStage;
+    const double* ptd = reinterpret_cast<const double*>(st + L::oPtd);
+    const int* seg = reinterpret_cast<const int*>(st + L::oSeg);
+    const int* s_first = reinterpret_cast<const int*>(st + L::oFirst);
+    const int* s_dst = reinterpret_cast<const int*>(st + L::oDst);
+    const int* s_items = reinterpret_cast<const int*>(st + L::oItems);
+    int blk_a, blk_b = -1, intr = 0;
+    unsigned int lplo;
     if (CB == 9) {
-      const double sI = dd * ra[21] + ff * rr * (ra[22] + rr * ra[23]);
-      u0 += uu * sI;
-      u1 += vv * sI;
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) GA[i][j] = G[i][0] * ra[j] + G[i][1] * ra[3 + j] + G[i][2] * ra[6 + j];
-    if (TWO && has_b) {
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) E[i][j] = (GA[i][0] * rb[j] + GA[i][1] * rb[3 + j] + GA[i][2] * rb[6 + j]) * s3[j];
+      const int2 c = reinterpret_cast<const int2*>(st + L::oCols)[tid];
+      blk_a = c.x;
+      lplo = static_cast<unsigned int>(c.y);
     } else {
+      const int4 c = reinterpret_cast<const int4*>(st + L::oCols)[tid];
+      blk_a = c.x;
+      blk_b = c.y;
+      lplo = static_cast<unsigned int>(c.z);
+      intr = c.w;
+    }
+    const bool active = blk_a >= 0;
+    const bool has_b = TWO && blk_b >= 0;
+    const int lp = lplo >> 16, lo = lplo & 0xffffu;
+    // ---- phase 1: geometry of this observation, u = F p, v = E^T u
+    // (xa, xb: the vector the rotation derivative crosses with: R X, or X itself in Ceres' small-angle branch)
+    double G[2][3], E[2][3], GA[2][3];
+    double xa[3] = {0.0, 0.0, 0.0}, xb[3] = {0.0, 0.0, 0.0};
+    double u0 = 0.0, u1 = 0.0, uu = 0.0, vv = 0.0, rr = 0.0, dd = 0.0, ff = 0.0;
+    if (active) {
+      double ra[ROW];
+      double rb[TWO ? ROW : 2];
+      double fx = 0.0, fy = 0.0, k0 = 0.0, k1 = 0.0;
+      load_row<ROW>(W.mf_rows + static_cast<int64_t>(blk_a) * ROW, ra);
+      if constexpr (TWO) {
+        if (has_b) load_row<ROW>(W.mf_rows + static_cast<int64_t>(blk_b) * ROW, rb);
+      }
+      if (CB != 9) {
+        const double2* ir = reinterpret_cast<const double2*>(intr_rows + intr);
+        const double2 f2 = __ldg(ir), k2 = __ldg(ir + 2);
+        fx = f2.x; fy = f2.y; k0 = k2.x; k1 = k2.y;
+      }
+      const double X[3] = {ptd[0 * PS + lp], ptd[1 * PS + lp], ptd[2 * PS + lp]};
+      double mid[3] = {X[0], X[1], X[2]};
+      double dmid[3] = {0.0, 0.0, 0.0};
+      if constexpr (TWO) {
+        if (has_b) {
+          double qb[3];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) qb[k] = rb[3 * k] * X[0] + rb[3 * k + 1] * X[1] + rb[3 * k + 2] * X[2];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            mid[k] = qb[k] + rb[9 + k];
+            xb[k] = X[k] + rb[SEL] * (qb[k] - X[k]);
+          }
+          dmid[0] = rb[13] * xb[2] - rb[14] * xb[1] + rb[15];
+          dmid[1] = rb[14] * xb[0] - rb[12] * xb[2] + rb[16];
+          dmid[2] = rb[12] * xb[1] - rb[13] * xb[0] + rb[17];
+        }
+      }
+      double qa[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) qa[k] = ra[3 * k] * mid[0] + ra[3 * k + 1] * mid[1] + ra[3 * k + 2] * mid[2];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xa[k] = mid[k] + ra[SEL] * (qa[k] - mid[k]);
+      const double cam[3] = {qa[0] + ra[9], qa[1] + ra[10], qa[2] + ra[11]};
+      if (CB == 9) {
+        fx = fy = ra[12];
+        k0 = ra[13];
+        k1 = ra[14];
+      }
+      ff = fx;
+      project_G(fx, fy, k0, k1, cam, G, uu, vv, rr, dd);
+      constexpr int PO = CB == 9 ? 15 : 12;  // p~ offset in the row
+      double dc[3];
+      dc[0] = ra[PO + 1] * xa[2] - ra[PO + 2] * xa[1] + ra[PO + 3];
+      dc[1] = ra[PO + 2] * xa[0] - ra[PO + 0] * xa[2] + ra[PO + 4];
+      dc[2] = ra[PO + 0] * xa[1] - ra[PO + 1] * xa[0] + ra[PO + 5];
+      if (TWO) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) dc[k] += ra[3 * k] * dmid[0] + ra[3 * k + 1] * dmid[1] + ra[3 * k + 2] * dmid[2];
+      }
+      u0 = G[0][0] * dc[0] + G[0][1] * dc[1] + G[0][2] * dc[2];
+      u1 = G[1][0] * dc[0] + G[1][1] * dc[1] + G[1][2] * dc[2];
+      if (CB == 9) {
+        const double sI = dd * ra[21] + ff * rr * (ra[22] + rr * ra[23]);
+        u0 += uu * sI;
+        u1 += vv * sI;
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) E[i][j] = GA[i][j] * s3[j];
-    }
+        for (int j = 0; j < 3; ++j) GA[i][j] = G[i][0] * ra[j] + G[i][1] * ra[3 + j] + G[i][2] * ra[6 + j];
+      if (TWO && has_b) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) sC[j * S + lo] = E[0][j] * u0 + E[1][j] * u1;
-  }
-  __syncthreads();
-  // ---- phase 2: y = C^-1 sum_{o in point} v_o
-  if (is_pt) {
-    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
-    for (int i = seg_a; i < seg_b; ++i) {
-      z0 += sC[0 * S + i];
-      z1 += sC[1 * S + i];
-      z2 += sC[2 * S + i];
-    }
-    sX[0 * T + tid] = ci0 * z0 + ci1 * z1 + ci2 * z2;
-    sX[1 * T + tid] = ci1 * z0 + ci3 * z1 + ci4 * z2;
-    sX[2 * T + tid] = ci2 * z0 + ci4 * z1 + ci5 * z2;
-  }
-  __syncthreads();
-  // ---- phase 3: w = u - E y, contributions F^T w in geometric coordinates
-  if (active) {
-    const double y0 = sX[0 * T + lp], y1 = sX[1 * T + lp], y2 = sX[2 * T + lp];
-    const double w0 = u0 - (E[0][0] * y0 + E[0][1] * y1 + E[0][2] * y2);
-    const double w1 = u1 - (E[1][0] * y0 + E[1][1] * y1 + E[1][2] * y2);
-    const double g0 = G[0][0] * w0 + G[1][0] * w1, g1 = G[0][1] * w0 + G[1][1] * w1, g2 = G[0][2] * w0 + G[1][2] * w1;
-    sC[0 * S + tid] = xa[1] * g2 - xa[2] * g1;
-    sC[1 * S + tid] = xa[2] * g0 - xa[0] * g2;
-    sC[2 * S + tid] = xa[0] * g1 - xa[1] * g0;
-    sC[3 * S + tid] = g0;
-    sC[4 * S + tid] = g1;
-    sC[5 * S + tid] = g2;
-    if (CB == 9) {
-      const double sw = uu * w0 + vv * w1;
-      const double ck0 = ff * rr * sw;
-      sC[6 * S + tid] = dd * sw;
-      sC[7 * S + tid] = ck0;
-      sC[8 * S + tid] = rr * ck0;
-    }
-    if (TWO) {
-      double h0 = 0.0, h1 = 0.0, h2 = 0.0;
-      if (has_b) {
-        h0 = GA[0][0] * w0 + GA[1][0] * w1;
-        h1 = GA[0][1] * w0 + GA[1][1] * w1;
-        h2 = GA[0][2] * w0 + GA[1][2] * w1;
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) E[i][j] = GA[i][0] * rb[j] + GA[i][1] * rb[3 + j] + GA[i][2] * rb[6 + j];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) E[i][j] = GA[i][j];
       }
-      sC[(CB + 0) * S + tid] = xb[1] * h2 - xb[2] * h1;
-      sC[(CB + 1) * S + tid] = xb[2] * h0 - xb[0] * h2;
-      sC[(CB + 2) * S + tid] = xb[0] * h1 - xb[1] * h0;
-      sC[(CB + 3) * S + tid] = h0;
-      sC[(CB + 4) * S + tid] = h1;
-      sC[(CB + 5) * S + tid] = h2;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) sV[j * S + lo] = E[0][j] * u0 + E[1][j] * u1;
     }
-  }
-  __syncthreads();
-  // ---- phase 4: tile-local reduce-by-camera over contiguous columns; one work item = (partial, 3 rows)
-  for (int wk = tid; wk < n_work; wk += T) {
-    const int lc = wk / KG, k0 = (wk - lc * KG) * 3;
-    const int i0 = s_first[lc], i1 = s_first[lc + 1];
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int i = i0; i < i1; ++i) {
-      int col = i, row = k0;
+    __syncthreads();  // [B]
+    // ---- phase 2: one thread per point, y' = sp * C^-1 (sp * sum_o v_o) (E is kept unscaled per
+    // observation; the Jacobi scale of the point columns is applied here, once per point)
+    if (tid < tm.n_pts) {
+      const int sa = seg[tid] - tm.obs0, sb = seg[tid + 1] - tm.obs0;
+      double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+      for (int i = sa; i < sb; ++i) {
+        z0 += sV[0 * S + i];
+        z1 += sV[1 * S + i];
+        z2 += sV[2 * S + i];
+      }
+      const double p0 = ptd[3 * PS + tid], p1 = ptd[4 * PS + tid], p2 = ptd[5 * PS + tid];
+      z0 *= p0;
+      z1 *= p1;
+      z2 *= p2;
+      const double c0 = ptd[6 * PS + tid], c1 = ptd[7 * PS + tid], c2 = ptd[8 * PS + tid], c3 = ptd[9 * PS + tid],
+                   c4 = ptd[10 * PS + tid], c5 = ptd[11 * PS + tid];
+      sY[0 * PS + tid] = p0 * (c0 * z0 + c1 * z1 + c2 * z2);
+      sY[1 * PS + tid] = p1 * (c1 * z0 + c3 * z1 + c4 * z2);
+      sY[2 * PS + tid] = p2 * (c2 * z0 + c4 * z1 + c5 * z2);
+    }
+    __syncthreads();  // [B']
+    // ---- phase 3: w = u - E y', contributions F^T w in geometric coordinates
+    if (active) {
+      const double y0 = sY[0 * PS + lp], y1 = sY[1 * PS + lp], y2 = sY[2 * PS + lp];
+      const double w0 = u0 - (E[0][0] * y0 + E[0][1] * y1 + E[0][2] * y2);
+      const double w1 = u1 - (E[1][0] * y0 + E[1][1] * y1 + E[1][2] * y2);
+      const double g0 = G[0][0] * w0 + G[1][0] * w1, g1 = G[0][1] * w0 + G[1][1] * w1, g2 = G[0][2] * w0 + G[1][2] * w1;
+      sC[0 * S + tid] = xa[1] * g2 - xa[2] * g1;
+      sC[1 * S + tid] = xa[2] * g0 - xa[0] * g2;
+      sC[2 * S + tid] = xa[0] * g1 - xa[1] * g0;
+      sC[3 * S + tid] = g0;
+      sC[4 * S + tid] = g1;
+      sC[5 * S + tid] = g2;
+      if (CB == 9) {
+        const double sw = uu * w0 + vv * w1;
+        const double ck0 = ff * rr * sw;
+        sC[6 * S + tid] = dd * sw;
+        sC[7 * S + tid] = ck0;
+        sC[8 * S + tid] = rr * ck0;
+      }
       if (TWO) {
-        const unsigned int it = s_items[i];
-        col = it & 0x7fffu;
-        row = (it >> 15) * CB + k0;
+        double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+        if (has_b) {
+          h0 = GA[0][0] * w0 + GA[1][0] * w1;
+          h1 = GA[0][1] * w0 + GA[1][1] * w1;
+          h2 = GA[0][2] * w0 + GA[1][2] * w1;
+        }
+        sC[(CB + 0) * S + tid] = xb[1] * h2 - xb[2] * h1;
+        sC[(CB + 1) * S + tid] = xb[2] * h0 - xb[0] * h2;
+        sC[(CB + 2) * S + tid] = xb[0] * h1 - xb[1] * h0;
+        sC[(CB + 3) * S + tid] = h0;
+        sC[(CB + 4) * S + tid] = h1;
+        sC[(CB + 5) * S + tid] = h2;
       }
-      a0 += sC[row * S + col];
-      a1 += sC[(row + 1) * S + col];
-      a2 += sC[(row + 2) * S + col];
     }
-    const int dst = wk == tid ? dst0 : D.part_dst[tm.g0 + lc];
-    double* out = W.partials_q + static_cast<int64_t>(dst) * CB + k0;
-    out[0] = a0;
-    out[1] = a1;
-    out[2] = a2;
+    __syncthreads();  // [C]
+    // ---- phase 4: tile-local reduce-by-camera over contiguous columns; one work item = (partial, 3 rows)
+    const int n_work = tm.n_parts * KG;
+    for (int wk = tid; wk < n_work; wk += T) {
+      const int lc = wk / KG, k0 = (wk - lc * KG) * 3;
+      const int i0 = s_first[lc], i1 = s_first[lc + 1];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int i = i0; i < i1; ++i) {
+        int col = i, row = k0;
+        if (TWO) {
+          const unsigned int it = static_cast<unsigned int>(s_items[i]);
+          col = it & 0x7fffu;
+          row = (it >> 15) * CB + k0;
+        }
+        a0 += sC[row * S + col];
+        a1 += sC[(row + 1) * S + col];
+        a2 += sC[(row + 2) * S + col];
+      }
+      double* out = W.partials_q + static_cast<int64_t>(s_dst[lc]) * CB + k0;
+      out[0] = a0;
+      out[1] = a1;
+      out[2] = a2;
+    }
+    if (!more) break;
+    t = t_next;
+    t_next += gridDim.x;
+    tm = tm_next;
+    tm_next = tm_after;
   }
 }
 
@@ -1575,7 +1646,17 @@ static void launch_spmv_mf_tt(const DeviceProblem& D, const ParamSet& P, const W
     cudaFuncSetAttribute(k_spmv_mf<CB, TWO, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     configured = true;
   }
-  k_spmv_mf<CB, TWO, T, MINB><<<D.n_tiles, T, smem, st>>>(D, W, P.pts, P.intr_rows);
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+  }
+  int resident = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_spmv_mf<CB, TWO, T, MINB>, T, smem);
+  const int grid = std::min(D.n_tiles, n_sm * std::max(resident, 1));
+  k_spmv_mf<CB, TWO, T, MINB><<<grid, T, smem, st>>>(D, W, P.pts, P.intr_rows);
 }
 // resident CTAs per SM requested from the register allocator for 256-thread tiles (tuning knob DBA_MF_MINB)
 static int mf_minb() {
@@ -1595,7 +1676,7 @@ static void launch_spmv_mf_t(const DeviceProblem& D, const ParamSet& P, const Wo
     else if (mb == 3) launch_spmv_mf_tt<CB, TWO, 256, 3>(D, P, W, st);
     else launch_spmv_mf_tt<CB, TWO, 256, 4>(D, P, W, st);
   } else if (D.tile == 512) {
-    launch_spmv_mf_tt<CB, TWO, 512, 1>(D, P, W, st);
+    launch_spmv_mf_tt<CB, TWO, 512, TWO ? 1 : 2>(D, P, W, st);
   } else if constexpr (!TWO) {
     launch_spmv_mf_tt<CB, TWO, 1024, 1>(D, P, W, st);
   }

@@ -19,6 +19,8 @@ namespace dba {
 constexpr int kTile = 256;       // default tile capacity (observations per tile == threads per tile CTA);
                                  // 512 / 1024 are selected when a point has a longer track
 constexpr int kMaxTile = 1024;
+// whole points per tile of capacity `tile` (bounds the staged per-point data of k_spmv_mf)
+__host__ __device__ constexpr int max_tile_points(int tile) { return tile >= 1024 ? 256 : 128; }
 constexpr int kPlaneR = 0;
 constexpr int kPlaneJp = 1;
 constexpr int kPlaneJA = 4;
@@ -70,7 +72,8 @@ struct DeviceProblem {
   const void* mf_cols;              // [n_tiles][tile] (padded, block a = -1) per column: CB = 9: int2 (block a, lp << 16 | lo);
                                     //   else int4 (block a, block b or -1, lp << 16 | lo, intrinsic);
                                     //   lo = point-sorted position in the tile, lp = tile-local point
-  const unsigned short* items_mf;   // two-pose problems: `items` with lo replaced by the column
+  const int* items_mf;              // two-pose problems: `items` with lo replaced by the column
+  const int* part_first;            // `part_first_rel` widened to int (cp.async granularity), same indexing
   const int* part_dst;              // [n_partials] row of partial g in the camera-grouped partial buffer
 };
 
