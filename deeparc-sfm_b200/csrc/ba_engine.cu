@@ -108,6 +108,7 @@ struct dba_handle {
   // matrix-free implicit Schur product (default); DBA_SPMV=planes selects the product that reads
   // the materialised Jacobian planes (kept for A/B measurements)
   int mf = 1;
+  int fuse_pcg = 1;  // single GPU: one cooperative launch for the PCG vector work (DBA_PCG_FUSED=0 disables)
   DevBuf<int> d_mf_cols, d_part_dst, d_items_mf, d_part_first;
   DevBuf<double> d_mf_rows, d_mf_T;
   DevBuf<int2> d_obs_ip;
@@ -419,6 +420,12 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
       } else {
         Scope s(h, "spmv_tile", tile_bytes);
         launch_spmv_tile(D, h->W, h->st);
+      }
+      if (fused && h->fuse_pcg) {
+        Scope s(h, "pcg_fused", part_bytes);
+        if (launch_pcg_fused(D, h->W, h->mf, tol2, o.pcg_min_iterations, h->st) != 0)
+          return h->fail(DBA_ERR_CUDA, "cooperative launch of k_pcg_fused failed: %s", cudaGetErrorString(cudaGetLastError()));
+        continue;
       }
       {
         Scope s(h, "partials_to_q", part_bytes);
@@ -758,9 +765,13 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     return h->fail(DBA_ERR_UNSUPPORTED, "a point has %lld observations; tracks longer than %d are not implemented",
                    (long long)max_track, tile_cap_max);
   int tile_cap = max_track <= 256 ? 256 : (max_track <= 512 ? 512 : 1024);
+  // single-pose problems large enough to fill the machine twice over use 512-observation tiles:
+  // half as many (tile, camera) partials and camera-row fetches per observation (measured on bal5m)
+  if (tile_cap == 256 && !two && !h->freeze && n / std::max(h->world, 1) >= int64_t{512} * 148 * 4) tile_cap = 512;
   if (const char* env = std::getenv("DBA_TILE")) {  // tuning knob: force a larger tile capacity
     const int forced = std::atoi(env);
     if ((forced == 512 || forced == 1024) && forced >= tile_cap && forced <= tile_cap_max) tile_cap = forced;
+    if (forced == 256 && max_track <= 256) tile_cap = 256;
   }
   std::vector<TileMeta> tile_meta;
   tile_meta.reserve(static_cast<size_t>(nl / 200 + 16));
@@ -1071,7 +1082,13 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_mf_T, static_cast<size_t>(n_ext) * (9 + cb)));
   {
     const char* env = std::getenv("DBA_SPMV");
-    h->mf = !(env && std::strcmp(env, "planes") == 0);
+    // default: matrix-free for single-pose problems; composed two-pose rigs (two row fetches, 128
+    // registers) measured faster on the plane product (arc1m: 360 vs 304 LM it/s)
+    h->mf = two ? 0 : 1;
+    if (env && std::strcmp(env, "planes") == 0) h->mf = 0;
+    if (env && std::strcmp(env, "mf") == 0) h->mf = 1;
+    const char* ef = std::getenv("DBA_PCG_FUSED");
+    h->fuse_pcg = !(ef && std::strcmp(ef, "0") == 0);
   }
   CU(h, ensure(h->d_partials_q, static_cast<size_t>(n_partials) * std::max(cb, 1)));
   CU(h, ensure(h->d_J, ld * h->j_planes));
@@ -1106,7 +1123,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_q, nvec));
   h->q_split = (n_ext >= 296 || !cb) ? 1 : std::min(32, (592 + std::max(n_ext, 1) - 1) / std::max(n_ext, 1));
   CU(h, ensure(h->d_q_split, nvec * static_cast<size_t>(h->q_split)));
-  CU(h, ensure(h->d_vec_partials, nvec / 128 + static_cast<size_t>(n_ext) + 64));  // k_partials_to_q: one partial per block
+  CU(h, ensure(h->d_vec_partials, nvec / 128 + 2 * static_cast<size_t>(n_ext) + 8192));  // k_partials_to_q: one partial per block
   CU(h, ensure(h->d_counters, 4));
   const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles) + 3,
                                           2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256), size_t{64}}) + 64;

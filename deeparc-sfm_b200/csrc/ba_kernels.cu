@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <cooperative_groups.h>
+
 #include "ba_kernels.cuh"
 
 namespace dba {
@@ -771,15 +773,16 @@ __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArra
 // from -[X]x dw by |w| <= 1.5e-8 relative — inside the product only, never in residuals or gradient.)
 // Threads of a tile map to observations in camera-block order (static `mf_cols`), so the
 // reduce-by-camera runs over contiguous columns and a warp's row loads hit few distinct rows.
+// camera row -> registers with 256-bit loads (sm_100 LDG.256: one L1 tag lookup per 32 B of a row
+// instead of one per 16 B; rows are 32-byte aligned and a multiple of 32 bytes long)
 template <int N>
 __device__ __forceinline__ void load_row(const double* __restrict__ row, double (&r)[N]) {
-  const double2* p = reinterpret_cast<const double2*>(row);
+  static_assert(N % 4 == 0, "row length must be a multiple of 4 doubles");
 #pragma unroll
-  for (int i = 0; i < N / 2; ++i) {
-    const double2 v = __ldg(p + i);
-    r[2 * i] = v.x;
-    r[2 * i + 1] = v.y;
-  }
+  for (int i = 0; i < N / 4; ++i)
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r[4 * i]), "=d"(r[4 * i + 1]), "=d"(r[4 * i + 2]), "=d"(r[4 * i + 3])
+                 : "l"(row + 4 * i));
 }
 
 // G = d r / d p_cam for projectPoint (snavely_reprojection_error.hh:38-78); also u, v, r^2, d
@@ -855,7 +858,7 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
                                                       const IntrRow* __restrict__ intr_rows) {
   if (W.pcg_state[1]) return;
   using L = MfSmem<CB, TWO, T>;
-  constexpr int S = L::S, PS = L::PS, ROW = mf_row_len(CB), SEL = ROW - 2, KG = CB / 3;
+  constexpr int S = L::S, PS = L::PS, ROW = mf_row_len(CB), SEL = CB == 9 ? 24 : 18;
   extern __shared__ __align__(16) unsigned char smem_mf[];
   double* sY = reinterpret_cast<double*>(smem_mf + L::oY);
   double* sV = reinterpret_cast<double*>(smem_mf + L::oV);
@@ -1075,27 +1078,23 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
       }
     }
     __syncthreads();  // [C]
-    // ---- phase 4: tile-local reduce-by-camera over contiguous columns; one work item = (partial, 3 rows)
-    const int n_work = tm.n_parts * KG;
+    // ---- phase 4: tile-local reduce-by-camera over contiguous columns; one work item = (partial, row):
+    // consecutive lanes read consecutive rows of one column run and write one 8*CB-byte partial row
+    const int n_work = tm.n_parts * CB;
     for (int wk = tid; wk < n_work; wk += T) {
-      const int lc = wk / KG, k0 = (wk - lc * KG) * 3;
+      const int lc = wk / CB, k = wk - lc * CB;
       const int i0 = s_first[lc], i1 = s_first[lc + 1];
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-      for (int i = i0; i < i1; ++i) {
-        int col = i, row = k0;
-        if (TWO) {
+      double a0 = 0.0;
+      if (TWO) {
+        for (int i = i0; i < i1; ++i) {
           const unsigned int it = static_cast<unsigned int>(s_items[i]);
-          col = it & 0x7fffu;
-          row = (it >> 15) * CB + k0;
+          a0 += sC[((it >> 15) * CB + k) * S + (it & 0x7fffu)];
         }
-        a0 += sC[row * S + col];
-        a1 += sC[(row + 1) * S + col];
-        a2 += sC[(row + 2) * S + col];
+      } else {
+        const double* src = sC + k * S;
+        for (int i = i0; i < i1; ++i) a0 += src[i];
       }
-      double* out = W.partials_q + static_cast<int64_t>(s_dst[lc]) * CB + k0;
-      out[0] = a0;
-      out[1] = a1;
-      out[2] = a2;
+      W.partials_q[static_cast<int64_t>(s_dst[lc]) * CB + k] = a0;
     }
     if (!more) break;
     t = t_next;
@@ -1128,8 +1127,10 @@ __global__ void __launch_bounds__(128) k_mf_rows(DeviceProblem D, ParamSet P, Wo
   const double wx = pr.w[0], wy = pr.w[1], wz = pr.w[2];
   const double th2 = wx * wx + wy * wy + wz * wz;
   double bc = pr.b, cc;
-  row[ROW - 2] = (th2 > DBL_EPSILON) ? 1.0 : 0.0;  // 0: Ceres' small-angle branch, derivative -[X]x
-  row[ROW - 1] = 0.0;
+  constexpr int SEL = CB == 9 ? 24 : 18;
+  row[SEL] = (th2 > DBL_EPSILON) ? 1.0 : 0.0;  // 0: Ceres' small-angle branch, derivative -[X]x
+#pragma unroll
+  for (int k = SEL + 1; k < ROW; ++k) row[k] = 0.0;
   if (!(th2 > DBL_EPSILON)) {
     bc = 0.0;
     cc = 0.0;
@@ -1308,6 +1309,131 @@ __global__ void __launch_bounds__(256) k_pcg_direction(DeviceProblem D, WorkArra
   const int n = D.n_blocks * D.cb;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) W.p[i] = W.z[i] + W.pcg_scal[3] * W.p[i];
+}
+
+// Single-GPU PCG iteration tail in ONE cooperative launch (grid = co-resident CTAs, grid.sync
+// between the phases): per camera block q = T^T sum(partials) + D_c^2 p and p.q | alpha, x, r,
+// z = M^-1 r and r.z | beta, p = z + beta p, p~ = T p.  Replaces k_partials_to_q + k_pcg_step +
+// k_mf_direction (three launch latencies per PCG iteration).  All sums are fixed-order.
+template <int CB, bool MF>
+__global__ void __launch_bounds__(256) k_pcg_fused(DeviceProblem D, WorkArrays W, double tol2, int min_iter) {
+  if (W.pcg_state[1]) return;
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[8][CB];
+  __shared__ double qg[CB], rn[CB];
+  __shared__ double red2[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nb = D.n_blocks;
+  double acc_dot = 0.0;
+  for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+    const int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
+    double acc[CB];
+#pragma unroll
+    for (int k = 0; k < CB; ++k) acc[k] = 0.0;
+    for (int i = i0 + tid; i < i1; i += 256) {
+      const double* pv = W.partials_q + static_cast<int64_t>(i) * CB;
+#pragma unroll
+      for (int k = 0; k < CB; ++k) acc[k] += pv[k];
+    }
+#pragma unroll
+    for (int k = 0; k < CB; ++k) {
+      const double sm = warp_sum(acc[k]);
+      if (lane == 0) red[wid][k] = sm;
+    }
+    __syncthreads();
+    if (tid < CB) {
+      double sm = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sm += red[w][tid];
+      qg[tid] = sm;
+    }
+    __syncthreads();
+    if (tid < CB) {
+      const int64_t i = static_cast<int64_t>(blk) * CB + tid;
+      double q = qg[tid];
+      if (MF) {
+        const double* Tm = W.mf_T + static_cast<int64_t>(blk) * (9 + CB);
+        if (tid < 3) q = Tm[tid] * qg[0] + Tm[3 + tid] * qg[1] + Tm[6 + tid] * qg[2];
+        q *= Tm[9 + tid];
+      }
+      const double p = W.p[i];
+      q += W.dc2[i] * p;
+      W.q[i] = q;
+      acc_dot += p * q;
+    }
+  }
+  if (tid < 32) {
+    const double sm = warp_sum(tid < CB ? acc_dot : 0.0);
+    if (tid == 0) W.vec_partials[blockIdx.x] = sm;
+  }
+  grid.sync();
+  const double pq = sum_partials(W.vec_partials, gridDim.x, red2);
+  const double rz = W.pcg_scal[0];
+  const bool breakdown = !(pq > 0.0) || !isfinite(pq);
+  acc_dot = 0.0;
+  if (!breakdown) {
+    const double alpha = rz / pq;
+    for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+      const int64_t i = static_cast<int64_t>(blk) * CB + tid;
+      if (tid < CB) {
+        W.x[i] += alpha * W.p[i];
+        const double r = W.r[i] - alpha * W.q[i];
+        W.r[i] = r;
+        rn[tid] = r;
+      }
+      __syncthreads();
+      if (tid < CB) {
+        const double* Mi = W.minv + i * CB;
+        double z = 0.0;
+#pragma unroll
+        for (int k = 0; k < CB; ++k) z += Mi[k] * rn[k];
+        W.z[i] = z;
+        acc_dot += rn[tid] * z;
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < 32) {
+    const double sm = warp_sum(tid < CB ? acc_dot : 0.0);
+    if (tid == 0) W.vec_partials[gridDim.x + blockIdx.x] = sm;
+  }
+  grid.sync();
+  if (breakdown) {
+    if (blockIdx.x == 0 && tid == 0) {
+      W.pcg_state[1] = 1;  // keep the current x
+      W.pcg_scal[3] = 0.0;
+    }
+    return;
+  }
+  const double rz_new = sum_partials(W.vec_partials + gridDim.x, gridDim.x, red2);
+  const double beta = rz_new / rz;
+  for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+    const int64_t i = static_cast<int64_t>(blk) * CB + tid;
+    if (tid < CB) {
+      const double p = W.z[i] + beta * W.p[i];
+      W.p[i] = p;
+      if (MF) rn[tid] = p * W.mf_T[static_cast<int64_t>(blk) * (9 + CB) + 9 + tid];
+    }
+    if (MF) {
+      __syncthreads();
+      if (tid < CB) {
+        constexpr int ROW = mf_row_len(CB), PO = CB == 9 ? 15 : 12;
+        const double* Tm = W.mf_T + static_cast<int64_t>(blk) * (9 + CB);
+        double v = rn[tid];
+        if (tid < 3) v = Tm[3 * tid] * rn[0] + Tm[3 * tid + 1] * rn[1] + Tm[3 * tid + 2] * rn[2];
+        W.mf_rows[static_cast<int64_t>(blk) * ROW + PO + tid] = v;
+      }
+      __syncthreads();
+    }
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    const int it = W.pcg_state[0] + 1;
+    W.pcg_state[0] = it;
+    W.pcg_scal[3] = beta;
+    W.pcg_scal[0] = rz_new;
+    if ((it >= min_iter && rz_new <= tol2 * W.pcg_scal[1]) || !(rz_new > 0.0)) W.pcg_state[1] = 1;
+  }
 }
 
 // ------------------------------------------------------------- K7 back-substitution
@@ -1621,6 +1747,28 @@ void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_
     if (mf) k_partials_to_q<9, true><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
     else k_partials_to_q<9, false><<<grid, 128, 0, st>>>(D, W, fuse_dot, n_split);
   }
+}
+
+template <int CB, bool MF>
+static int launch_pcg_fused_t(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st) {
+  static int resident = 0;
+  if (resident == 0) {
+    int dev = 0, n_sm = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_fused<CB, MF>, 256, 0);
+    resident = std::max(1, n_sm * per_sm);
+  }
+  const int grid = std::min(D.n_blocks, resident);
+  DeviceProblem d = D;
+  WorkArrays w = W;
+  void* args[] = {&d, &w, &tol2, &min_iter};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_fused<CB, MF>), dim3(grid), dim3(256), args, 0, st) == cudaSuccess ? 0 : -1;
+}
+int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, cudaStream_t st) {
+  if (D.n_blocks == 0) return 0;
+  if (D.cb == 6) return mf ? launch_pcg_fused_t<6, true>(D, W, tol2, min_iter, st) : launch_pcg_fused_t<6, false>(D, W, tol2, min_iter, st);
+  return mf ? launch_pcg_fused_t<9, true>(D, W, tol2, min_iter, st) : launch_pcg_fused_t<9, false>(D, W, tol2, min_iter, st);
 }
 
 void launch_mf_rows(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {

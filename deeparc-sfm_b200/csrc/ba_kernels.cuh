@@ -77,7 +77,7 @@ struct DeviceProblem {
   const int* part_dst;              // [n_partials] row of partial g in the camera-grouped partial buffer
 };
 
-__host__ __device__ constexpr int mf_row_len(int cb) { return cb == 9 ? 26 : 20; }
+__host__ __device__ constexpr int mf_row_len(int cb) { return cb == 9 ? 28 : 20; }  // multiples of 4 doubles (256-bit loads)
 
 struct ParamSet {
   double* pts;        // [n_pts_local][3]
@@ -116,7 +116,7 @@ struct WorkArrays {
   double* q_split;     // [n_split][n_blocks * cb] slices of q when the per-camera sum is split
   double* partials_q;  // [n_partials][cb] tile-local partial products of the implicit Schur product
   // matrix-free product: one row per camera block, rebuilt after every Jacobian evaluation
-  //   CB = 6: R[9] t[3] p~[6] sel 0      CB = 9: R[9] t[3] f k0 k1 p~[9] sel 0
+  //   CB = 6: R[9] t[3] p~[6] sel 0      CB = 9: R[9] t[3] f k0 k1 p~[9] sel 0 0 0
   //   (sel = 0 in Ceres' small-angle branch of AngleAxisRotatePoint, else 1)
   // p~ = T p is the PCG direction in "geometric" coordinates, T = blockdiag(J_l(w), I, I) diag(sc * free)
   // (J_l = left Jacobian of SO(3): d(R X) = (J_l dw) x (R X)); rewritten every PCG iteration
@@ -177,6 +177,8 @@ void launch_fold_q(const DeviceProblem& D, const WorkArrays& W, int n_split, cud
 void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st);
 void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
 void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
+// single GPU: partial sum + all three vector phases in one cooperative launch; returns 0 on success
+int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, cudaStream_t st);
 // dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
 void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st);
 // candidate = current + scale * step; partials[2*cta + {0,1}] = {sum step^2, sum x^2}

@@ -154,21 +154,23 @@ def test_matrix_free_product_matches_plane_product(engine, name, monkeypatch):
     kw = dict(max_num_iterations=4, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
               linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=0.0, pcg_max_iterations=12)
     runs = {}
-    for mode in ("planes", "mf"):
-        if mode == "planes":
-            monkeypatch.setenv("DBA_SPMV", "planes")
-        else:
-            monkeypatch.delenv("DBA_SPMV", raising=False)
+    for mode in ("planes", "mf", "mf_unfused"):
+        monkeypatch.delenv("DBA_SPMV", raising=False)
+        monkeypatch.delenv("DBA_PCG_FUSED", raising=False)
+        monkeypatch.setenv("DBA_SPMV", "planes" if mode == "planes" else "mf")
+        if mode == "mf_unfused":  # separate k_partials_to_q / k_pcg_step / k_mf_direction launches
+            monkeypatch.setenv("DBA_PCG_FUSED", "0")
         engine.problem_set(p)
         s = engine.solve(capi.make_options(**kw))
         runs[mode] = (s, engine.params_get())
     sa, xa = runs["planes"]
-    sb, xb = runs["mf"]
-    assert np.array_equal(sa.trace("step_is_successful"), sb.trace("step_is_successful"))
-    np.testing.assert_allclose(sb.trace("cost"), sa.trace("cost"), rtol=1e-9)
-    for k in ("pts", "ext_rot", "ext_trans", "intr_focal", "intr_dist"):
-        scale = max(np.max(np.abs(xa[k])), 1e-300)
-        assert np.max(np.abs(xa[k] - xb[k])) <= 1e-8 * scale, k
+    for other in ("mf", "mf_unfused"):
+        sb, xb = runs[other]
+        assert np.array_equal(sa.trace("step_is_successful"), sb.trace("step_is_successful"))
+        np.testing.assert_allclose(sb.trace("cost"), sa.trace("cost"), rtol=1e-9)
+        for k in ("pts", "ext_rot", "ext_trans", "intr_focal", "intr_dist"):
+            scale = max(np.max(np.abs(xa[k])), 1e-300)
+            assert np.max(np.abs(xa[k] - xb[k])) <= 1e-8 * scale, (other, k)
 
 
 @pytest.mark.parametrize("kind", ["rig_512", "bal_1024"])
