@@ -671,6 +671,14 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   const int64_t n = p->n_obs;
   const int n_ext = p->n_ext, n_intr = p->n_intr;
 
+  const bool timing = std::getenv("DBA_TIMING") != nullptr;
+  double t_mark = now_s();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    const double t = now_s();
+    std::fprintf(stderr, "[dba_problem_set] %-28s %8.2f ms\n", what, 1e3 * (t - t_mark));
+    t_mark = t;
+  };
   // ---- pass 1 (parallel): validation, two-pose detection, sortedness
   int64_t bad_index = -1;
   int two = 0, sorted = 1, intr_is_pose = 1;
@@ -704,6 +712,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   h->n_intr = n_intr;
   const int cb = h->cb;
 
+  mark("validate");
   // ---- observations per point (global), shard of this rank
   std::vector<int64_t> pt_count(static_cast<size_t>(p->n_pts) + 1, 0);
   if (sorted) {
@@ -754,6 +763,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   }
   const int64_t* perm = h->perm.data();
 
+  mark("point counts + permutation");
   // ---- tiles of whole points (greedy, serial: O(n_pts))
   // tile capacity: 256 unless some point has a longer track (then 512 / 1024; two-pose
   // problems stop at 512 because a 1024-observation two-pose tile exceeds shared memory)
@@ -802,6 +812,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   }
   const int n_tiles = static_cast<int>(tile_meta.size());
 
+  mark("tiles");
   // ---- sizes of everything that goes through the pinned arena
   const int64_t ld = std::max<int64_t>(((nl + 63) / 64) * 64, 64);
   const int64_t n_ent_max = cb ? 2 * nl : 0;
@@ -829,6 +840,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, cudaStreamSynchronize(h->st));  // the arena may still feed copies of a previous call
   CU(h, A.reserve(arena_bytes));
 
+  mark("arena reserve");
   // ---- per-observation arrays (parallel)
   double2* s_xy = A.take<double2>(nl);
   int2* s_ip = A.take<int2>(nl);
@@ -845,6 +857,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
 #pragma omp parallel for schedule(static)
   for (int i = 0; i <= n_pts; ++i) s_pt_first[i] = static_cast<int>(pt_count[pt_lo + i] - obs_lo);
 
+  mark("per-observation arrays");
   // ---- camera-sorted incidence: stable parallel counting sort of (obs, slot) entries by block
   int* s_cam_entries = A.take<int>(static_cast<size_t>(n_ent_max));
   int4* s_cam_chunks = nullptr;
@@ -906,6 +919,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     s_cam_chunks = A.take<int4>(1);
   }
 
+  mark("camera-sorted incidence");
   // ---- static tile-local camera incidence (parallel over tiles, two passes)
   unsigned short* s_items = A.take<unsigned short>(static_cast<size_t>(std::max<int64_t>(n_entries, 1)));
   unsigned short* s_part_first_rel = A.take<unsigned short>(static_cast<size_t>(n_entries + n_tiles + 1));
@@ -1055,6 +1069,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   s_tile_obs[n_tiles] = static_cast<int>(nl);
   s_tile_pt[n_tiles] = n_pts;
 
+  mark("tile incidence + columns");
   // ---- device buffers (kept across calls, grow only)
   h->plane_w = 4 + cb + ((two && cb) ? 6 : 0);
   h->j_planes = h->plane_w;
@@ -1179,7 +1194,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * n_ext));
   CU(h, up(h->d_focal[2].p, p->intr_focal, 2 * sizeof(double) * n_intr));
   CU(h, up(h->d_dist[2].p, p->intr_dist, 2 * sizeof(double) * n_intr));
+  mark("alloc + enqueue copies");
   CU(h, cudaStreamSynchronize(h->st));  // caller buffers and local staging may go away now
+  mark("copies complete");
   h->n_cam_entries = n_entries;
 
   DeviceProblem& D = h->D;

@@ -80,8 +80,10 @@ class Problem:
         return Problem(**kw)
 
     def normalised(self) -> "Problem":
-        """Contiguous arrays of the exact dtypes the C ABI expects."""
-        p = self.copy()
+        """Contiguous arrays of the exact dtypes the C ABI expects.  Arrays that already conform are
+        passed through without a copy (the C ABI copies what it needs; callers' buffers are not
+        retained past dba_problem_set)."""
+        p = dataclasses.replace(self)
         for name in ("obs_xy", "pts", "ext_rot", "ext_trans", "intr_center", "intr_focal", "intr_dist"):
             setattr(p, name, np.ascontiguousarray(getattr(p, name), dtype=np.float64))
         for name in ("obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "intr_nf", "intr_nd"):
