@@ -194,7 +194,11 @@ def main():
         return 0
 
     # ----------------------------------------------------------------------------- our arm
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    # stdout carries exactly ONE line (the JSON): everything libraries print while the bench runs
+    # (NCCL's version banner, ...) goes to stderr; the saved descriptor gets the result at the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from deeparc_sfm_b200 import capi
@@ -261,15 +265,14 @@ def main():
     barrier()
     stats = {k["name"]: k for k in eng.kernel_stats()}
     eng.kernel_stats_enable(False)
+    loop2_s = max_over_ranks(s2.loop_device_time_in_seconds)
     # keep the GPU under the same load until the sampler has a few dozen samples (a timed region of
     # K = 10 iterations lasts ~60 ms; nvidia-smi needs ~0.2 s to start reporting)
-    t_load = time.perf_counter()
-    while rank == 0 and time.perf_counter() - t_load < 1.0:
+    for _ in range(int(min(max(1.0 / max(loop2_s, 1e-4), 1), 200))):  # same count on every rank (collective solves)
         eng.params_reset()
         eng.solve(opts)
     clocks = sampler.stop() if rank == 0 else None
     barrier()
-    loop2_s = max_over_ranks(s2.loop_device_time_in_seconds)
 
     # ---- end to end through the C ABI with host buffers
     barrier()
@@ -299,12 +302,15 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     roof = None
     live = lambda n: n in stats and stats[n]["launches"] > 0
-    prod = "spmv_mf" if live("spmv_mf") else ("spmv_tile" if live("spmv_tile") else None)
+    prod = next((n for n in ("spmv_mf_pcg", "spmv_mf", "spmv_tile") if live(n)), None)
     if prod:
-        # the product is two launches: the tile kernel (one partial vector per (tile, camera)) and
-        # the per-camera sum of the partials — fused with the PCG vector phases in k_pcg_fused
-        tail = "pcg_fused" if live("pcg_fused") else "partials_to_q"
-        ka, kb = stats[prod], stats[tail]
+        # the product = the tile kernel (one partial vector per (tile, camera)) + the per-camera sum of
+        # the partials.  Default (spmv_mf_pcg): ONE launch, k_spmv_mf with the PCG tail as its epilogue
+        # (partial sum, peer exchange, vector updates).  Otherwise a second launch: k_pcg_fused or
+        # k_partials_to_q.
+        tail = None if prod == "spmv_mf_pcg" else ("pcg_fused" if live("pcg_fused") else "partials_to_q")
+        ka = stats[prod]
+        kb = stats[tail] if tail else {"total_ms": 0.0, "launches": 0, "algorithmic_bytes": 0.0}
         ms_a, ms_b = ka["total_ms"] / ka["launches"], kb["total_ms"] / max(kb["launches"], 1)
         cb = 9 if p.free_intrinsics else 6
         planes = 3 + cb + (6 if (p.obs_pose_b >= 0).any() else 0)
@@ -316,12 +322,13 @@ def main():
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
-            tj = json.load(open(tpath)).get(f"{args.workload}:k_{prod}")
+            tj = json.load(open(tpath)).get(f"{args.workload}:k_{'spmv_mf' if prod == 'spmv_mf_pcg' else prod}")
             if tj:
                 traffic = tj["dram_bytes_per_launch"] * (n_obs_rank / tj["n_obs"])
-        kname = {"spmv_mf": "k_spmv_mf (matrix-free: Jacobian recomputed per observation)",
+        kname = {"spmv_mf_pcg": "k_spmv_mf (matrix-free: Jacobian recomputed per observation; epilogue = per-camera sum + PCG vector updates)",
+                 "spmv_mf": "k_spmv_mf (matrix-free: Jacobian recomputed per observation)",
                  "spmv_tile": "k_spmv_tile (materialised Jacobian planes)"}[prod]
-        roof = {"bound": "hbm", "kernel": f"implicit Schur product = {kname} + k_{tail}",
+        roof = {"bound": "hbm", "kernel": f"implicit Schur product = {kname}" + (f" + k_{tail}" if tail else ""),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": model_bytes,
                 "model": "materialised single-pass model of SURVEY 8(d): %d B/observation (indices + Jc + Jp planes read once); "
@@ -331,11 +338,11 @@ def main():
                 "phases": {f"k_{prod}": {"mean_ms": ms_a, "bytes": ka["algorithmic_bytes"],
                                           "gbs": ka["algorithmic_bytes"] / (ms_a * 1e-3) / 1e9,
                                           "frac": ka["algorithmic_bytes"] / (ms_a * 1e-3) / 1e9 / peak},
-                           f"k_{tail}": {"mean_ms": ms_b, "bytes": kb["algorithmic_bytes"],
-                                          "gbs": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 if ms_b > 0 else None,
-                                          "frac": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 / peak if ms_b > 0 else None}},
+                           **({f"k_{tail}": {"mean_ms": ms_b, "bytes": kb["algorithmic_bytes"],
+                                              "gbs": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 if ms_b > 0 else None,
+                                              "frac": kb["algorithmic_bytes"] / (ms_b * 1e-3) / 1e9 / peak if ms_b > 0 else None}} if tail else {})},
                 "share_of_kernel_time": (ka["total_ms"] + kb["total_ms"]) / total_ms if total_ms > 0 else None}
-        if prod == "spmv_mf":
+        if prod in ("spmv_mf", "spmv_mf_pcg"):
             # the matrix-free kernel trades the 200 B/observation for ~MF_FLOPS fp64 operations
             flops = MF_FLOPS_PER_OBS[(cb, planes > 3 + cb)] * n_obs_rank
             roof["fp64"] = {"flops_per_launch": flops, "tflops": flops / (ms_a * 1e-3) / 1e12,
@@ -374,7 +381,8 @@ def main():
         "initial_cost": s.initial_cost, "ms_per_step_with_event_timers": 1e3 * loop2_s / max(steps_done, 1),
         "kernels": kernels,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     return 0
 
 

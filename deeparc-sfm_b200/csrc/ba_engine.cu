@@ -108,7 +108,21 @@ struct dba_handle {
   // matrix-free implicit Schur product (default); DBA_SPMV=planes selects the product that reads
   // the materialised Jacobian planes (kept for A/B measurements)
   int mf = 1;
-  int fuse_pcg = 1;  // single GPU: one cooperative launch for the PCG vector work (DBA_PCG_FUSED=0 disables)
+  int fuse_pcg = 1;  // one cooperative launch for the PCG vector work (DBA_PCG_FUSED=0 disables)
+  // multi-GPU: peer windows of the fused PCG tail (CUDA IPC over NVLink); DBA_P2P=0 keeps the
+  // ncclAllReduce path (kept for A/B measurements and for boxes without peer access)
+  // the planes / cost partials / camera rows currently describe the CANDIDATE (speculative evaluation)
+  bool pcg_pending = false;  // h_pcg_state is in flight (valid after the next stream synchronisation)
+  bool jacobian_at_candidate = false;
+  int mf_tail = 1;    // DBA_MF_TAIL=0: PCG tail as a separate launch (k_pcg_fused) instead of the k_spmv_mf epilogue
+  int speculate = 1;  // DBA_SPECULATE=0: always evaluate candidates with the residual-only kernel
+  bool p2p_ready = false;
+  void* win_local = nullptr;
+  size_t win_bytes = 0, win_slot_cap = 0;
+  void* win_peer[kMaxPeers] = {};
+  PeerWin pw{};
+  unsigned long long p2p_seq = 0;
+  DevBuf<unsigned char> d_ipc;
   DevBuf<int> d_mf_cols, d_part_dst, d_items_mf, d_part_first;
   DevBuf<double> d_mf_rows, d_mf_T;
   DevBuf<int2> d_obs_ip;
@@ -288,6 +302,105 @@ int reduce_scalars_and_fetch(dba_handle* h) {
 
 double bytes_per_obs_planes(const dba_handle* h, int planes) { return 16.0 * planes * static_cast<double>(h->n_obs); }
 
+// ---- peer windows (multi-GPU fused PCG tail) ------------------------------------------
+// Collective over the ranks of the handle (called from dba_problem_set, which already is): every
+// rank allocates its window, the 64-byte CUDA IPC handles travel through one ncclAllGather, every
+// rank maps the windows of its peers.  Any failure on any rank (no peer access, IPC disabled in
+// the container) leaves ALL ranks on the ncclAllReduce path — agreed through one allreduce.
+void close_peer_windows(dba_handle* h) {
+  for (int r = 0; r < kMaxPeers; ++r) {
+    if (h->win_peer[r]) cudaIpcCloseMemHandle(h->win_peer[r]);
+    h->win_peer[r] = nullptr;
+  }
+  h->p2p_ready = false;
+}
+
+int setup_peer_windows(dba_handle* h, size_t nvec) {
+  if (h->world == 1) return DBA_OK;
+  const char* env = std::getenv("DBA_P2P");
+  const bool wanted = h->world <= kMaxPeers && !(env && std::strcmp(env, "0") == 0);
+  const size_t slot_len = (std::max<size_t>(nvec, 1) + 31) / 32 * 32;
+  const size_t flag_bytes = 256;
+  if (wanted && h->p2p_ready && h->win_slot_cap >= slot_len) {  // same decision on every rank (same nvec)
+    h->pw.slot_len = static_cast<long long>(slot_len);
+    return DBA_OK;
+  }
+  // tear down the old mapping everywhere before anyone frees its window
+  close_peer_windows(h);
+  double ok = wanted ? 1.0 : 0.0;
+  DevBuf<double> d_ok;
+  CU(h, d_ok.alloc(1));
+  auto agree = [&]() -> int {  // min over ranks of `ok` (doubles as a barrier)
+    const double neg = -ok;
+    CU(h, cudaMemcpyAsync(d_ok.p, &neg, sizeof neg, cudaMemcpyHostToDevice, h->st));
+    int rc = nccl_api().AllReduce(d_ok.p, d_ok.p, 1, kNcclFloat64, kNcclMax, h->comm, h->st);
+    if (rc != 0) return h->fail(DBA_ERR_NCCL, "ncclAllReduce: %s", nccl_api().GetErrorString(rc));
+    double out = 0.0;
+    CU(h, cudaMemcpyAsync(&out, d_ok.p, sizeof out, cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+    ok = -out;
+    return DBA_OK;
+  };
+  int rc = agree();
+  if (rc != DBA_OK) return rc;
+  if (h->win_local) cudaFree(h->win_local);
+  h->win_local = nullptr;
+  h->win_bytes = 0;
+  h->win_slot_cap = 0;
+  if (ok < 0.5) return DBA_OK;
+
+  const size_t data_bytes = 2 * static_cast<size_t>(h->world) * slot_len * sizeof(double);
+  const size_t bytes = data_bytes + flag_bytes;
+  cudaIpcMemHandle_t mine{};
+  if (cudaMalloc(&h->win_local, bytes) != cudaSuccess || cudaMemsetAsync(h->win_local, 0, bytes, h->st) != cudaSuccess ||
+      cudaIpcGetMemHandle(&mine, h->win_local) != cudaSuccess) {
+    cudaGetLastError();
+    ok = 0.0;
+  }
+  CU(h, ensure(h->d_ipc, sizeof(cudaIpcMemHandle_t) * (static_cast<size_t>(h->world) + 1)));
+  unsigned char* d_send = h->d_ipc.p + sizeof(cudaIpcMemHandle_t) * h->world;
+  CU(h, cudaMemcpyAsync(d_send, &mine, sizeof mine, cudaMemcpyHostToDevice, h->st));
+  rc = nccl_api().AllGather(d_send, h->d_ipc.p, sizeof mine, kNcclUint8, h->comm, h->st);
+  if (rc != 0) return h->fail(DBA_ERR_NCCL, "ncclAllGather: %s", nccl_api().GetErrorString(rc));
+  std::vector<cudaIpcMemHandle_t> all(h->world);
+  CU(h, cudaMemcpyAsync(all.data(), h->d_ipc.p, sizeof mine * h->world, cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaStreamSynchronize(h->st));
+  if ((rc = agree()) != DBA_OK) return rc;  // did every rank get a window?
+  if (ok > 0.5) {
+    for (int r = 0; r < h->world && ok > 0.5; ++r) {
+      if (r == h->rank) continue;
+      if (cudaIpcOpenMemHandle(&h->win_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        h->win_peer[r] = nullptr;
+        ok = 0.0;
+      }
+    }
+  }
+  if ((rc = agree()) != DBA_OK) return rc;  // did every rank map every peer?
+  if (ok < 0.5) {
+    close_peer_windows(h);
+    if (h->verbose && h->rank == 0) std::fprintf(stderr, "[dba] peer windows unavailable: PCG uses ncclAllReduce\n");
+    return DBA_OK;
+  }
+  h->win_bytes = bytes;
+  h->win_slot_cap = slot_len;
+  PeerWin& pw = h->pw;
+  pw = PeerWin{};
+  pw.world = h->world;
+  pw.rank = h->rank;
+  pw.slot_len = static_cast<long long>(slot_len);
+  pw.timeout_ns = 20LL * 1000 * 1000 * 1000;
+  if (const char* t = std::getenv("DBA_P2P_TIMEOUT_MS")) pw.timeout_ns = std::max(1LL, std::atoll(t)) * 1000 * 1000;
+  for (int r = 0; r < h->world; ++r) {
+    char* base = static_cast<char*>(r == h->rank ? h->win_local : h->win_peer[r]);
+    pw.data[r] = reinterpret_cast<double*>(base);
+    pw.flags[r] = reinterpret_cast<unsigned long long*>(base + data_bytes);
+  }
+  pw.go = pw.flags[h->rank] + kMaxPeers;
+  h->p2p_ready = true;
+  return DBA_OK;
+}
+
 // ---- LM building blocks ---------------------------------------------------------------
 void fill_ones(dba_handle* h, double* p, size_t n) {
   std::vector<double> ones(n, 1.0);
@@ -355,10 +468,12 @@ int prepare_step(dba_handle* h, double radius, const dba_solve_options& o) {
     launch_point_prepare(D, h->W, radius, o.min_lm_diagonal, o.max_lm_diagonal, 1, h->d_partA.p, h->st);
   }
   {
-    Scope s(h, "reduce", 0.0, 3);
-    launch_reduce_sum(h->d_partA.p, D.n_tiles, 3, 0, h->W.scalars + S_GSQ_PT, h->st);
-    launch_reduce_max(h->d_partA.p, D.n_tiles, 3, 1, h->W.scalars + S_GMAX_PT, h->st);
-    launch_reduce_sum(h->d_partA.p, D.n_tiles, 3, 2, h->W.scalars + S_BAD_PT, h->st);
+    Scope s(h, "reduce");
+    ReduceJobs j;
+    j.sum(h->d_partA.p, D.n_tiles, 3, 0, h->W.scalars + S_GSQ_PT);
+    j.max(h->d_partA.p, D.n_tiles, 3, 1, h->W.scalars + S_GMAX_PT);
+    j.sum(h->d_partA.p, D.n_tiles, 3, 2, h->W.scalars + S_BAD_PT);
+    launch_reduce_multi(j, h->st);
   }
   if (h->cb) {
     {
@@ -373,10 +488,12 @@ int prepare_step(dba_handle* h, double radius, const dba_solve_options& o) {
       launch_camera_finalize(D, h->W, radius, o.min_lm_diagonal, o.max_lm_diagonal, h->d_partB.p, h->st);
     }
     const int g = camera_finalize_grid(D);
-    Scope s(h, "reduce", 0.0, 3);
-    launch_reduce_sum(h->d_partB.p, g, 3, 0, h->W.scalars + S_GSQ_CAM, h->st);
-    launch_reduce_max(h->d_partB.p, g, 3, 1, h->W.scalars + S_GMAX_CAM, h->st);
-    launch_reduce_sum(h->d_partB.p, g, 3, 2, h->W.scalars + S_BAD_CAM, h->st);
+    Scope s(h, "reduce");
+    ReduceJobs j;
+    j.sum(h->d_partB.p, g, 3, 0, h->W.scalars + S_GSQ_CAM);
+    j.max(h->d_partB.p, g, 3, 1, h->W.scalars + S_GMAX_CAM);
+    j.sum(h->d_partB.p, g, 3, 2, h->W.scalars + S_BAD_CAM);
+    launch_reduce_multi(j, h->st);
   } else {
     CU(h, cudaMemsetAsync(h->W.scalars + S_GSQ_CAM, 0, 3 * sizeof(double), h->st));
   }
@@ -409,27 +526,44 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   const int nvec = D.n_blocks * h->cb;
   int issued = 0;
   const int check_every = (o.pcg_rel_tolerance > 0.0) ? 8 : max_it;
-  const int fused = (h->world == 1 && h->q_split == 1) ? 1 : 0;  // q sum + D^2 p + p.q in one kernel
+  // q sum (+ the cross-rank exchange through the peer windows) + D^2 p + p.q + the vector phases in one kernel
+  const int fused = (h->q_split == 1 && (h->world == 1 || h->p2p_ready)) ? 1 : 0;
+  const PeerWin no_peers{};
   *iters_out = 0;
   while (issued < max_it) {
     const int batch = std::min(check_every > 0 ? check_every : max_it, max_it - issued);
     for (int i = 0; i < batch; ++i) {
       if (h->mf) {
-        Scope s(h, "spmv_mf", mf_bytes);
-        launch_spmv_mf(D, h->P[h->cur], h->W, h->st);
+        // default: the rest of the PCG iteration runs as the epilogue of the product kernel
+        MfTail tail;
+        if (fused && h->fuse_pcg && h->mf_tail) {
+          tail.fuse = 1;
+          tail.tol2 = tol2;
+          tail.min_iter = o.pcg_min_iterations;
+          if (h->world > 1) {
+            h->pw.seq = ++h->p2p_seq;
+            tail.pw = h->pw;
+          }
+        }
+        Scope s(h, tail.fuse ? "spmv_mf_pcg" : "spmv_mf", mf_bytes + (tail.fuse ? part_bytes : 0.0));
+        if (launch_spmv_mf(D, h->P[h->cur], h->W, tail, h->st) != 0)
+          return h->fail(DBA_ERR_CUDA, "cooperative launch of k_spmv_mf failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (tail.fuse) continue;
       } else {
         Scope s(h, "spmv_tile", tile_bytes);
         launch_spmv_tile(D, h->W, h->st);
       }
       if (fused && h->fuse_pcg) {
         Scope s(h, "pcg_fused", part_bytes);
-        if (launch_pcg_fused(D, h->W, h->mf, tol2, o.pcg_min_iterations, h->st) != 0)
+        if (h->world > 1) h->pw.seq = ++h->p2p_seq;
+        if (launch_pcg_fused(D, h->W, h->mf, tol2, o.pcg_min_iterations, h->world > 1 ? h->pw : no_peers, h->st) != 0)
           return h->fail(DBA_ERR_CUDA, "cooperative launch of k_pcg_fused failed: %s", cudaGetErrorString(cudaGetLastError()));
         continue;
       }
+      const int fuse_dot = (h->world == 1 && h->q_split == 1) ? 1 : 0;
       {
         Scope s(h, "partials_to_q", part_bytes);
-        launch_partials_to_q(D, h->W, fused, h->q_split, h->mf, h->st);
+        launch_partials_to_q(D, h->W, fuse_dot, h->q_split, h->mf, h->st);
       }
       if (h->world > 1) {
         if (h->q_split > 1) {  // fold the slices before the allreduce
@@ -439,8 +573,8 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
         int rc = allreduce(h, h->W.q, nvec, kNcclSum);
         if (rc != DBA_OK) return rc;
       }
-      Scope s(h, "pcg_vector", 0.0, fused ? 2 : 3);
-      if (!fused) launch_pcg_dot(D, h->W, h->world > 1 ? 1 : h->q_split, h->st);
+      Scope s(h, "pcg_vector", 0.0, fuse_dot ? 2 : 3);
+      if (!fuse_dot) launch_pcg_dot(D, h->W, h->world > 1 ? 1 : h->q_split, h->st);
       launch_pcg_step(D, h->W, tol2, o.pcg_min_iterations, h->st);
       if (h->mf)
         launch_mf_direction(D, h->W, /*init=*/0, h->st);
@@ -449,8 +583,16 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
     }
     issued += batch;
     CU(h, cudaMemcpyAsync(h->h_pcg_state, h->W.pcg_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    if (o.pcg_rel_tolerance <= 0.0) {
+      // fixed iteration count: nothing to decide here, the state is read together with the LM
+      // scalars at the next synchronisation (pcg_collect) — one host round trip less per LM iteration
+      h->pcg_pending = true;
+      *iters_out = issued;
+      break;
+    }
     CU(h, cudaStreamSynchronize(h->st));
     *iters_out = h->h_pcg_state[0];
+    if (h->h_pcg_state[2]) return h->fail(DBA_ERR_NCCL, "peer exchange timed out: a rank of this handle stopped responding");
     if (h->h_pcg_state[1]) break;
   }
   if (max_it == 0) {
@@ -461,46 +603,84 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   return DBA_OK;
 }
 
-// step -> candidate parameters, model cost change, norms, candidate cost
-int apply_step_and_evaluate(dba_handle* h) {
+// after a stream synchronisation: the PCG state copied by a pcg_solve that did not wait for it
+int pcg_collect(dba_handle* h, int* iters) {
+  if (!h->pcg_pending) return DBA_OK;
+  h->pcg_pending = false;
+  *iters = h->h_pcg_state[0];
+  if (h->h_pcg_state[2]) return h->fail(DBA_ERR_NCCL, "peer exchange timed out: a rank of this handle stopped responding");
+  return DBA_OK;
+}
+
+// step -> candidate parameters, model cost change, norms, candidate cost.
+// speculate: evaluate the candidate with the Jacobian kernel instead of the residual-only kernel
+// (same residual code, same partial-sum order), so that an accepted step needs no second pass over
+// the observations: the planes, the cost and the matrix-free camera rows are already those of the
+// new point.  A step that is not accepted restores them (restore_current_jacobian).
+int apply_step_and_evaluate(dba_handle* h, bool speculate) {
   const DeviceProblem& D = h->D;
   const ParamSet& cur = h->P[h->cur];
   const ParamSet& cand = h->P[1 - h->cur];
   const int nplanes = 4 + h->cb + (h->two && h->cb ? 6 : 0);
+  const int gp = update_points_grid(D), gc = update_cameras_grid(D);
+  // three disjoint partial ranges of d_partA so that ONE launch reduces everything at the end
+  double* pa_model = h->d_partA.p;
+  double* pa_upd = pa_model + ((D.n_tiles + 31) / 32) * 32;
+  double* pa_cost = pa_upd + ((2 * gp + 31) / 32) * 32;
   {
     Scope s(h, "back_substitute", (8.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs));
-    launch_back_substitute(D, h->W, h->d_partA.p, h->st);
+    launch_back_substitute(D, h->W, pa_model, h->st);
   }
-  {
-    Scope s(h, "reduce");
-    launch_reduce_sum(h->d_partA.p, D.n_tiles, 1, 0, h->W.scalars + S_MODEL, h->st);
-  }
-  const int gp = update_points_grid(D), gc = update_cameras_grid(D);
   {
     Scope s(h, "param_update", 0.0, 2);
-    launch_update_points(D, cur, cand, h->W, h->d_partA.p, h->st);
+    launch_update_points(D, cur, cand, h->W, pa_upd, h->st);
     launch_update_cameras(D, cur, cand, h->W, h->d_partB.p, h->st);
-  }
-  {
-    Scope s(h, "reduce", 0.0, 4);
-    launch_reduce_sum(h->d_partA.p, gp, 2, 0, h->W.scalars + S_STEP_PT, h->st);
-    launch_reduce_sum(h->d_partA.p, gp, 2, 1, h->W.scalars + S_X_PT, h->st);
-    launch_reduce_sum(h->d_partB.p, gc, 2, 0, h->W.scalars + S_STEP_CAM, h->st);
-    launch_reduce_sum(h->d_partB.p, gc, 2, 1, h->W.scalars + S_X_CAM, h->st);
   }
   {
     Scope s(h, "pose_rows");
     launch_pose_rows(cand, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
   }
-  {
+  if (speculate) {
+    {
+      Scope s(h, "jacobian", (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs));
+      launch_jacobian(D, cand, h->W, h->cb, h->two, /*unit_scale=*/0, pa_cost, h->st);
+    }
+    if (h->mf && h->cb) {
+      Scope s(h, "mf_rows");
+      launch_mf_rows(D, cand, h->W, h->st);
+    }
+    h->jacobian_at_candidate = true;
+  } else {
     Scope s(h, "cost", 24.0 * static_cast<double>(h->n_obs));
-    launch_cost(D, cand, h->d_partA.p, nullptr, h->st);
+    launch_cost(D, cand, pa_cost, nullptr, h->st);
   }
   {
     Scope s(h, "reduce");
-    launch_reduce_sum(h->d_partA.p, cost_grid(D), 1, 0, h->W.scalars + S_CAND, h->st);
+    ReduceJobs j;
+    j.sum(pa_model, D.n_tiles, 1, 0, h->W.scalars + S_MODEL);
+    j.sum(pa_upd, gp, 2, 0, h->W.scalars + S_STEP_PT);
+    j.sum(pa_upd, gp, 2, 1, h->W.scalars + S_X_PT);
+    j.sum(h->d_partB.p, gc, 2, 0, h->W.scalars + S_STEP_CAM);
+    j.sum(h->d_partB.p, gc, 2, 1, h->W.scalars + S_X_CAM);
+    j.sum(pa_cost, cost_grid(D), 1, 0, h->W.scalars + S_CAND);
+    launch_reduce_multi(j, h->st);
   }
   CU(h, cudaGetLastError());
+  return DBA_OK;
+}
+
+// The speculative evaluation left the Jacobian of a candidate that was not accepted: back to x.
+int restore_current_jacobian(dba_handle* h, bool jacobi_scaling) {
+  if (!h->jacobian_at_candidate) return DBA_OK;
+  h->jacobian_at_candidate = false;
+  return evaluate_jacobian(h, /*first=*/false, jacobi_scaling);
+}
+
+// The candidate of a speculative evaluation was accepted (h->cur already flipped): its cost is the
+// cost at x now; planes and camera rows are in place.
+int adopt_candidate_jacobian(dba_handle* h) {
+  h->jacobian_at_candidate = false;
+  CU(h, cudaMemcpyAsync(h->W.scalars + S_COST, h->W.scalars + S_CAND, sizeof(double), cudaMemcpyDeviceToDevice, h->st));
   return DBA_OK;
 }
 
@@ -592,7 +772,9 @@ void dba_destroy(dba_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   drain_events(h);
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
-  if (h->comm) nccl_api().CommDestroy(h->comm);
+  close_peer_windows(h);
+  if (h->comm) nccl_api().CommDestroy(h->comm);  // (a barrier in practice: peers have unmapped before the window goes)
+  if (h->win_local) cudaFree(h->win_local);
   delete h->upload;
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_pcg_state) cudaFreeHost(h->h_pcg_state);
@@ -1104,6 +1286,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     if (env && std::strcmp(env, "mf") == 0) h->mf = 1;
     const char* ef = std::getenv("DBA_PCG_FUSED");
     h->fuse_pcg = !(ef && std::strcmp(ef, "0") == 0);
+    const char* et = std::getenv("DBA_MF_TAIL");
+    h->mf_tail = !(et && std::strcmp(et, "0") == 0);
+    const char* es = std::getenv("DBA_SPECULATE");
+    h->speculate = !(es && std::strcmp(es, "0") == 0);
   }
   CU(h, ensure(h->d_partials_q, static_cast<size_t>(n_partials) * std::max(cb, 1)));
   CU(h, ensure(h->d_J, ld * h->j_planes));
@@ -1137,11 +1323,16 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_p, nvec));
   CU(h, ensure(h->d_q, nvec));
   h->q_split = (n_ext >= 296 || !cb) ? 1 : std::min(32, (592 + std::max(n_ext, 1) - 1) / std::max(n_ext, 1));
+  if (h->world > 1 && cb) {
+    int rc = setup_peer_windows(h, nvec);
+    if (rc != DBA_OK) return rc;
+  }
   CU(h, ensure(h->d_q_split, nvec * static_cast<size_t>(h->q_split)));
   CU(h, ensure(h->d_vec_partials, nvec / 128 + 2 * static_cast<size_t>(n_ext) + 8192));  // k_partials_to_q: one partial per block
   CU(h, ensure(h->d_counters, 4));
-  const size_t n_part = std::max<size_t>({static_cast<size_t>((nl + 255) / 256), 3 * static_cast<size_t>(n_tiles) + 3,
-                                          2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256), size_t{64}}) + 64;
+  // largest user: apply_step_and_evaluate keeps three ranges side by side (tiles | point update | cost)
+  const size_t n_part = static_cast<size_t>((nl + 255) / 256) + 3 * static_cast<size_t>(n_tiles) + 3 +
+                        2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256) + 256;
   CU(h, ensure(h->d_partA, n_part));
   CU(h, ensure(h->d_partB, 3 * static_cast<size_t>((std::max(n_ext, n_intr) + 63) / 64) + 64));
   CU(h, ensure(h->d_scalars, S_TOTAL));
@@ -1488,9 +1679,13 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
 
   if (h->n_obs_global == 0 || (h->n_pts_global == 0)) return finish(DBA_CONVERGENCE, "Function tolerance reached. No non-constant parameter blocks found.");
 
+  h->jacobian_at_candidate = false;
   int rc = evaluate_jacobian(h, /*first=*/true, o.jacobi_scaling != 0);
   if (rc != DBA_OK) return rc;
   sum->jacobian_evaluations += o.jacobi_scaling ? 2 : 1;
+  // speculate while steps keep being accepted (rejections cluster: after one, evaluate candidates
+  // with the cheap residual-only kernel until a step succeeds again)
+  bool expect_success = true;
   double radius = o.initial_trust_region_radius;
   double decrease_factor = 2.0;
   if ((rc = prepare_step(h, radius, o)) != DBA_OK) return rc;
@@ -1569,11 +1764,14 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     if (!linear_failure) {
       if (h->cb) {
         if ((rc = pcg_solve(h, o, &pcg_iters)) != DBA_OK) return rc;
-        sum->pcg_iterations_total += pcg_iters;
       }
-      if ((rc = apply_step_and_evaluate(h)) != DBA_OK) return rc;
+      const bool spec = h->speculate && expect_success;
+      if ((rc = apply_step_and_evaluate(h, spec)) != DBA_OK) return rc;
       sum->residual_evaluations++;
+      if (spec) sum->jacobian_evaluations++;
       if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
+      if ((rc = pcg_collect(h, &pcg_iters)) != DBA_OK) return rc;
+      sum->pcg_iterations_total += pcg_iters;
       model_cost_change = -S[S_MODEL];
       step_valid = std::isfinite(model_cost_change) && model_cost_change > 0.0 &&
                    std::isfinite(S[S_STEP_PT] + S[S_STEP_CAM]);
@@ -1598,6 +1796,8 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
       it.cost = x_cost;
       it.gradient_max_norm = prev.gradient_max_norm;
       it.gradient_norm = prev.gradient_norm;
+      expect_success = false;
+      if ((rc = restore_current_jacobian(h, o.jacobi_scaling != 0)) != DBA_OK) return rc;
       if ((rc = prepare_step(h, radius, o)) != DBA_OK) return rc;
       if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
       linear_failure = (S[S_BAD_PT] + S[S_BAD_CAM]) > 0.0;
@@ -1635,8 +1835,13 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     if (it.relative_decrease > o.min_relative_decrease) {
       // HandleSuccessfulStep: the candidate becomes x; Jacobian at the new point
       h->cur = 1 - h->cur;
-      if ((rc = evaluate_jacobian(h, false, o.jacobi_scaling != 0)) != DBA_OK) return rc;
-      sum->jacobian_evaluations++;
+      if (h->jacobian_at_candidate) {
+        if ((rc = adopt_candidate_jacobian(h)) != DBA_OK) return rc;
+      } else {
+        if ((rc = evaluate_jacobian(h, false, o.jacobi_scaling != 0)) != DBA_OK) return rc;
+        sum->jacobian_evaluations++;
+      }
+      expect_success = true;
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
       radius = std::min(o.max_trust_region_radius, radius);
       decrease_factor = 2.0;
@@ -1654,6 +1859,8 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
       it.gradient_norm = prev.gradient_norm;
       radius = radius / decrease_factor;
       decrease_factor *= 2.0;
+      expect_success = false;
+      if ((rc = restore_current_jacobian(h, o.jacobi_scaling != 0)) != DBA_OK) return rc;
       if ((rc = prepare_step(h, radius, o)) != DBA_OK) return rc;
       if ((rc = reduce_scalars_and_fetch(h)) != DBA_OK) return rc;
     }
@@ -1675,7 +1882,7 @@ int dba_params_get(dba_handle* h, double* pts, double* ext_rot, double* ext_tran
     } else {
       // every rank returns the full array: zero-padded local slice, summed over ranks
       const size_t total = 3 * static_cast<size_t>(h->n_pts_global);
-      CU(h, h->d_full_pts.alloc(std::max<size_t>(total, 1)));
+      CU(h, ensure(h->d_full_pts, total));  // grow-only: cudaMalloc is slow once peer windows are mapped
       CU(h, cudaMemsetAsync(h->d_full_pts.p, 0, total * sizeof(double), h->st));
       CU(h, cudaMemcpyAsync(h->d_full_pts.p + 3 * static_cast<size_t>(h->pt_lo), h->d_pts[c].p,
                             3 * sizeof(double) * h->n_pts, cudaMemcpyDeviceToDevice, h->st));

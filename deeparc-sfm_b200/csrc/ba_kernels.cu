@@ -21,6 +21,12 @@ namespace dba {
 
 namespace {
 
+// butterfly: every lane ends with the same total (fixed order)
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -850,12 +856,17 @@ struct MfSmem {
   static constexpr size_t kBytes = oC + static_cast<size_t>(NC) * S * sizeof(double);
 };
 
+template <int CB, bool MF>
+__device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter,
+                                         const PeerWin& pw, double* red, int* s_flag);
+
 // Persistent CTAs (grid = resident CTAs), each walking tiles blockIdx.x, += gridDim.x.  Everything a
 // tile needs from HBM is fetched one tile ahead with cp.async into the other stage buffer, so the
 // only exposed latency per tile is the L1/L2-resident camera-row load.
 template <int CB, bool TWO, int T, int MINB>
 __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays W, const double* __restrict__ pts,
-                                                      const IntrRow* __restrict__ intr_rows) {
+                                                      const IntrRow* __restrict__ intr_rows, int fuse_tail, double tol2,
+                                                      int min_iter, PeerWin pw) {
   if (W.pcg_state[1]) return;
   using L = MfSmem<CB, TWO, T>;
   constexpr int S = L::S, PS = L::PS, ROW = mf_row_len(CB), SEL = CB == 9 ? 24 : 18;
@@ -899,15 +910,17 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
   };
 
   int t = blockIdx.x;
-  if (t >= D.n_tiles) return;
-  TileMeta tm = D.tile_meta[t];
-  issue(0, t, tm);
+  TileMeta tm{};
+  if (t < D.n_tiles) {
+    tm = D.tile_meta[t];
+    issue(0, t, tm);
+  }
   cp_async_commit();
   int t_next = t + gridDim.x;
   TileMeta tm_next = tm;
   if (t_next < D.n_tiles) tm_next = D.tile_meta[t_next];
 
-  for (int k = 0;; ++k) {
+  for (int k = 0; t < D.n_tiles; ++k) {
     const int buf = k & 1;
     cp_async_wait_all();
     __syncthreads();  // [A] tile k landed for every thread; everyone is done with tile k-1
@@ -1101,6 +1114,12 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
     t_next += gridDim.x;
     tm = tm_next;
     tm_next = tm_after;
+  }
+  // ---- epilogue (cooperative launch only): the rest of the PCG iteration in the same kernel —
+  // per-camera sum of the partials just written, the cross-rank exchange, x / r / z / p updates
+  if (fuse_tail) {
+    cooperative_groups::this_grid().sync();  // every partial of every tile is in memory
+    pcg_tail<CB, true>(D, W, tol2, min_iter, pw, reinterpret_cast<double*>(smem_mf), reinterpret_cast<int*>(smem_mf + 512));
   }
 }
 
@@ -1311,93 +1330,179 @@ __global__ void __launch_bounds__(256) k_pcg_direction(DeviceProblem D, WorkArra
   if (i < n) W.p[i] = W.z[i] + W.pcg_scal[3] * W.p[i];
 }
 
-// Single-GPU PCG iteration tail in ONE cooperative launch (grid = co-resident CTAs, grid.sync
-// between the phases): per camera block q = T^T sum(partials) + D_c^2 p and p.q | alpha, x, r,
-// z = M^-1 r and r.z | beta, p = z + beta p, p~ = T p.  Replaces k_partials_to_q + k_pcg_step +
-// k_mf_direction (three launch latencies per PCG iteration).  All sums are fixed-order.
+// system-scope flag accesses of the peer exchange
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// PCG iteration tail in ONE cooperative launch (grid = co-resident CTAs, grid.sync between the
+// phases): per camera block q = T^T sum(partials) + D_c^2 p and p.q | alpha, x, r, z = M^-1 r and
+// r.z | beta, p = z + beta p, p~ = T p.  Replaces k_partials_to_q + k_pcg_step + k_mf_direction
+// (three launch latencies per PCG iteration).  All sums are fixed-order.
+// Multi-GPU (pw.world > 1): the allreduce of q is part of the same launch — each rank stores its
+// share of q into slot `rank` of every rank's peer window (NVLink P2P stores), raises one flag per
+// peer, waits for its own flags and adds the slots in rank order; x, r, z, p then evolve
+// bit-identically on every rank, so the dot products need no further communication.
+// The tail of one PCG iteration, executed by EVERY thread of a cooperative grid (any grid / block
+// shape; `red` = 32 doubles of shared memory).  One WARP per camera block, no block-level barrier
+// inside the phases:
+//   1. q = T^T sum(partials) [+ exchange with the peers] + D_c^2 p, p.q        | grid.sync
+//   2. alpha = rz / p.q; x += alpha p; r -= alpha q; z = M^-1 r; r.z            | grid.sync
+//   3. beta = r.z / rz; p = z + beta p; p~ = T p into the camera rows (MF)
+// Every sum has a fixed order (lane-strided rows, butterfly, per-CTA partials in CTA order).
 template <int CB, bool MF>
-__global__ void __launch_bounds__(256) k_pcg_fused(DeviceProblem D, WorkArrays W, double tol2, int min_iter) {
-  if (W.pcg_state[1]) return;
+__device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter,
+                                         const PeerWin& pw, double* red, int* s_flag) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
-  __shared__ double red[8][CB];
-  __shared__ double qg[CB], rn[CB];
-  __shared__ double red2[32];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wpb = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * wpb + (tid >> 5), n_warps = gridDim.x * wpb;
   const int nb = D.n_blocks;
+  const bool exchange = pw.world > 1;
+  const long long buf_off = static_cast<long long>(pw.seq & 1ull) * pw.world * pw.slot_len;
   double acc_dot = 0.0;
-  for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
+  // ---- phase 1
+  for (int blk = gwarp; blk < nb; blk += n_warps) {
     const int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
+    // the block's partial rows are one contiguous run of (i1 - i0) * CB doubles: the warp streams it
+    // with fully coalesced 8-byte loads, kM loads (= one chunk of 32 * kM elements, a whole number
+    // of rows) in flight per lane; element e of the run belongs to column e % CB, and within a
+    // chunk lane l / load m always sees column (32 m + l) % CB
+    constexpr int kG = (CB % 2 == 0) ? 2 : 1;  // gcd(32, CB) for CB in {6, 9}
+    constexpr int kM = CB / kG;
+    const double* run = W.partials_q + static_cast<int64_t>(i0) * CB;
+    const int n_el = (i1 - i0) * CB;
+    double part[kM];
+#pragma unroll
+    for (int m = 0; m < kM; ++m) part[m] = 0.0;
+    for (int e = lane; e < n_el; e += 32 * kM) {
+#pragma unroll
+      for (int m = 0; m < kM; ++m) {
+        const int ee = e + 32 * m;
+        if (ee < n_el) part[m] += __ldcg(run + ee);
+      }
+    }
     double acc[CB];
 #pragma unroll
-    for (int k = 0; k < CB; ++k) acc[k] = 0.0;
-    for (int i = i0 + tid; i < i1; i += 256) {
-      const double* pv = W.partials_q + static_cast<int64_t>(i) * CB;
-#pragma unroll
-      for (int k = 0; k < CB; ++k) acc[k] += pv[k];
-    }
-#pragma unroll
     for (int k = 0; k < CB; ++k) {
-      const double sm = warp_sum(acc[k]);
-      if (lane == 0) red[wid][k] = sm;
-    }
-    __syncthreads();
-    if (tid < CB) {
-      double sm = 0.0;
+      double v = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) sm += red[w][tid];
-      qg[tid] = sm;
+      for (int m = 0; m < kM; ++m) v = ((32 * m + lane) % CB == k) ? part[m] : v;
+      acc[k] = warp_sum_all(v);
     }
-    __syncthreads();
-    if (tid < CB) {
-      const int64_t i = static_cast<int64_t>(blk) * CB + tid;
-      double q = qg[tid];
+    double q = 0.0;
+#pragma unroll
+    for (int k = 0; k < CB; ++k)
+      if (lane == k) q = acc[k];
+    if (lane < CB) {
+      const int64_t i = static_cast<int64_t>(blk) * CB + lane;
       if (MF) {
         const double* Tm = W.mf_T + static_cast<int64_t>(blk) * (9 + CB);
-        if (tid < 3) q = Tm[tid] * qg[0] + Tm[3 + tid] * qg[1] + Tm[6 + tid] * qg[2];
-        q *= Tm[9 + tid];
+        if (lane < 3) q = Tm[lane] * acc[0] + Tm[3 + lane] * acc[1] + Tm[6 + lane] * acc[2];
+        q *= Tm[9 + lane];
       }
-      const double p = W.p[i];
-      q += W.dc2[i] * p;
-      W.q[i] = q;
-      acc_dot += p * q;
+      if (exchange) {
+        // push this rank's share of q into slot `rank` of every window (own window included)
+        const long long off = buf_off + static_cast<long long>(pw.rank) * pw.slot_len + i;
+#pragma unroll 1
+        for (int r = 0; r < pw.world; ++r) pw.data[r][off] = q;
+      } else {
+        const double p = W.p[i];
+        q += W.dc2[i] * p;
+        W.q[i] = q;
+        acc_dot += p * q;
+      }
     }
   }
-  if (tid < 32) {
-    const double sm = warp_sum(tid < CB ? acc_dot : 0.0);
-    if (tid == 0) W.vec_partials[blockIdx.x] = sm;
+  if (exchange) {
+    __threadfence_system();  // the pushed values are visible system-wide before any flag is raised
+    grid.sync();
+    if (blockIdx.x == 0) {
+      if (tid < pw.world && tid != pw.rank) st_release_sys(pw.flags[tid] + pw.rank, pw.seq);
+      int ok = 1;
+      if (tid < pw.world && tid != pw.rank) {
+        const long long t0 = global_ns();
+        while (ld_acquire_sys(pw.flags[pw.rank] + tid) < pw.seq) {
+          if (global_ns() - t0 > pw.timeout_ns) {
+            ok = 0;
+            break;
+          }
+          __nanosleep(100);
+        }
+      }
+      ok = __syncthreads_and(ok);
+      if (tid == 0) {
+        if (!ok) {
+          W.pcg_state[2] = 1;
+          W.pcg_state[1] = 1;
+        }
+        st_release_sys(pw.go, ok ? pw.seq : ~0ull);
+        *s_flag = ok;
+      }
+    } else if (tid == 0) {
+      unsigned long long g;
+      while ((g = ld_acquire_sys(pw.go)) < pw.seq) __nanosleep(50);
+      *s_flag = g != ~0ull;
+    }
+    __syncthreads();
+    if (!*s_flag) return;  // every CTA takes the same exit: no grid.sync is left half-attended
+    // q = sum of the slots in rank order (the same order on every rank) + D_c^2 p
+    const double* mine = pw.data[pw.rank] + buf_off;
+    for (int blk = gwarp; blk < nb; blk += n_warps) {
+      if (lane < CB) {
+        const int64_t i = static_cast<int64_t>(blk) * CB + lane;
+        double q = 0.0;
+#pragma unroll 1
+        for (int r = 0; r < pw.world; ++r) q += __ldcg(mine + static_cast<long long>(r) * pw.slot_len + i);
+        const double p = W.p[i];
+        q += W.dc2[i] * p;
+        W.q[i] = q;
+        acc_dot += p * q;
+      }
+    }
   }
+  acc_dot = block_sum(acc_dot, red);
+  if (tid == 0) W.vec_partials[blockIdx.x] = acc_dot;
   grid.sync();
-  const double pq = sum_partials(W.vec_partials, gridDim.x, red2);
+  // ---- phase 2
+  const double pq = sum_partials(W.vec_partials, gridDim.x, red);
   const double rz = W.pcg_scal[0];
   const bool breakdown = !(pq > 0.0) || !isfinite(pq);
   acc_dot = 0.0;
   if (!breakdown) {
     const double alpha = rz / pq;
-    for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
-      const int64_t i = static_cast<int64_t>(blk) * CB + tid;
-      if (tid < CB) {
+    for (int blk = gwarp; blk < nb; blk += n_warps) {
+      const int64_t i = static_cast<int64_t>(blk) * CB + lane;
+      double r = 0.0;
+      if (lane < CB) {
         W.x[i] += alpha * W.p[i];
-        const double r = W.r[i] - alpha * W.q[i];
+        r = W.r[i] - alpha * W.q[i];
         W.r[i] = r;
-        rn[tid] = r;
       }
-      __syncthreads();
-      if (tid < CB) {
-        const double* Mi = W.minv + i * CB;
-        double z = 0.0;
+      double z = 0.0;
+      const double* Mi = W.minv + (lane < CB ? i : static_cast<int64_t>(blk) * CB) * CB;
 #pragma unroll
-        for (int k = 0; k < CB; ++k) z += Mi[k] * rn[k];
+      for (int k = 0; k < CB; ++k) z += Mi[k] * __shfl_sync(kFull, r, k);
+      if (lane < CB) {
         W.z[i] = z;
-        acc_dot += rn[tid] * z;
+        acc_dot += r * z;
       }
-      __syncthreads();
     }
   }
-  if (tid < 32) {
-    const double sm = warp_sum(tid < CB ? acc_dot : 0.0);
-    if (tid == 0) W.vec_partials[gridDim.x + blockIdx.x] = sm;
-  }
+  acc_dot = block_sum(acc_dot, red);
+  if (tid == 0) W.vec_partials[gridDim.x + blockIdx.x] = acc_dot;
   grid.sync();
   if (breakdown) {
     if (blockIdx.x == 0 && tid == 0) {
@@ -1406,25 +1511,26 @@ __global__ void __launch_bounds__(256) k_pcg_fused(DeviceProblem D, WorkArrays W
     }
     return;
   }
-  const double rz_new = sum_partials(W.vec_partials + gridDim.x, gridDim.x, red2);
+  // ---- phase 3
+  const double rz_new = sum_partials(W.vec_partials + gridDim.x, gridDim.x, red);
   const double beta = rz_new / rz;
-  for (int blk = blockIdx.x; blk < nb; blk += gridDim.x) {
-    const int64_t i = static_cast<int64_t>(blk) * CB + tid;
-    if (tid < CB) {
+  for (int blk = gwarp; blk < nb; blk += n_warps) {
+    const int64_t i = static_cast<int64_t>(blk) * CB + lane;
+    double ps = 0.0;
+    if (lane < CB) {
       const double p = W.z[i] + beta * W.p[i];
       W.p[i] = p;
-      if (MF) rn[tid] = p * W.mf_T[static_cast<int64_t>(blk) * (9 + CB) + 9 + tid];
+      if (MF) ps = p * W.mf_T[static_cast<int64_t>(blk) * (9 + CB) + 9 + lane];
     }
     if (MF) {
-      __syncthreads();
-      if (tid < CB) {
-        constexpr int ROW = mf_row_len(CB), PO = CB == 9 ? 15 : 12;
+      constexpr int ROW = mf_row_len(CB), PO = CB == 9 ? 15 : 12;
+      const double p0 = __shfl_sync(kFull, ps, 0), p1 = __shfl_sync(kFull, ps, 1), p2 = __shfl_sync(kFull, ps, 2);
+      if (lane < CB) {
         const double* Tm = W.mf_T + static_cast<int64_t>(blk) * (9 + CB);
-        double v = rn[tid];
-        if (tid < 3) v = Tm[3 * tid] * rn[0] + Tm[3 * tid + 1] * rn[1] + Tm[3 * tid + 2] * rn[2];
-        W.mf_rows[static_cast<int64_t>(blk) * ROW + PO + tid] = v;
+        double v = ps;
+        if (lane < 3) v = Tm[3 * lane] * p0 + Tm[3 * lane + 1] * p1 + Tm[3 * lane + 2] * p2;
+        W.mf_rows[static_cast<int64_t>(blk) * ROW + PO + lane] = v;
       }
-      __syncthreads();
     }
   }
   if (blockIdx.x == 0 && tid == 0) {
@@ -1434,6 +1540,17 @@ __global__ void __launch_bounds__(256) k_pcg_fused(DeviceProblem D, WorkArrays W
     W.pcg_scal[0] = rz_new;
     if ((it >= min_iter && rz_new <= tol2 * W.pcg_scal[1]) || !(rz_new > 0.0)) W.pcg_state[1] = 1;
   }
+}
+
+// Stand-alone launch of the tail (after k_spmv_tile, or after a k_spmv_mf that could not be
+// launched cooperatively); k_spmv_mf normally runs it as its own epilogue.
+constexpr int kFusedThreads = 256;
+template <int CB, bool MF>
+__global__ void __launch_bounds__(kFusedThreads) k_pcg_fused(DeviceProblem D, WorkArrays W, double tol2, int min_iter, PeerWin pw) {
+  if (W.pcg_state[1]) return;
+  __shared__ double red[32];
+  __shared__ int s_flag;
+  pcg_tail<CB, MF>(D, W, tol2, min_iter, pw, red, &s_flag);
 }
 
 // ------------------------------------------------------------- K7 back-substitution
@@ -1612,6 +1729,21 @@ __global__ void __launch_bounds__(1024) k_reduce_max(const double* __restrict__ 
   if (threadIdx.x == 0) *out = acc;
 }
 
+// several of those in one launch: CTA j runs job j (same summation order as the single kernels)
+__global__ void __launch_bounds__(1024) k_reduce_multi(ReduceJobs J) {
+  __shared__ double red[32];
+  const ReduceJob job = J.job[blockIdx.x];
+  double acc = 0.0;
+  if (job.is_max) {
+    for (int i = threadIdx.x; i < job.n; i += blockDim.x) acc = fmax(acc, job.in[static_cast<int64_t>(i) * job.stride + job.offset]);
+    acc = block_max(acc, red);
+  } else {
+    for (int i = threadIdx.x; i < job.n; i += blockDim.x) acc += job.in[static_cast<int64_t>(i) * job.stride + job.offset];
+    acc = block_sum(acc, red);
+  }
+  if (threadIdx.x == 0) *job.out = acc;
+}
+
 }  // namespace
 
 // ================================================================== launch wrappers
@@ -1750,25 +1882,29 @@ void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_
 }
 
 template <int CB, bool MF>
-static int launch_pcg_fused_t(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st) {
+static int launch_pcg_fused_t(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, const PeerWin& pw,
+                              cudaStream_t st) {
   static int resident = 0;
   if (resident == 0) {
     int dev = 0, n_sm = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_fused<CB, MF>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_fused<CB, MF>, kFusedThreads, 0);
     resident = std::max(1, n_sm * per_sm);
   }
   const int grid = std::min(D.n_blocks, resident);
   DeviceProblem d = D;
   WorkArrays w = W;
-  void* args[] = {&d, &w, &tol2, &min_iter};
-  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_fused<CB, MF>), dim3(grid), dim3(256), args, 0, st) == cudaSuccess ? 0 : -1;
+  PeerWin win = pw;
+  void* args[] = {&d, &w, &tol2, &min_iter, &win};
+  return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_fused<CB, MF>), dim3(grid), dim3(kFusedThreads), args, 0, st) == cudaSuccess ? 0 : -1;
 }
-int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, cudaStream_t st) {
+int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, const PeerWin& pw,
+                     cudaStream_t st) {
   if (D.n_blocks == 0) return 0;
-  if (D.cb == 6) return mf ? launch_pcg_fused_t<6, true>(D, W, tol2, min_iter, st) : launch_pcg_fused_t<6, false>(D, W, tol2, min_iter, st);
-  return mf ? launch_pcg_fused_t<9, true>(D, W, tol2, min_iter, st) : launch_pcg_fused_t<9, false>(D, W, tol2, min_iter, st);
+  if (D.cb == 6)
+    return mf ? launch_pcg_fused_t<6, true>(D, W, tol2, min_iter, pw, st) : launch_pcg_fused_t<6, false>(D, W, tol2, min_iter, pw, st);
+  return mf ? launch_pcg_fused_t<9, true>(D, W, tol2, min_iter, pw, st) : launch_pcg_fused_t<9, false>(D, W, tol2, min_iter, pw, st);
 }
 
 void launch_mf_rows(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
@@ -1786,7 +1922,7 @@ void launch_mf_direction(const DeviceProblem& D, const WorkArrays& W, int init, 
 }
 
 template <int CB, bool TWO, int T, int MINB>
-static void launch_spmv_mf_tt(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
+static int launch_spmv_mf_tt(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, const MfTail& tail, cudaStream_t st) {
   static bool configured = false;
   constexpr size_t smem = MfSmem<CB, TWO, T>::kBytes;
   static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
@@ -1804,7 +1940,20 @@ static void launch_spmv_mf_tt(const DeviceProblem& D, const ParamSet& P, const W
   int resident = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, k_spmv_mf<CB, TWO, T, MINB>, T, smem);
   const int grid = std::min(D.n_tiles, n_sm * std::max(resident, 1));
-  k_spmv_mf<CB, TWO, T, MINB><<<grid, T, smem, st>>>(D, W, P.pts, P.intr_rows);
+  if (tail.fuse) {
+    // the grid is exactly the co-resident CTAs, so it qualifies for a cooperative launch (grid.sync)
+    DeviceProblem d = D;
+    WorkArrays w = W;
+    const double* pts = P.pts;
+    const IntrRow* ir = P.intr_rows;
+    int fuse = 1, min_iter = tail.min_iter;
+    double tol2 = tail.tol2;
+    PeerWin pw = tail.pw;
+    void* args[] = {&d, &w, &pts, &ir, &fuse, &tol2, &min_iter, &pw};
+    return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_spmv_mf<CB, TWO, T, MINB>), dim3(grid), dim3(T), args, smem, st) == cudaSuccess ? 0 : -1;
+  }
+  k_spmv_mf<CB, TWO, T, MINB><<<grid, T, smem, st>>>(D, W, P.pts, P.intr_rows, 0, 0.0, 0, PeerWin{});
+  return 0;
 }
 // resident CTAs per SM requested from the register allocator for 256-thread tiles (tuning knob DBA_MF_MINB)
 static int mf_minb() {
@@ -1817,27 +1966,25 @@ static int mf_minb() {
   return v;
 }
 template <int CB, bool TWO>
-static void launch_spmv_mf_t(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
+static int launch_spmv_mf_t(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, const MfTail& tail, cudaStream_t st) {
   if (D.tile == 256) {
     const int mb = mf_minb();
-    if (mb == 2) launch_spmv_mf_tt<CB, TWO, 256, 2>(D, P, W, st);
-    else if (mb == 3) launch_spmv_mf_tt<CB, TWO, 256, 3>(D, P, W, st);
-    else launch_spmv_mf_tt<CB, TWO, 256, 4>(D, P, W, st);
+    if (mb == 2) return launch_spmv_mf_tt<CB, TWO, 256, 2>(D, P, W, tail, st);
+    if (mb == 3) return launch_spmv_mf_tt<CB, TWO, 256, 3>(D, P, W, tail, st);
+    return launch_spmv_mf_tt<CB, TWO, 256, 4>(D, P, W, tail, st);
   } else if (D.tile == 512) {
-    launch_spmv_mf_tt<CB, TWO, 512, TWO ? 1 : 2>(D, P, W, st);
+    return launch_spmv_mf_tt<CB, TWO, 512, TWO ? 1 : 2>(D, P, W, tail, st);
   } else if constexpr (!TWO) {
-    launch_spmv_mf_tt<CB, TWO, 1024, 1>(D, P, W, st);
+    return launch_spmv_mf_tt<CB, TWO, 1024, 1>(D, P, W, tail, st);
   }
+  return -1;
 }
 
-void launch_spmv_mf(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
-  if (D.n_tiles == 0) return;
-  if (D.cb == 6 && !D.two)
-    launch_spmv_mf_t<6, false>(D, P, W, st);
-  else if (D.cb == 6)
-    launch_spmv_mf_t<6, true>(D, P, W, st);
-  else
-    launch_spmv_mf_t<9, false>(D, P, W, st);
+int launch_spmv_mf(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, const MfTail& tail, cudaStream_t st) {
+  if (D.n_tiles == 0) return tail.fuse ? -1 : 0;
+  if (D.cb == 6 && !D.two) return launch_spmv_mf_t<6, false>(D, P, W, tail, st);
+  if (D.cb == 6) return launch_spmv_mf_t<6, true>(D, P, W, tail, st);
+  return launch_spmv_mf_t<9, false>(D, P, W, tail, st);
 }
 
 // q = sum of the slices (multi-GPU with n_split > 1: input of the allreduce)
@@ -1923,6 +2070,9 @@ void launch_reduce_sum(const double* partials, int n, int stride, int offset, do
 }
 void launch_reduce_max(const double* partials, int n, int stride, int offset, double* out, cudaStream_t st) {
   k_reduce_max<<<1, 1024, 0, st>>>(partials, n, stride, offset, out);
+}
+void launch_reduce_multi(const ReduceJobs& jobs, cudaStream_t st) {
+  if (jobs.count > 0) k_reduce_multi<<<jobs.count, 1024, 0, st>>>(jobs);
 }
 
 }  // namespace dba

@@ -111,7 +111,7 @@ struct WorkArrays {
   double *x, *r, *z, *p, *q;
   double* partials;  // [n_partials] per-CTA partial sums (deterministic reductions)
   double* scalars;   // [32] reduced scalars, copied to the host
-  int* pcg_state;    // [4] iter, done, -, -
+  int* pcg_state;    // [4] iter, done, peer exchange timed out, -
   double* pcg_scal;  // [4] rz, rz0, p.q, beta
   double* q_split;     // [n_split][n_blocks * cb] slices of q when the per-camera sum is split
   double* partials_q;  // [n_partials][cb] tile-local partial products of the implicit Schur product
@@ -124,6 +124,23 @@ struct WorkArrays {
   double* mf_T;      // [n_blocks][9 + cb]  J_l row-major, then sc * free
   double* vec_partials;    // per-CTA partials of the PCG vector kernels
   unsigned int* counters;  // [4] "last block" arrival counters
+};
+
+// Peer windows of the fused PCG tail (multi-GPU): every rank owns one window in its HBM,
+//   data  [2 buffers][world slots][slot_len] doubles   slot s = camera-space vector pushed by rank s
+//   flags [world] u64 | go u64                         flags[s] = last exchange whose slot s is complete
+// mapped into the other ranks through CUDA IPC, so a rank PUSHES its partial q = S p straight into
+// the HBM of every peer over NVLink (plain stores), raises the flags, waits for its own flags and
+// sums the slots in rank order (bit-identical on every rank, no NCCL call on the PCG path).
+constexpr int kMaxPeers = 8;
+struct PeerWin {
+  int world = 1, rank = 0;
+  unsigned long long seq = 0;   // number of this exchange (1, 2, ...), identical on every rank
+  long long slot_len = 0;       // doubles per slot
+  long long timeout_ns = 0;     // give up waiting for a peer after this long (error flag, no hang)
+  double* data[kMaxPeers] = {};
+  unsigned long long* flags[kMaxPeers] = {};
+  unsigned long long* go = nullptr;  // local: CTA 0 publishes `seq` (all slots in) or ~0 (timeout)
 };
 
 // scalar slots in WorkArrays::scalars
@@ -171,14 +188,23 @@ void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_
 // matrix-free variant: camera rows (static part) after a Jacobian evaluation; p (+)= ..., p~ = T p; the product
 void launch_mf_rows(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st);
 void launch_mf_direction(const DeviceProblem& D, const WorkArrays& W, int init, cudaStream_t st);
-void launch_spmv_mf(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st);
+// tail.fuse: cooperative launch whose epilogue is the rest of the PCG iteration (pcg_tail: per-camera
+// partial sum, peer exchange, vector updates).  Returns 0 on success, -1 when the launch failed.
+struct MfTail {
+  int fuse = 0, min_iter = 0;
+  double tol2 = 0.0;
+  PeerWin pw{};
+};
+int launch_spmv_mf(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, const MfTail& tail, cudaStream_t st);
 // PCG vector phases: q += D_c^2 p and p.q; the x/r/z update with r.z; the new direction
 void launch_fold_q(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st);
 void launch_pcg_dot(const DeviceProblem& D, const WorkArrays& W, int n_split, cudaStream_t st);
 void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, cudaStream_t st);
 void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // single GPU: partial sum + all three vector phases in one cooperative launch; returns 0 on success
-int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, cudaStream_t st);
+// pw.world > 1: the partial q of every rank is exchanged through the peer windows inside the launch
+int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, const PeerWin& pw,
+                     cudaStream_t st);
 // dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
 void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st);
 // candidate = current + scale * step; partials[2*cta + {0,1}] = {sum step^2, sum x^2}
@@ -191,5 +217,18 @@ void launch_update_cameras(const DeviceProblem& D, const ParamSet& cur, const Pa
 // deterministic single-CTA reductions of strided partials
 void launch_reduce_sum(const double* partials, int n, int stride, int offset, double* out, cudaStream_t st);
 void launch_reduce_max(const double* partials, int n, int stride, int offset, double* out, cudaStream_t st);
+// up to 8 of them in one launch (one CTA per job)
+struct ReduceJob {
+  const double* in;
+  double* out;
+  int n, stride, offset, is_max;
+};
+struct ReduceJobs {
+  ReduceJob job[8];
+  int count = 0;
+  void sum(const double* in, int n, int stride, int offset, double* out) { job[count++] = ReduceJob{in, out, n, stride, offset, 0}; }
+  void max(const double* in, int n, int stride, int offset, double* out) { job[count++] = ReduceJob{in, out, n, stride, offset, 1}; }
+};
+void launch_reduce_multi(const ReduceJobs& jobs, cudaStream_t st);
 
 }  // namespace dba

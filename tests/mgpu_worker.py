@@ -1,6 +1,7 @@
 """Worker of the 2-GPU test (launched by torch.distributed.run, one rank per GPU): the
-point-sharded solve with NCCL allreduce of the camera-space vectors must reproduce the
-single-GPU solve to reduction-order round-off."""
+point-sharded solve must reproduce the single-GPU solve to reduction-order round-off — with the
+camera-space vectors combined by ncclAllReduce (few camera blocks: the per-camera sum is split)
+and by the fused PCG tail that exchanges them through the NVLink peer windows ("bal320")."""
 import ctypes
 import os
 import sys
@@ -25,14 +26,21 @@ dist.broadcast(buf, 0)
 uid = bytes(buf.cpu().numpy().tobytes())
 
 eng = capi.Engine(device=local, rank=rank, world_size=world, nccl_unique_id=uid)  # one communicator per unique id
+fused_before = 0
 for name, p in (("bal", synthetic.bal_like(n_cam=60, n_pts=6000, window=12, seed=91)),
-                ("rig", synthetic.arc_rig(n_arc=4, n_ring=5, n_pts=3000, obs_per_point=8, seed=92))):
+                ("rig", synthetic.arc_rig(n_arc=4, n_ring=5, n_pts=3000, obs_per_point=8, seed=92)),
+                ("bal320", synthetic.bal_like(n_cam=320, n_pts=24000, window=20, seed=93))):
     opts = capi.make_options(max_num_iterations=5, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
                              linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=1e-13, pcg_max_iterations=3000)
     eng.problem_set(p)
     c0 = eng.eval(residuals=False)["cost"]
     s = eng.solve(opts)
     x = eng.params_get()
+    launched = {k["name"]: k["launches"] for k in eng.kernel_stats()}
+    if name == "bal320" and os.environ.get("DBA_P2P", "1") != "0":
+        # >= 296 camera blocks: one fused launch per PCG iteration, no ncclAllReduce on the PCG path
+        assert launched.get("pcg_fused", 0) > 0 and launched.get("partials_to_q", 0) == fused_before, launched
+    fused_before = launched.get("partials_to_q", 0)
     if rank == 0:
         one = capi.Engine(device=local)
         one.problem_set(p)
