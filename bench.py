@@ -275,6 +275,7 @@ def main():
     barrier()
 
     # ---- end to end through the C ABI with host buffers
+    eng.params_get()  # warm-up of the read-back path (first large NCCL message, staging buffers)
     barrier()
     t0 = time.perf_counter()
     eng.problem_set(p)

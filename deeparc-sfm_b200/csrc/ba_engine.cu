@@ -1018,6 +1018,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   want((n_ent_max + n_tiles + 1) * sizeof(int));    // part_first
   want((n_ent_max / 1024 + n_ext + 2) * sizeof(int4));  // cam_chunks
   want((n_ext + 1) * sizeof(int) * 3);
+  want(3 * sizeof(double) * static_cast<size_t>(h->n_pts));  // the caller's points (pageable) staged for the async copy
   PinnedArena& A = arena_of(h);
   CU(h, cudaStreamSynchronize(h->st));  // the arena may still feed copies of a previous call
   CU(h, A.reserve(arena_bytes));
@@ -1380,7 +1381,20 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_nf.p, p->intr_nf, sizeof(int) * n_intr));
   CU(h, up(h->d_nd.p, p->intr_nd, sizeof(int) * n_intr));
   // slot 2 = pristine copy for dba_params_reset, slot 0 = current
-  CU(h, up(h->d_pts[2].p, p->pts + 3 * static_cast<size_t>(pt_lo), 3 * sizeof(double) * n_pts));
+  {
+    // pageable -> pinned with all host cores, then one asynchronous copy (a pageable cudaMemcpy of
+    // 24 MB runs at a fraction of the link rate)
+    const size_t n3 = 3 * static_cast<size_t>(n_pts);
+    double* s_pts = A.take<double>(std::max<size_t>(n3, 1));
+    const double* src = p->pts + 3 * static_cast<size_t>(pt_lo);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < static_cast<int64_t>((n3 + 65535) / 65536); ++c) {
+      const size_t a = static_cast<size_t>(c) * 65536, b = std::min(n3, a + 65536);
+      std::memcpy(s_pts + a, src + a, (b - a) * sizeof(double));
+    }
+    CU(h, up(h->d_pts[2].p, s_pts, n3 * sizeof(double)));
+  }
+  if (h->world > 1) CU(h, ensure(h->d_full_pts, 3 * static_cast<size_t>(h->n_pts_global)));  // dba_params_get
   CU(h, up(h->d_rot[2].p, p->ext_rot, 3 * sizeof(double) * n_ext));
   CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * n_ext));
   CU(h, up(h->d_focal[2].p, p->intr_focal, 2 * sizeof(double) * n_intr));
@@ -1877,18 +1891,29 @@ int dba_params_get(dba_handle* h, double* pts, double* ext_rot, double* ext_tran
   CU(h, cudaSetDevice(h->device));
   const int c = h->cur;
   if (pts) {
+    // device -> pinned arena (one asynchronous copy at link rate) -> the caller's buffer (all host cores)
+    const size_t total = 3 * static_cast<size_t>(h->world == 1 ? h->n_pts : h->n_pts_global);
+    PinnedArena& A = arena_of(h);
+    CU(h, cudaStreamSynchronize(h->st));
+    CU(h, A.reserve(std::max(A.cap, total * sizeof(double) + 512)));
+    double* stage = A.take<double>(std::max<size_t>(total, 1));
     if (h->world == 1) {
-      CU(h, cudaMemcpyAsync(pts, h->d_pts[c].p, 3 * sizeof(double) * h->n_pts, cudaMemcpyDeviceToHost, h->st));
+      CU(h, cudaMemcpyAsync(stage, h->d_pts[c].p, total * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     } else {
       // every rank returns the full array: zero-padded local slice, summed over ranks
-      const size_t total = 3 * static_cast<size_t>(h->n_pts_global);
       CU(h, ensure(h->d_full_pts, total));  // grow-only: cudaMalloc is slow once peer windows are mapped
       CU(h, cudaMemsetAsync(h->d_full_pts.p, 0, total * sizeof(double), h->st));
       CU(h, cudaMemcpyAsync(h->d_full_pts.p + 3 * static_cast<size_t>(h->pt_lo), h->d_pts[c].p,
                             3 * sizeof(double) * h->n_pts, cudaMemcpyDeviceToDevice, h->st));
       int rc = allreduce(h, h->d_full_pts.p, total, kNcclSum);
       if (rc != DBA_OK) return rc;
-      CU(h, cudaMemcpyAsync(pts, h->d_full_pts.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+      CU(h, cudaMemcpyAsync(stage, h->d_full_pts.p, total * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    }
+    CU(h, cudaStreamSynchronize(h->st));
+#pragma omp parallel for schedule(static)
+    for (int64_t ch = 0; ch < static_cast<int64_t>((total + 65535) / 65536); ++ch) {
+      const size_t a = static_cast<size_t>(ch) * 65536, b = std::min(total, a + 65536);
+      std::memcpy(pts + a, stage + a, (b - a) * sizeof(double));
     }
   }
   if (ext_rot) CU(h, cudaMemcpyAsync(ext_rot, h->d_rot[c].p, 3 * sizeof(double) * h->n_ext, cudaMemcpyDeviceToHost, h->st));

@@ -39,7 +39,7 @@ for name, p in (("bal", synthetic.bal_like(n_cam=60, n_pts=6000, window=12, seed
     launched = {k["name"]: k["launches"] for k in eng.kernel_stats()}
     if name == "bal320" and os.environ.get("DBA_P2P", "1") != "0":
         # >= 296 camera blocks: one fused launch per PCG iteration, no ncclAllReduce on the PCG path
-        assert launched.get("pcg_fused", 0) > 0 and launched.get("partials_to_q", 0) == fused_before, launched
+        assert launched.get("spmv_mf_pcg", 0) + launched.get("pcg_fused", 0) > 0 and launched.get("partials_to_q", 0) == fused_before, launched
     fused_before = launched.get("partials_to_q", 0)
     if rank == 0:
         one = capi.Engine(device=local)

@@ -154,23 +154,68 @@ def test_matrix_free_product_matches_plane_product(engine, name, monkeypatch):
     kw = dict(max_num_iterations=4, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
               linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=0.0, pcg_max_iterations=12)
     runs = {}
-    for mode in ("planes", "mf", "mf_unfused"):
+    for mode in ("planes", "mf", "mf_tail_off", "mf_unfused"):
         monkeypatch.delenv("DBA_SPMV", raising=False)
         monkeypatch.delenv("DBA_PCG_FUSED", raising=False)
+        monkeypatch.delenv("DBA_MF_TAIL", raising=False)
         monkeypatch.setenv("DBA_SPMV", "planes" if mode == "planes" else "mf")
+        if mode == "mf_tail_off":  # PCG tail as its own cooperative launch instead of the k_spmv_mf epilogue
+            monkeypatch.setenv("DBA_MF_TAIL", "0")
         if mode == "mf_unfused":  # separate k_partials_to_q / k_pcg_step / k_mf_direction launches
             monkeypatch.setenv("DBA_PCG_FUSED", "0")
         engine.problem_set(p)
         s = engine.solve(capi.make_options(**kw))
         runs[mode] = (s, engine.params_get())
     sa, xa = runs["planes"]
-    for other in ("mf", "mf_unfused"):
+    for other in ("mf", "mf_tail_off", "mf_unfused"):
         sb, xb = runs[other]
         assert np.array_equal(sa.trace("step_is_successful"), sb.trace("step_is_successful"))
         np.testing.assert_allclose(sb.trace("cost"), sa.trace("cost"), rtol=1e-9)
         for k in ("pts", "ext_rot", "ext_trans", "intr_focal", "intr_dist"):
             scale = max(np.max(np.abs(xa[k])), 1e-300)
             assert np.max(np.abs(xa[k] - xb[k])) <= 1e-8 * scale, (other, k)
+
+
+def _perturbed_bal(pt_noise, rot_noise):
+    p = synthetic.bal_like(n_cam=40, n_pts=1500, window=10, seed=31)
+    rng = np.random.default_rng(5)
+    p.pts = p.pts + pt_noise * rng.standard_normal(p.pts.shape)
+    p.ext_rot = p.ext_rot + rot_noise * rng.standard_normal(p.ext_rot.shape)
+    return p
+
+
+def test_lm_with_rejected_step_matches_oracle(engine, oracle):
+    """A start far enough from the optimum that the trust region rejects a step (iteration 4):
+    the reject branch (radius /= nu, nu *= 2, Jacobian restored after the speculative
+    evaluation of the candidate) follows the oracle."""
+    sg, so = _compare_solve(engine, oracle, _perturbed_bal(0.2, 0.05), n_iter=7)
+    assert 0 < sg.num_unsuccessful_steps == so.num_unsuccessful_steps
+
+
+def test_speculative_evaluation_does_not_change_the_trace(engine, monkeypatch):
+    """Candidates are evaluated by the Jacobian kernel while steps are being accepted and by the
+    residual-only kernel after a rejection (DBA_SPECULATE=0: always the latter).  Same residual
+    code and summation order: a trace with streaks of rejected and invalid steps is unchanged."""
+    p = _perturbed_bal(1.0, 0.1)
+    kw = dict(max_num_iterations=11, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+              linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=1e-13, pcg_max_iterations=2000,
+              initial_trust_region_radius=1e6)
+    runs = {}
+    for spec in ("1", "0"):
+        monkeypatch.setenv("DBA_SPECULATE", spec)
+        engine.problem_set(p)
+        s = engine.solve(capi.make_options(**kw))
+        runs[spec] = (s, engine.params_get())
+    monkeypatch.delenv("DBA_SPECULATE", raising=False)
+    (sa, xa), (sb, xb) = runs["1"], runs["0"]
+    assert sa.num_unsuccessful_steps >= 3 and sa.num_successful_steps >= 3
+    assert sa.jacobian_evaluations > sb.jacobian_evaluations  # speculation really ran
+    assert np.array_equal(sa.trace("step_is_successful"), sb.trace("step_is_successful"))
+    np.testing.assert_allclose(sa.trace("cost"), sb.trace("cost"), rtol=1e-9)
+    np.testing.assert_allclose(sa.trace("trust_region_radius"), sb.trace("trust_region_radius"), rtol=1e-9)
+    for k in ("pts", "ext_rot", "ext_trans", "intr_focal", "intr_dist"):
+        scale = max(np.max(np.abs(xa[k])), 1e-300)
+        assert np.max(np.abs(xa[k] - xb[k])) <= 1e-8 * scale, k
 
 
 @pytest.mark.parametrize("kind", ["rig_512", "bal_1024"])
