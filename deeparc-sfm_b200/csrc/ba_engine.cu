@@ -1024,6 +1024,12 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, A.reserve(arena_bytes));
 
   mark("arena reserve");
+  // Copies are enqueued as soon as a group of arrays is complete, so the DMA engine works while
+  // the host builds the next group (everything staged is pinned: the copies are truly asynchronous).
+  auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->st);
+  };
   // ---- per-observation arrays (parallel)
   double2* s_xy = A.take<double2>(nl);
   int2* s_ip = A.take<int2>(nl);
@@ -1040,6 +1046,28 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
 #pragma omp parallel for schedule(static)
   for (int i = 0; i <= n_pts; ++i) s_pt_first[i] = static_cast<int>(pt_count[pt_lo + i] - obs_lo);
 
+  CU(h, ensure(h->d_obs_xy, nl));
+  CU(h, ensure(h->d_obs_ip, nl));
+  CU(h, ensure(h->d_obs_ab, nl));
+  CU(h, ensure(h->d_pt_first, n_pts + 1));
+  CU(h, up(h->d_obs_xy.p, s_xy, nl * sizeof(double2)));
+  CU(h, up(h->d_obs_ip.p, s_ip, nl * sizeof(int2)));
+  CU(h, up(h->d_obs_ab.p, s_ab, nl * sizeof(int2)));
+  CU(h, up(h->d_pt_first.p, s_pt_first, (static_cast<size_t>(n_pts) + 1) * sizeof(int)));
+  {
+    // the caller's points: pageable -> pinned with all host cores, then one asynchronous copy
+    // (slot 2 = pristine copy for dba_params_reset)
+    const size_t n3 = 3 * static_cast<size_t>(n_pts);
+    for (int sl = 0; sl < 3; ++sl) CU(h, ensure(h->d_pts[sl], n3));
+    double* s_pts = A.take<double>(std::max<size_t>(n3, 1));
+    const double* src = p->pts + 3 * static_cast<size_t>(pt_lo);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < static_cast<int64_t>((n3 + 65535) / 65536); ++c) {
+      const size_t a = static_cast<size_t>(c) * 65536, b = std::min(n3, a + 65536);
+      std::memcpy(s_pts + a, src + a, (b - a) * sizeof(double));
+    }
+    CU(h, up(h->d_pts[2].p, s_pts, n3 * sizeof(double)));
+  }
   mark("per-observation arrays");
   // ---- camera-sorted incidence: stable parallel counting sort of (obs, slot) entries by block
   int* s_cam_entries = A.take<int>(static_cast<size_t>(n_ent_max));
@@ -1102,6 +1130,12 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     s_cam_chunks = A.take<int4>(1);
   }
 
+  CU(h, ensure(h->d_cam_entries, static_cast<size_t>(n_entries)));
+  CU(h, ensure(h->d_cam_chunks, n_chunks));
+  CU(h, ensure(h->d_cam_chunk_first, n_ext + 1));
+  CU(h, up(h->d_cam_entries.p, s_cam_entries, n_entries * sizeof(int)));
+  CU(h, up(h->d_cam_chunks.p, s_cam_chunks, n_chunks * sizeof(int4)));
+  CU(h, up(h->d_cam_chunk_first.p, s_cam_chunk_first, (n_ext + 1) * sizeof(int)));
   mark("camera-sorted incidence");
   // ---- static tile-local camera incidence (parallel over tiles, two passes)
   unsigned short* s_items = A.take<unsigned short>(static_cast<size_t>(std::max<int64_t>(n_entries, 1)));
@@ -1345,20 +1379,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, cudaMemsetAsync(h->d_x.p, 0, std::max<size_t>(nvec, 1) * sizeof(double), h->st));
   CU(h, cudaMemsetAsync(h->d_pcg_state.p, 0, 4 * sizeof(int), h->st));
 
-  auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-    if (bytes == 0) return cudaSuccess;
-    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->st);
-  };
-  CU(h, up(h->d_obs_xy.p, s_xy, nl * sizeof(double2)));
-  CU(h, up(h->d_obs_ip.p, s_ip, nl * sizeof(int2)));
-  CU(h, up(h->d_obs_ab.p, s_ab, nl * sizeof(int2)));
   CU(h, up(h->d_obs_lp.p, s_lp, nl * sizeof(unsigned short)));
   CU(h, up(h->d_tile_obs.p, s_tile_obs, (n_tiles + 1) * sizeof(int)));
   CU(h, up(h->d_tile_pt.p, s_tile_pt, (n_tiles + 1) * sizeof(int)));
-  CU(h, up(h->d_pt_first.p, s_pt_first, (static_cast<size_t>(n_pts) + 1) * sizeof(int)));
-  CU(h, up(h->d_cam_entries.p, s_cam_entries, n_entries * sizeof(int)));
-  CU(h, up(h->d_cam_chunks.p, s_cam_chunks, n_chunks * sizeof(int4)));
-  CU(h, up(h->d_cam_chunk_first.p, s_cam_chunk_first, (n_ext + 1) * sizeof(int)));
   CU(h, up(h->d_tile_part_first.p, s_tile_part_first, (n_tiles + 1) * sizeof(int)));
   CU(h, up(h->d_tile_meta.p, s_tile_meta, n_tiles * sizeof(TileMeta)));
   CU(h, up(h->d_part_first_rel.p, s_part_first_rel, (n_entries + n_tiles + 1) * sizeof(unsigned short)));
@@ -1381,19 +1404,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_nf.p, p->intr_nf, sizeof(int) * n_intr));
   CU(h, up(h->d_nd.p, p->intr_nd, sizeof(int) * n_intr));
   // slot 2 = pristine copy for dba_params_reset, slot 0 = current
-  {
-    // pageable -> pinned with all host cores, then one asynchronous copy (a pageable cudaMemcpy of
-    // 24 MB runs at a fraction of the link rate)
-    const size_t n3 = 3 * static_cast<size_t>(n_pts);
-    double* s_pts = A.take<double>(std::max<size_t>(n3, 1));
-    const double* src = p->pts + 3 * static_cast<size_t>(pt_lo);
-#pragma omp parallel for schedule(static)
-    for (int64_t c = 0; c < static_cast<int64_t>((n3 + 65535) / 65536); ++c) {
-      const size_t a = static_cast<size_t>(c) * 65536, b = std::min(n3, a + 65536);
-      std::memcpy(s_pts + a, src + a, (b - a) * sizeof(double));
-    }
-    CU(h, up(h->d_pts[2].p, s_pts, n3 * sizeof(double)));
-  }
   if (h->world > 1) CU(h, ensure(h->d_full_pts, 3 * static_cast<size_t>(h->n_pts_global)));  // dba_params_get
   CU(h, up(h->d_rot[2].p, p->ext_rot, 3 * sizeof(double) * n_ext));
   CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * n_ext));
