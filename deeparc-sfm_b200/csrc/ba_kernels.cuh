@@ -77,7 +77,7 @@ struct DeviceProblem {
   const int* part_dst;              // [n_partials] row of partial g in the camera-grouped partial buffer
 };
 
-__host__ __device__ constexpr int mf_row_len(int cb) { return cb == 9 ? 28 : 20; }  // multiples of 4 doubles (256-bit loads)
+__host__ __device__ constexpr int mf_row_len(int cb) { return cb == 9 ? 24 : 20; }  // multiples of 4 doubles (256-bit loads)
 
 struct ParamSet {
   double* pts;        // [n_pts_local][3]
@@ -116,8 +116,9 @@ struct WorkArrays {
   double* q_split;     // [n_split][n_blocks * cb] slices of q when the per-camera sum is split
   double* partials_q;  // [n_partials][cb] tile-local partial products of the implicit Schur product
   // matrix-free product: one row per camera block, rebuilt after every Jacobian evaluation
-  //   CB = 6: R[9] t[3] p~[6] sel 0      CB = 9: R[9] t[3] f k0 k1 p~[9] sel 0 0 0
-  //   (sel = 0 in Ceres' small-angle branch of AngleAxisRotatePoint, else 1)
+  //   CB = 6: R[9] t[3] p~[6] 0 0      CB = 9: R[9] t[3] f k0 k1 p~[9]
+  //   (the last mantissa bit of t_x is the branch selector: 0 in Ceres' small-angle branch of
+  //   AngleAxisRotatePoint, else 1)
   // p~ = T p is the PCG direction in "geometric" coordinates, T = blockdiag(J_l(w), I, I) diag(sc * free)
   // (J_l = left Jacobian of SO(3): d(R X) = (J_l dw) x (R X)); rewritten every PCG iteration
   double* mf_rows;   // [n_blocks][mf_row_len(cb)]
