@@ -527,7 +527,7 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   int issued = 0;
   const int check_every = (o.pcg_rel_tolerance > 0.0) ? 8 : max_it;
   // q sum (+ the cross-rank exchange through the peer windows) + D^2 p + p.q + the vector phases in one kernel
-  const int fused = (h->q_split == 1 && (h->world == 1 || h->p2p_ready)) ? 1 : 0;
+  const int fused = (h->world == 1 || h->p2p_ready) ? 1 : 0;
   const PeerWin no_peers{};
   *iters_out = 0;
   while (issued < max_it) {
@@ -537,7 +537,7 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
         // default: the rest of the PCG iteration runs as the epilogue of the product kernel
         MfTail tail;
         if (fused && h->fuse_pcg && h->mf_tail) {
-          tail.fuse = 1;
+          tail.fuse = std::max(h->q_split, 1);
           tail.tol2 = tol2;
           tail.min_iter = o.pcg_min_iterations;
           if (h->world > 1) {
@@ -556,7 +556,7 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
       if (fused && h->fuse_pcg) {
         Scope s(h, "pcg_fused", part_bytes);
         if (h->world > 1) h->pw.seq = ++h->p2p_seq;
-        if (launch_pcg_fused(D, h->W, h->mf, tol2, o.pcg_min_iterations, h->world > 1 ? h->pw : no_peers, h->st) != 0)
+        if (launch_pcg_fused(D, h->W, h->mf, tol2, o.pcg_min_iterations, h->q_split, h->world > 1 ? h->pw : no_peers, h->st) != 0)
           return h->fail(DBA_ERR_CUDA, "cooperative launch of k_pcg_fused failed: %s", cudaGetErrorString(cudaGetLastError()));
         continue;
       }

@@ -862,7 +862,7 @@ struct MfSmem {
 };
 
 template <int CB, bool MF>
-__device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter,
+__device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, int n_split,
                                          const PeerWin& pw, double* red, int* s_flag);
 
 // Persistent CTAs (grid = resident CTAs), each walking tiles blockIdx.x, += gridDim.x.  Everything a
@@ -1124,7 +1124,7 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
   // per-camera sum of the partials just written, the cross-rank exchange, x / r / z / p updates
   if (fuse_tail) {
     cooperative_groups::this_grid().sync();  // every partial of every tile is in memory
-    pcg_tail<CB, true>(D, W, tol2, min_iter, pw, reinterpret_cast<double*>(smem_mf), reinterpret_cast<int*>(smem_mf + 512));
+    pcg_tail<CB, true>(D, W, tol2, min_iter, fuse_tail, pw, reinterpret_cast<double*>(smem_mf), reinterpret_cast<int*>(smem_mf + 512));
   }
 }
 
@@ -1371,7 +1371,7 @@ __device__ __forceinline__ long long global_ns() {
 //   3. beta = r.z / rz; p = z + beta p; p~ = T p into the camera rows (MF)
 // Every sum has a fixed order (lane-strided rows, butterfly, per-CTA partials in CTA order).
 template <int CB, bool MF>
-__device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter,
+__device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, int n_split,
                                          const PeerWin& pw, double* red, int* s_flag) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
@@ -1384,16 +1384,15 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
   const long long buf_off = static_cast<long long>(pw.seq & 1ull) * pw.world * pw.slot_len;
   double acc_dot = 0.0;
   // ---- phase 1
-  for (int blk = gwarp; blk < nb; blk += n_warps) {
-    const int i0 = D.cam_part_first[blk], i1 = D.cam_part_first[blk + 1];
-    // the block's partial rows are one contiguous run of (i1 - i0) * CB doubles: the warp streams it
-    // with fully coalesced 8-byte loads, kM loads (= one chunk of 32 * kM elements, a whole number
-    // of rows) in flight per lane; element e of the run belongs to column e % CB, and within a
-    // chunk lane l / load m always sees column (32 m + l) % CB
+  // streams rows [r0, r1) of the camera-grouped partial buffer: one contiguous run of (r1 - r0) * CB
+  // doubles, fully coalesced 8-byte loads, kM loads (= one chunk of 32 * kM elements, a whole number
+  // of rows) in flight per lane; element e of the run belongs to column e % CB, and within a chunk
+  // lane l / load m always sees column (32 m + l) % CB.  Returns column `lane` in lane < CB.
+  auto run_sum = [&](int r0, int r1) -> double {
     constexpr int kG = (CB % 2 == 0) ? 2 : 1;  // gcd(32, CB) for CB in {6, 9}
     constexpr int kM = CB / kG;
-    const double* run = W.partials_q + static_cast<int64_t>(i0) * CB;
-    const int n_el = (i1 - i0) * CB;
+    const double* run = W.partials_q + static_cast<int64_t>(r0) * CB;
+    const int n_el = (r1 - r0) * CB;
     double part[kM];
 #pragma unroll
     for (int m = 0; m < kM; ++m) part[m] = 0.0;
@@ -1404,23 +1403,46 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
         if (ee < n_el) part[m] += __ldcg(run + ee);
       }
     }
-    double acc[CB];
+    double mine = 0.0;
 #pragma unroll
     for (int k = 0; k < CB; ++k) {
       double v = 0.0;
 #pragma unroll
       for (int m = 0; m < kM; ++m) v = ((32 * m + lane) % CB == k) ? part[m] : v;
-      acc[k] = warp_sum_all(v);
+      v = warp_sum_all(v);
+      if (lane == k) mine = v;
     }
+    return mine;
+  };
+  if (n_split > 1) {
+    // few camera blocks, long partial lists: n_split warps per block sum one slice each, then the
+    // slices are added in slice order
+    const int n_items = nb * n_split;
+    for (int w = gwarp; w < n_items; w += n_warps) {
+      const int blk = w / n_split, sl = w - blk * n_split;
+      const int i0 = D.cam_part_first[blk], len = D.cam_part_first[blk + 1] - i0;
+      const int r0 = i0 + static_cast<int>(static_cast<int64_t>(len) * sl / n_split);
+      const int r1 = i0 + static_cast<int>(static_cast<int64_t>(len) * (sl + 1) / n_split);
+      const double v = run_sum(r0, r1);
+      if (lane < CB) W.q_split[static_cast<int64_t>(sl) * nb * CB + static_cast<int64_t>(blk) * CB + lane] = v;
+    }
+    grid.sync();
+  }
+  for (int blk = gwarp; blk < nb; blk += n_warps) {
     double q = 0.0;
-#pragma unroll
-    for (int k = 0; k < CB; ++k)
-      if (lane == k) q = acc[k];
+    if (n_split > 1) {
+      if (lane < CB)
+        for (int sl = 0; sl < n_split; ++sl)
+          q += __ldcg(W.q_split + static_cast<int64_t>(sl) * nb * CB + static_cast<int64_t>(blk) * CB + lane);
+    } else {
+      q = run_sum(D.cam_part_first[blk], D.cam_part_first[blk + 1]);
+    }
+    const double a0 = __shfl_sync(kFull, q, 0), a1 = __shfl_sync(kFull, q, 1), a2 = __shfl_sync(kFull, q, 2);
     if (lane < CB) {
       const int64_t i = static_cast<int64_t>(blk) * CB + lane;
       if (MF) {
         const double* Tm = W.mf_T + static_cast<int64_t>(blk) * (9 + CB);
-        if (lane < 3) q = Tm[lane] * acc[0] + Tm[3 + lane] * acc[1] + Tm[6 + lane] * acc[2];
+        if (lane < 3) q = Tm[lane] * a0 + Tm[3 + lane] * a1 + Tm[6 + lane] * a2;
         q *= Tm[9 + lane];
       }
       if (exchange) {
@@ -1556,11 +1578,12 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
 // launched cooperatively); k_spmv_mf normally runs it as its own epilogue.
 constexpr int kFusedThreads = 256;
 template <int CB, bool MF>
-__global__ void __launch_bounds__(kFusedThreads) k_pcg_fused(DeviceProblem D, WorkArrays W, double tol2, int min_iter, PeerWin pw) {
+__global__ void __launch_bounds__(kFusedThreads) k_pcg_fused(DeviceProblem D, WorkArrays W, double tol2, int min_iter, int n_split,
+                                                             PeerWin pw) {
   if (W.pcg_state[1]) return;
   __shared__ double red[32];
   __shared__ int s_flag;
-  pcg_tail<CB, MF>(D, W, tol2, min_iter, pw, red, &s_flag);
+  pcg_tail<CB, MF>(D, W, tol2, min_iter, n_split, pw, red, &s_flag);
 }
 
 // ------------------------------------------------------------- K7 back-substitution
@@ -1892,8 +1915,8 @@ void launch_partials_to_q(const DeviceProblem& D, const WorkArrays& W, int fuse_
 }
 
 template <int CB, bool MF>
-static int launch_pcg_fused_t(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, const PeerWin& pw,
-                              cudaStream_t st) {
+static int launch_pcg_fused_t(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, int n_split,
+                              const PeerWin& pw, cudaStream_t st) {
   static int resident = 0;
   if (resident == 0) {
     int dev = 0, n_sm = 0, per_sm = 0;
@@ -1902,19 +1925,22 @@ static int launch_pcg_fused_t(const DeviceProblem& D, const WorkArrays& W, doubl
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg_fused<CB, MF>, kFusedThreads, 0);
     resident = std::max(1, n_sm * per_sm);
   }
-  const int grid = std::min(D.n_blocks, resident);
+  // one warp per (camera block, slice)
+  const int grid = std::max(1, std::min((D.n_blocks * std::max(n_split, 1) + kFusedThreads / 32 - 1) / (kFusedThreads / 32), resident));
   DeviceProblem d = D;
   WorkArrays w = W;
   PeerWin win = pw;
-  void* args[] = {&d, &w, &tol2, &min_iter, &win};
+  void* args[] = {&d, &w, &tol2, &min_iter, &n_split, &win};
   return cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_pcg_fused<CB, MF>), dim3(grid), dim3(kFusedThreads), args, 0, st) == cudaSuccess ? 0 : -1;
 }
-int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, const PeerWin& pw,
-                     cudaStream_t st) {
+int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, int n_split,
+                     const PeerWin& pw, cudaStream_t st) {
   if (D.n_blocks == 0) return 0;
   if (D.cb == 6)
-    return mf ? launch_pcg_fused_t<6, true>(D, W, tol2, min_iter, pw, st) : launch_pcg_fused_t<6, false>(D, W, tol2, min_iter, pw, st);
-  return mf ? launch_pcg_fused_t<9, true>(D, W, tol2, min_iter, pw, st) : launch_pcg_fused_t<9, false>(D, W, tol2, min_iter, pw, st);
+    return mf ? launch_pcg_fused_t<6, true>(D, W, tol2, min_iter, n_split, pw, st)
+              : launch_pcg_fused_t<6, false>(D, W, tol2, min_iter, n_split, pw, st);
+  return mf ? launch_pcg_fused_t<9, true>(D, W, tol2, min_iter, n_split, pw, st)
+            : launch_pcg_fused_t<9, false>(D, W, tol2, min_iter, n_split, pw, st);
 }
 
 void launch_mf_rows(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, cudaStream_t st) {
@@ -1956,7 +1982,7 @@ static int launch_spmv_mf_tt(const DeviceProblem& D, const ParamSet& P, const Wo
     WorkArrays w = W;
     const double* pts = P.pts;
     const IntrRow* ir = P.intr_rows;
-    int fuse = 1, min_iter = tail.min_iter;
+    int fuse = std::max(tail.fuse, 1), min_iter = tail.min_iter;  // the flag doubles as the slice count of the tail
     double tol2 = tail.tol2;
     PeerWin pw = tail.pw;
     void* args[] = {&d, &w, &pts, &ir, &fuse, &tol2, &min_iter, &pw};

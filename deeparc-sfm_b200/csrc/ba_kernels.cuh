@@ -192,7 +192,8 @@ void launch_mf_direction(const DeviceProblem& D, const WorkArrays& W, int init, 
 // tail.fuse: cooperative launch whose epilogue is the rest of the PCG iteration (pcg_tail: per-camera
 // partial sum, peer exchange, vector updates).  Returns 0 on success, -1 when the launch failed.
 struct MfTail {
-  int fuse = 0, min_iter = 0;
+  int fuse = 0;  // 0: product only; n >= 1: run the tail with n slices per camera block
+  int min_iter = 0;
   double tol2 = 0.0;
   PeerWin pw{};
 };
@@ -204,8 +205,9 @@ void launch_pcg_step(const DeviceProblem& D, const WorkArrays& W, double tol2, i
 void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // single GPU: partial sum + all three vector phases in one cooperative launch; returns 0 on success
 // pw.world > 1: the partial q of every rank is exchanged through the peer windows inside the launch
-int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, const PeerWin& pw,
-                     cudaStream_t st);
+// n_split > 1: few camera blocks with long partial lists — n_split warps per block (W.q_split holds the slices)
+int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, int n_split,
+                     const PeerWin& pw, cudaStream_t st);
 // dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
 void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st);
 // candidate = current + scale * step; partials[2*cta + {0,1}] = {sum step^2, sum x^2}
