@@ -1346,7 +1346,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   const size_t nvec = static_cast<size_t>(n_ext) * std::max(cb, 1);
   CU(h, ensure(h->d_sp, 3 * static_cast<size_t>(n_pts)));
   CU(h, ensure(h->d_cinv, 6 * static_cast<size_t>(n_pts)));
-  CU(h, ensure(h->d_tp, 3 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_tp, 4 * static_cast<size_t>(n_pts)));
   CU(h, ensure(h->d_dp, 3 * static_cast<size_t>(n_pts)));
   CU(h, ensure(h->d_sc, nvec));
   CU(h, ensure(h->d_cam_acc, nvec * (std::max(cb, 1) + 3)));

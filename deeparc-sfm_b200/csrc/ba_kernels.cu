@@ -92,6 +92,19 @@ __device__ __forceinline__ double sum_partials(const volatile double* part, int 
 
 __device__ __forceinline__ double dot2(const double2 a, const double2 b) { return a.x * b.x + a.y * b.y; }
 
+// camera row -> registers with 256-bit loads (sm_100 LDG.256: one L1 tag lookup per 32 B of a row
+// instead of one per 16 B; rows are 32-byte aligned and a multiple of 32 bytes long)
+template <int N>
+__device__ __forceinline__ void load_row(const double* __restrict__ row, double (&r)[N]) {
+  static_assert(N % 4 == 0, "row length must be a multiple of 4 doubles");
+#pragma unroll
+  for (int i = 0; i < N / 4; ++i)
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r[4 * i]), "=d"(r[4 * i + 1]), "=d"(r[4 * i + 2]), "=d"(r[4 * i + 3])
+                 : "l"(row + 4 * i));
+}
+
+
 // ------------------------------------------------------------------------- pose rows
 __global__ void k_pose_rows(ParamSet P, const uint8_t* __restrict__ ext_const, int freeze_all, int n_ext, int n_intr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,9 +146,9 @@ __device__ __forceinline__ void forward(const ParamSet& P, const int2 ab, const 
 // ------------------------------------------------------------------------ K1 jacobian
 // One thread per observation (point-sorted).  Reads 16 B (xy) + 8 B (indices) + L1/L2-resident
 // tables; writes (1 + 3 + CB [+6]) double2 planes.
-template <int CB, bool TWO>
-__global__ void __launch_bounds__(256) k_jacobian(DeviceProblem D, ParamSet P, WorkArrays W, int unit_scale,
-                                                   double* __restrict__ partial_cost) {
+template <int CB, bool TWO, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_jacobian(DeviceProblem D, ParamSet P, WorkArrays W, int unit_scale,
+                                                         double* __restrict__ partial_cost) {
   __shared__ double red[32];
   const int64_t o = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
   double c = 0.0;
@@ -245,8 +258,8 @@ __global__ void __launch_bounds__(256) k_cost(DeviceProblem D, ParamSet P, doubl
 // One CTA per tile of whole points (<= 256 observations).  Per point: H = E^T E (6 unique),
 // g = E^T r; mode 0: Jacobi scale sp = 1/(1+sqrt(diag H)); mode 1: C = H + D^2, C^-1, t = C^-1 g
 // and the point part of the gradient norms.  Reads Jp + r planes only (64 B / observation).
-template <int T>
-__global__ void __launch_bounds__(T) k_point_prepare(DeviceProblem D, WorkArrays W, double radius,
+template <int T, int MB>
+__global__ void __launch_bounds__(T, MB) k_point_prepare(DeviceProblem D, WorkArrays W, double radius,
                                                           double min_diag, double max_diag, int mode,
                                                           double* __restrict__ partials) {
   extern __shared__ __align__(16) unsigned char smem_pp[];
@@ -300,9 +313,11 @@ __global__ void __launch_bounds__(T) k_point_prepare(DeviceProblem D, WorkArrays
       double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
 #pragma unroll
       for (int k = 0; k < 6; ++k) ci[k] = inv[k];
-      W.tp[p3 + 0] = inv[0] * s[6] + inv[1] * s[7] + inv[2] * s[8];
-      W.tp[p3 + 1] = inv[1] * s[6] + inv[3] * s[7] + inv[4] * s[8];
-      W.tp[p3 + 2] = inv[2] * s[6] + inv[4] * s[7] + inv[5] * s[8];
+      double* tpo = W.tp + 4 * static_cast<int64_t>(pt);  // rows of 4 doubles: one 32-byte load per gather
+      tpo[0] = inv[0] * s[6] + inv[1] * s[7] + inv[2] * s[8];
+      tpo[1] = inv[1] * s[6] + inv[3] * s[7] + inv[4] * s[8];
+      tpo[2] = inv[2] * s[6] + inv[4] * s[7] + inv[5] * s[8];
+      tpo[3] = 0.0;
       // unscaled gradient = scaled gradient / scale
       const double g0 = s[6] / W.sp[p3 + 0], g1 = s[7] / W.sp[p3 + 1], g2 = s[8] / W.sp[p3 + 2];
       gsq = g0 * g0 + g1 * g1 + g2 * g2;
@@ -354,9 +369,13 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
       const double2 r = J[kPlaneR * ld];
       const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
       const int pt = D.obs_ip[o].y;
-      const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
-      const double* tp = W.tp + 3 * static_cast<int64_t>(pt);
-      const double c0 = ci[0], c1 = ci[1], c2 = ci[2], c3 = ci[3], c4 = ci[4], c5 = ci[5];
+      // the kernel is bound by L1 tag lookups (one per gathered sector): C^-1 in three 16-byte
+      // loads, t in one 32-byte load
+      const double2* ci2 = reinterpret_cast<const double2*>(W.cinv + 6 * static_cast<int64_t>(pt));
+      const double2 ca = ci2[0], cbb = ci2[1], cc = ci2[2];
+      const double c0 = ca.x, c1 = ca.y, c2 = cbb.x, c3 = cbb.y, c4 = cc.x, c5 = cc.y;
+      double tp[4];
+      load_row<4>(W.tp + 4 * static_cast<int64_t>(pt), tp);
       // M = E C^-1 (2x3), P = I - M E^T (2x2 symmetric)
       const double m00 = e0.x * c0 + e1.x * c1 + e2.x * c2, m01 = e0.x * c1 + e1.x * c3 + e2.x * c4,
                    m02 = e0.x * c2 + e1.x * c4 + e2.x * c5;
@@ -779,18 +798,6 @@ __global__ void __launch_bounds__(128) k_partials_to_q(DeviceProblem D, WorkArra
 // from -[X]x dw by |w| <= 1.5e-8 relative — inside the product only, never in residuals or gradient.)
 // Threads of a tile map to observations in camera-block order (static `mf_cols`), so the
 // reduce-by-camera runs over contiguous columns and a warp's row loads hit few distinct rows.
-// camera row -> registers with 256-bit loads (sm_100 LDG.256: one L1 tag lookup per 32 B of a row
-// instead of one per 16 B; rows are 32-byte aligned and a multiple of 32 bytes long)
-template <int N>
-__device__ __forceinline__ void load_row(const double* __restrict__ row, double (&r)[N]) {
-  static_assert(N % 4 == 0, "row length must be a multiple of 4 doubles");
-#pragma unroll
-  for (int i = 0; i < N / 4; ++i)
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-                 : "=d"(r[4 * i]), "=d"(r[4 * i + 1]), "=d"(r[4 * i + 2]), "=d"(r[4 * i + 3])
-                 : "l"(row + 4 * i));
-}
-
 // branch selector of a camera row: the last mantissa bit of its t_x (see k_mf_rows)
 __device__ __forceinline__ double mf_row_sel(double tx) { return static_cast<double>(__double2loint(tx) & 1); }
 
@@ -1588,8 +1595,8 @@ __global__ void __launch_bounds__(kFusedThreads) k_pcg_fused(DeviceProblem D, Wo
 
 // ------------------------------------------------------------- K7 back-substitution
 // dp_i = -t_i - C_i^-1 sum_o E_o^T F_o x ;  partial of sum (J d).(r + J d / 2)
-template <int CB, bool TWO, int T>
-__global__ void __launch_bounds__(T) k_back_substitute(DeviceProblem D, WorkArrays W,
+template <int CB, bool TWO, int T, int MB>
+__global__ void __launch_bounds__(T, MB) k_back_substitute(DeviceProblem D, WorkArrays W,
                                                             double* __restrict__ partial_model) {
   extern __shared__ __align__(16) unsigned char smem_bs[];
   double(*v)[T] = reinterpret_cast<double(*)[T]>(smem_bs);  // [3][T]
@@ -1649,7 +1656,7 @@ __global__ void __launch_bounds__(T) k_back_substitute(DeviceProblem D, WorkArra
       z2 += v[2][i];
     }
     const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
-    const double* tp = W.tp + 3 * static_cast<int64_t>(pt);
+    const double* tp = W.tp + 4 * static_cast<int64_t>(pt);
     const double d0 = -tp[0] - (ci[0] * z0 + ci[1] * z1 + ci[2] * z2);
     const double d1 = -tp[1] - (ci[1] * z0 + ci[3] * z1 + ci[4] * z2);
     const double d2 = -tp[2] - (ci[2] * z0 + ci[4] * z1 + ci[5] * z2);
@@ -1790,20 +1797,49 @@ void launch_pose_rows(const ParamSet& P, const uint8_t* ext_const, int freeze_al
   k_pose_rows<<<(n + 127) / 128, 128, 0, st>>>(P, ext_const, freeze_all, n_ext, n_intr);
 }
 
+// resident 512-thread CTAs per SM for the per-tile kernels of the Schur front/back half (DBA_TILE_MINB = 2 | 3)
+static int tile_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("DBA_TILE_MINB");
+    v = e ? std::atoi(e) : 3;
+    if (v != 2) v = 3;
+  }
+  return v;
+}
+// resident CTAs per SM asked of the register allocator (2 = 96 registers, 3 = 80, 4 = 64 with spills);
+// the kernel is latency-bound on the camera-table gathers, so occupancy is the lever (DBA_JAC_MINB)
+static int jac_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("DBA_JAC_MINB");
+    v = e ? std::atoi(e) : 4;
+    if (v < 2 || v > 4) v = 4;
+  }
+  return v;
+}
+template <int CB, bool TWO>
+static void launch_jacobian_t(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, int unit_scale, double* partial_cost,
+                              cudaStream_t st) {
+  const int grid = cost_grid(D);
+  const int mb = jac_minb();
+  if (mb == 2) k_jacobian<CB, TWO, 2><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+  else if (mb == 3) k_jacobian<CB, TWO, 3><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+  else k_jacobian<CB, TWO, 4><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+}
 void launch_jacobian(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, int cb_store, int store_two,
                      int unit_scale, double* partial_cost, cudaStream_t st) {
   if (D.n_obs == 0) return;
-  const int grid = cost_grid(D);
   if (cb_store == 0)
-    k_jacobian<0, false><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+    launch_jacobian_t<0, false>(D, P, W, unit_scale, partial_cost, st);
   else if (cb_store == 6 && !store_two)
-    k_jacobian<6, false><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+    launch_jacobian_t<6, false>(D, P, W, unit_scale, partial_cost, st);
   else if (cb_store == 6 && store_two)
-    k_jacobian<6, true><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+    launch_jacobian_t<6, true>(D, P, W, unit_scale, partial_cost, st);
   else if (cb_store == 9 && !store_two)
-    k_jacobian<9, false><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+    launch_jacobian_t<9, false>(D, P, W, unit_scale, partial_cost, st);
   else
-    k_jacobian<9, true><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);
+    launch_jacobian_t<9, true>(D, P, W, unit_scale, partial_cost, st);
 }
 
 void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost, double* mse_out, cudaStream_t st) {
@@ -1814,19 +1850,23 @@ void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost
 void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
                           double max_diag, int mode, double* partials, cudaStream_t st) {
   if (D.n_tiles == 0) return;
-  auto go = [&](auto tag) {
+  auto go = [&](auto tag, auto mb) {
     constexpr int T = decltype(tag)::value;
+    constexpr int MB = decltype(mb)::value;
     constexpr size_t smem = 9 * T * sizeof(double);
     static bool configured = false;
     if (!configured) {
-      cudaFuncSetAttribute(k_point_prepare<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      cudaFuncSetAttribute(k_point_prepare<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       configured = true;
     }
-    k_point_prepare<T><<<D.n_tiles, T, smem, st>>>(D, W, radius, min_diag, max_diag, mode, partials);
+    k_point_prepare<T, MB><<<D.n_tiles, T, smem, st>>>(D, W, radius, min_diag, max_diag, mode, partials);
   };
-  if (D.tile == 256) go(std::integral_constant<int, 256>());
-  else if (D.tile == 512) go(std::integral_constant<int, 512>());
-  else go(std::integral_constant<int, 1024>());
+  using std::integral_constant;
+  if (D.tile == 256) go(integral_constant<int, 256>(), integral_constant<int, 1>());
+  else if (D.tile == 512) {
+    if (tile_minb() == 3) go(integral_constant<int, 512>(), integral_constant<int, 3>());
+    else go(integral_constant<int, 512>(), integral_constant<int, 2>());
+  } else go(integral_constant<int, 1024>(), integral_constant<int, 1>());
 }
 
 static size_t cam_acc_doubles(const DeviceProblem& D) {
@@ -2054,19 +2094,23 @@ void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStrea
 
 template <int CB, bool TWO>
 static void launch_back_substitute_t(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st) {
-  auto go = [&](auto tag) {
+  auto go = [&](auto tag, auto mb) {
     constexpr int T = decltype(tag)::value;
+    constexpr int MB = decltype(mb)::value;
     constexpr size_t smem = 6 * T * sizeof(double);
     static bool configured = false;
     if (!configured) {
-      cudaFuncSetAttribute(k_back_substitute<CB, TWO, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      cudaFuncSetAttribute(k_back_substitute<CB, TWO, T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       configured = true;
     }
-    k_back_substitute<CB, TWO, T><<<D.n_tiles, T, smem, st>>>(D, W, partial_model);
+    k_back_substitute<CB, TWO, T, MB><<<D.n_tiles, T, smem, st>>>(D, W, partial_model);
   };
-  if (D.tile == 256) go(std::integral_constant<int, 256>());
-  else if (D.tile == 512) go(std::integral_constant<int, 512>());
-  else go(std::integral_constant<int, 1024>());
+  using std::integral_constant;
+  if (D.tile == 256) go(integral_constant<int, 256>(), integral_constant<int, 1>());
+  else if (D.tile == 512) {
+    if (tile_minb() == 3) go(integral_constant<int, 512>(), integral_constant<int, 3>());
+    else go(integral_constant<int, 512>(), integral_constant<int, 2>());
+  } else go(integral_constant<int, 1024>(), integral_constant<int, 1>());
 }
 
 void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st) {

@@ -97,7 +97,7 @@ struct WorkArrays {
   double* sp;      // [n_pts][3] Jacobi scale of point columns
   double* sc;      // [n_blocks][cb] Jacobi scale of camera columns
   double* cinv;    // [n_pts][6]  (E^T E + D^2)^-1
-  double* tp;      // [n_pts][3]  C^-1 g_p
+  double* tp;      // [n_pts][4]  C^-1 g_p (padded rows: one 32-byte load)
   double* gp;      // [n_pts][3]  E^T r  (scaled gradient)
   double* diag_p;  // [n_pts][3]  diag(E^T E) at the last accepted point (for D and for scaling)
   double* dp;      // [n_pts][3]  point step (scaled space)
