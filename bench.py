@@ -50,6 +50,9 @@ WORKLOADS = {
     "stress50m": dict(kind="bal", n_cam=10_000, n_pts=10_000_000, obs_per_point=5, window=50),
     "arc1m": dict(kind="rig", n_arc=10, n_ring=10, n_pts=100_000, obs_per_point=10),
     "small": dict(kind="bal", n_cam=200, n_pts=50_000, obs_per_point=5, window=50),
+    # stand-in for BASELINE.json configs[0..1] (the teabottle_green files are not in the reference checkout):
+    # shared-extrinsic rig 10 arcs x 41 rings, 20k points, ~8 observations per point, intrinsics as shipped
+    "teabottle": dict(kind="teabottle", n_pts=20_000, obs_per_point=8),
 }
 
 
@@ -59,6 +62,10 @@ def build_workload(name: str):
     kind = kw.pop("kind")
     if kind == "bal":
         return synthetic.bal_like(**kw, name=name)
+    if kind == "teabottle":
+        p = synthetic.teabottle_like(**kw)
+        p.name = name
+        return p
     return synthetic.arc_rig(**kw, name=name)
 
 
