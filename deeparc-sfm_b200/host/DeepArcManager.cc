@@ -2,7 +2,11 @@
 // function names the lines it mirrors.  Quirks that a drop-in must keep are marked QUIRK.
 #include "DeepArcManager.hh"
 
+#include <omp.h>
+
 #include <algorithm>
+#include <charconv>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,7 +26,9 @@ namespace {
 // ~10x faster than iostream extraction, which matters at 5-50 M observation lines.
 class Tokens {
  public:
-  explicit Tokens(std::string data) : data_(std::move(data)), p_(data_.c_str()) {}
+  explicit Tokens(const std::string& data) : p_(data.c_str()) {}  // the caller keeps `data` alive
+  const char* pos() const { return p_; }
+  void seek(const char* p) { p_ = p; }
   bool nextDouble(double* v) {
     skip();
     if (!*p_) return false;
@@ -48,14 +54,103 @@ class Tokens {
   void skip() {
     while (*p_ == ' ' || *p_ == '\n' || *p_ == '\t' || *p_ == '\r' || *p_ == '\f' || *p_ == '\v') ++p_;
   }
-  std::string data_;
   const char* p_;
 };
 
+inline bool is_ws(char c) { return c == ' ' || c == '\n' || c == '\t' || c == '\r' || c == '\f' || c == '\v'; }
+
+// Start of every record of `stride` whitespace-separated tokens in [b, e): rec[r] = first byte of
+// token r * stride for r = 0 .. n_rec (entry n_rec = the token after the last record, or e).
+// Two parallel passes over the bytes (count token starts per chunk, then place).  Returns false
+// when the text holds fewer than n_rec * stride tokens.
+bool record_starts(const char* b, const char* e, int64_t n_rec, int stride, std::vector<const char*>* rec) {
+  rec->assign(static_cast<size_t>(n_rec) + 1, nullptr);
+  const int64_t len = e - b;
+  const int n_chunk = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(omp_get_max_threads() * 8, len / 65536 + 1)));
+  std::vector<int64_t> first(static_cast<size_t>(n_chunk) + 1, 0);
+  auto starts_here = [b](const char* p) { return !is_ws(*p) && (p == b || is_ws(p[-1])); };
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int c = 0; c < n_chunk; ++c) {
+    const char* p = b + len * c / n_chunk;
+    const char* q = b + len * (c + 1) / n_chunk;
+    int64_t n = 0;
+    for (; p < q; ++p) n += starts_here(p);
+    first[c + 1] = n;
+  }
+  for (int c = 0; c < n_chunk; ++c) first[c + 1] += first[c];
+  const int64_t need = n_rec * stride;
+  if (first[n_chunk] < need) return false;
+  (*rec)[n_rec] = e;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int c = 0; c < n_chunk; ++c) {
+    int64_t g = first[c];
+    if (g > need) continue;
+    const char* p = b + len * c / n_chunk;
+    const char* q = b + len * (c + 1) / n_chunk;
+    for (; p < q && g <= need; ++p)
+      if (starts_here(p)) {
+        if (g % stride == 0) (*rec)[g / stride] = p;
+        ++g;
+      }
+  }
+  return true;
+}
+
+// strict token parsers for the parallel sections: the whole token must be a number (anything else
+// sends the loader back to the serial tokenizer, which has istream's prefix semantics)
+inline bool parse_int(const char*& p, const char* e, int* v) {
+  while (p < e && is_ws(*p)) ++p;
+  const char* s = p;
+  if (s < e && *s == '+') ++s;
+  auto r = std::from_chars(s, e, *v);
+  if (r.ec != std::errc() || (r.ptr < e && !is_ws(*r.ptr))) return false;
+  p = r.ptr;
+  return true;
+}
+inline bool parse_double(const char*& p, const char* e, double* v) {
+  while (p < e && is_ws(*p)) ++p;
+  const char* s = p;
+  if (s < e && *s == '+') ++s;
+  auto r = std::from_chars(s, e, *v, std::chars_format::general);
+  if (r.ec != std::errc() || (r.ptr < e && !is_ws(*r.ptr))) return false;
+  p = r.ptr;
+  return true;
+}
+
+// "%.6f".  Fast path: |v| < 1e6 and v * 1e6 further than 1e-3 from a rounding tie — the product
+// carries an absolute error below 1.2e-4 there, so rounding it to an integer is the correctly
+// rounded decimal printf produces; anything else goes through snprintf.
 void fmt6(std::string* out, double v) {
-  char buf[64];
+  const double a = std::fabs(v);
+  if (a < 1e6) {  // false for NaN
+    const double q = a * 1e6;
+    const double r = std::nearbyint(q);
+    if (std::fabs(std::fabs(q - r) - 0.5) > 1e-3) {
+      unsigned long long n = static_cast<unsigned long long>(r);
+      char buf[24];
+      int pos = 24;
+      for (int i = 0; i < 6; ++i) {
+        buf[--pos] = static_cast<char>('0' + n % 10);
+        n /= 10;
+      }
+      buf[--pos] = '.';
+      do {
+        buf[--pos] = static_cast<char>('0' + n % 10);
+        n /= 10;
+      } while (n);
+      if (std::signbit(v)) buf[--pos] = '-';
+      out->append(buf + pos, static_cast<size_t>(24 - pos));
+      return;
+    }
+  }
+  char buf[400];  // DBL_MAX has 309 integer digits
   std::snprintf(buf, sizeof buf, "%.6f", v);
   out->append(buf);
+}
+void fmti(std::string* out, long long v) {
+  char buf[24];
+  auto r = std::to_chars(buf, buf + sizeof buf, v);
+  out->append(buf, static_cast<size_t>(r.ptr - buf));
 }
 void fmtg(std::string* out, double v) {  // default ostream formatting of a double (precision 6)
   char buf[64];
@@ -64,6 +159,12 @@ void fmtg(std::string* out, double v) {  // default ostream formatting of a doub
 }
 
 }  // namespace
+
+std::string deeparc_format_fixed6(double v) {
+  std::string s;
+  fmt6(&s, v);
+  return s;
+}
 
 DeepArcManager::DeepArcManager() : arc_size_(0), ring_size_(0), share_extrinsic_(false) {}
 
@@ -86,17 +187,64 @@ int DeepArcManager::ringSlot(int ring_position, int arc_size) {
   return ring_position == 0 ? 0 : ring_position + arc_size - 1;
 }
 
-// DeepArcManager.cc:26-74
+// DeepArcManager.cc:26-74.  The two O(n) sections (observations, points) are parsed, allocated
+// and linked by all host cores (at 5-50 M observation lines the reference's
+// iostream loader takes longer than the GPU solve by two orders of magnitude); the small sections
+// and any file the strict parallel parser does not accept go through the serial tokenizer.
 bool DeepArcManager::read(std::string filename) {
-  std::ifstream file(filename, std::ios::binary);
-  if (file.fail()) {
+  std::FILE* fp = std::fopen(filename.c_str(), "rb");
+  if (!fp) {
     std::cout << "Cannot read " << filename << std::endl;
     throw "Cannot read input file";
   }
-  std::ostringstream ss;
-  ss << file.rdbuf();
-  file.close();
-  Tokens tok(ss.str());
+  std::string data;
+  std::fseek(fp, 0, SEEK_END);
+  const long size = std::ftell(fp);
+  std::fseek(fp, 0, SEEK_SET);
+  if (size > 0) {
+    data.resize(static_cast<size_t>(size));
+    const size_t got = std::fread(&data[0], 1, data.size(), fp);
+    data.resize(got);
+  }
+  std::fclose(fp);
+  const char* serial = std::getenv("DEEPARC_SERIAL_IO");
+  const bool parallel = !(serial && serial[0] == '1');
+  if (parallel && readText(data, true)) return true;
+  if (parallel) clearScene();  // the strict parser met a token it does not take: start over
+  readText(data, false);
+  return true;
+}
+
+void DeepArcManager::clearScene() {
+  for (ParameterBlock* b : params_) {
+    if (b) b->point3d_unlinked(nullptr);
+    delete b;
+  }
+  for (Point3d* p : point3d_) delete p;
+  for (Intrinsic* i : intrinsics_) delete i;
+  for (Extrinsic* e : extrinsics_) delete e;
+  for (Camera* c : camera_) delete c;
+  for (auto& row : hemisphere_)
+    for (auto& cell : row.second) delete cell.second;
+  params_.clear();
+  point3d_.clear();
+  intrinsics_.clear();
+  extrinsics_.clear();
+  camera_.clear();
+  hemisphere_.clear();
+}
+
+bool DeepArcManager::readText(const std::string& data, bool parallel) {
+  const bool timing = std::getenv("DBA_TIMING") != nullptr;
+  double t_mark = omp_get_wtime();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    const double t = omp_get_wtime();
+    std::fprintf(stderr, "[DeepArcManager::read] %-24s %8.2f ms\n", what, 1e3 * (t - t_mark));
+    t_mark = t;
+  };
+  Tokens tok(data);
+  const char* const end = data.c_str() + data.size();
 
   double version = 0.0;
   int n_block = 0, n_intrinsic = 0, n_arc = 0, n_ring = 0, n_point = 0;
@@ -112,17 +260,40 @@ bool DeepArcManager::read(std::string filename) {
   const int n_extrinsic = n_ring != 0 ? n_arc + n_ring - 1 : n_arc;
 
   // observations: pos_arc pos_ring point3d_id x y   (:76-91)
-  params_.reserve(params_.size() + static_cast<size_t>(std::max(n_block, 0)));
-  for (int i = 0; i < n_block; ++i) {
-    int a = 0, r = 0, pid = 0;
-    double x = 0.0, y = 0.0;
-    tok.nextInt(&a);
-    tok.nextInt(&r);
-    tok.nextInt(&pid);
-    tok.nextDouble(&x);
-    tok.nextDouble(&y);
-    params_.push_back(new ParameterBlock(a, r, pid, new Point2d(x, y)));
+  const size_t first_block = params_.size();
+  if (parallel && n_block > 0) {
+    std::vector<const char*> rec;
+    if (!record_starts(tok.pos(), end, n_block, 5, &rec)) return false;
+    mark("observation record index");
+    params_.resize(first_block + static_cast<size_t>(n_block), nullptr);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int i = 0; i < n_block; ++i) {
+      const char* p = rec[i];
+      const char* e = rec[i + 1];
+      int a = 0, r = 0, pid = 0;
+      double x = 0.0, y = 0.0;
+      if (parse_int(p, e, &a) && parse_int(p, e, &r) && parse_int(p, e, &pid) && parse_double(p, e, &x) && parse_double(p, e, &y))
+        params_[first_block + i] = new ParameterBlock(a, r, pid, new Point2d(x, y));
+      else
+        bad |= 1;
+    }
+    if (bad) return false;
+    tok.seek(rec[n_block]);
+  } else {
+    params_.reserve(params_.size() + static_cast<size_t>(std::max(n_block, 0)));
+    for (int i = 0; i < n_block; ++i) {
+      int a = 0, r = 0, pid = 0;
+      double x = 0.0, y = 0.0;
+      tok.nextInt(&a);
+      tok.nextInt(&r);
+      tok.nextInt(&pid);
+      tok.nextDouble(&x);
+      tok.nextDouble(&y);
+      params_.push_back(new ParameterBlock(a, r, pid, new Point2d(x, y)));
+    }
   }
+  mark("observations");
   // intrinsics: cx cy nf f.. nd k..   (:93-122)
   std::vector<Intrinsic*> intrinsics;
   for (int i = 0; i < n_intrinsic; ++i) {
@@ -171,40 +342,105 @@ bool DeepArcManager::read(std::string filename) {
     ex->rotation(nrot == 3 ? rot : aa);  // any other count: zero rotation (reference: uninitialised)
     extrinsics.push_back(ex);
   }
-  // points: x y z r g b (colour parsed as double, stored as int; :153-164)
-  std::vector<Point3d*> points;
-  points.reserve(static_cast<size_t>(std::max(n_point, 0)));
-  for (int i = 0; i < n_point; ++i) {
-    double v[6] = {0, 0, 0, 0, 0, 0};
-    for (double& x : v) tok.nextDouble(&x);
-    points.push_back(new Point3d(v[0], v[1], v[2], static_cast<int>(v[3]), static_cast<int>(v[4]), static_cast<int>(v[5])));
-  }
-
   intrinsics_ = intrinsics;
   extrinsics_ = extrinsics;
-  point3d_ = points;
+  // points: x y z r g b (colour parsed as double, stored as int; :153-164)
+  std::vector<Point3d*> points;
+  if (parallel && n_point > 0) {
+    std::vector<const char*> rec;
+    if (!record_starts(tok.pos(), end, n_point, 6, &rec)) return false;
+    mark("point record index");
+    points.assign(static_cast<size_t>(n_point), nullptr);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int i = 0; i < n_point; ++i) {
+      const char* p = rec[i];
+      const char* e = rec[i + 1];
+      double v[6] = {0, 0, 0, 0, 0, 0};
+      bool ok = true;
+      for (double& x : v) ok = ok && parse_double(p, e, &x);
+      if (ok)
+        points[i] = new Point3d(v[0], v[1], v[2], static_cast<int>(v[3]), static_cast<int>(v[4]), static_cast<int>(v[5]));
+      else
+        bad |= 1;
+    }
+    point3d_ = points;  // owned from here on (clearScene frees them if the strict parser gives up)
+    if (bad) return false;
+  } else {
+    points.reserve(static_cast<size_t>(std::max(n_point, 0)));
+    for (int i = 0; i < n_point; ++i) {
+      double v[6] = {0, 0, 0, 0, 0, 0};
+      for (double& x : v) tok.nextDouble(&x);
+      points.push_back(new Point3d(v[0], v[1], v[2], static_cast<int>(v[3]), static_cast<int>(v[4]), static_cast<int>(v[5])));
+    }
+    point3d_ = points;
+  }
+
+  mark("points");
   if (share_extrinsic_)
     buildHemisphere();
   else
     buildCameras();
+  mark("cameras");
   linkBlocks(share_extrinsic_ ? arc_size_ : 0);
+  mark("link");
   return true;
 }
 
 // DeepArcManager.cc:173-196 — resolve ids to pointers; out-of-range ids throw std::out_of_range
 void DeepArcManager::linkBlocks(int arc_size) {
-  for (ParameterBlock* p : params_) {
-    p->intrinsic(intrinsics_.at(p->intrinsic_id()));
-    p->point3d(point3d_.at(p->point3d_id()));
+  const int64_t n = static_cast<int64_t>(params_.size());
+  const int n_in = static_cast<int>(intrinsics_.size()), n_ex = static_cast<int>(extrinsics_.size());
+  const int n_pt = static_cast<int>(point3d_.size());
+  // pass 1 (parallel): ids -> pointers; the first id out of range is reported like vector::at()
+  int64_t first_bad = n;
+#pragma omp parallel for schedule(static) reduction(min : first_bad)
+  for (int64_t i = 0; i < n; ++i) {
+    ParameterBlock* p = params_[i];
+    const int ring_slot = arc_size != 0 ? ringSlot(p->pos_ring(), arc_size) : 0;
+    const bool ok = p->intrinsic_id() >= 0 && p->intrinsic_id() < n_in && p->point3d_id() >= 0 && p->point3d_id() < n_pt &&
+                    (arc_size != 0 ? (p->pos_arc() >= 0 && p->pos_arc() < n_ex && ring_slot >= 0 && ring_slot < n_ex)
+                                   : (p->extrinsic_id() >= 0 && p->extrinsic_id() < n_ex));
+    if (!ok) {
+      first_bad = std::min(first_bad, i);
+      continue;
+    }
+    p->intrinsic(intrinsics_[p->intrinsic_id()]);
+    p->point3d_unlinked(point3d_[p->point3d_id()]);
     if (arc_size != 0) {
-      p->arc(extrinsics_.at(p->pos_arc()));
-      p->ring(extrinsics_.at(ringSlot(p->pos_ring(), arc_size)));
+      p->arc(extrinsics_[p->pos_arc()]);
+      p->ring(extrinsics_[ring_slot]);
       p->share_extrinsic(true);
     } else {
-      p->extrinsic(extrinsics_.at(p->extrinsic_id()));
+      p->extrinsic(extrinsics_[p->extrinsic_id()]);
       p->share_extrinsic(false);
     }
   }
+  if (first_bad < n) {
+    // blocks that never got a point must not unlink from one in their destructor
+    for (int64_t i = 0; i < n; ++i) params_[i]->point3d_unlinked(nullptr);
+    throw std::out_of_range("vector::_M_range_check: DeepArcManager::linkBlocks: id out of range in observation " +
+                            std::to_string(first_bad));
+  }
+  // pass 2: back-links point -> observations, grouped by point without a lock
+  std::vector<int> count(static_cast<size_t>(n_pt), 0), cursor(static_cast<size_t>(n_pt), 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+#pragma omp atomic
+    count[params_[i]->point3d_id()]++;
+  }
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_pt; ++i) point3d_[i]->link_slots(static_cast<size_t>(count[i]));
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    const int pid = params_[i]->point3d_id();
+    int slot;
+#pragma omp atomic capture
+    slot = cursor[pid]++;
+    point3d_[pid]->link_slot(static_cast<size_t>(slot), params_[i]);
+  }
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_pt; ++i) point3d_[i]->link_finish();
 }
 
 // DeepArcManager.cc:198-218.  QUIRK: extrinsic ids are overwritten with their arc / ring
@@ -222,8 +458,26 @@ void DeepArcManager::buildHemisphere() {
 
 // DeepArcManager.cc:220-240 — one camera per distinct extrinsic id, first intrinsic seen wins
 void DeepArcManager::buildCameras() {
-  std::map<int, int> intrinsic_of;
-  for (ParameterBlock* p : params_) intrinsic_of.insert(std::make_pair(p->extrinsic_id(), p->intrinsic_id()));
+  // extrinsic id -> first intrinsic id seen with it, visited in extrinsic-id order (the reference's
+  // std::map<int,int>::insert per observation); ids inside the table use a flat array
+  const int n_ex = static_cast<int>(extrinsics_.size());
+  std::vector<int> first_intr(static_cast<size_t>(std::max(n_ex, 0)), -1);
+  std::vector<char> seen(first_intr.size(), 0);
+  std::map<int, int> outside;  // ids that at() will reject below, exactly like the reference
+  for (ParameterBlock* p : params_) {
+    const int e = p->extrinsic_id();
+    if (e >= 0 && e < n_ex) {
+      if (!seen[e]) {
+        seen[e] = 1;
+        first_intr[e] = p->intrinsic_id();
+      }
+    } else {
+      outside.insert(std::make_pair(e, p->intrinsic_id()));
+    }
+  }
+  std::map<int, int> intrinsic_of(outside);
+  for (int e = 0; e < n_ex; ++e)
+    if (seen[e]) intrinsic_of.insert(std::make_pair(e, first_intr[e]));
   for (const auto& kv : intrinsic_of) camera_.push_back(new Camera(intrinsics_.at(kv.second), extrinsics_.at(kv.first)));
 }
 
@@ -382,58 +636,85 @@ void DeepArcManager::filterPoint3d(double error_boundary, double* hemisphere_cen
 // `.deeparc` v0.01 text, fixed 6 decimals, points re-indexed, rotations always angle-axis
 // (DeepArcManager.cc:426-499).
 void DeepArcManager::write(std::string filename) {
-  for (size_t i = 0; i < point3d_.size(); ++i) point3d_[i]->id(static_cast<int>(i));
-  std::string out;
-  out.reserve(48 * params_.size() + 80 * point3d_.size() + 4096);
-  out += "0.010000\n" + std::to_string(params_.size()) + " " + std::to_string(intrinsics_.size()) + " ";
+  const int64_t n_pts = static_cast<int64_t>(point3d_.size()), n_obs = static_cast<int64_t>(params_.size());
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_pts; ++i) point3d_[i]->id(static_cast<int>(i));
+  std::string head, mid;
+  head += "0.010000\n" + std::to_string(params_.size()) + " " + std::to_string(intrinsics_.size()) + " ";
   if (share_extrinsic_)
-    out += std::to_string(arc_size_) + " " + std::to_string(ring_size_) + " ";
+    head += std::to_string(arc_size_) + " " + std::to_string(ring_size_) + " ";
   else
-    out += std::to_string(camera_.size()) + " 0 ";
-  out += std::to_string(point3d_.size()) + "\n";
-  for (ParameterBlock* b : params_) {
-    out += std::to_string(b->intrinsic()->id()) + " ";
-    out += std::to_string(share_extrinsic_ ? b->ring()->id() : b->extrinsic()->id()) + " ";
-    out += std::to_string(b->point3d()->id()) + " ";
-    fmt6(&out, b->point2d()->x());
-    out += ' ';
-    fmt6(&out, b->point2d()->y());
-    out += '\n';
+    head += std::to_string(camera_.size()) + " 0 ";
+  head += std::to_string(point3d_.size()) + "\n";
+  // the two O(n) sections are formatted by all host cores, one contiguous range per thread
+  const int n_thr = std::max(1, omp_get_max_threads());
+  std::vector<std::string> obs_part(static_cast<size_t>(n_thr)), pt_part(static_cast<size_t>(n_thr));
+#pragma omp parallel num_threads(n_thr)
+  {
+    const int t = omp_get_thread_num();
+    std::string& o = obs_part[t];
+    const int64_t b0 = n_obs * t / n_thr, b1 = n_obs * (t + 1) / n_thr;
+    o.reserve(static_cast<size_t>(b1 - b0) * 44 + 64);
+    for (int64_t i = b0; i < b1; ++i) {
+      ParameterBlock* b = params_[i];
+      fmti(&o, b->intrinsic()->id());
+      o += ' ';
+      fmti(&o, share_extrinsic_ ? b->ring()->id() : b->extrinsic()->id());
+      o += ' ';
+      fmti(&o, b->point3d()->id());
+      o += ' ';
+      fmt6(&o, b->point2d()->x());
+      o += ' ';
+      fmt6(&o, b->point2d()->y());
+      o += '\n';
+    }
+    std::string& q = pt_part[t];
+    const int64_t p0 = n_pts * t / n_thr, p1 = n_pts * (t + 1) / n_thr;
+    q.reserve(static_cast<size_t>(p1 - p0) * 48 + 64);
+    for (int64_t i = p0; i < p1; ++i) {
+      Point3d* p = point3d_[i];
+      for (int j = 0; j < 3; ++j) {
+        fmt6(&q, p->position()[j]);
+        q += ' ';
+      }
+      fmti(&q, p->r());
+      q += ' ';
+      fmti(&q, p->g());
+      q += ' ';
+      fmti(&q, p->b());
+      q += '\n';
+    }
   }
   for (Intrinsic* in : intrinsics_) {
-    fmt6(&out, in->center()[0]);
-    out += ' ';
-    fmt6(&out, in->center()[1]);
-    out += ' ' + std::to_string(in->focal_size());
+    fmt6(&mid, in->center()[0]);
+    mid += ' ';
+    fmt6(&mid, in->center()[1]);
+    mid += ' ' + std::to_string(in->focal_size());
     for (int j = 0; j < in->focal_size(); ++j) {
-      out += ' ';
-      fmt6(&out, in->focal()[j]);
+      mid += ' ';
+      fmt6(&mid, in->focal()[j]);
     }
-    out += ' ' + std::to_string(in->distrotion_size());
+    mid += ' ' + std::to_string(in->distrotion_size());
     for (int j = 0; j < in->distrotion_size(); ++j) {
-      out += ' ';
-      fmt6(&out, in->distrotion()[j]);
+      mid += ' ';
+      fmt6(&mid, in->distrotion()[j]);
     }
-    out += '\n';
+    mid += '\n';
   }
   for (Extrinsic* ex : extrinsics_) {
     for (int j = 0; j < 3; ++j) {
-      fmt6(&out, ex->translation()[j]);
-      out += ' ';
+      fmt6(&mid, ex->translation()[j]);
+      mid += ' ';
     }
-    out += "3 ";
+    mid += "3 ";
     for (int j = 0; j < 3; ++j) {
-      fmt6(&out, ex->rotation()[j]);
-      out += j < 2 ? " " : "\n";
+      fmt6(&mid, ex->rotation()[j]);
+      mid += j < 2 ? " " : "\n";
     }
-  }
-  for (Point3d* p : point3d_) {
-    for (int j = 0; j < 3; ++j) {
-      fmt6(&out, p->position()[j]);
-      out += ' ';
-    }
-    out += std::to_string(p->r()) + ' ' + std::to_string(p->g()) + ' ' + std::to_string(p->b()) + '\n';
   }
   std::ofstream of(filename, std::ios::binary);
-  of.write(out.data(), static_cast<std::streamsize>(out.size()));
+  of.write(head.data(), static_cast<std::streamsize>(head.size()));
+  for (const std::string& s : obs_part) of.write(s.data(), static_cast<std::streamsize>(s.size()));
+  of.write(mid.data(), static_cast<std::streamsize>(mid.size()));
+  for (const std::string& s : pt_part) of.write(s.data(), static_cast<std::streamsize>(s.size()));
 }

@@ -48,6 +48,8 @@ class DeepArcManager {
   std::vector<Point3d*> point3d_;
 
   static int ringSlot(int ring_position, int arc_size);
+  bool readText(const std::string& data, bool parallel);  // false: the strict parallel parser gave up
+  void clearScene();
   void linkBlocks(int arc_size);
   void buildHemisphere();
   void buildCameras();
@@ -55,5 +57,8 @@ class DeepArcManager {
   std::vector<double> centreOf(Extrinsic* arc, Extrinsic* ring);
   std::vector<double> centreOfCamera(int arc, int ring, bool* single_pose);
 };
+
+// the writer's "%.6f" formatter (exposed for the byte-parity test)
+std::string deeparc_format_fixed6(double v);
 
 #endif  // DEEPARC_B200_DEEPARC_MANAGER_HH_

@@ -1,6 +1,8 @@
 // See ba_client.hh.
 #include "ba_client.hh"
 
+#include <omp.h>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -82,18 +84,22 @@ void flatten(DeepArcManager& m, bool freeze_camera, FlatProblem* out) {
       if (k < intrs[i]->distrotion_size()) f.intr_dist[2 * i + k] = intrs[i]->distrotion()[k];
     }
   }
-  const size_t n = blocks.size();
-  f.obs_xy.resize(2 * n);
-  f.obs_pt.resize(n);
-  f.obs_pose_a.resize(n);
-  f.obs_pose_b.resize(n);
-  f.obs_intr.resize(n);
-  for (size_t i = 0; i < n; ++i) {
+  const int64_t n = static_cast<int64_t>(blocks.size());
+  f.obs_xy.resize(2 * static_cast<size_t>(n));
+  f.obs_pt.resize(static_cast<size_t>(n));
+  f.obs_pose_a.resize(static_cast<size_t>(n));
+  f.obs_pose_b.resize(static_cast<size_t>(n));
+  f.obs_intr.resize(static_cast<size_t>(n));
+  // the per-observation gather runs on all host cores (the index maps are only read); an
+  // observation that points outside the scene is reported like std::unordered_map::at()
+  int64_t first_bad = n;
+  const int n_thr = std::max(1, omp_get_max_threads());
+  std::vector<std::vector<uint8_t> > gauge(static_cast<size_t>(n_thr), std::vector<uint8_t>(exts.size(), 0));
+#pragma omp parallel for schedule(static) reduction(min : first_bad) num_threads(n_thr)
+  for (int64_t i = 0; i < n; ++i) {
     ParameterBlock* b = blocks[i];
     f.obs_xy[2 * i] = b->point2d()->x();
     f.obs_xy[2 * i + 1] = b->point2d()->y();
-    f.obs_pt[i] = pt_index.at(b->point3d());
-    f.obs_intr[i] = intr_index.at(b->intrinsic());
     // the poses behind params[4],[5] (and [6],[7]) exactly as ParameterBlock::get() picks them
     Extrinsic *pa, *pb = nullptr;
     if (!b->share_extrinsic())
@@ -106,11 +112,25 @@ void flatten(DeepArcManager& m, bool freeze_camera, FlatProblem* out) {
       pa = b->arc();
       pb = b->ring();
     }
-    f.obs_pose_a[i] = ext_index.at(pa);
-    f.obs_pose_b[i] = pb ? ext_index.at(pb) : -1;
+    const auto ip = pt_index.find(b->point3d());
+    const auto ii = intr_index.find(b->intrinsic());
+    const auto ia = ext_index.find(pa);
+    const auto ib = pb ? ext_index.find(pb) : ext_index.end();
+    if (ip == pt_index.end() || ii == intr_index.end() || ia == ext_index.end() || (pb && ib == ext_index.end())) {
+      first_bad = std::min(first_bad, i);
+      continue;
+    }
+    f.obs_pt[i] = ip->second;
+    f.obs_intr[i] = ii->second;
+    f.obs_pose_a[i] = ia->second;
+    f.obs_pose_b[i] = pb ? ib->second : -1;
     // gauge: blocks at (arc 0, ring 0) pin params[4],[5] (sfm.cc:50-53)
-    if (b->pos_arc() == 0 && b->pos_ring() == 0) f.ext_const[f.obs_pose_a[i]] = 1;
+    if (b->pos_arc() == 0 && b->pos_ring() == 0) gauge[omp_get_thread_num()][ia->second] = 1;
   }
+  if (first_bad < n)
+    throw std::out_of_range("flatten: observation " + std::to_string(first_bad) + " refers to an object outside the scene");
+  for (const auto& g : gauge)
+    for (size_t e = 0; e < exts.size(); ++e) f.ext_const[e] |= g[e];
 }
 
 void scatter(const FlatProblem& f, const std::vector<double>& pts, const std::vector<double>& ext_rot,

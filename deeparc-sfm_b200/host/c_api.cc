@@ -110,5 +110,11 @@ int dam_manager_camera_centers(void* h, double* out, int capacity) {
   return n;
 }
 void dam_engine_release(void) { deeparc::engine_release(); }
+// test hook: the writer's "%.6f" (fast path + snprintf fallback) into out[>= 400]; returns the length
+int dam_format_fixed6(double v, char* out) {
+  const std::string s = deeparc_format_fixed6(v);
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return static_cast<int>(s.size());
+}
 
 }  // extern "C"

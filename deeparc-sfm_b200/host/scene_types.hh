@@ -13,7 +13,9 @@
 #ifndef DEEPARC_B200_SCENE_TYPES_HH_
 #define DEEPARC_B200_SCENE_TYPES_HH_
 
+#include <algorithm>
 #include <array>
+#include <functional>
 #include <set>
 #include <vector>
 
@@ -43,17 +45,33 @@ class Point3d {
   double* position() { return position_.data(); }
   void require_remove(bool remove) { remove_ = remove; }
   bool require_remove() const { return remove_; }
-  void link(ParameterBlock* block) { blocks_.insert(block); }
-  void unlink(ParameterBlock* block) { blocks_.erase(block); }
-  std::set<ParameterBlock*> total_link() const { return blocks_; }
+  // Observations of this point.  The reference keeps a std::set<ParameterBlock*>; here it is a sorted
+  // vector (same iteration order, one allocation per point instead of one per observation) and
+  // total_link() materialises the set the reference's interface returns.
+  void link(ParameterBlock* block) {
+    auto it = std::lower_bound(blocks_.begin(), blocks_.end(), block, std::less<ParameterBlock*>());
+    if (it == blocks_.end() || *it != block) blocks_.insert(it, block);
+  }
+  void unlink(ParameterBlock* block) {
+    auto it = std::lower_bound(blocks_.begin(), blocks_.end(), block, std::less<ParameterBlock*>());
+    if (it != blocks_.end() && *it == block) blocks_.erase(it);
+  }
+  std::set<ParameterBlock*> total_link() const { return std::set<ParameterBlock*>(blocks_.begin(), blocks_.end()); }
   bool empty() const { return blocks_.empty(); }
+  // bulk construction (the parallel loader): slots filled in any order, then sorted once
+  void link_slots(size_t n) { blocks_.assign(n, nullptr); }
+  void link_slot(size_t i, ParameterBlock* block) { blocks_[i] = block; }
+  void link_finish() {
+    std::sort(blocks_.begin(), blocks_.end(), std::less<ParameterBlock*>());
+    blocks_.erase(std::unique(blocks_.begin(), blocks_.end()), blocks_.end());
+  }
 
  private:
   bool remove_;
   std::array<int, 3> rgb_;
   int id_;
   std::array<double, 3> position_;
-  std::set<ParameterBlock*> blocks_;
+  std::vector<ParameterBlock*> blocks_;
 };
 
 // principal point, 1-2 focal lengths, 0-2 radial distortion coefficients (Intrinsic.hh)
@@ -162,6 +180,8 @@ class ParameterBlock {
     point3d_ = p;
     if (point3d_) point3d_->link(this);
   }
+  // sets the pointer only; the caller links in bulk (Point3d::link_slots / link_slot / link_finish)
+  void point3d_unlinked(Point3d* p) { point3d_ = p; }
   void share_extrinsic(bool v) { share_extrinsic_ = v; }
   void require_remove(bool v) { require_remove_ = v; }
 

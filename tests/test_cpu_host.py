@@ -156,6 +156,88 @@ def test_host_mirror_bad_point_id_raises_out_of_range(tmp_path):
     assert "vector" in H.last_error() or "range" in H.last_error()
 
 
+# --------------------------------------------------------------- parallel loader / writer
+def test_fixed6_formatter_is_byte_identical_to_printf():
+    """The writer formats "%.6f" with an integer fast path and falls back to snprintf near rounding
+    ties and for large values: every output must be what printf gives (DeepArcManager.cc:428)."""
+    import ctypes
+    H = oracle_lib.HostMirror()
+    f = H.lib.dam_format_fixed6
+    f.argtypes = [ctypes.c_double, ctypes.c_char_p]
+    f.restype = ctypes.c_int
+    buf = ctypes.create_string_buffer(512)
+    rng = np.random.default_rng(7)
+    vals = [0.0, -0.0, 1e-7, -1e-7, 4.9e-7, 5e-7, -5e-7, 5.1e-7, 0.0078125, 0.0000005, 1.0000005, 2.5e-6, 3.5e-6,
+            0.1234565, 0.1234575, 999999.9999994, 999999.9999996, 1e6, -1e6, 123456789.123456789, 1e15, 1e22, -3e300,
+            4949.234294, 923.0, 0.5, 1 / 3, 2 / 3, 1e-300, 5e-324, float("inf"), float("-inf")]
+    vals += [(k + 0.5) / 1e6 for k in range(0, 4000, 7)] + [-(k + 0.5) / 1e6 for k in range(1, 400, 3)]
+    vals += [k / 64.0 + j * 2.0 ** -20 for k in range(40) for j in range(4)]  # dyadic: exact ties possible
+    vals += list(rng.standard_normal(4000) * 10.0 ** rng.integers(-8, 9, 4000))
+    vals += list(np.nextafter(np.array([(k + 0.5) / 1e6 for k in range(50)]), 1e9))
+    vals += list(np.nextafter(np.array([(k + 0.5) / 1e6 for k in range(50)]), -1e9))
+    for v in vals:
+        v = float(v)
+        n = f(v, buf)
+        assert buf.value[:n].decode() == "%.6f" % v, (v, buf.value, "%.6f" % v)
+
+
+def test_parallel_loader_and_writer_match_the_serial_path(tmp_path, monkeypatch):
+    """DeepArcManager::read parses, allocates and links the observation and point sections with all
+    host cores; DEEPARC_SERIAL_IO=1 selects the single-threaded tokenizer.  Same scene, same bytes."""
+    H = oracle_lib.HostMirror()
+    outs = {}
+    for kind, p in (("rig", synthetic.arc_rig(n_arc=4, n_ring=6, n_pts=3000, obs_per_point=7, seed=61)),
+                    ("bal", synthetic.bal_like(n_cam=40, n_pts=20000, window=10, seed=62, free_intrinsics=0))):
+        f = str(tmp_path / (kind + ".deeparc"))
+        synthetic.write_deeparc(p, f)
+        for mode in ("1", "0"):
+            monkeypatch.setenv("DEEPARC_SERIAL_IO", mode)
+            h = H.read(f)
+            outs[mode] = (H.counts(h), H.export(h))
+            H.write(h, f + ".out" + mode)
+            H.write_ply(h, f + ".ply" + mode)
+            H.free(h)
+        assert outs["0"][0] == outs["1"][0]
+        for k in ("obs_xy", "obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "pts", "pts_rgb", "ext_rot", "ext_trans",
+                  "intr_center", "intr_focal", "intr_dist", "intr_nf", "intr_nd", "ext_const"):
+            assert np.array_equal(getattr(outs["0"][1], k), getattr(outs["1"][1], k)), (kind, k)
+        assert np.array_equal(outs["0"][1].obs_pt, p.obs_pt)
+        assert filecmp.cmp(f + ".out0", f + ".out1", shallow=False)
+        assert filecmp.cmp(f + ".ply0", f + ".ply1", shallow=False)
+
+
+def test_parallel_loader_falls_back_on_tokens_it_does_not_take(tmp_path, monkeypatch):
+    """The parallel parser is strict (a token must be one number); a file with e.g. a hexadecimal
+    float or a truncated tail is re-read by the serial tokenizer, which has the reference's
+    istream-like prefix semantics.  Both routes give the same scene."""
+    H = oracle_lib.HostMirror()
+    p = synthetic.bal_like(n_cam=6, n_pts=50, window=4, seed=63, free_intrinsics=0)
+    f = str(tmp_path / "odd.deeparc")
+    synthetic.write_deeparc(p, f)
+    text = open(f).read().split("\n")
+    rec = text[2].split()          # first observation line: a r pid x y
+    rec[3] = float(rec[3]).hex()   # strtod reads it, std::from_chars(general) does not
+    text[2] = " ".join(rec)
+    open(f, "w").write("\n".join(text))
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DEEPARC_SERIAL_IO", mode)
+        h = H.read(f)
+        res[mode] = H.export(h)
+        H.free(h)
+    assert np.array_equal(res["0"].obs_xy, res["1"].obs_xy) and np.array_equal(res["0"].obs_pt, res["1"].obs_pt)
+    assert abs(res["0"].obs_xy[0, 0] - p.obs_xy[0, 0]) < 1e-6
+    # truncated file: fewer tokens than the header promises -> the serial path's zeros, no crash
+    open(f, "w").write("\n".join(text[: len(text) // 2]))
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DEEPARC_SERIAL_IO", mode)
+        try:
+            h = H.read(f)
+            H.free(h)
+        except IOError:
+            pass  # ids of the missing sections may be out of range, as in the reference
+
+
 # ------------------------------------------------------------------------- sharding plan
 def test_shard_plan_covers_and_balances():
     p = synthetic.bal_like(n_cam=40, n_pts=5000, window=10, seed=61)
