@@ -205,6 +205,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.dba_fit_hemisphere.argtypes = [C.c_void_p, _dp, C.c_int32, _dp, _dp, C.POINTER(DbaSolveOptions),
                                        C.POINTER(DbaSummary)]
     lib.dba_filter_mse.argtypes = [C.c_void_p, _dp]
+    lib.dba_filter.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dba_filter.restype = C.c_int
     lib.dba_kernel_stats_enable.argtypes = [C.c_void_p, C.c_int32]
     lib.dba_kernel_stats_reset.argtypes = [C.c_void_p]
     lib.dba_kernel_stats.argtypes = [C.c_void_p, C.POINTER(DbaKernelStat), C.c_int32]
@@ -308,6 +310,18 @@ class Engine:
         self._check(self.lib.dba_fit_hemisphere(self.h, _ptr(centres), centres.shape[0], _ptr(c), C.byref(rho),
                                                 C.byref(o), C.byref(s.struct)))
         return c, rho.value, s
+
+    def filter(self, error_boundary: float, centre=None, rho: float = 0.0):
+        """filterPoint3d decisions on the device: (obs_remove, pt_remove) uint8 arrays, caller order."""
+        p = self.problem.p
+        obs = np.zeros(p.n_obs, dtype=np.uint8)
+        pts = np.zeros(p.n_pts, dtype=np.uint8)
+        c = None if centre is None else np.ascontiguousarray(centre, dtype=np.float64)
+        n_obs, n_pts = C.c_int64(0), C.c_int32(0)
+        self._check(self.lib.dba_filter(self.h, float(error_boundary), None if c is None else c.ctypes.data, float(rho),
+                                        obs.ctypes.data, pts.ctypes.data, C.byref(n_obs), C.byref(n_pts)))
+        assert n_obs.value == int(obs.sum()) and n_pts.value == int(pts.sum())
+        return obs, pts
 
     def filter_mse(self) -> np.ndarray:
         out = np.zeros(self.problem.p.n_obs)

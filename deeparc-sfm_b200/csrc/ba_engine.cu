@@ -1630,6 +1630,51 @@ int dba_filter_mse(dba_handle* h, double* mse) {
   return DBA_OK;
 }
 
+int dba_filter(dba_handle* h, double error_boundary, const double* centre, double rho, uint8_t* obs_remove, uint8_t* pt_remove,
+               int64_t* n_obs_removed, int32_t* n_pts_removed) {
+  if (!h || !obs_remove || !pt_remove) return DBA_ERR_INVALID_ARGUMENT;
+  if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
+  if (h->world > 1) return h->fail(DBA_ERR_UNSUPPORTED, "per-observation outputs need a single-GPU handle");
+  CU(h, cudaSetDevice(h->device));
+  const ParamSet& P = h->P[h->cur];
+  const int64_t n = h->n_obs;
+  const int n_pts = h->n_pts;
+  DevBuf<double> d_mse;
+  DevBuf<uint8_t> d_obs, d_pt;
+  CU(h, d_mse.alloc(std::max<int64_t>(n, 1)));
+  CU(h, d_obs.alloc(std::max<int64_t>(n, 1)));
+  CU(h, d_pt.alloc(std::max(n_pts, 1)));
+  {
+    Scope s(h, "pose_rows");
+    launch_pose_rows(P, h->d_ext_const.p, h->freeze, h->n_ext, h->n_intr, h->st);
+  }
+  {
+    Scope s(h, "cost", 24.0 * static_cast<double>(n));
+    launch_cost(h->D, P, h->d_partA.p, d_mse.p, h->st);
+  }
+  {
+    Scope s(h, "filter_flags", 9.0 * static_cast<double>(n) + 25.0 * n_pts);
+    launch_filter_flags(h->D, P, d_mse.p, error_boundary, centre, rho, d_obs.p, d_pt.p, h->st);
+  }
+  std::vector<uint8_t> sorted_flags(static_cast<size_t>(n));
+  CU(h, cudaMemcpyAsync(sorted_flags.data(), d_obs.p, static_cast<size_t>(n), cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaMemcpyAsync(pt_remove, d_pt.p, static_cast<size_t>(n_pts), cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaStreamSynchronize(h->st));
+  CU(h, cudaGetLastError());
+  int64_t n_obs_gone = 0;
+  const int64_t* perm = h->perm.data();
+#pragma omp parallel for schedule(static) reduction(+ : n_obs_gone)
+  for (int64_t k = 0; k < n; ++k) {
+    obs_remove[perm[k]] = sorted_flags[k];
+    n_obs_gone += sorted_flags[k];
+  }
+  int n_pts_gone = 0;
+  for (int i = 0; i < n_pts; ++i) n_pts_gone += pt_remove[i];
+  if (n_obs_removed) *n_obs_removed = n_obs_gone;
+  if (n_pts_removed) *n_pts_removed = n_pts_gone;
+  return DBA_OK;
+}
+
 // --------------------------------------------------------------------------- solve
 void dba_solve_options_default(dba_solve_options* o) {
   if (!o) return;

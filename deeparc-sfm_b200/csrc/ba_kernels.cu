@@ -1750,6 +1750,31 @@ __global__ void __launch_bounds__(256) k_update_cameras(DeviceProblem D, ParamSe
   }
 }
 
+// ------------------------------------------------- filterPoint3d decisions (DeepArcManager.cc:331-424)
+// One thread per point over its (point-sorted) observations: an observation goes when its mse is
+// below the boundary, a point goes when nothing is left of it or when it lies outside the
+// hemisphere, and then takes its remaining observations along.  NaN compares false, as on the host.
+__global__ void __launch_bounds__(256) k_filter_flags(DeviceProblem D, const double* __restrict__ pts,
+                                                       const double* __restrict__ mse, double boundary, int use_sphere,
+                                                       double cx, double cy, double cz, double half_rho,
+                                                       uint8_t* __restrict__ obs_remove, uint8_t* __restrict__ pt_remove) {
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= D.n_pts) return;
+  const int a = D.pt_first[pt], b = D.pt_first[pt + 1];
+  int kept = 0;
+  for (int o = a; o < b; ++o) kept += (mse[o] < boundary) ? 0 : 1;
+  bool gone = kept == 0;
+  if (!gone && use_sphere) {
+    const double dx = pts[3 * static_cast<int64_t>(pt)] - cx, dy = pts[3 * static_cast<int64_t>(pt) + 1] - cy,
+                 dz = pts[3 * static_cast<int64_t>(pt) + 2] - cz;
+    // summed in the reference's order: ((dx^2 + dy^2) + dz^2)
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    gone = d2 > half_rho;
+  }
+  pt_remove[pt] = gone ? 1 : 0;
+  for (int o = a; o < b; ++o) obs_remove[o] = (gone || mse[o] < boundary) ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------ reductions
 // Deterministic single-CTA reductions of per-CTA partials.
 __global__ void __launch_bounds__(1024) k_reduce_sum(const double* __restrict__ in, int n, int stride, int offset,
@@ -1840,6 +1865,14 @@ void launch_jacobian(const DeviceProblem& D, const ParamSet& P, const WorkArrays
     launch_jacobian_t<9, false>(D, P, W, unit_scale, partial_cost, st);
   else
     launch_jacobian_t<9, true>(D, P, W, unit_scale, partial_cost, st);
+}
+
+void launch_filter_flags(const DeviceProblem& D, const ParamSet& P, const double* mse, double boundary, const double* centre,
+                         double rho, uint8_t* obs_remove, uint8_t* pt_remove, cudaStream_t st) {
+  if (D.n_pts == 0) return;
+  k_filter_flags<<<(D.n_pts + 255) / 256, 256, 0, st>>>(D, P.pts, mse, boundary, centre ? 1 : 0, centre ? centre[0] : 0.0,
+                                                         centre ? centre[1] : 0.0, centre ? centre[2] : 0.0, rho / 2, obs_remove,
+                                                         pt_remove);
 }
 
 void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost, double* mse_out, cudaStream_t st) {

@@ -168,6 +168,9 @@ void launch_jacobian(const DeviceProblem& D, const ParamSet& P, const WorkArrays
                      int unit_scale, double* partial_cost, cudaStream_t st);
 // residual-only cost at P: per-CTA partial sums of r^2; optional per-observation mse.
 void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost, double* mse_out, cudaStream_t st);
+// filterPoint3d decisions from the per-observation mse (sorted order): removal flags per observation / point
+void launch_filter_flags(const DeviceProblem& D, const ParamSet& P, const double* mse, double boundary, const double* centre,
+                         double rho, uint8_t* obs_remove, uint8_t* pt_remove, cudaStream_t st);
 int cost_grid(const DeviceProblem& D);
 int tile_grid(const DeviceProblem& D);
 // per point: H = E^T E, g = E^T r.  mode 0: Jacobi scales sp.  mode 1: C = H + D^2, C^-1,

@@ -581,56 +581,41 @@ void DeepArcManager::writePly(std::string filename) {
 // GPU engine at the parameters currently in the scene graph; the pointer-graph surgery that
 // follows is the reference's, step for step.
 void DeepArcManager::filterPoint3d(double error_boundary, double* hemisphere_center, double hemisphere_radius) {
+  // The three removal rules (:347-350 mse < boundary, :368-378 points left empty, :380-408 points
+  // outside the hemisphere with their observations) are DECIDED on the device in one call
+  // (dba_filter: one byte per observation / point comes back); what follows is the reference's
+  // pointer-graph surgery, which leaves the same survivors in the same order.
+  std::vector<uint8_t> obs_gone(params_.size(), 0), pt_gone;
   if (!params_.empty()) {
     deeparc::FlatProblem flat;
     deeparc::flatten(*this, /*freeze_camera=*/false, &flat);
     dba_problem view = flat.view();
     dba_handle* h = deeparc::engine();
     deeparc::check(dba_problem_set(h, &view), "dba_problem_set");
-    std::vector<double> mse(params_.size());
-    deeparc::check(dba_filter_mse(h, mse.data()), "dba_filter_mse");
+    pt_gone.assign(flat.point_of.size(), 0);
+    deeparc::check(dba_filter(h, error_boundary, hemisphere_center, hemisphere_radius, obs_gone.data(), pt_gone.data(), nullptr, nullptr),
+                   "dba_filter");
     for (size_t i = 0; i < params_.size(); ++i)
-      if (mse[i] < error_boundary) params_[i]->require_remove(true);  // QUIRK: "<" as written (:348)
+      if (obs_gone[i]) params_[i]->require_remove(true);  // QUIRK: "<" as written (:348)
+    for (size_t i = 0; i < flat.point_of.size(); ++i)
+      if (pt_gone[i]) flat.point_of[i]->require_remove(true);
+  } else {
+    for (Point3d* p : point3d_) p->require_remove(true);  // nothing observes them: all empty (:368-378)
   }
-  auto drop_flagged_blocks = [this]() {
-    params_.erase(std::remove_if(params_.begin(), params_.end(),
-                                 [](ParameterBlock* b) {
-                                   const bool gone = b->require_remove();
-                                   if (gone) delete b;
-                                   return gone;
-                                 }),
-                  params_.end());
-  };
-  drop_flagged_blocks();
-  // points left without observations (:368-378)
+  params_.erase(std::remove_if(params_.begin(), params_.end(),
+                               [](ParameterBlock* b) {
+                                 const bool gone = b->require_remove();
+                                 if (gone) delete b;  // unlinks itself from its point
+                                 return gone;
+                               }),
+                params_.end());
   point3d_.erase(std::remove_if(point3d_.begin(), point3d_.end(),
                                 [](Point3d* p) {
-                                  const bool gone = p->empty();
+                                  const bool gone = p->require_remove() || p->empty();
                                   if (gone) delete p;
                                   return gone;
                                 }),
                  point3d_.end());
-  // points outside the hemisphere: |x - c|^2 > rho / 2, rho being the squared radius (:380-390)
-  for (Point3d* p : point3d_) {
-    const double* x = p->position();
-    double d2 = 0.0;
-    for (int i = 0; i < 3; ++i) d2 += (x[i] - hemisphere_center[i]) * (x[i] - hemisphere_center[i]);
-    if (d2 > hemisphere_radius / 2) p->require_remove(true);
-  }
-  point3d_.erase(std::remove_if(point3d_.begin(), point3d_.end(),
-                                [](Point3d* p) {
-                                  const bool gone = p->require_remove();
-                                  if (gone) {
-                                    for (ParameterBlock* b : p->total_link()) {
-                                      b->require_remove(true);
-                                      b->point3d(NULL);
-                                    }
-                                    delete p;
-                                  }
-                                  return gone;
-                                }),
-                 point3d_.end());
-  drop_flagged_blocks();
 }
 
 // `.deeparc` v0.01 text, fixed 6 decimals, points re-indexed, rotations always angle-axis

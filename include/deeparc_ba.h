@@ -245,6 +245,20 @@ int dba_fit_hemisphere(dba_handle* h, const double* centres /* [n][3] */, int32_
  * mse[i] = (r0^2 + r1^2) / 2 at the current device parameters, caller's order.      */
 int dba_filter_mse(dba_handle* h, double* mse /* [n_obs] */);
 
+/* The decisions of filterPoint3d (DeepArcManager.cc:331-424) taken on the device at the
+ * current parameters, so that only one byte per observation / point crosses the bus:
+ *  (1) observations with mse = (r0^2 + r1^2) / 2 < error_boundary go (:347-350; "<" as the
+ *      reference writes it),
+ *  (2) points left without observations go (:368-378),
+ *  (3) points with |x - centre|^2 > rho / 2 go together with all their observations
+ *      (:380-408; rho is the SQUARED radius fitted by dba_fit_hemisphere); centre == NULL
+ *      skips this rule.
+ * obs_remove[n_obs] / pt_remove[n_pts]: 1 = removed, caller's order; the counts are
+ * optional.  The pointer-graph surgery itself stays with the caller.                  */
+int dba_filter(dba_handle* h, double error_boundary, const double* centre /* [3] or NULL */,
+               double rho, uint8_t* obs_remove /* [n_obs] */, uint8_t* pt_remove /* [n_pts] */,
+               int64_t* n_obs_removed, int32_t* n_pts_removed);
+
 /* Kernel statistics since the last dba_kernel_stats_reset; returns the number of
  * entries written (<= capacity).  Timing is only collected when enabled.            */
 int dba_kernel_stats_enable(dba_handle* h, int32_t enable);

@@ -97,6 +97,42 @@ def test_filter_mse_matches_oracle(engine, oracle):
     assert np.all(np.abs(m - ref) <= 1e-9 * np.abs(ref) + 1e-9)
 
 
+def test_filter_decisions_follow_the_reference_rules(engine, oracle):
+    """dba_filter = the three removal rules of filterPoint3d (DeepArcManager.cc:347-350, :368-378,
+    :380-408) decided on the device; checked against the rules applied on the host to the oracle's
+    per-observation mse."""
+    p = PROBLEMS["rig"]
+    engine.problem_set(p)
+    mse = oracle.filter_mse(p)
+    boundary = float(np.median(mse))  # removes about half of the observations, empties some points
+    centre = p.pts.mean(axis=0)
+    d2 = ((p.pts - centre) ** 2).sum(axis=1)
+    rho = 2.0 * float(np.quantile(d2, 0.8))  # |x - c|^2 > rho / 2 for ~20 % of the points
+    for c, r in ((centre, rho), (None, 0.0)):
+        obs, pts = engine.filter(boundary, c, r)
+        low = mse < boundary
+        margin = np.abs(mse - boundary) < 1e-9 * boundary  # decisions at the boundary may differ by rounding
+        kept = np.bincount(p.obs_pt[~low], minlength=p.n_pts)
+        far = (d2 > r / 2) if c is not None else np.zeros(p.n_pts, bool)
+        pt_expected = (kept == 0) | far
+        obs_expected = low | pt_expected[p.obs_pt]
+        touchy_pts = np.zeros(p.n_pts, bool)
+        touchy_pts[p.obs_pt[margin]] = True
+        ok_pts = ~touchy_pts
+        assert np.array_equal(pts.astype(bool)[ok_pts], pt_expected[ok_pts])
+        ok_obs = ~margin & ok_pts[p.obs_pt]
+        assert np.array_equal(obs.astype(bool)[ok_obs], obs_expected[ok_obs])
+        assert 0 < obs.sum() < p.n_obs and 0 < pts.sum() < p.n_pts
+    # a point nobody observes is dropped by rule (2)
+    q = p.copy()
+    q.pts = np.vstack([q.pts, [[0.0, 0.0, 0.0]]])
+    if q.pts_rgb is not None:
+        q.pts_rgb = np.vstack([q.pts_rgb, [[0, 0, 0]]])
+    engine.problem_set(q)
+    obs, pts = engine.filter(0.0)
+    assert pts[-1] == 1 and pts[:-1].sum() == 0 and obs.sum() == 0
+
+
 def _compare_solve(engine, oracle, p, n_iter, linear_solver=capi.DBA_LS_PCG, check_trace=True):
     """Fixed number of LM iterations (tolerances off), identical damping.  n_iter is chosen so
     the run stops before the cost reaches its rounding-noise floor (beyond it accept/reject
