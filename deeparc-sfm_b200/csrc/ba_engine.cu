@@ -134,6 +134,7 @@ struct dba_handle {
   DevBuf<PoseRow> d_pose_rows[2];
   DevBuf<IntrRow> d_intr_rows[2];
   DevBuf<double> d_sp, d_sc, d_cinv, d_tp, d_dp, d_cam_acc, d_minv, d_dc2, d_x, d_r, d_z, d_p, d_q;
+  DevBuf<double> d_cam_chunk_acc;
   DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts, d_vec_partials;
   double* h_scalars = nullptr;  // pinned
   int* h_pcg_state = nullptr;   // pinned
@@ -1350,6 +1351,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_dp, 3 * static_cast<size_t>(n_pts)));
   CU(h, ensure(h->d_sc, nvec));
   CU(h, ensure(h->d_cam_acc, nvec * (std::max(cb, 1) + 3)));
+  CU(h, ensure(h->d_cam_chunk_acc, static_cast<size_t>(std::max(n_chunks, 1)) * (std::max(cb, 1) * (std::max(cb, 1) + 1) / 2 + 3 * std::max(cb, 1))));
   CU(h, ensure(h->d_minv, nvec * std::max(cb, 1)));
   CU(h, ensure(h->d_dc2, nvec));
   CU(h, ensure(h->d_x, nvec));
@@ -1471,6 +1473,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.diag_p = nullptr;
   W.dp = h->d_dp.p;
   W.cam_acc = h->d_cam_acc.p;
+  W.cam_chunk_acc = h->d_cam_chunk_acc.p;
   W.minv = h->d_minv.p;
   W.dc2 = h->d_dc2.p;
   W.diag_c = nullptr;

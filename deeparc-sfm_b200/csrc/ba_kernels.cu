@@ -341,14 +341,14 @@ __global__ void __launch_bounds__(T, MB) k_point_prepare(DeviceProblem D, WorkAr
 // of the chunk's observations (16 B per plane per observation), accumulates in registers
 //   mode 0: diag(F^T F)                      -> Jacobi scales
 //   mode 1: B = F^T (I - E C^-1 E^T) F (upper), diag(F^T F), g = F^T r, rhs = -F^T (r - E t)
-// then reduces across the CTA and adds to the per-block accumulators (few atomics per CTA).
+// then reduces across the CTA into one row of sums per chunk (k_camera_combine adds the rows of a
+// camera block in chunk order: no atomics).
 template <int CB, int MODE>
 __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArrays W) {
   constexpr int NU = CB * (CB + 1) / 2;
   constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
   __shared__ double red[4][NACC];
-  const int4 ch = D.cam_chunks[blockIdx.x];
-  const int blk = ch.x;
+  const int4 ch = D.cam_chunks[blockIdx.x];  // (block, first entry, last entry, -)
   double acc[NACC];
 #pragma unroll
   for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
@@ -412,27 +412,41 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
     if (lane == 0) red[wid][k] = s;
   }
   __syncthreads();
+  // one row of sums per chunk; k_camera_combine adds the rows of a camera block in chunk order
+  // (no atomics: the accumulators, hence the whole solve, are bit-reproducible)
+  for (int k = threadIdx.x; k < NACC; k += blockDim.x)
+    W.cam_chunk_acc[static_cast<int64_t>(blockIdx.x) * NACC + k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+}
+
+// Fixed-order sum of the chunk rows of every camera block into the accumulator layout
+//   B [n_blocks][cb][cb] | diagF [n_blocks][cb] | gc [n_blocks][cb] | rhs [n_blocks][cb]
+// one thread per (camera block, accumulator); blocks without observations get zeros.
+template <int CB, int MODE>
+__global__ void __launch_bounds__(128) k_camera_combine(DeviceProblem D, WorkArrays W) {
+  constexpr int NU = CB * (CB + 1) / 2;
+  constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nb = D.n_blocks;
-  const int cb = D.cb;  // accumulator layout uses the problem's block size (== CB)
-  for (int k = threadIdx.x; k < NACC; k += blockDim.x) {
-    const double s = red[0][k] + red[1][k] + red[2][k] + red[3][k];
-    if (MODE == 0) {
-      atomicAdd(W.cam_acc + static_cast<int64_t>(nb) * cb * cb + static_cast<int64_t>(blk) * cb + k, s);
-    } else if (k < NU) {
-      // unpack upper-triangular index k -> (i, j)
-      int i = 0, rem = k;
-      while (rem >= CB - i) {
-        rem -= CB - i;
-        ++i;
-      }
-      const int j = i + rem;
-      double* Bm = W.cam_acc + static_cast<int64_t>(blk) * cb * cb;
-      atomicAdd(Bm + i * cb + j, s);
-      if (i != j) atomicAdd(Bm + j * cb + i, s);
-    } else {
-      const int which = (k - NU) / CB, i = (k - NU) % CB;
-      atomicAdd(W.cam_acc + static_cast<int64_t>(nb) * cb * cb + (static_cast<int64_t>(which) * nb + blk) * cb + i, s);
+  if (idx >= nb * NACC) return;
+  const int blk = idx / NACC, k = idx - blk * NACC;
+  double s = 0.0;
+  for (int c = D.cam_chunk_first[blk]; c < D.cam_chunk_first[blk + 1]; ++c) s += W.cam_chunk_acc[static_cast<int64_t>(c) * NACC + k];
+  if (MODE == 0) {
+    W.cam_acc[static_cast<int64_t>(nb) * CB * CB + static_cast<int64_t>(blk) * CB + k] = s;
+  } else if (k < NU) {
+    // unpack upper-triangular index k -> (i, j)
+    int i = 0, rem = k;
+    while (rem >= CB - i) {
+      rem -= CB - i;
+      ++i;
     }
+    const int j = i + rem;
+    double* Bm = W.cam_acc + static_cast<int64_t>(blk) * CB * CB;
+    Bm[i * CB + j] = s;
+    if (i != j) Bm[j * CB + i] = s;
+  } else {
+    const int which = (k - NU) / CB, i = (k - NU) % CB;
+    W.cam_acc[static_cast<int64_t>(nb) * CB * CB + (static_cast<int64_t>(which) * nb + blk) * CB + i] = s;
   }
 }
 
@@ -1906,20 +1920,22 @@ static size_t cam_acc_doubles(const DeviceProblem& D) {
   return static_cast<size_t>(D.n_blocks) * D.cb * D.cb + 3 * static_cast<size_t>(D.n_blocks) * D.cb;
 }
 
+template <int CB, int MODE>
+static void launch_camera_gather_t(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+  constexpr int NACC = MODE == 0 ? CB : CB * (CB + 1) / 2 + 3 * CB;
+  if (D.n_chunks > 0) k_camera_gather<CB, MODE><<<D.n_chunks, 128, 0, st>>>(D, W);
+  const int n = D.n_blocks * NACC;
+  k_camera_combine<CB, MODE><<<(n + 127) / 128, 128, 0, st>>>(D, W);
+}
 void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st) {
-  if (D.cb == 0) return;
-  cudaMemsetAsync(W.cam_acc, 0, cam_acc_doubles(D) * sizeof(double), st);
-  if (D.n_chunks == 0) return;
+  if (D.cb == 0 || D.n_blocks == 0) return;
+  if (mode == 0) cudaMemsetAsync(W.cam_acc, 0, cam_acc_doubles(D) * sizeof(double), st);  // mode 0 fills diagF only
   if (D.cb == 6) {
-    if (mode == 0)
-      k_camera_gather<6, 0><<<D.n_chunks, 128, 0, st>>>(D, W);
-    else
-      k_camera_gather<6, 1><<<D.n_chunks, 128, 0, st>>>(D, W);
+    if (mode == 0) launch_camera_gather_t<6, 0>(D, W, st);
+    else launch_camera_gather_t<6, 1>(D, W, st);
   } else {
-    if (mode == 0)
-      k_camera_gather<9, 0><<<D.n_chunks, 128, 0, st>>>(D, W);
-    else
-      k_camera_gather<9, 1><<<D.n_chunks, 128, 0, st>>>(D, W);
+    if (mode == 0) launch_camera_gather_t<9, 0>(D, W, st);
+    else launch_camera_gather_t<9, 1>(D, W, st);
   }
 }
 

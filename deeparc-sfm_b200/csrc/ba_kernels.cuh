@@ -104,6 +104,7 @@ struct WorkArrays {
   // camera accumulators, ONE contiguous buffer (single allreduce):
   //   B [n_blocks][cb][cb] | diagF [n_blocks][cb] | gc [n_blocks][cb] | rhs [n_blocks][cb]
   double* cam_acc;
+  double* cam_chunk_acc;  // [n_chunks][cb (cb + 1) / 2 + 3 cb] per-chunk sums of k_camera_gather, combined in chunk order
   double* minv;    // [n_blocks][cb][cb] inverse of the block-Jacobi preconditioner
   double* dc2;     // [n_blocks][cb] D_c^2
   double* diag_c;  // [n_blocks][cb] diag(F^T F) kept from the last accepted point

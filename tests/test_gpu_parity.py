@@ -327,3 +327,85 @@ def test_error_paths(engine):
     with pytest.raises(capi.EngineError) as e:
         engine.problem_set(q)
     assert e.value.status == capi.DBA_ERR_UNSUPPORTED
+
+
+# --------------------------------------------------------- edge cases and full-size properties
+def test_empty_and_ragged_problems(engine, oracle):
+    """No observations at all; points nobody observes; points with a single observation; a camera
+    without observations; observations handed over in random order (the upload sorts by point)."""
+    p = PROBLEMS["plain"]
+    empty = p.copy()
+    for k in ("obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr"):
+        setattr(empty, k, getattr(p, k)[:0].copy())
+    empty.obs_xy = p.obs_xy[:0].copy()
+    engine.problem_set(empty)
+    s = engine.solve(capi.make_options(max_num_iterations=5))
+    assert s.termination == capi.DBA_CONVERGENCE and s.final_cost == 0.0
+    assert np.array_equal(engine.params_get()["pts"], p.pts)
+
+    # ragged: drop every observation of the first 7 points and of camera 3, keep one observation of points 7..20
+    keep = np.ones(p.n_obs, bool)
+    keep[p.obs_pt < 7] = False
+    keep[p.obs_pose_a == 3] = False
+    for pt in range(7, 21):
+        idx = np.flatnonzero((p.obs_pt == pt) & keep)
+        keep[idx[1:]] = False
+    rag = p.copy()
+    for k in ("obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "obs_xy"):
+        setattr(rag, k, getattr(p, k)[keep].copy())
+    engine.problem_set(rag)
+    g = engine.eval(residuals=True, jacobians=False)
+    o = oracle.eval(rag, residuals=True, jacobians=False)
+    _check_residuals(g["residuals"], o["residuals"], rag.obs_xy)
+    sg, so = _compare_solve(engine, oracle, rag, n_iter=4)
+    x = engine.params_get()
+    assert np.array_equal(x["pts"][:7], rag.pts[:7])            # unobserved points do not move
+    assert np.array_equal(x["ext_rot"][3], rag.ext_rot[3])       # nor does the unobserved camera
+
+    # the same problem with its observations shuffled: same trace (the engine sorts by point on upload)
+    perm = np.random.default_rng(3).permutation(rag.n_obs)
+    shuf = rag.copy()
+    for k in ("obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "obs_xy"):
+        setattr(shuf, k, getattr(rag, k)[perm].copy())
+    engine.problem_set(shuf)
+    r = engine.eval(residuals=True, jacobians=False)["residuals"]
+    assert np.array_equal(r, g["residuals"][perm])
+    kw = dict(max_num_iterations=4, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+              linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=1e-13, pcg_max_iterations=2000)
+    ss = engine.solve(capi.make_options(**kw))
+    np.testing.assert_allclose(ss.trace("cost"), sg.trace("cost"), rtol=1e-9)
+
+
+def test_full_size_properties_bal5m(engine):
+    """BASELINE.json configs[3] at full size (1.7k cameras, 1M points, 5M observations), where the CPU
+    oracle takes minutes: size-independent properties instead —
+      * the cost of the Jacobian kernel's residuals equals an independent numpy evaluation of the
+        forward model over all 5M observations (1e-10 relative),
+      * ten LM iterations decrease the cost monotonically down to the statistical floor
+        sigma^2 / 2 * (2 N_obs - N_params) of the synthetic pixel noise (2 %),
+      * a second run reproduces the trace bit for bit (no atomics on the solver path)."""
+    p = synthetic.bal_like(n_cam=1700, n_pts=1_000_000, obs_per_point=5, window=50, name="bal5m")
+    engine.problem_set(p)
+    c_gpu = engine.eval(residuals=False)["cost"]
+    r = synthetic.project(p) - p.obs_xy
+    c_np = 0.5 * float(np.sum(r.astype(np.longdouble) ** 2))
+    assert abs(c_gpu - c_np) <= 1e-10 * c_np, (c_gpu, c_np)
+    kw = dict(max_num_iterations=10, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
+              linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=0.0, pcg_max_iterations=20)
+    s1 = engine.solve(capi.make_options(**kw))
+    cost = s1.trace("cost")
+    assert np.all(np.diff(cost) < 0) and s1.num_successful_steps == 10
+    n_params = 3 * p.n_pts + 9 * p.n_ext
+    floor = 0.5 * 0.5 ** 2 * (2 * p.n_obs - n_params)
+    assert abs(s1.final_cost - floor) <= 0.02 * floor, (s1.final_cost, floor)
+    # (distance to the generating parameters is not a property: nothing fixes the 7-dof gauge here)
+    x = engine.params_get()
+    r = synthetic.project(p, pts=x["pts"], ext_rot=x["ext_rot"], ext_trans=x["ext_trans"])
+    q = p.copy()
+    q.intr_focal, q.intr_dist = x["intr_focal"], x["intr_dist"]
+    r = synthetic.project(q, pts=x["pts"], ext_rot=x["ext_rot"], ext_trans=x["ext_trans"]) - p.obs_xy
+    c_final = 0.5 * float(np.sum(r.astype(np.longdouble) ** 2))
+    assert abs(s1.final_cost - c_final) <= 1e-10 * c_final  # the returned parameters have the reported cost
+    engine.params_reset()
+    s2 = engine.solve(capi.make_options(**kw))
+    assert np.array_equal(s2.trace("cost"), cost)
