@@ -123,7 +123,8 @@ struct dba_handle {
   PeerWin pw{};
   unsigned long long p2p_seq = 0;
   DevBuf<unsigned char> d_ipc;
-  DevBuf<int> d_mf_cols, d_part_dst, d_items_mf, d_part_first;
+  DevBuf<int> d_mf_cols, d_part_dst, d_part_blk, d_items_mf, d_part_first;
+  DevBuf<ushort2> d_obs_lc;
   DevBuf<double> d_mf_rows, d_mf_T;
   DevBuf<int2> d_obs_ip;
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
@@ -451,7 +452,7 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
   }
   {
     Scope s(h, "reduce");
-    launch_reduce_sum(h->d_partA.p, cost_grid(D), 1, 0, h->W.scalars + S_COST, h->st);
+    launch_reduce_sum(h->d_partA.p, jacobian_partials(D), 1, 0, h->W.scalars + S_COST, h->st);
   }
   if (h->mf && h->cb) {
     Scope s(h, "mf_rows");
@@ -663,7 +664,7 @@ int apply_step_and_evaluate(dba_handle* h, bool speculate) {
     j.sum(pa_upd, gp, 2, 1, h->W.scalars + S_X_PT);
     j.sum(h->d_partB.p, gc, 2, 0, h->W.scalars + S_STEP_CAM);
     j.sum(h->d_partB.p, gc, 2, 1, h->W.scalars + S_X_CAM);
-    j.sum(pa_cost, cost_grid(D), 1, 0, h->W.scalars + S_CAND);
+    j.sum(pa_cost, speculate ? jacobian_partials(D) : cost_grid(D), 1, 0, h->W.scalars + S_CAND);
     launch_reduce_multi(j, h->st);
   }
   CU(h, cudaGetLastError());
@@ -1014,6 +1015,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   want((n_ent_max + 1) * sizeof(int));  // part_item_first
   want(n_ent_max * sizeof(int));        // cam_part_idx
   want(n_ent_max * sizeof(int));        // part_dst
+  want(n_ent_max * sizeof(int));        // part_blk
+  want(nl * sizeof(ushort2));           // obs_lc
   want(cb ? (static_cast<size_t>(n_tiles) * tile_cap) * sizeof(int4) : 0);  // mf_cols (padded per tile)
   want((two && cb) ? n_ent_max * sizeof(int) : 0);  // items_mf
   want((n_ent_max + n_tiles + 1) * sizeof(int));    // part_first
@@ -1150,6 +1153,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   int* s_mf_cols = A.take<int>(std::max<size_t>(n_cols * mf_w, 1));
   int* s_items_mf = A.take<int>((two && cb) ? static_cast<size_t>(std::max<int64_t>(n_entries, 1)) : 1);
   int* s_part_first = A.take<int>(static_cast<size_t>(n_entries + n_tiles + 1));
+  ushort2* s_obs_lc = A.take<ushort2>(static_cast<size_t>(std::max<int64_t>(nl, 1)));
   int n_partials = 0;
   std::vector<int> part_block;
   {
@@ -1195,7 +1199,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
         m.n_parts = tile_np[t + 1] - tile_np[t];
         m.item0 = tile_ni[t];
         m.n_items = tile_ni[t + 1] - tile_ni[t];
-        for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) s_lp[k] = static_cast<unsigned short>(s_ip[k].y - m.pt0);
+        for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) {
+          s_lp[k] = static_cast<unsigned short>(s_ip[k].y - m.pt0);
+          s_obs_lc[k] = make_ushort2(0xffff, 0xffff);
+        }
         if (!cb) continue;
         locals.clear();
         count.clear();
@@ -1222,6 +1229,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
         }
         for (size_t lc = 0; lc < locals.size(); ++lc) part_block[m.g0 + lc] = locals[lc];
         for (int k = m.obs0; k < m.obs0 + m.n_obs; ++k) {
+          s_obs_lc[k] = make_ushort2(static_cast<unsigned short>(local_of[s_ab[k].x]),
+                                     s_ab[k].y >= 0 ? static_cast<unsigned short>(local_of[s_ab[k].y]) : 0xffff);
           const int lo = k - m.obs0;
           for (int slot = 0; slot < 2; ++slot) {
             const int blk = slot ? s_ab[k].y : s_ab[k].x;
@@ -1308,6 +1317,8 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_cam_part_first, n_ext + 1));
   CU(h, ensure(h->d_cam_part_idx, n_partials));
   CU(h, ensure(h->d_part_dst, n_partials));
+  CU(h, ensure(h->d_part_blk, n_partials));
+  CU(h, ensure(h->d_obs_lc, nl));
   CU(h, ensure(h->d_mf_cols, std::max<size_t>(n_cols * mf_w, 1)));
   CU(h, ensure(h->d_items_mf, (two && cb) ? n_entries : 1));
   CU(h, ensure(h->d_part_first, n_entries + n_tiles + 1));
@@ -1391,6 +1402,12 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_cam_part_first.p, s_cam_part_first, (n_ext + 1) * sizeof(int)));
   CU(h, up(h->d_cam_part_idx.p, s_cam_part_idx, n_partials * sizeof(int)));
   CU(h, up(h->d_part_dst.p, s_part_dst, n_partials * sizeof(int)));
+  {
+    int* s_part_blk = A.take<int>(static_cast<size_t>(std::max(n_partials, 1)));
+    if (n_partials) std::memcpy(s_part_blk, part_block.data(), sizeof(int) * n_partials);
+    CU(h, up(h->d_part_blk.p, s_part_blk, n_partials * sizeof(int)));
+    CU(h, up(h->d_obs_lc.p, s_obs_lc, nl * sizeof(ushort2)));
+  }
   if (cb) CU(h, up(h->d_mf_cols.p, s_mf_cols, n_cols * mf_w * sizeof(int)));
   if (two && cb) CU(h, up(h->d_items_mf.p, s_items_mf, n_entries * sizeof(int)));
   if (cb) CU(h, up(h->d_part_first.p, s_part_first, (n_entries + n_tiles + 1) * sizeof(int)));
@@ -1450,6 +1467,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.mf_cols = h->d_mf_cols.p;
   D.items_mf = h->d_items_mf.p;
   D.part_dst = h->d_part_dst.p;
+  D.part_blk = h->d_part_blk.p;
+  D.obs_lc = h->d_obs_lc.p;
+  D.intr_is_pose = intr_is_pose;
   D.part_first = h->d_part_first.p;
   for (int s = 0; s < 2; ++s) {
     ParamSet& P = h->P[s];
@@ -1600,7 +1620,8 @@ int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, dou
   if (cost) {
     {
       Scope s(h, "reduce");
-      launch_reduce_sum(h->d_partA.p, cost_grid(D0), 1, 0, h->W.scalars + S_COST, h->st);
+      // the cost partials come from k_cost (one per 256 observations) or from the Jacobian kernel
+      launch_reduce_sum(h->d_partA.p, (!want_jac && !residuals) ? cost_grid(D0) : jacobian_partials(D0), 1, 0, h->W.scalars + S_COST, h->st);
     }
     int rc = reduce_scalars_and_fetch(h);
     if (rc != DBA_OK) return rc;

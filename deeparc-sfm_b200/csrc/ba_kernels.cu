@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include <cooperative_groups.h>
@@ -144,6 +145,72 @@ __device__ __forceinline__ void forward(const ParamSet& P, const int2 ab, const 
 }
 
 // ------------------------------------------------------------------------ K1 jacobian
+// Residual + analytic Jacobian of ONE observation written to its planes (Jacobi scales and constancy
+// masks applied).  The camera-side inputs are references so that the caller decides where they live
+// (global tables, or the tile's rows staged in shared memory).
+template <int CB, bool TWO>
+__device__ __forceinline__ double jacobian_obs(const DeviceProblem& D, int64_t o, const PoseRow& A, const PoseRow* B,
+                                               const IntrRow& I, const double* scA, const double* scB,
+                                               const double* X, const double* sp, double2 xy) {
+  ObsJacobian j;
+  observation_jacobian(A, B, I, X, xy.x, xy.y, CB > 0, j);
+  double2* J = D.J + o;
+  const int64_t ld = D.ld;
+  J[kPlaneR * ld] = make_double2(j.r0, j.r1);
+  {
+    const double s0 = sp ? sp[0] : 1.0, s1 = sp ? sp[1] : 1.0, s2 = sp ? sp[2] : 1.0;
+    J[(kPlaneJp + 0) * ld] = make_double2(j.Jp[0][0] * s0, j.Jp[1][0] * s0);
+    J[(kPlaneJp + 1) * ld] = make_double2(j.Jp[0][1] * s1, j.Jp[1][1] * s1);
+    J[(kPlaneJp + 2) * ld] = make_double2(j.Jp[0][2] * s2, j.Jp[1][2] * s2);
+  }
+  if (CB >= 6) {
+    double s[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = 1.0;
+    if (scA) {
+#pragma unroll
+      for (int k = 0; k < CB; ++k) s[k] = scA[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] *= A.free_;  // constant pose: its six columns vanish
+    }
+    double2 FA[CB > 0 ? CB : 1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      FA[k] = make_double2(j.JwA[0][k] * s[k], j.JwA[1][k] * s[k]);
+      FA[3 + k] = make_double2(j.JtA[0][k] * s[3 + k], j.JtA[1][k] * s[3 + k]);
+    }
+    if (CB == 9) {
+      FA[6] = make_double2(j.df[0] * s[6], j.df[1] * s[6]);
+      FA[7] = make_double2(j.dk0[0] * s[7], j.dk0[1] * s[7]);
+      FA[8] = make_double2(j.dk1[0] * s[8], j.dk1[1] * s[8]);
+    }
+#pragma unroll
+    for (int k = 0; k < CB; ++k) J[(kPlaneJA + k) * ld] = FA[k];
+    if (TWO) {
+      const int pb = kPlaneJA + CB;
+      if (B) {
+        double sb[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+        if (scB) {
+#pragma unroll
+          for (int k = 0; k < 6; ++k) sb[k] = scB[k] * B->free_;
+        }
+        double2 FB[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          FB[k] = make_double2(j.JwB[0][k] * sb[k], j.JwB[1][k] * sb[k]);
+          FB[3 + k] = make_double2(j.JtB[0][k] * sb[3 + k], j.JtB[1][k] * sb[3 + k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = FB[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = make_double2(0.0, 0.0);
+      }
+    }
+  }
+  return j.r0 * j.r0 + j.r1 * j.r1;
+}
+
 // One thread per observation (point-sorted).  Reads 16 B (xy) + 8 B (indices) + L1/L2-resident
 // tables; writes (1 + 3 + CB [+6]) double2 planes.
 template <int CB, bool TWO, int MINB>
@@ -156,80 +223,78 @@ __global__ void __launch_bounds__(256, MINB) k_jacobian(DeviceProblem D, ParamSe
     const double2 xy = D.obs_xy[o];
     const int2 idx = D.obs_ip[o];  // (intrinsic, local point)
     const int2 ab = D.obs_ab[o];   // (block a, block b or -1)
-    struct { int pose_a, pose_b; } v = {ab.x, ab.y};
     const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
     const double X[3] = {Xp[0], Xp[1], Xp[2]};
-    const PoseRow& A = P.pose_rows[v.pose_a];
-    const bool two = v.pose_b >= 0;
-    const PoseRow* B = two ? P.pose_rows + v.pose_b : nullptr;
-    ObsJacobian j;
-    observation_jacobian(A, B, P.intr_rows[idx.x], X, xy.x, xy.y, CB > 0, j);
-    c = j.r0 * j.r0 + j.r1 * j.r1;
-    double2* J = D.J + o;
-    const int64_t ld = D.ld;
-    J[kPlaneR * ld] = make_double2(j.r0, j.r1);
-    {
-      double s0 = 1.0, s1 = 1.0, s2 = 1.0;
-      if (!unit_scale) {
-        const double* sp = W.sp + 3 * static_cast<int64_t>(idx.y);
-        s0 = sp[0];
-        s1 = sp[1];
-        s2 = sp[2];
-      }
-      J[(kPlaneJp + 0) * ld] = make_double2(j.Jp[0][0] * s0, j.Jp[1][0] * s0);
-      J[(kPlaneJp + 1) * ld] = make_double2(j.Jp[0][1] * s1, j.Jp[1][1] * s1);
-      J[(kPlaneJp + 2) * ld] = make_double2(j.Jp[0][2] * s2, j.Jp[1][2] * s2);
-    }
-    if (CB >= 6) {
-      double s[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) s[k] = 1.0;
-      if (!unit_scale) {
-        const double* sc = W.sc + static_cast<int64_t>(v.pose_a) * CB;
-#pragma unroll
-        for (int k = 0; k < CB; ++k) s[k] = sc[k];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s[k] *= A.free_;  // constant pose: its six columns vanish
-      }
-      double2 FA[CB > 0 ? CB : 1];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        FA[k] = make_double2(j.JwA[0][k] * s[k], j.JwA[1][k] * s[k]);
-        FA[3 + k] = make_double2(j.JtA[0][k] * s[3 + k], j.JtA[1][k] * s[3 + k]);
-      }
-      if (CB == 9) {
-        FA[6] = make_double2(j.df[0] * s[6], j.df[1] * s[6]);
-        FA[7] = make_double2(j.dk0[0] * s[7], j.dk0[1] * s[7]);
-        FA[8] = make_double2(j.dk1[0] * s[8], j.dk1[1] * s[8]);
-      }
-#pragma unroll
-      for (int k = 0; k < CB; ++k) J[(kPlaneJA + k) * ld] = FA[k];
-      if (TWO) {
-        const int pb = kPlaneJA + CB;
-        if (two) {
-          double sb[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
-          if (!unit_scale) {
-            const double* sc = W.sc + static_cast<int64_t>(v.pose_b) * CB;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) sb[k] = sc[k] * B->free_;
-          }
-          double2 FB[6];
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            FB[k] = make_double2(j.JwB[0][k] * sb[k], j.JwB[1][k] * sb[k]);
-            FB[3 + k] = make_double2(j.JtB[0][k] * sb[3 + k], j.JtB[1][k] * sb[3 + k]);
-          }
-#pragma unroll
-          for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = FB[k];
-        } else {
-#pragma unroll
-          for (int k = 0; k < 6; ++k) J[(pb + k) * ld] = make_double2(0.0, 0.0);
-        }
-      }
-    }
+    const PoseRow* B = ab.y >= 0 ? P.pose_rows + ab.y : nullptr;  // (TWO only says whether block-B planes are stored)
+    c = jacobian_obs<CB, TWO>(D, o, P.pose_rows[ab.x], B, P.intr_rows[idx.x],
+                              (unit_scale || CB == 0) ? nullptr : W.sc + static_cast<int64_t>(ab.x) * CB,
+                              (unit_scale || CB == 0 || !B) ? nullptr : W.sc + static_cast<int64_t>(ab.y) * CB, X,
+                              unit_scale ? nullptr : W.sp + 3 * static_cast<int64_t>(idx.y), xy);
   }
   c = block_sum(c, red);
   if (threadIdx.x == 0 && partial_cost) partial_cost[blockIdx.x] = c;
+}
+
+// The same per point tile, with the camera-side inputs of the tile's camera blocks staged in shared
+// memory first.  In point order a warp's 32 observations belong to 32 different cameras: gathered
+// from the global tables that is 32 L1 tag lookups per load instruction, and the flat kernel is
+// bound by exactly that (ncu: L1 data pipe 67 %, DRAM 33 %).  A tile touches few distinct camera
+// blocks (its partial list), so their rows (pose row 160 B, Jacobi scales, and the intrinsic row
+// when intrinsics are per camera) are copied once per tile and read from shared memory by local index.
+constexpr int kJacRowCap = 96;                  // staged camera blocks per tile; the rest falls back to the tables
+constexpr int kJacRowLen = 20 + 8 + 9 + 2;      // PoseRow | IntrRow | scales | pad: 39 doubles (odd: spreads the banks)
+constexpr int kJacThreads = 256;                // a tile of up to 1024 observations is walked in batches of 256
+template <int CB, bool TWO, int MINB>
+__global__ void __launch_bounds__(kJacThreads, MINB) k_jacobian_tile(DeviceProblem D, ParamSet P, WorkArrays W, int unit_scale,
+                                                                      int intr_is_pose, double* __restrict__ partial_cost) {
+  constexpr int T = kJacThreads;
+  __shared__ double red[32];
+  __shared__ double rows[kJacRowCap * kJacRowLen];
+  const int t = blockIdx.x, tid = threadIdx.x;
+  const TileMeta tm = D.tile_meta[t];
+  const int n_stage = min(tm.n_parts, kJacRowCap);
+  constexpr int kCopy = 20 + 8 + (CB > 0 ? CB : 1);
+  for (int i = tid; i < n_stage * kCopy; i += T) {
+    const int r = i / kCopy, f = i - r * kCopy;
+    const int blk = D.part_blk[tm.g0 + r];
+    double v;
+    if (f < 20)
+      v = reinterpret_cast<const double*>(P.pose_rows + blk)[f];
+    else if (f < 28)
+      v = intr_is_pose ? reinterpret_cast<const double*>(P.intr_rows + blk)[f - 20] : 0.0;
+    else
+      v = (CB > 0 && !unit_scale) ? W.sc[static_cast<int64_t>(blk) * CB + (f - 28)] : 1.0;
+    rows[r * kJacRowLen + f] = v;
+  }
+  __syncthreads();
+  double c = 0.0;
+  for (int i = tid; i < tm.n_obs; i += T) {
+    const int64_t o = tm.obs0 + i;
+    const double2 xy = D.obs_xy[o];
+    const int2 idx = D.obs_ip[o];
+    const int2 ab = D.obs_ab[o];
+    const ushort2 lc = D.obs_lc[o];
+    const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
+    const double X[3] = {Xp[0], Xp[1], Xp[2]};
+    const double* sp = unit_scale ? nullptr : W.sp + 3 * static_cast<int64_t>(idx.y);
+    const bool has_b = ab.y >= 0;  // (TWO only says whether block-B planes are stored)
+    const bool no_scale = unit_scale || CB == 0;
+    if (lc.x < kJacRowCap && (!has_b || lc.y < kJacRowCap)) {
+      // everything camera-side out of shared memory
+      const double* rowA = rows + lc.x * kJacRowLen;
+      const double* rowB = rows + (has_b ? lc.y : 0) * kJacRowLen;
+      const IntrRow& I = intr_is_pose ? *reinterpret_cast<const IntrRow*>(rowA + 20) : P.intr_rows[idx.x];
+      c += jacobian_obs<CB, TWO>(D, o, *reinterpret_cast<const PoseRow*>(rowA), has_b ? reinterpret_cast<const PoseRow*>(rowB) : nullptr,
+                                I, no_scale ? nullptr : rowA + 28, (no_scale || !has_b) ? nullptr : rowB + 28, X, sp, xy);
+    } else {
+      // a tile with more camera blocks than the staging area holds: the global tables
+      c += jacobian_obs<CB, TWO>(D, o, P.pose_rows[ab.x], has_b ? P.pose_rows + ab.y : nullptr, P.intr_rows[idx.x],
+                                no_scale ? nullptr : W.sc + static_cast<int64_t>(ab.x) * CB,
+                                (no_scale || !has_b) ? nullptr : W.sc + static_cast<int64_t>(ab.y) * CB, X, sp, xy);
+    }
+  }
+  c = block_sum(c, red);
+  if (tid == 0 && partial_cost) partial_cost[t] = c;
 }
 
 // ---------------------------------------------------------------------------- K2 cost
@@ -1846,20 +1911,39 @@ static int tile_minb() {
   }
   return v;
 }
-// resident CTAs per SM asked of the register allocator (2 = 96 registers, 3 = 80, 4 = 64 with spills);
-// the kernel is latency-bound on the camera-table gathers, so occupancy is the lever (DBA_JAC_MINB)
+// resident 256-thread CTAs per SM asked of the register allocator for the Jacobian kernels (2 = 128
+// registers, 3 = 80, 4 = 64 with more spills).  Measured on bal5m: tiled 403 / 352 / 382 us, flat
+// 424 / 400 / 385 us (DBA_JAC_MINB; DBA_JAC=flat selects the flat kernel)
 static int jac_minb() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("DBA_JAC_MINB");
-    v = e ? std::atoi(e) : 4;
-    if (v < 2 || v > 4) v = 4;
+    v = e ? std::atoi(e) : 3;
+    if (v < 2 || v > 4) v = 3;
   }
   return v;
 }
+// DBA_JAC=flat keeps the one-thread-per-observation kernel that gathers from the global tables
+static bool jac_tiled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("DBA_JAC");
+    v = (e && std::strcmp(e, "flat") == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+int jacobian_partials(const DeviceProblem& D) { return (jac_tiled() && D.obs_lc) ? D.n_tiles : cost_grid(D); }
+
 template <int CB, bool TWO>
 static void launch_jacobian_t(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, int unit_scale, double* partial_cost,
                               cudaStream_t st) {
+  if (jac_tiled() && D.obs_lc) {
+    const int mb = jac_minb();
+    if (mb == 2) k_jacobian_tile<CB, TWO, 2><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost);
+    else if (mb == 3) k_jacobian_tile<CB, TWO, 3><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost);
+    else k_jacobian_tile<CB, TWO, 4><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost);
+    return;
+  }
   const int grid = cost_grid(D);
   const int mb = jac_minb();
   if (mb == 2) k_jacobian<CB, TWO, 2><<<grid, 256, 0, st>>>(D, P, W, unit_scale, partial_cost);

@@ -75,6 +75,9 @@ struct DeviceProblem {
   const int* items_mf;              // two-pose problems: `items` with lo replaced by the column
   const int* part_first;            // `part_first_rel` widened to int (cp.async granularity), same indexing
   const int* part_dst;              // [n_partials] row of partial g in the camera-grouped partial buffer
+  const int* part_blk;              // [n_partials] camera block of partial g (rows staged by k_jacobian_tile)
+  const ushort2* obs_lc;            // [n_obs] tile-local camera block (= partial) of block a / block b (0xffff: none)
+  int intr_is_pose;                 // every observation uses intrinsic == block a (per-camera intrinsics)
 };
 
 __host__ __device__ constexpr int mf_row_len(int cb) { return cb == 9 ? 24 : 20; }  // multiples of 4 doubles (256-bit loads)
@@ -173,6 +176,7 @@ void launch_cost(const DeviceProblem& D, const ParamSet& P, double* partial_cost
 void launch_filter_flags(const DeviceProblem& D, const ParamSet& P, const double* mse, double boundary, const double* centre,
                          double rho, uint8_t* obs_remove, uint8_t* pt_remove, cudaStream_t st);
 int cost_grid(const DeviceProblem& D);
+int jacobian_partials(const DeviceProblem& D);  // entries launch_jacobian writes into partial_cost
 int tile_grid(const DeviceProblem& D);
 // per point: H = E^T E, g = E^T r.  mode 0: Jacobi scales sp.  mode 1: C = H + D^2, C^-1,
 // t = C^-1 g, partials[3*tile + {0,1,2}] = {sum g^2, max |g|, #non-SPD blocks}.
