@@ -1,13 +1,22 @@
 // Hand-written sm_100a kernels of the bundle-adjustment hot path.  fp64 throughout; the path
-// is HBM-bound streaming + segmented reductions (no dense contraction, so no tensor cores).
-// Kernel <-> reference map (DESIGN.md has the byte models):
+// is streaming + segmented reductions (no dense contraction, so no tensor cores).
+// Kernel <-> reference map (DESIGN.md has the byte models and the measured bounds):
 //   k_pose_rows        per-extrinsic trig hoisting for rotatePoint (snavely_reprojection_error.hh:80-91)
-//   k_jacobian   (K1)  residual + analytic Jacobian of operator() (:93-118), replaces Ceres autodiff
-//   k_cost       (K2)  residual-only evaluation (trial point; filterPoint3d, DeepArcManager.cc:335-347)
-//   k_point_prepare, k_camera_gather, k_camera_finalize (K3)  Schur elimination front half
-//   k_spmv_tile + k_partials_to_q (K5)  implicit Schur complement product, one pass, atomic-free
-//   k_pcg_init / k_pcg_dot / k_pcg_step / k_pcg_direction (K6)  block-Jacobi PCG vector work
-//   k_back_substitute (K7), k_param_update  point back-substitution, x + delta, norms
+//   k_jacobian_tile / k_jacobian (K1)  residual + analytic Jacobian of operator() (:93-118), replaces
+//                      Ceres autodiff; per point tile with the tile's camera rows staged in shared memory
+//   k_cost       (K2)  residual-only evaluation (rejected-step streaks; filterPoint3d, DeepArcManager.cc:335-347)
+//   k_filter_flags     the three removal rules of filterPoint3d decided per point (DeepArcManager.cc:347-408)
+//   k_point_prepare, k_camera_gather + k_camera_combine, k_camera_finalize (K3)  Schur elimination
+//                      front half: C^-1, t per point; block-Jacobi blocks, gradient, rhs per camera (no atomics)
+//   k_spmv_mf    (K5)  matrix-free implicit Schur complement product, persistent CTAs, cp.async tile
+//                      staging; launched cooperatively with pcg_tail (per-camera sum of the partials,
+//                      cross-rank exchange through NVLink peer windows, PCG vector updates) as its epilogue
+//   k_spmv_tile + k_partials_to_q  the same product from the materialised planes (TMA-staged tiles)
+//   k_pcg_fused        pcg_tail as its own cooperative launch
+//   k_pcg_init / k_pcg_dot / k_pcg_step / k_pcg_direction / k_mf_direction / k_fold_q  plain-launch PCG
+//                      vector work (DBA_PCG_FUSED=0, few-camera multi-GPU without peer windows)
+//   k_back_substitute (K7), k_update_points / k_update_cameras, k_reduce_multi  point back-substitution,
+//                      x + delta, norms, fixed-order reductions
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
