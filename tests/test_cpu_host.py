@@ -306,3 +306,29 @@ def test_generators_follow_the_reference_aliasing_rules():
     assert p.n_ext == A + p.n_ring - 1
     r = synthetic.project(p, pts=p.truth["pts"], ext_rot=p.truth["ext_rot"], ext_trans=p.truth["ext_trans"]) - p.obs_xy
     assert 0.3 < r.std() < 0.7  # 0.5 px observation noise around the ground truth
+
+
+# ------------------------------------------------------------------------- bench contract
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU oracle timed on the host cores) prints exactly one JSON line
+    carrying the contract keys; it needs no GPU."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small",
+                        "--steps", "1", "--cpu-budget", "5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "lm_iters_per_sec" and d["unit"] == "LM iterations/s"
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_bench_fails_loudly_without_a_device():
+    if not _no_gpu():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "small", "--steps", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
