@@ -837,6 +837,19 @@ int dba_shard_plan(const dba_problem* p, int32_t world_size, int32_t* pt_begin, 
   return DBA_OK;
 }
 
+// Host threads of the upload: with one rank per GPU on one host, every rank builds its shard at the
+// same time, so each takes its share of the cores instead of oversubscribing them world-fold
+// (DBA_HOST_THREADS overrides); the caller's OpenMP setting is restored on the way out.
+struct OmpThreadScope {
+  int saved;
+  explicit OmpThreadScope(int world) : saved(omp_get_max_threads()) {
+    int n = world > 1 ? std::max(1, omp_get_num_procs() / world) : 0;
+    if (const char* e = std::getenv("DBA_HOST_THREADS")) n = std::atoi(e);
+    if (n > 0) omp_set_num_threads(n);
+  }
+  ~OmpThreadScope() { omp_set_num_threads(saved); }
+};
+
 // ------------------------------------------------------------------- problem upload
 // Host side of the upload: every O(n_obs) step is a parallel pass (OpenMP over the host cores)
 // writing straight into the pinned staging arena, copied with a handful of large async memcpys.
@@ -855,6 +868,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   const int64_t n = p->n_obs;
   const int n_ext = p->n_ext, n_intr = p->n_intr;
 
+  OmpThreadScope omp_scope(h->world);
   const bool timing = std::getenv("DBA_TIMING") != nullptr;
   double t_mark = now_s();
   auto mark = [&](const char* what) {
