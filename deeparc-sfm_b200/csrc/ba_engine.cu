@@ -984,28 +984,21 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   std::vector<TileMeta> tile_meta;
   tile_meta.reserve(static_cast<size_t>(nl / 200 + 16));
   {
-    int cur_obs = 0, t_pt0 = 0;
-    for (int i = 0; i < n_pts; ++i) {
-      const int len = static_cast<int>(pt_count[pt_lo + i + 1] - pt_count[pt_lo + i]);
-      if (cur_obs + len > tile_cap || i - t_pt0 >= max_tile_points(tile_cap)) {  // whole points, <= tile_cap observations, <= max_tile_points
-        TileMeta m{};
-        m.obs0 = static_cast<int>(pt_count[pt_lo + t_pt0] - obs_lo);
-        m.n_obs = cur_obs;
-        m.pt0 = t_pt0;
-        m.n_pts = i - t_pt0;
-        tile_meta.push_back(m);
-        t_pt0 = i;
-        cur_obs = 0;
-      }
-      cur_obs += len;
-    }
-    if (n_pts > t_pt0) {
+    // greedy packing = from each tile start, the longest run of whole points within the capacity:
+    // one binary search in the prefix sums per TILE instead of one step per point
+    const int64_t* first = pt_count.data() + pt_lo;  // first[i] = first observation of local point i (global position)
+    const int max_pts = max_tile_points(tile_cap);
+    for (int s = 0; s < n_pts;) {
+      const int64_t limit = first[s] + tile_cap;
+      int end = static_cast<int>(std::upper_bound(first + s + 1, first + n_pts + 1, limit) - first) - 1;
+      end = std::max(std::min(end, s + max_pts), s + 1);
       TileMeta m{};
-      m.obs0 = static_cast<int>(pt_count[pt_lo + t_pt0] - obs_lo);
-      m.n_obs = cur_obs;
-      m.pt0 = t_pt0;
-      m.n_pts = n_pts - t_pt0;
+      m.obs0 = static_cast<int>(first[s] - obs_lo);
+      m.n_obs = static_cast<int>(first[end] - first[s]);
+      m.pt0 = s;
+      m.n_pts = end - s;
       tile_meta.push_back(m);
+      s = end;
     }
   }
   const int n_tiles = static_cast<int>(tile_meta.size());

@@ -1900,6 +1900,17 @@ __global__ void __launch_bounds__(1024) k_reduce_multi(ReduceJobs J) {
 }  // namespace
 
 // ================================================================== launch wrappers
+// true the first time it is called on the current device (function attributes such as the dynamic
+// shared-memory limit are per device; a process may hold handles on several devices)
+static bool first_use_on_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 int tile_grid(const DeviceProblem& D) { return D.n_tiles; }
 int cost_grid(const DeviceProblem& D) { return static_cast<int>((D.n_obs + 255) / 256); }
 
@@ -1994,10 +2005,9 @@ void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double ra
     constexpr int T = decltype(tag)::value;
     constexpr int MB = decltype(mb)::value;
     constexpr size_t smem = 9 * T * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;  // per device: function attributes are
+    if (first_use_on_device(&configured)) {
       cudaFuncSetAttribute(k_point_prepare<T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      configured = true;
     }
     k_point_prepare<T, MB><<<D.n_tiles, T, smem, st>>>(D, W, radius, min_diag, max_diag, mode, partials);
   };
@@ -2057,12 +2067,11 @@ void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t s
 
 template <int CB, bool TWO, int T>
 static void launch_spmv_tile_tt(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
-  static bool configured = false;
+  static unsigned long long configured = 0;  // per device: function attributes are
   constexpr size_t smem = SpmvSmem<CB, TWO, T>::kBytes;
   static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
-  if (!configured) {
+  if (first_use_on_device(&configured)) {
     cudaFuncSetAttribute(k_spmv_tile<CB, TWO, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    configured = true;
   }
   k_spmv_tile<CB, TWO, T><<<D.n_tiles, T, smem, st>>>(D, W);
 }
@@ -2141,12 +2150,11 @@ void launch_mf_direction(const DeviceProblem& D, const WorkArrays& W, int init, 
 
 template <int CB, bool TWO, int T, int MINB>
 static int launch_spmv_mf_tt(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, const MfTail& tail, cudaStream_t st) {
-  static bool configured = false;
+  static unsigned long long configured = 0;  // per device: function attributes are
   constexpr size_t smem = MfSmem<CB, TWO, T>::kBytes;
   static_assert(smem <= 227 * 1024, "tile does not fit in shared memory");
-  if (!configured) {
+  if (first_use_on_device(&configured)) {
     cudaFuncSetAttribute(k_spmv_mf<CB, TWO, T, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    configured = true;
   }
   static int n_sm = 0;
   if (n_sm == 0) {
@@ -2240,10 +2248,9 @@ static void launch_back_substitute_t(const DeviceProblem& D, const WorkArrays& W
     constexpr int T = decltype(tag)::value;
     constexpr int MB = decltype(mb)::value;
     constexpr size_t smem = 6 * T * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;  // per device: function attributes are
+    if (first_use_on_device(&configured)) {
       cudaFuncSetAttribute(k_back_substitute<CB, TWO, T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      configured = true;
     }
     k_back_substitute<CB, TWO, T, MB><<<D.n_tiles, T, smem, st>>>(D, W, partial_model);
   };
