@@ -206,6 +206,30 @@ def test_parallel_loader_and_writer_match_the_serial_path(tmp_path, monkeypatch)
         assert filecmp.cmp(f + ".ply0", f + ".ply1", shallow=False)
 
 
+def test_parallel_loader_handles_free_form_whitespace(tmp_path, monkeypatch):
+    """The format is a token stream (the reference reads it with operator>>): CRLF line ends, tabs, runs of
+    blanks, several records per line and records split across lines load the same as the canonical layout."""
+    H = oracle_lib.HostMirror()
+    p = synthetic.arc_rig(n_arc=3, n_ring=4, n_pts=400, obs_per_point=6, seed=64)
+    f = str(tmp_path / "canon.deeparc")
+    synthetic.write_deeparc(p, f)
+    tokens = open(f).read().split()
+    rng = np.random.default_rng(11)
+    seps = [" ", "  ", "\t", "\r\n", "\n", " \n\t "]
+    messy = "".join(tok + seps[int(rng.integers(len(seps)))] for tok in tokens)
+    g = str(tmp_path / "messy.deeparc")
+    open(g, "w", newline="").write("\r\n \t" + messy)
+    monkeypatch.setenv("DEEPARC_SERIAL_IO", "0")
+    ha, hb = H.read(f), H.read(g)
+    a, b = H.export(ha), H.export(hb)
+    for k in ("obs_xy", "obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "pts", "pts_rgb", "ext_rot", "ext_trans",
+              "intr_center", "intr_focal", "intr_dist", "ext_const"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    H.write(ha, f + ".out"), H.write(hb, g + ".out")
+    assert filecmp.cmp(f + ".out", g + ".out", shallow=False)
+    H.free(ha), H.free(hb)
+
+
 def test_parallel_loader_falls_back_on_tokens_it_does_not_take(tmp_path, monkeypatch):
     """The parallel parser is strict (a token must be one number); a file with e.g. a hexadecimal
     float or a truncated tail is re-read by the serial tokenizer, which has the reference's
