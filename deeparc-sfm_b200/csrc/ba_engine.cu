@@ -99,7 +99,7 @@ struct dba_handle {
 
   // device storage
   DevBuf<double2> d_obs_xy, d_J;
-  DevBuf<int> d_tile_part_first, d_part_item_first, d_cam_part_first, d_cam_part_idx;
+  DevBuf<int> d_cam_part_first;
   DevBuf<unsigned short> d_items, d_obs_lp, d_part_first_rel;
   DevBuf<TileMeta> d_tile_meta;
   DevBuf<int2> d_obs_ab;
@@ -1019,8 +1019,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   want(n_ent_max * sizeof(int));       // cam_entries
   want(n_ent_max * sizeof(unsigned short));  // items
   want((n_ent_max + n_tiles + 1) * sizeof(unsigned short));  // part_first_rel
-  want((n_ent_max + 1) * sizeof(int));  // part_item_first
-  want(n_ent_max * sizeof(int));        // cam_part_idx
   want(n_ent_max * sizeof(int));        // part_dst
   want(n_ent_max * sizeof(int));        // part_blk
   want(nl * sizeof(ushort2));           // obs_lc
@@ -1151,9 +1149,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   // ---- static tile-local camera incidence (parallel over tiles, two passes)
   unsigned short* s_items = A.take<unsigned short>(static_cast<size_t>(std::max<int64_t>(n_entries, 1)));
   unsigned short* s_part_first_rel = A.take<unsigned short>(static_cast<size_t>(n_entries + n_tiles + 1));
-  int* s_tile_part_first = A.take<int>(static_cast<size_t>(n_tiles) + 1);
   int* s_cam_part_first = A.take<int>(static_cast<size_t>(n_ext) + 1);
-  int* s_cam_part_idx = nullptr;
   int* s_part_dst = nullptr;
   const int mf_w = cb == 9 ? 2 : 4;  // ints per column record
   const size_t n_cols = cb ? static_cast<size_t>(n_tiles) * tile_cap : 0;  // padded: tile t owns [t * tile_cap, (t + 1) * tile_cap)
@@ -1194,7 +1190,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     }
     n_partials = tile_np[n_tiles];
     part_block.resize(static_cast<size_t>(n_partials));
-    for (int t = 0; t <= n_tiles; ++t) s_tile_part_first[t] = tile_np[t];
     // pass B: fill (items grouped by local block, in order of first appearance)
 #pragma omp parallel
     {
@@ -1283,12 +1278,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     for (int b = 0; b <= n_ext; ++b) s_cam_part_first[b] = 0;
     for (int g = 0; g < n_partials; ++g) s_cam_part_first[part_block[g] + 1]++;
     for (int b = 0; b < n_ext; ++b) s_cam_part_first[b + 1] += s_cam_part_first[b];
-    s_cam_part_idx = A.take<int>(static_cast<size_t>(std::max(n_partials, 1)));
     std::vector<int> cur(s_cam_part_first, s_cam_part_first + n_ext);
     s_part_dst = A.take<int>(static_cast<size_t>(std::max(n_partials, 1)));
     for (int g = 0; g < n_partials; ++g) {
       const int pos = cur[part_block[g]]++;
-      s_cam_part_idx[pos] = g;
       s_part_dst[g] = pos;
     }
   }
@@ -1317,12 +1310,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, ensure(h->d_cam_entries, n_entries));
   CU(h, ensure(h->d_cam_chunks, n_chunks));
   CU(h, ensure(h->d_cam_chunk_first, n_ext + 1));
-  CU(h, ensure(h->d_tile_part_first, n_tiles + 1));
   CU(h, ensure(h->d_tile_meta, n_tiles));
   CU(h, ensure(h->d_part_first_rel, n_entries + n_tiles + 1));
   CU(h, ensure(h->d_items, n_entries));
   CU(h, ensure(h->d_cam_part_first, n_ext + 1));
-  CU(h, ensure(h->d_cam_part_idx, n_partials));
   CU(h, ensure(h->d_part_dst, n_partials));
   CU(h, ensure(h->d_part_blk, n_partials));
   CU(h, ensure(h->d_obs_lc, nl));
@@ -1402,12 +1393,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   CU(h, up(h->d_obs_lp.p, s_lp, nl * sizeof(unsigned short)));
   CU(h, up(h->d_tile_obs.p, s_tile_obs, (n_tiles + 1) * sizeof(int)));
   CU(h, up(h->d_tile_pt.p, s_tile_pt, (n_tiles + 1) * sizeof(int)));
-  CU(h, up(h->d_tile_part_first.p, s_tile_part_first, (n_tiles + 1) * sizeof(int)));
   CU(h, up(h->d_tile_meta.p, s_tile_meta, n_tiles * sizeof(TileMeta)));
   CU(h, up(h->d_part_first_rel.p, s_part_first_rel, (n_entries + n_tiles + 1) * sizeof(unsigned short)));
   CU(h, up(h->d_items.p, s_items, n_entries * sizeof(unsigned short)));
   CU(h, up(h->d_cam_part_first.p, s_cam_part_first, (n_ext + 1) * sizeof(int)));
-  CU(h, up(h->d_cam_part_idx.p, s_cam_part_idx, n_partials * sizeof(int)));
   CU(h, up(h->d_part_dst.p, s_part_dst, n_partials * sizeof(int)));
   {
     int* s_part_blk = A.take<int>(static_cast<size_t>(std::max(n_partials, 1)));
@@ -1461,15 +1450,12 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   D.cam_chunk_first = h->d_cam_chunk_first.p;
   D.n_chunks = n_chunks;
   D.J = h->d_J.p;
-  D.tile_part_first = h->d_tile_part_first.p;
   D.tile_meta = h->d_tile_meta.p;
   D.obs_ab = h->d_obs_ab.p;
   D.obs_lp = h->d_obs_lp.p;
   D.part_first_rel = h->d_part_first_rel.p;
-  D.part_item_first = nullptr;
   D.items = h->d_items.p;
   D.cam_part_first = h->d_cam_part_first.p;
-  D.cam_part_idx = h->d_cam_part_idx.p;
   D.n_partials = n_partials;
   D.mf_cols = h->d_mf_cols.p;
   D.items_mf = h->d_items_mf.p;
@@ -1496,20 +1482,16 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.sc = h->d_sc.p;
   W.cinv = h->d_cinv.p;
   W.tp = h->d_tp.p;
-  W.gp = nullptr;
-  W.diag_p = nullptr;
   W.dp = h->d_dp.p;
   W.cam_acc = h->d_cam_acc.p;
   W.cam_chunk_acc = h->d_cam_chunk_acc.p;
   W.minv = h->d_minv.p;
   W.dc2 = h->d_dc2.p;
-  W.diag_c = nullptr;
   W.x = h->d_x.p;
   W.r = h->d_r.p;
   W.z = h->d_z.p;
   W.p = h->d_p.p;
   W.q = h->d_q.p;
-  W.partials = h->d_partA.p;
   W.scalars = h->d_scalars.p;
   W.pcg_state = h->d_pcg_state.p;
   W.pcg_scal = h->d_pcg_scal.p;

@@ -59,11 +59,8 @@ struct DeviceProblem {
   const int2* obs_ab;               // [n_obs] (block a, block b or -1) of each observation
   const unsigned short* obs_lp;     // [n_obs] point index local to the tile
   const unsigned short* part_first_rel;  // per tile t, n_parts + 1 item offsets relative to item0, at [g0 + t]
-  const int* tile_part_first;       // [n_tiles + 1] first partial of each tile
-  const int* part_item_first;       // [n_partials + 1] first item of each partial
   const unsigned short* items;      // [n_entries] local observation | slot << 15, grouped by partial
   const int* cam_part_first;        // [n_blocks + 1] camera block -> its partials
-  const int* cam_part_idx;          // [n_partials]
   int n_partials;
   double2* J;               // planes
   // matrix-free implicit Schur product (k_spmv_mf): observations of a tile re-ordered by camera
@@ -101,8 +98,6 @@ struct WorkArrays {
   double* sc;      // [n_blocks][cb] Jacobi scale of camera columns
   double* cinv;    // [n_pts][6]  (E^T E + D^2)^-1
   double* tp;      // [n_pts][4]  C^-1 g_p (padded rows: one 32-byte load)
-  double* gp;      // [n_pts][3]  E^T r  (scaled gradient)
-  double* diag_p;  // [n_pts][3]  diag(E^T E) at the last accepted point (for D and for scaling)
   double* dp;      // [n_pts][3]  point step (scaled space)
   // camera accumulators, ONE contiguous buffer (single allreduce):
   //   B [n_blocks][cb][cb] | diagF [n_blocks][cb] | gc [n_blocks][cb] | rhs [n_blocks][cb]
@@ -110,10 +105,8 @@ struct WorkArrays {
   double* cam_chunk_acc;  // [n_chunks][cb (cb + 1) / 2 + 3 cb] per-chunk sums of k_camera_gather, combined in chunk order
   double* minv;    // [n_blocks][cb][cb] inverse of the block-Jacobi preconditioner
   double* dc2;     // [n_blocks][cb] D_c^2
-  double* diag_c;  // [n_blocks][cb] diag(F^T F) kept from the last accepted point
   // PCG vectors [n_blocks * cb]
   double *x, *r, *z, *p, *q;
-  double* partials;  // [n_partials] per-CTA partial sums (deterministic reductions)
   double* scalars;   // [32] reduced scalars, copied to the host
   int* pcg_state;    // [4] iter, done, peer exchange timed out, -
   double* pcg_scal;  // [4] rz, rz0, p.q, beta
@@ -146,20 +139,6 @@ struct PeerWin {
   double* data[kMaxPeers] = {};
   unsigned long long* flags[kMaxPeers] = {};
   unsigned long long* go = nullptr;  // local: CTA 0 publishes `seq` (all slots in) or ~0 (timeout)
-};
-
-// scalar slots in WorkArrays::scalars
-enum ScalarSlot {
-  kSCost = 0,          // sum r^2 at x
-  kSCostCand = 1,      // sum r^2 at x + delta
-  kSGradMax = 2,       // max |g_unscaled|
-  kSGradSq = 3,        // sum g_unscaled^2
-  kSModel = 4,         // sum (J d).(r + J d / 2)
-  kSStepSq = 5,        // sum (s d)^2
-  kSXSq = 6,           // sum x^2 over free parameters
-  kSBadPoint = 7,      // count of non-SPD point blocks
-  kSColPt = 8,
-  kSCount = 16
 };
 
 // ---- launches (all asynchronous on `st`) ---------------------------------------------
