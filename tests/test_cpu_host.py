@@ -338,7 +338,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     carrying the contract keys; it needs no GPU."""
     import json
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small",
-                        "--steps", "1", "--cpu-budget", "5"], capture_output=True, text=True, timeout=600)
+                        "--steps", "1", "--cpu-budget", "120"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
