@@ -48,8 +48,13 @@ typedef struct dba_config {
   int32_t device;     /* CUDA device ordinal                                            */
   int32_t rank;       /* 0 .. world_size-1                                              */
   int32_t world_size; /* 1 = single GPU.  >1: every rank passes the FULL problem to
-                         dba_problem_set and keeps only its own contiguous point range;
-                         camera-space vectors are combined by NCCL allreduce.           */
+                         dba_problem_set and keeps only its own contiguous point range.
+                         The ranks must share one node: the camera-space vector of every
+                         PCG iteration is exchanged through CUDA-IPC peer windows over
+                         NVLink inside the PCG launch (ncclAllReduce when peer access is
+                         not available); the once-per-iteration camera accumulators and
+                         scalars go through ncclAllReduce.  dba_problem_set, dba_solve,
+                         dba_eval and dba_params_get are collective calls.               */
   const void* nccl_unique_id; /* 128 bytes from dba_nccl_unique_id() on rank 0,
                                  broadcast by the caller; NULL when world_size == 1     */
   int32_t verbose;
