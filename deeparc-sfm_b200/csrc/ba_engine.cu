@@ -922,7 +922,18 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
       for (int q = lo; q <= hi; ++q) pt_count[q] = i;
     }
   } else {
-    for (int64_t i = 0; i < n; ++i) pt_count[p->obs_pt[i] + 1]++;
+    // unsorted input (the usual case for a scene graph in file order): stable counting sort by point,
+    // lock-free — every thread scans all observations and counts those of ITS range of points
+#pragma omp parallel
+    {
+      const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+      const int p0 = static_cast<int>(static_cast<int64_t>(p->n_pts) * t / nt);
+      const int p1 = static_cast<int>(static_cast<int64_t>(p->n_pts) * (t + 1) / nt);
+      for (int64_t i = 0; i < n; ++i) {
+        const int pt = p->obs_pt[i];
+        if (pt >= p0 && pt < p1) pt_count[pt + 1]++;
+      }
+    }
     for (int i = 0; i < p->n_pts; ++i) pt_count[i + 1] += pt_count[i];
   }
   int pt_lo = 0, pt_hi = p->n_pts;
@@ -952,11 +963,18 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < nl; ++k) h->perm[k] = obs_lo + k;
   } else {
+    // second pass of the counting sort, same split: a thread places the observations of its points in
+    // index order (stable), so no two threads touch the same cursor
     std::vector<int64_t> cursor(pt_count.begin() + pt_lo, pt_count.begin() + pt_hi);
-    for (int64_t i = 0; i < n; ++i) {
-      const int pt = p->obs_pt[i];
-      if (pt < pt_lo || pt >= pt_hi) continue;
-      h->perm[cursor[pt - pt_lo]++ - obs_lo] = i;
+#pragma omp parallel
+    {
+      const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+      const int q0 = pt_lo + static_cast<int>(static_cast<int64_t>(pt_hi - pt_lo) * t / nt);
+      const int q1 = pt_lo + static_cast<int>(static_cast<int64_t>(pt_hi - pt_lo) * (t + 1) / nt);
+      for (int64_t i = 0; i < n; ++i) {
+        const int pt = p->obs_pt[i];
+        if (pt >= q0 && pt < q1) h->perm[cursor[pt - pt_lo]++ - obs_lo] = i;
+      }
     }
   }
   const int64_t* perm = h->perm.data();
