@@ -102,10 +102,13 @@ typedef struct dba_problem {
  * linear_solver_type, minimizer_progress_to_stdout, max_num_iterations, num_threads,
  * max_solver_time_in_seconds; everything else is the Ceres default).               */
 typedef enum dba_linear_solver {
-  DBA_LS_AUTO = 0,  /* DENSE when the reduced camera system is small, else PCG          */
+  DBA_LS_AUTO = 0,  /* currently the same as DBA_LS_PCG                                  */
   DBA_LS_PCG = 1,   /* implicit Schur complement + block-Jacobi preconditioned CG       */
-  DBA_LS_DENSE = 2  /* explicit reduced system + dense Cholesky (the reference's
-                       DENSE_SCHUR semantics: an exact step)                            */
+  DBA_LS_DENSE = 2  /* the reference's DENSE_SCHUR semantics (an exact step).  Round 1:
+                       obtained by running the PCG to pcg_rel_tolerance (set it to ~1e-13
+                       and pcg_max_iterations to a few thousand, as host/solve.cc does);
+                       dba_summary.linear_solver_used reports DBA_LS_PCG.  An explicit
+                       reduced system + Cholesky for small camera counts is planned.    */
 } dba_linear_solver;
 
 typedef struct dba_solve_options {
