@@ -84,9 +84,10 @@ def describe(name: str, p, pcg_iters: int, n_gpus: int):
     }
 
 
-def solve_options(capi, steps: int, pcg_iters: int):
+def solve_options(capi, steps: int, pcg_iters: int, linear_solver: str = "pcg"):
+    ls = {"pcg": capi.DBA_LS_PCG, "dense": capi.DBA_LS_DENSE}[linear_solver]
     return capi.make_options(max_num_iterations=steps, function_tolerance=0.0, gradient_tolerance=0.0,
-                             parameter_tolerance=0.0, linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=0.0,
+                             parameter_tolerance=0.0, linear_solver=ls, pcg_rel_tolerance=0.0,
                              pcg_max_iterations=pcg_iters, pcg_min_iterations=0, progress_to_stdout=0)
 
 
@@ -173,6 +174,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="bal5m", choices=list(WORKLOADS))
     ap.add_argument("--pcg-iters", type=int, default=20)
+    ap.add_argument("--linear-solver", default="pcg", choices=["pcg", "dense"],
+                    help="dense = explicit reduced system + device Cholesky (the reference's DENSE_SCHUR); small camera counts only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=40.0, help="seconds of CPU LM iterations")
     args = ap.parse_args()
@@ -247,12 +250,12 @@ def main():
         return float(t.item())
 
     eng.problem_set(p)
-    opts_w = solve_options(capi, max(args.warmup, 3), args.pcg_iters)
+    opts_w = solve_options(capi, max(args.warmup, 3), args.pcg_iters, args.linear_solver)
     eng.solve(opts_w)  # warm-up steps (untimed)
     eng.params_reset()
 
     # ---- timed: exactly K LM iterations, device resident
-    opts = solve_options(capi, args.steps, args.pcg_iters)
+    opts = solve_options(capi, args.steps, args.pcg_iters, args.linear_solver)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -279,7 +282,7 @@ def main():
     # 10 launches of the residual + Jacobian kernel (unit-scale pass and scaled pass), CUDA events
     eng.kernel_stats_enable(True)
     eng.kernel_stats_reset()
-    opts0 = solve_options(capi, 0, args.pcg_iters)
+    opts0 = solve_options(capi, 0, args.pcg_iters, args.linear_solver)
     for _ in range(5):
         eng.params_reset()
         eng.solve(opts0)

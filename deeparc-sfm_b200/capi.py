@@ -77,7 +77,8 @@ class DbaSummary(C.Structure):
                 ("kernel_launches", C.c_int64), ("jacobian_evaluations", C.c_int64),
                 ("residual_evaluations", C.c_int64), ("pcg_iterations_total", C.c_int64),
                 ("message", C.c_char * 192), ("iterations", C.POINTER(DbaIteration)),
-                ("iterations_capacity", C.c_int32)]
+                ("iterations_capacity", C.c_int32), ("linear_solver_failures", C.c_int32),
+                ("pcg_unconverged_solves", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class DbaKernelStat(C.Structure):

@@ -1,0 +1,448 @@
+// Explicit reduced camera system + on-device Cholesky: the reference's DENSE_SCHUR linear solver
+// (reference src/sfm.cc:67, :95; upstream Ceres schur_eliminator_impl.h + DenseSchurComplementSolver,
+// restated on the CPU in oracle/mini_ceres.cc::EliminateAndSolve) for problems whose reduced system is
+// small — the reference's own rigs have 19..50 pose blocks, i.e. 114..300 reduced unknowns.
+//
+//   S = F^T F + D_c^2 - sum_points Y_i C_i^-1 Y_i^T,   Y_i[A] = sum_{o in i, o uses A} F_{o,A}^T E_o
+//
+// k_schur_dense   (K4)  one THREAD per camera-block pair (A <= B) keeps the CB x CB block S_AB in
+//                       registers and walks a fixed slice of the points; per batch of points the CTA
+//                       first builds, in shared memory, the compact list of camera blocks each point
+//                       touches and Z_i[A] = Y_i[A] L_i with C_i^-1 = L_i L_i^T, so the elimination
+//                       term of a pair is the 3-deep product Z_i[A] Z_i[B]^T.  F^T F blocks are added
+//                       from the point's observations that carry exactly that pair.  No atomics:
+//                       every pair is owned by one thread, slices are summed in slice order.
+// k_dense_combine       fixed-order sum of the slices into the dense n x n matrix (both triangles)
+// k_dense_cholesky (K9) one CTA: blocked left-looking Cholesky of S + D_c^2 with the right-hand side
+//                       carried as an extra row (so L^-1 rhs falls out of the factorisation), then the
+//                       blocked back substitution; writes the camera step W.x.  A non-positive pivot
+//                       makes the step NaN, which the LM driver treats as a linear-solver failure
+//                       exactly like the CPU oracle does.
+#include <cstdio>
+
+#include "ba_kernels.cuh"
+
+namespace dba {
+
+namespace {
+
+constexpr int kDnThreads = 256;  // pair threads per CTA == pairs per pair group
+
+// packed upper-triangular pair index -> (A, B), A <= B, row-major over A
+__device__ __forceinline__ void pair_decode(int q, int nb, int& A, int& B) {
+  int a = 0, rem = q;
+  while (rem >= nb - a) {
+    rem -= nb - a;
+    ++a;
+  }
+  A = a;
+  B = a + rem;
+}
+
+template <int CB>
+struct DnSmem {
+  static constexpr int ZS = (3 * CB) | 1;  // odd stride (19 / 27 doubles): entries of different blocks on different banks
+  static constexpr size_t oZ = 0;
+  static constexpr size_t oL = oZ + sizeof(double) * kDnEntCap * ZS;
+  static constexpr size_t oBase = oL + sizeof(double) * kDnPtsCap * 6;
+  static constexpr size_t oSeg = oBase + sizeof(int) * (kDnPtsCap + 4);
+  static constexpr size_t oEnt = oSeg + sizeof(int) * (kDnPtsCap + 4);          // entry -> (point << 16 | block), 0xffffffff = unused
+  static constexpr size_t oLook = oEnt + sizeof(unsigned int) * kDnEntCap;      // [point][block] -> entry index + 1 within the point
+  static size_t bytes(int nb) { return oLook + sizeof(unsigned short) * kDnPtsCap * ((nb + 1) & ~1); }
+};
+
+template <int CB, int MINB>
+__global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem D, WorkArrays W, DenseWork Q) {
+  using L = DnSmem<CB>;
+  constexpr int ZS = L::ZS;
+  extern __shared__ __align__(16) unsigned char smem_dn[];
+  double* sZ = reinterpret_cast<double*>(smem_dn + L::oZ);
+  double* sL = reinterpret_cast<double*>(smem_dn + L::oL);
+  int* sBase = reinterpret_cast<int*>(smem_dn + L::oBase);
+  int* sSeg = reinterpret_cast<int*>(smem_dn + L::oSeg);
+  unsigned int* sEnt = reinterpret_cast<unsigned int*>(smem_dn + L::oEnt);
+  unsigned short* sLook = reinterpret_cast<unsigned short*>(smem_dn + L::oLook);
+  const int tid = threadIdx.x;
+  const int nb = D.n_blocks, nbs = (nb + 1) & ~1;
+  const int q = blockIdx.y * kDnThreads + tid;
+  const bool has_pair = q < Q.n_pairs;
+  int A = 0, B = 0;
+  if (has_pair) pair_decode(q, nb, A, B);
+  double acc[CB * CB];
+#pragma unroll
+  for (int k = 0; k < CB * CB; ++k) acc[k] = 0.0;
+  const int64_t ld = D.ld;
+  const int b0 = static_cast<int>(static_cast<int64_t>(Q.n_batches) * blockIdx.x / gridDim.x);
+  const int b1 = static_cast<int>(static_cast<int64_t>(Q.n_batches) * (blockIdx.x + 1) / gridDim.x);
+  for (int b = b0; b < b1; ++b) {
+    const int p0 = Q.batch_pt[b], np = Q.batch_pt[b + 1] - p0;
+    // ---- the batch's points: segments, entry capacities, cleared lookup
+    for (int i = tid; i < (np * nbs) / 2; i += kDnThreads) reinterpret_cast<unsigned int*>(sLook)[i] = 0u;
+    if (tid <= np) sSeg[tid] = D.pt_first[p0 + tid];
+    __syncthreads();
+    if (tid < 32) {
+      // exclusive scan of the capacities min(2 k_i, nb) (np <= kDnPtsCap = 2 per lane)
+      int c[kDnPtsCap / 32], tot = 0;
+#pragma unroll
+      for (int j = 0; j < kDnPtsCap / 32; ++j) {
+        const int p = tid * (kDnPtsCap / 32) + j;
+        c[j] = p < np ? min(2 * (sSeg[p + 1] - sSeg[p]), nb) : 0;
+        tot += c[j];
+      }
+      int incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      int run = incl - tot;
+#pragma unroll
+      for (int j = 0; j < kDnPtsCap / 32; ++j) {
+        const int p = tid * (kDnPtsCap / 32) + j;
+        if (p <= np) sBase[p] = run;
+        run += c[j];
+      }
+      if (tid == 31 && np == kDnPtsCap) sBase[np] = run;
+    }
+    __syncthreads();
+    // ---- one thread per point: compact list of the camera blocks it touches; L with C^-1 = L L^T
+    if (tid < np) {
+      const int base = sBase[tid], cap = sBase[tid + 1] - base;
+      int cnt = 0;
+      unsigned short* look = sLook + tid * nbs;
+      for (int o = sSeg[tid]; o < sSeg[tid + 1]; ++o) {
+        const int2 ab = D.obs_ab[o];
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+          const int blk = slot ? ab.y : ab.x;
+          if (blk < 0 || look[blk]) continue;
+          look[blk] = static_cast<unsigned short>(++cnt);
+          sEnt[base + cnt - 1] = (static_cast<unsigned int>(tid) << 16) | static_cast<unsigned int>(blk);
+        }
+      }
+      for (int e = cnt; e < cap; ++e) sEnt[base + e] = 0xffffffffu;
+      const double* ci = W.cinv + 6 * static_cast<int64_t>(p0 + tid);
+      double l00 = 0.0, l10 = 0.0, l20 = 0.0, l11 = 0.0, l21 = 0.0, l22 = 0.0;
+      if (ci[0] > 0.0) {  // a point whose C was not positive definite carries C^-1 = 0 (flagged by k_point_prepare)
+        l00 = sqrt(ci[0]);
+        l10 = ci[1] / l00;
+        l20 = ci[2] / l00;
+        l11 = sqrt(fmax(ci[3] - l10 * l10, 0.0));
+        l21 = l11 > 0.0 ? (ci[4] - l20 * l10) / l11 : 0.0;
+        l22 = sqrt(fmax(ci[5] - l20 * l20 - l21 * l21, 0.0));
+      }
+      double* Lp = sL + tid * 6;
+      Lp[0] = l00; Lp[1] = l10; Lp[2] = l20; Lp[3] = l11; Lp[4] = l21; Lp[5] = l22;
+    }
+    __syncthreads();
+    // ---- one work item per (entry, row of the block): Y row = sum F[:, row]^T E, Z row = Y row * L
+    const int n_items = sBase[np] * CB;
+    for (int it = tid; it < n_items; it += kDnThreads) {
+      const int e = it / CB, i = it - e * CB;
+      const unsigned int ent = sEnt[e];
+      if (ent == 0xffffffffu) continue;
+      const int pt = ent >> 16, blk = ent & 0xffffu;
+      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+      for (int o = sSeg[pt]; o < sSeg[pt + 1]; ++o) {
+        const int2 ab = D.obs_ab[o];
+        const double2* J = D.J + o;
+        double2 F;
+        if (ab.x == blk) F = J[(kPlaneJA + i) * ld];
+        else if (ab.y == blk && i < 6) F = J[(kPlaneJA + CB + i) * ld];
+        else continue;
+        const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
+        y0 += F.x * e0.x + F.y * e0.y;
+        y1 += F.x * e1.x + F.y * e1.y;
+        y2 += F.x * e2.x + F.y * e2.y;
+      }
+      const double* Lp = sL + pt * 6;
+      double* z = sZ + e * ZS + 3 * i;
+      z[0] = y0 * Lp[0] + y1 * Lp[1] + y2 * Lp[2];
+      z[1] = y1 * Lp[3] + y2 * Lp[4];
+      z[2] = y2 * Lp[5];
+    }
+    __syncthreads();
+    // ---- the pair threads: S_AB -= Z_A Z_B^T (+= F_A^T F_B of the observations carrying the pair)
+    if (has_pair) {
+      for (int p = 0; p < np; ++p) {
+        const int ia = sLook[p * nbs + A];
+        if (!ia) continue;
+        const int ib = (A == B) ? ia : sLook[p * nbs + B];
+        if (!ib) continue;
+        const double* za = sZ + (sBase[p] + ia - 1) * ZS;
+        const double* zb = sZ + (sBase[p] + ib - 1) * ZS;
+        double a[3 * CB];
+#pragma unroll
+        for (int k = 0; k < 3 * CB; ++k) a[k] = za[k];
+#pragma unroll
+        for (int j = 0; j < CB; ++j) {
+          const double z0 = zb[3 * j], z1 = zb[3 * j + 1], z2 = zb[3 * j + 2];
+#pragma unroll
+          for (int i = 0; i < CB; ++i) acc[i * CB + j] -= a[3 * i] * z0 + a[3 * i + 1] * z1 + a[3 * i + 2] * z2;
+        }
+        for (int o = sSeg[p]; o < sSeg[p + 1]; ++o) {
+          const int2 ab = D.obs_ab[o];
+          const double2* J = D.J + o;
+          if (A == B) {
+            if (ab.x == A) {
+              double2 F[CB];
+#pragma unroll
+              for (int k = 0; k < CB; ++k) F[k] = J[(kPlaneJA + k) * ld];
+#pragma unroll
+              for (int i = 0; i < CB; ++i)
+#pragma unroll
+                for (int j = 0; j < CB; ++j) acc[i * CB + j] += F[i].x * F[j].x + F[i].y * F[j].y;
+            }
+            if (ab.y == A) {
+              double2 F[6];
+#pragma unroll
+              for (int k = 0; k < 6; ++k) F[k] = J[(kPlaneJA + CB + k) * ld];
+#pragma unroll
+              for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc[i * CB + j] += F[i].x * F[j].x + F[i].y * F[j].y;
+            }
+          } else if ((ab.x == A && ab.y == B) || (ab.x == B && ab.y == A)) {
+            // rows: block A, columns: block B (block b of an observation has six columns)
+            const bool a_first = ab.x == A;
+            const int pa = a_first ? kPlaneJA : kPlaneJA + CB, pb = a_first ? kPlaneJA + CB : kPlaneJA;
+            const int na = a_first ? CB : 6, nbk = a_first ? 6 : CB;
+            double2 FB[CB];
+#pragma unroll
+            for (int k = 0; k < CB; ++k) FB[k] = k < nbk ? J[(pb + k) * ld] : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int i = 0; i < CB; ++i) {
+              if (i < na) {
+                const double2 fa = J[(pa + i) * ld];
+#pragma unroll
+                for (int j = 0; j < CB; ++j) acc[i * CB + j] += fa.x * FB[j].x + fa.y * FB[j].y;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();  // the next batch overwrites the staging
+  }
+  if (has_pair) {
+    double* out = Q.S_part + (static_cast<int64_t>(blockIdx.x) * Q.n_pairs + q) * (CB * CB);
+#pragma unroll
+    for (int k = 0; k < CB * CB; ++k) out[k] = acc[k];
+  }
+}
+
+// S[A-block rows, B-block cols] = sum over slices (slice order) of the pair's partial blocks; mirrored.
+template <int CB>
+__global__ void __launch_bounds__(256) k_dense_combine(DenseWork Q, int nb, int n_slices) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(Q.n_pairs) * (CB * CB)) return;
+  const int q = static_cast<int>(idx / (CB * CB)), e = static_cast<int>(idx - static_cast<int64_t>(q) * (CB * CB));
+  double s = 0.0;
+  for (int sl = 0; sl < n_slices; ++sl) s += Q.S_part[(static_cast<int64_t>(sl) * Q.n_pairs + q) * (CB * CB) + e];
+  int A, B;
+  pair_decode(q, nb, A, B);
+  const int i = e / CB, j = e - i * CB;
+  const int64_t n = static_cast<int64_t>(nb) * CB;
+  const int64_t r = static_cast<int64_t>(A) * CB + i, c = static_cast<int64_t>(B) * CB + j;
+  Q.S[r * n + c] = s;
+  if (A != B) Q.S[c * n + r] = s;
+}
+
+// ----------------------------------------------------------------- K9 dense Cholesky + solve
+// One CTA of 1024 threads, thread t <-> row j0 + t of the current panel (panel width 16).  Row n is
+// the right-hand side, so after the last panel it holds y = L^-1 rhs.  The factor overwrites the
+// lower triangle of S.
+constexpr int kChNB = 16;
+constexpr int kChLS = 18;  // row stride of the staged panel rows: 16-byte aligned rows, spread over the banks
+constexpr int kChThreads = 1024;
+
+__global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __restrict__ S, int n, const double* __restrict__ dc2,
+                                                                   const double* __restrict__ rhs, double* __restrict__ x,
+                                                                   int* __restrict__ fail_flag) {
+  extern __shared__ __align__(16) unsigned char smem_ch[];
+  double* sLjT = reinterpret_cast<double*>(smem_ch);          // [j0][kChLS]: L[j0 + c][k] at [k][c]
+  double* sy = sLjT + static_cast<size_t>(n) * kChLS;         // [n + 16] y, then x
+  __shared__ double sD[kChNB][kChNB + 1];
+  __shared__ int s_ok;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_ok = 1;
+  for (int j0 = 0; j0 < n; j0 += kChNB) {
+    const int w = min(kChNB, n - j0);
+    const int row = j0 + tid;
+    const bool active = row <= n;
+    __syncthreads();  // previous panel written back (global + sy)
+    // stage L[j0 .. j0+w) x [0, j0) transposed
+    for (int i = tid; i < w * j0; i += kChThreads) {
+      const int c = i / j0, k = i - c * j0;
+      sLjT[k * kChLS + c] = S[static_cast<int64_t>(j0 + c) * n + k];
+    }
+    double p[kChNB];
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < kChNB; ++c) {
+        double v = 0.0;
+        if (c < w) {
+          if (row < n) {
+            if (j0 + c <= row) v = S[static_cast<int64_t>(row) * n + j0 + c] + (j0 + c == row ? dc2[row] : 0.0);
+          } else {
+            v = rhs[j0 + c];
+          }
+        }
+        p[c] = v;
+      }
+    }
+    __syncthreads();
+    if (active && j0 > 0) {
+      const double* lrow = row < n ? S + static_cast<int64_t>(row) * n : sy;
+      for (int k = 0; k < j0; ++k) {
+        const double l = lrow[k];
+        const double2* lj = reinterpret_cast<const double2*>(sLjT + k * kChLS);
+#pragma unroll
+        for (int c = 0; c < kChNB / 2; ++c) {
+          const double2 v = lj[c];
+          p[2 * c] -= l * v.x;
+          p[2 * c + 1] -= l * v.y;
+        }
+      }
+    }
+    // diagonal block rows -> shared memory, factorised by warp 0
+    if (tid < w) {
+#pragma unroll
+      for (int c = 0; c < kChNB; ++c) sD[tid][c] = p[c];
+    }
+    __syncthreads();
+    if (tid < 32) {
+      for (int k = 0; k < w; ++k) {
+        __syncwarp();
+        double d = sD[k][k];
+        const bool good = d > 0.0;
+        d = sqrt(good ? d : 1.0);
+        __syncwarp();
+        if (tid == k) {
+          sD[k][k] = d;
+          if (!good) s_ok = 0;
+        }
+        if (tid > k && tid < w) sD[tid][k] /= d;
+        __syncwarp();
+        if (tid > k && tid < w)
+          for (int c = k + 1; c <= tid; ++c) sD[tid][c] -= sD[tid][k] * sD[c][k];
+      }
+    }
+    __syncthreads();
+    if (!s_ok) break;
+    if (active) {
+      if (tid < w) {
+        // a row of the diagonal block: its factor comes from shared memory
+#pragma unroll
+        for (int c = 0; c < kChNB; ++c)
+          if (c <= tid) S[static_cast<int64_t>(row) * n + j0 + c] = sD[tid][c];
+      } else {
+        // triangular solve of the row against the diagonal block
+#pragma unroll
+        for (int c = 0; c < kChNB; ++c) {
+          if (c < w) {
+            double v = p[c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) v -= p[k] * sD[c][k];
+            p[c] = v / sD[c][c];
+          }
+        }
+        if (row < n) {
+#pragma unroll
+          for (int c = 0; c < kChNB; ++c)
+            if (c < w) S[static_cast<int64_t>(row) * n + j0 + c] = p[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < kChNB; ++c)
+            if (c < w) sy[j0 + c] = p[c];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!s_ok) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = tid; i < n; i += kChThreads) x[i] = nan;
+    if (tid == 0 && fail_flag) *fail_flag = 1;
+    return;
+  }
+  // ---- back substitution L^T x = y, panels from the bottom; thread i owns unknown i
+  double v = 0.0;
+  if (tid < n) v = sy[tid];
+  const int last = ((n - 1) / kChNB) * kChNB;
+  for (int j0 = last; j0 >= 0; j0 -= kChNB) {
+    const int w = min(kChNB, n - j0);
+    __syncthreads();
+    if (tid >= j0 && tid < j0 + w) sy[tid] = v;  // current right-hand side of the panel's unknowns
+    __syncthreads();
+    if (tid < 32) {
+      for (int k = w - 1; k >= 0; --k) {
+        __syncwarp();
+        if (tid == 0) sy[j0 + k] /= S[static_cast<int64_t>(j0 + k) * n + j0 + k];
+        __syncwarp();
+        const double xk = sy[j0 + k];
+        if (tid < k) sy[j0 + tid] -= S[static_cast<int64_t>(j0 + k) * n + j0 + tid] * xk;
+      }
+    }
+    __syncthreads();
+    if (tid < j0) {
+      for (int k = 0; k < w; ++k) v -= S[static_cast<int64_t>(j0 + k) * n + tid] * sy[j0 + k];
+    }
+  }
+  __syncthreads();
+  if (tid < n) x[tid] = sy[tid];
+}
+
+}  // namespace
+
+int dense_slices(const DenseWork& Q) {
+  // a fixed function of the problem (not of the device), so that runs are reproducible: enough
+  // CTAs to fill 148 SMs twice over, at least four batches per slice
+  const int groups = (Q.n_pairs + kDnThreads - 1) / kDnThreads;
+  int s = std::max(1, 296 / std::max(groups, 1));
+  s = std::min(s, std::max(1, Q.n_batches / 2));
+  return std::max(s, 1);
+}
+
+template <int CB, int MINB>
+static int launch_schur_dense_t(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st) {
+  const size_t smem = DnSmem<CB>::bytes(D.n_blocks);
+  static unsigned long long configured = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(configured & (1ull << (dev & 63)))) {
+    configured |= 1ull << (dev & 63);
+    cudaFuncSetAttribute(k_schur_dense<CB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }
+  const int groups = (Q.n_pairs + kDnThreads - 1) / kDnThreads;
+  const int slices = dense_slices(Q);
+  k_schur_dense<CB, MINB><<<dim3(slices, groups), kDnThreads, smem, st>>>(D, W, Q);
+  const int64_t total = static_cast<int64_t>(Q.n_pairs) * CB * CB;
+  k_dense_combine<CB><<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(Q, D.n_blocks, slices);
+  return 0;
+}
+
+int launch_schur_dense(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st) {
+  if (D.n_blocks == 0 || Q.n_pairs == 0) return 0;
+  if (D.cb == 6) return launch_schur_dense_t<6, 2>(D, W, Q, st);
+  if (D.cb == 9) return launch_schur_dense_t<9, 1>(D, W, Q, st);
+  return -1;
+}
+
+int launch_dense_cholesky(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st) {
+  const int n = D.n_blocks * D.cb;
+  if (n == 0) return 0;
+  const size_t smem = sizeof(double) * (static_cast<size_t>(n) * kChLS + n + kChNB);
+  static unsigned long long configured = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(configured & (1ull << (dev & 63)))) {
+    configured |= 1ull << (dev & 63);
+    cudaFuncSetAttribute(k_dense_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  }
+  const double* rhs = W.cam_acc + static_cast<int64_t>(D.n_blocks) * D.cb * D.cb + 2 * static_cast<int64_t>(n);
+  k_dense_cholesky<<<1, kChThreads, smem, st>>>(Q.S, n, W.dc2, rhs, W.x, Q.fail_flag);
+  return 0;
+}
+
+}  // namespace dba

@@ -137,6 +137,13 @@ struct dba_handle {
   DevBuf<double> d_sp, d_sc, d_cinv, d_tp, d_dp, d_cam_acc, d_minv, d_dc2, d_x, d_r, d_z, d_p, d_q;
   DevBuf<double> d_cam_chunk_acc;
   DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts, d_vec_partials;
+  // explicit reduced system + device Cholesky (DENSE_SCHUR) for small camera counts
+  bool dense_ok = false;     // the problem fits the dense path (set by dba_problem_set)
+  bool use_dense = false;    // linear solver of the running dba_solve
+  DenseWork Q{};
+  DevBuf<int> d_dn_batch;
+  DevBuf<double> d_dn_S, d_dn_Spart;
+  int dense_failures = 0, pcg_unconverged = 0;  // per dba_solve
   double* h_scalars = nullptr;  // pinned
   int* h_pcg_state = nullptr;   // pinned
   struct dba_upload_state* upload = nullptr;  // pinned staging arena (grow-only)
@@ -155,6 +162,7 @@ struct dba_handle {
   };
   std::vector<Pending> pending;
   std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t ev_solve[3] = {nullptr, nullptr, nullptr};  // start / end / loop start of dba_solve (created once)
 
   int fail(int status, const char* fmt, ...) {
     char buf[512];
@@ -480,14 +488,15 @@ int prepare_step(dba_handle* h, double radius, const dba_solve_options& o) {
   if (h->cb) {
     {
       // gather: Jc + Jp + r planes at sector granularity, plus C^-1 and t per observation
+      // (the dense reduced system does not need the block-Jacobi blocks: mode 2)
       Scope s(h, "camera_gather", 0.0, 2);
-      launch_camera_gather(D, h->W, 1, h->st);
+      launch_camera_gather(D, h->W, h->use_dense ? 2 : 1, h->st);
     }
     int rc = allreduce(h, h->W.cam_acc, static_cast<size_t>(D.n_blocks) * h->cb * (h->cb + 3), kNcclSum);
     if (rc != DBA_OK) return rc;
     {
       Scope s(h, "camera_finalize");
-      launch_camera_finalize(D, h->W, radius, o.min_lm_diagonal, o.max_lm_diagonal, h->d_partB.p, h->st);
+      launch_camera_finalize(D, h->W, radius, o.min_lm_diagonal, o.max_lm_diagonal, h->d_partB.p, h->use_dense ? 0 : 1, h->st);
     }
     const int g = camera_finalize_grid(D);
     Scope s(h, "reduce");
@@ -596,6 +605,7 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
     *iters_out = h->h_pcg_state[0];
     if (h->h_pcg_state[2]) return h->fail(DBA_ERR_NCCL, "peer exchange timed out: a rank of this handle stopped responding");
     if (h->h_pcg_state[1]) break;
+    if (issued >= max_it) h->pcg_unconverged++;  // the tolerance was asked for and not reached
   }
   if (max_it == 0) {
     CU(h, cudaMemcpyAsync(h->h_pcg_state, h->W.pcg_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
@@ -605,10 +615,42 @@ int pcg_solve(dba_handle* h, const dba_solve_options& o, int* iters_out) {
   return DBA_OK;
 }
 
-// after a stream synchronisation: the PCG state copied by a pcg_solve that did not wait for it
+// DENSE_SCHUR (reference sfm.cc:67): explicit reduced system S from the planes, allreduce over the
+// ranks, Cholesky + substitutions in one CTA -> W.x.  A failed factorisation leaves NaN in W.x (the
+// step is then invalid, as with the CPU oracle) and raises pcg_state[3], read at the next
+// synchronisation by pcg_collect.
+int dense_solve(dba_handle* h, int* iters_out) {
+  const DeviceProblem& D = h->D;
+  const int n = D.n_blocks * h->cb;
+  const int nplanes = 3 + h->cb + (h->two ? 6 : 0);
+  CU(h, cudaMemsetAsync(h->W.pcg_state, 0, 4 * sizeof(int), h->st));
+  {
+    Scope s(h, "schur_dense", 16.0 * nplanes * static_cast<double>(h->n_obs), 2);
+    if (launch_schur_dense(D, h->W, h->Q, h->st) != 0) return h->fail(DBA_ERR_UNSUPPORTED, "dense reduced system: unsupported camera block");
+  }
+  int rc = allreduce(h, h->Q.S, static_cast<size_t>(n) * n, kNcclSum);
+  if (rc != DBA_OK) return rc;
+  {
+    Scope s(h, "dense_cholesky", 8.0 * n * n);
+    launch_dense_cholesky(D, h->W, h->Q, h->st);
+  }
+  CU(h, cudaMemcpyAsync(h->h_pcg_state, h->W.pcg_state, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  h->pcg_pending = true;
+  *iters_out = 1;
+  CU(h, cudaGetLastError());
+  return DBA_OK;
+}
+
+// after a stream synchronisation: the linear-solver state copied by a pcg_solve / dense_solve that
+// did not wait for it
 int pcg_collect(dba_handle* h, int* iters) {
   if (!h->pcg_pending) return DBA_OK;
   h->pcg_pending = false;
+  if (h->use_dense) {
+    *iters = 1;
+    if (h->h_pcg_state[3]) h->dense_failures++;
+    return DBA_OK;
+  }
   *iters = h->h_pcg_state[0];
   if (h->h_pcg_state[2]) return h->fail(DBA_ERR_NCCL, "peer exchange timed out: a rank of this handle stopped responding");
   return DBA_OK;
@@ -774,6 +816,8 @@ void dba_destroy(dba_handle* h) {
   if (h->st) cudaStreamSynchronize(h->st);
   drain_events(h);
   for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_solve)
+    if (e) cudaEventDestroy(e);
   close_peer_windows(h);
   if (h->comm) nccl_api().CommDestroy(h->comm);  // (a barrier in practice: peers have unmapped before the window goes)
   if (h->win_local) cudaFree(h->win_local);
@@ -1045,6 +1089,9 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   want((n_ent_max + n_tiles + 1) * sizeof(int));    // part_first
   want((n_ent_max / 1024 + n_ext + 2) * sizeof(int4));  // cam_chunks
   want((n_ext + 1) * sizeof(int) * 3);
+  // dense reduced system (DENSE_SCHUR): eligible when the camera side is small
+  const bool dense_ok = cb > 0 && n_ext <= kDnMaxBlocks && n_ext * cb <= kDnMaxSize;
+  want(dense_ok ? (static_cast<size_t>(n_pts) + 2) * sizeof(int) : 0);  // dn_batch
   want(3 * sizeof(double) * static_cast<size_t>(h->n_pts));  // the caller's points (pageable) staged for the async copy
   PinnedArena& A = arena_of(h);
   CU(h, cudaStreamSynchronize(h->st));  // the arena may still feed copies of a previous call
@@ -1314,6 +1361,26 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   s_tile_obs[n_tiles] = static_cast<int>(nl);
   s_tile_pt[n_tiles] = n_pts;
 
+  // ---- point batches of the dense reduced-system kernel: greedy runs of whole points with at most
+  // kDnPtsCap points and kDnEntCap (point, camera block) entries, entry capacity min(2 k_i, n_blocks)
+  int n_dn_batches = 0;
+  int* s_dn_batch = nullptr;
+  if (dense_ok) {
+    s_dn_batch = A.take<int>(static_cast<size_t>(n_pts) + 2);
+    const int64_t* first = pt_count.data() + pt_lo;
+    int start = 0, ents = 0;
+    s_dn_batch[0] = 0;
+    for (int i = 0; i < n_pts; ++i) {
+      const int c = static_cast<int>(std::min<int64_t>(2 * (first[i + 1] - first[i]), n_ext));
+      if (i > start && (i - start >= kDnPtsCap || ents + c > kDnEntCap)) {
+        s_dn_batch[++n_dn_batches] = i;
+        start = i;
+        ents = 0;
+      }
+      ents += c;
+    }
+    if (n_pts > 0) s_dn_batch[++n_dn_batches] = n_pts;
+  }
   mark("tile incidence + columns");
   // ---- device buffers (kept across calls, grow only)
   h->plane_w = 4 + cb + ((two && cb) ? 6 : 0);
@@ -1390,6 +1457,19 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   if (h->world > 1 && cb) {
     int rc = setup_peer_windows(h, nvec);
     if (rc != DBA_OK) return rc;
+  }
+  h->dense_ok = dense_ok;
+  h->Q = DenseWork{};
+  if (dense_ok) {
+    h->Q.n_batches = n_dn_batches;
+    h->Q.n_pairs = n_ext * (n_ext + 1) / 2;
+    CU(h, ensure(h->d_dn_batch, static_cast<size_t>(n_dn_batches) + 1));
+    CU(h, ensure(h->d_dn_S, nvec * nvec));
+    CU(h, ensure(h->d_dn_Spart, static_cast<size_t>(dense_slices(h->Q)) * h->Q.n_pairs * cb * cb));
+    CU(h, up(h->d_dn_batch.p, s_dn_batch, (static_cast<size_t>(n_dn_batches) + 1) * sizeof(int)));
+    h->Q.batch_pt = h->d_dn_batch.p;
+    h->Q.S = h->d_dn_S.p;
+    h->Q.S_part = h->d_dn_Spart.p;
   }
   CU(h, ensure(h->d_q_split, nvec * static_cast<size_t>(h->q_split)));
   CU(h, ensure(h->d_vec_partials, nvec / 128 + 2 * static_cast<size_t>(n_ext) + 8192));  // k_partials_to_q: one partial per block
@@ -1519,6 +1599,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.mf_T = h->d_mf_T.p;
   W.vec_partials = h->d_vec_partials.p;
   W.counters = h->d_counters.p;
+  h->Q.fail_flag = h->d_pcg_state.p + 3;
   h->have_problem = true;
   return dba_params_reset(h);
 }
@@ -1740,14 +1821,33 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
   std::memset(sum, 0, sizeof *sum);
   sum->iterations = it_buf;
   sum->iterations_capacity = it_cap;
-  sum->linear_solver_used = DBA_LS_PCG;
+  sum->termination = DBA_FAILURE;  // until finish() says otherwise: an error return never reads as converged
   sum->reduced_system_size = h->n_ext * h->cb;
+  // linear solver: DENSE = the reference's DENSE_SCHUR (sfm.cc:67) as an explicit reduced system +
+  // Cholesky; AUTO takes it whenever the reduced system is small enough, else the implicit PCG
+  h->use_dense = false;
+  if (h->cb) {
+    if (o.linear_solver == DBA_LS_DENSE) {
+      if (!h->dense_ok)
+        return h->fail(DBA_ERR_UNSUPPORTED,
+                       "DBA_LS_DENSE: the reduced system (%d camera blocks, %d unknowns) exceeds the dense path (%d blocks, %d unknowns); use DBA_LS_PCG or DBA_LS_AUTO",
+                       h->n_ext, h->n_ext * h->cb, kDnMaxBlocks, kDnMaxSize);
+      h->use_dense = true;
+    } else if (o.linear_solver == DBA_LS_AUTO) {
+      h->use_dense = h->dense_ok && h->n_ext * h->cb <= o.dense_max_size;
+    } else if (o.linear_solver != DBA_LS_PCG) {
+      return h->fail(DBA_ERR_INVALID_ARGUMENT, "unknown linear_solver %d", o.linear_solver);
+    }
+  }
+  sum->linear_solver_used = (h->use_dense || !h->cb) ? DBA_LS_DENSE : DBA_LS_PCG;
+  h->dense_failures = 0;
+  h->pcg_unconverged = 0;
+  h->pcg_pending = false;
   const int64_t launches0 = h->launches;
   const double t_start = now_s();
-  cudaEvent_t ev0, ev1, ev_loop;
-  CU(h, cudaEventCreate(&ev0));
-  CU(h, cudaEventCreate(&ev1));
-  CU(h, cudaEventCreate(&ev_loop));
+  for (cudaEvent_t& e : h->ev_solve)
+    if (!e) CU(h, cudaEventCreate(&e));
+  const cudaEvent_t ev0 = h->ev_solve[0], ev1 = h->ev_solve[1], ev_loop = h->ev_solve[2];
   CU(h, cudaEventRecord(ev0, h->st));
   bool loop_started = false;
 
@@ -1763,9 +1863,6 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     float ms = 0.f, ms_loop = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     if (loop_started) cudaEventElapsedTime(&ms_loop, ev_loop, ev1);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    cudaEventDestroy(ev_loop);
     sum->loop_device_time_in_seconds = ms_loop * 1e-3;
     sum->termination = termination;
     sum->num_iterations = std::min(n_it, it_cap);
@@ -1773,6 +1870,8 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     sum->total_time_in_seconds = now_s() - t_start;
     sum->device_time_in_seconds = ms * 1e-3;
     sum->kernel_launches = h->launches - launches0;
+    sum->linear_solver_failures = h->dense_failures;
+    sum->pcg_unconverged_solves = h->pcg_unconverged;
     std::snprintf(sum->message, sizeof sum->message, "%s", msg);
     return DBA_OK;
   };
@@ -1863,7 +1962,7 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     double model_cost_change = 0.0;
     if (!linear_failure) {
       if (h->cb) {
-        if ((rc = pcg_solve(h, o, &pcg_iters)) != DBA_OK) return rc;
+        if ((rc = h->use_dense ? dense_solve(h, &pcg_iters) : pcg_solve(h, o, &pcg_iters)) != DBA_OK) return rc;
       }
       const bool spec = h->speculate && expect_success;
       if ((rc = apply_step_and_evaluate(h, spec)) != DBA_OK) return rc;

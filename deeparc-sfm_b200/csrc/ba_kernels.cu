@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(T, MB) k_point_prepare(DeviceProblem D, WorkAr
 // camera block in chunk order: no atomics).
 template <int CB, int MODE>
 __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArrays W) {
-  constexpr int NU = CB * (CB + 1) / 2;
+  constexpr int NU = MODE == 1 ? CB * (CB + 1) / 2 : 0;  // mode 2: no block-Jacobi blocks
   constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
   __shared__ double red[4][NACC];
   const int4 ch = D.cam_chunks[blockIdx.x];  // (block, first entry, last entry, -)
@@ -451,13 +451,16 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
       double tp[4];
       load_row<4>(W.tp + 4 * static_cast<int64_t>(pt), tp);
       // M = E C^-1 (2x3), P = I - M E^T (2x2 symmetric)
-      const double m00 = e0.x * c0 + e1.x * c1 + e2.x * c2, m01 = e0.x * c1 + e1.x * c3 + e2.x * c4,
-                   m02 = e0.x * c2 + e1.x * c4 + e2.x * c5;
-      const double m10 = e0.y * c0 + e1.y * c1 + e2.y * c2, m11 = e0.y * c1 + e1.y * c3 + e2.y * c4,
-                   m12 = e0.y * c2 + e1.y * c4 + e2.y * c5;
-      const double p00 = 1.0 - (m00 * e0.x + m01 * e1.x + m02 * e2.x);
-      const double p01 = -(m00 * e0.y + m01 * e1.y + m02 * e2.y);
-      const double p11 = 1.0 - (m10 * e0.y + m11 * e1.y + m12 * e2.y);
+      double p00 = 0.0, p01 = 0.0, p11 = 0.0;
+      if (MODE == 1) {
+        const double m00 = e0.x * c0 + e1.x * c1 + e2.x * c2, m01 = e0.x * c1 + e1.x * c3 + e2.x * c4,
+                     m02 = e0.x * c2 + e1.x * c4 + e2.x * c5;
+        const double m10 = e0.y * c0 + e1.y * c1 + e2.y * c2, m11 = e0.y * c1 + e1.y * c3 + e2.y * c4,
+                     m12 = e0.y * c2 + e1.y * c4 + e2.y * c5;
+        p00 = 1.0 - (m00 * e0.x + m01 * e1.x + m02 * e2.x);
+        p01 = -(m00 * e0.y + m01 * e1.y + m02 * e2.y);
+        p11 = 1.0 - (m10 * e0.y + m11 * e1.y + m12 * e2.y);
+      }
       // rr = r - E t
       const double t0 = tp[0], t1 = tp[1], t2 = tp[2];
       const double rr0 = r.x - (e0.x * t0 + e1.x * t1 + e2.x * t2);
@@ -465,13 +468,15 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
       int u = 0;
 #pragma unroll
       for (int i = 0; i < CB; ++i) {
-        // (P F)_i
-        const double pf0 = p00 * F[i].x + p01 * F[i].y;
-        const double pf1 = p01 * F[i].x + p11 * F[i].y;
+        if (MODE == 1) {
+          // (P F)_i
+          const double pf0 = p00 * F[i].x + p01 * F[i].y;
+          const double pf1 = p01 * F[i].x + p11 * F[i].y;
 #pragma unroll
-        for (int j = i; j < CB; ++j) {
-          acc[u] += pf0 * F[j].x + pf1 * F[j].y;
-          ++u;
+          for (int j = i; j < CB; ++j) {
+            acc[u] += pf0 * F[j].x + pf1 * F[j].y;
+            ++u;
+          }
         }
         acc[NU + i] += dot2(F[i], F[i]);
         acc[NU + CB + i] += dot2(F[i], r);
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
 // one thread per (camera block, accumulator); blocks without observations get zeros.
 template <int CB, int MODE>
 __global__ void __launch_bounds__(128) k_camera_combine(DeviceProblem D, WorkArrays W) {
-  constexpr int NU = CB * (CB + 1) / 2;
+  constexpr int NU = MODE == 1 ? CB * (CB + 1) / 2 : 0;
   constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nb = D.n_blocks;
@@ -536,7 +541,7 @@ __global__ void k_camera_scales(DeviceProblem D, WorkArrays W) {
 
 // One thread per camera block: D_c^2 = clamp(diag F^T F)/radius, M = B + D_c^2, M^-1 by
 // Cholesky, camera part of the gradient norms.
-template <int CB>
+template <int CB, bool MINV>
 __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArrays W, double radius, double min_diag,
                                                          double max_diag, double* __restrict__ partials) {
   __shared__ double red[32];
@@ -560,6 +565,7 @@ __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArr
     }
     // in-place lower Cholesky
     bool ok = true;
+    if (MINV) {
 #pragma unroll
     for (int j = 0; j < CB; ++j) {
       double d = L[j][j];
@@ -602,6 +608,7 @@ __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArr
       }
 #pragma unroll
       for (int i = 0; i < CB; ++i) Mi[i * CB + c] = ok ? y[i] : (i == c ? 1.0 : 0.0);
+    }
     }
   }
   gsq = block_sum(gsq, red);
@@ -2025,7 +2032,7 @@ static size_t cam_acc_doubles(const DeviceProblem& D) {
 
 template <int CB, int MODE>
 static void launch_camera_gather_t(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
-  constexpr int NACC = MODE == 0 ? CB : CB * (CB + 1) / 2 + 3 * CB;
+  constexpr int NACC = MODE == 0 ? CB : (MODE == 1 ? CB * (CB + 1) / 2 : 0) + 3 * CB;
   if (D.n_chunks > 0) k_camera_gather<CB, MODE><<<D.n_chunks, 128, 0, st>>>(D, W);
   const int n = D.n_blocks * NACC;
   k_camera_combine<CB, MODE><<<(n + 127) / 128, 128, 0, st>>>(D, W);
@@ -2035,10 +2042,12 @@ void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode,
   if (mode == 0) cudaMemsetAsync(W.cam_acc, 0, cam_acc_doubles(D) * sizeof(double), st);  // mode 0 fills diagF only
   if (D.cb == 6) {
     if (mode == 0) launch_camera_gather_t<6, 0>(D, W, st);
-    else launch_camera_gather_t<6, 1>(D, W, st);
+    else if (mode == 1) launch_camera_gather_t<6, 1>(D, W, st);
+    else launch_camera_gather_t<6, 2>(D, W, st);
   } else {
     if (mode == 0) launch_camera_gather_t<9, 0>(D, W, st);
-    else launch_camera_gather_t<9, 1>(D, W, st);
+    else if (mode == 1) launch_camera_gather_t<9, 1>(D, W, st);
+    else launch_camera_gather_t<9, 2>(D, W, st);
   }
 }
 
@@ -2051,13 +2060,16 @@ void launch_camera_scales(const DeviceProblem& D, const WorkArrays& W, cudaStrea
 int camera_finalize_grid(const DeviceProblem& D) { return (D.n_blocks + 63) / 64; }
 
 void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
-                            double max_diag, double* partials, cudaStream_t st) {
+                            double max_diag, double* partials, int with_minv, cudaStream_t st) {
   if (D.cb == 0 || D.n_blocks == 0) return;
   const int grid = camera_finalize_grid(D);
-  if (D.cb == 6)
-    k_camera_finalize<6><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
-  else
-    k_camera_finalize<9><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+  if (D.cb == 6) {
+    if (with_minv) k_camera_finalize<6, true><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+    else k_camera_finalize<6, false><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+  } else {
+    if (with_minv) k_camera_finalize<9, true><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+    else k_camera_finalize<9, false><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+  }
 }
 
 void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {

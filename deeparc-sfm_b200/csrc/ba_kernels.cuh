@@ -141,6 +141,26 @@ struct PeerWin {
   unsigned long long* go = nullptr;  // local: CTA 0 publishes `seq` (all slots in) or ~0 (timeout)
 };
 
+// Explicit reduced system + Cholesky (ba_dense.cu): DENSE_SCHUR for small camera counts.
+constexpr int kDnPtsCap = 64;      // points per batch of k_schur_dense
+constexpr int kDnEntCap = 384;     // (point, camera block) entries per batch
+constexpr int kDnMaxBlocks = 128;  // camera blocks (the per-point block lookup is a 16-bit table in shared memory)
+constexpr int kDnMaxSize = 1008;   // reduced unknowns (one CTA of 1024 threads owns the rows of the factorisation)
+struct DenseWork {
+  const int* batch_pt = nullptr;  // [n_batches + 1] first local point of each batch (whole points; sum of
+                                  // min(2 k_i, n_blocks) over a batch <= kDnEntCap, points <= kDnPtsCap)
+  int n_batches = 0;
+  int n_pairs = 0;                // n_blocks (n_blocks + 1) / 2 camera-block pairs A <= B
+  double* S_part = nullptr;       // [slices][n_pairs][cb * cb]
+  double* S = nullptr;            // [n][n] reduced matrix without D_c^2, then its Cholesky factor (lower)
+  int* fail_flag = nullptr;       // set to 1 when a pivot is not positive
+};
+int dense_slices(const DenseWork& Q);
+// S (both triangles, without D_c^2) from the Jacobian planes and W.cinv; returns 0 on success
+int launch_schur_dense(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st);
+// W.x = (S + D_c^2)^-1 rhs  (rhs = the fourth region of W.cam_acc); NaN and *fail_flag = 1 when not positive definite
+int launch_dense_cholesky(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st);
+
 // ---- launches (all asynchronous on `st`) ---------------------------------------------
 void launch_pose_rows(const ParamSet& P, const uint8_t* ext_const, int freeze_all, int n_ext, int n_intr,
                       cudaStream_t st);
@@ -161,13 +181,15 @@ int tile_grid(const DeviceProblem& D);
 // t = C^-1 g, partials[3*tile + {0,1,2}] = {sum g^2, max |g|, #non-SPD blocks}.
 void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
                           double max_diag, int mode, double* partials, cudaStream_t st);
-// camera-sorted gather into W.cam_acc (zeroed here).  mode 0: diag F^T F only; mode 1: everything.
+// camera-sorted gather into W.cam_acc (zeroed here).  mode 0: diag F^T F only; mode 1: everything;
+// mode 2: everything but the block-Jacobi blocks B (dense reduced system: they are not needed).
 void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st);
 void launch_camera_scales(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // D_c^2, block-Jacobi inverse; partials[3*cta + {0,1,2}] as above for the camera side
 int camera_finalize_grid(const DeviceProblem& D);
+// with_minv = 0 (dense reduced system): D_c^2 and the gradient norms only
 void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
-                            double max_diag, double* partials, cudaStream_t st);
+                            double max_diag, double* partials, int with_minv, cudaStream_t st);
 void launch_pcg_init(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // implicit Schur complement product: one pass over point tiles -> W.partials_q, then the
 // per-camera fixed-order sum -> W.q

@@ -22,6 +22,8 @@ void print_full_report(const dba_summary& s, const deeparc::FlatProblem& f, bool
   std::printf("Linear solver      %s, reduced system %d\n",
               s.linear_solver_used == DBA_LS_DENSE ? "explicit Schur + dense Cholesky" : "implicit Schur + block-Jacobi PCG",
               s.reduced_system_size);
+  if (s.linear_solver_failures) std::printf("Linear solver failures (step rejected) %d\n", s.linear_solver_failures);
+  if (s.pcg_unconverged_solves) std::printf("WARNING: %d PCG solve(s) stopped at the iteration cap before reaching the tolerance\n", s.pcg_unconverged_solves);
   std::printf("\nCost:\nInitial          %30e\nFinal            %30e\nChange           %30e\n\n", s.initial_cost,
               s.final_cost, s.initial_cost - s.final_cost);
   std::printf("Minimizer iterations %d\nSuccessful steps     %d\nUnsuccessful steps   %d\n\n", s.num_iterations,
@@ -46,11 +48,14 @@ void solve(DeepArcManager& deeparcManager, int max_iteration, int max_second, bo
 
   dba_solve_options options;
   dba_solve_options_default(&options);            // Ceres defaults (not overridden at sfm.cc:66-71)
-  options.linear_solver = DBA_LS_AUTO;            // sfm.cc:67 DENSE_SCHUR -> exact where it fits
+  // sfm.cc:67 DENSE_SCHUR: the explicit reduced system + device Cholesky whenever the camera side
+  // fits it (every rig the reference was written for: 19..50 pose blocks); only scenes with
+  // hundreds of free cameras fall back to the PCG, driven to the exact step, and the report says so
+  options.linear_solver = DBA_LS_AUTO;
   options.progress_to_stdout = 1;                 // sfm.cc:68
   options.max_num_iterations = max_iteration;     // sfm.cc:69
   options.max_solver_time_in_seconds = max_second;  // sfm.cc:71
-  options.pcg_rel_tolerance = 1e-13;              // drive the inexact solve to the exact step
+  options.pcg_rel_tolerance = 1e-13;
   options.pcg_max_iterations = 4000;
   // (sfm.cc:70 num_threads has no meaning here)
   g_iterations.assign(static_cast<size_t>(max_iteration) + 2, dba_iteration());

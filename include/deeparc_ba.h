@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DBA_ABI_VERSION 1
+#define DBA_ABI_VERSION 2
 
 typedef enum dba_status {
   DBA_OK = 0,
@@ -102,13 +102,14 @@ typedef struct dba_problem {
  * linear_solver_type, minimizer_progress_to_stdout, max_num_iterations, num_threads,
  * max_solver_time_in_seconds; everything else is the Ceres default).               */
 typedef enum dba_linear_solver {
-  DBA_LS_AUTO = 0,  /* currently the same as DBA_LS_PCG                                  */
+  DBA_LS_AUTO = 0,  /* DBA_LS_DENSE when the reduced system has at most dense_max_size
+                       unknowns (and fits the dense path), else DBA_LS_PCG              */
   DBA_LS_PCG = 1,   /* implicit Schur complement + block-Jacobi preconditioned CG       */
-  DBA_LS_DENSE = 2  /* the reference's DENSE_SCHUR semantics (an exact step).  Round 1:
-                       obtained by running the PCG to pcg_rel_tolerance (set it to ~1e-13
-                       and pcg_max_iterations to a few thousand, as host/solve.cc does);
-                       dba_summary.linear_solver_used reports DBA_LS_PCG.  An explicit
-                       reduced system + Cholesky for small camera counts is planned.    */
+  DBA_LS_DENSE = 2  /* the reference's DENSE_SCHUR (sfm.cc:67, :95): explicit reduced camera
+                       system assembled on the device + dense Cholesky, an exact step.
+                       Limits: at most 128 camera blocks and 1008 reduced unknowns (the
+                       reference's rigs have 19..50 blocks); beyond them dba_solve returns
+                       DBA_ERR_UNSUPPORTED — it never substitutes the PCG silently.      */
 } dba_linear_solver;
 
 typedef struct dba_solve_options {
@@ -129,7 +130,7 @@ typedef struct dba_solve_options {
   int32_t pcg_max_iterations;             /* 500                                        */
   int32_t pcg_min_iterations;             /* 0                                          */
   double pcg_rel_tolerance;               /* stop when r'z <= tol^2 * r0'z0; 1e-12      */
-  int32_t dense_max_size;                 /* DBA_LS_AUTO picks DENSE up to this many
+  int32_t dense_max_size;                 /* DBA_LS_AUTO picks DBA_LS_DENSE up to this many
                                              reduced unknowns (default 768)             */
   int32_t progress_to_stdout;             /* reference: true (sfm.cc:68)                */
 } dba_solve_options;
@@ -176,6 +177,11 @@ typedef struct dba_summary {
   char message[192];
   dba_iteration* iterations;  /* caller-provided array, may be NULL                     */
   int32_t iterations_capacity;
+  int32_t linear_solver_failures;  /* DBA_LS_DENSE: factorisations that met a non-positive
+                                      pivot (the step is then invalid, as in Ceres)          */
+  int32_t pcg_unconverged_solves;  /* DBA_LS_PCG with pcg_rel_tolerance > 0: solves that hit
+                                      pcg_max_iterations before reaching the tolerance       */
+  int32_t reserved_;
 } dba_summary;
 
 /* Per-kernel accounting (CUDA events on the launching stream), for bench.py. */

@@ -29,9 +29,12 @@ eng = capi.Engine(device=local, rank=rank, world_size=world, nccl_unique_id=uid)
 fused_before = 0
 for name, p in (("bal", synthetic.bal_like(n_cam=60, n_pts=6000, window=12, seed=91)),
                 ("rig", synthetic.arc_rig(n_arc=4, n_ring=5, n_pts=3000, obs_per_point=8, seed=92)),
+                ("rig_dense", synthetic.arc_rig(n_arc=4, n_ring=5, n_pts=3000, obs_per_point=8, seed=92)),
                 ("bal320", synthetic.bal_like(n_cam=320, n_pts=24000, window=20, seed=93))):
+    # "rig_dense": the explicit reduced system, summed over the ranks by one ncclAllReduce, factorised on every rank
     opts = capi.make_options(max_num_iterations=5, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0,
-                             linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=1e-13, pcg_max_iterations=3000)
+                             linear_solver=capi.DBA_LS_DENSE if name == "rig_dense" else capi.DBA_LS_PCG,
+                             pcg_rel_tolerance=1e-13, pcg_max_iterations=3000)
     eng.problem_set(p)
     c0 = eng.eval(residuals=False)["cost"]
     s = eng.solve(opts)

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.load_library()
     missing = [n for n in declared if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.dba_abi_version() == 1
+    assert lib.dba_abi_version() == 2
 
 
 def test_struct_layouts_match_header_sizes():

@@ -1,0 +1,107 @@
+"""GPU tests of the explicit reduced system + device Cholesky (DBA_LS_DENSE), the engine's
+counterpart of the reference's `options.linear_solver_type = ceres::DENSE_SCHUR`
+(reference src/sfm.cc:67, :95), against the CPU oracle's exact DENSE_SCHUR step
+(oracle/mini_ceres.cc::EliminateAndSolve).  No PCG anywhere in these runs: the step of every
+LM iteration is the exact solution of the damped normal equations on both sides."""
+import numpy as np
+import pytest
+
+from deeparc_sfm_b200 import capi, synthetic
+from tests.test_gpu_parity import PROBLEMS, _compare_solve, _perturbed_bal
+
+pytestmark = pytest.mark.gpu
+
+FIXED = dict(function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
+
+
+@pytest.mark.parametrize("name,n_iter", [("rig", 5), ("plain", 6), ("bal", 6), ("nf2_nd2", 4), ("small_angle", 4), ("nd1", 4)])
+def test_dense_schur_matches_oracle(engine, oracle, name, n_iter):
+    """Every problem shape: composed arc o ring poses with the gauge block constant (19 blocks),
+    6-dof plain poses, 9-dof cameras, nf = 2 / nd = 2, the small-angle branch."""
+    sg, so = _compare_solve(engine, oracle, PROBLEMS[name], n_iter=n_iter, linear_solver=capi.DBA_LS_DENSE)
+    assert sg.linear_solver_used == capi.DBA_LS_DENSE == so.linear_solver_used
+    assert sg.pcg_iterations_total == n_iter and sg.linear_solver_failures == 0
+    assert np.all(sg.trace("linear_solver_iterations")[1:] == 1)
+    # an exact step on both sides: the traces agree far inside the 1e-6 budget
+    np.testing.assert_allclose(sg.trace("cost"), so.trace("cost"), rtol=1e-9)
+    np.testing.assert_allclose(sg.trace("model_cost_change")[1:], so.trace("model_cost_change")[1:], rtol=1e-7)
+
+
+def test_dense_schur_with_rejected_and_invalid_steps(engine, oracle):
+    """Trust-region rejections with the dense solver (40 cameras x 9 = 360 unknowns)."""
+    sg, so = _compare_solve(engine, oracle, _perturbed_bal(0.2, 0.05), n_iter=7, linear_solver=capi.DBA_LS_DENSE)
+    assert 0 < sg.num_unsuccessful_steps == so.num_unsuccessful_steps
+
+
+def test_dense_schur_points_only_and_default_tolerances(engine, oracle):
+    """freeze_camera: no camera side at all (the reduced system is empty); then the driver's own
+    call: 100 iterations, Ceres default tolerances, DBA_LS_AUTO -> DENSE for a 19-block rig."""
+    p = PROBLEMS["rig"].copy()
+    p.freeze_camera = 1
+    _compare_solve(engine, oracle, p, n_iter=3, linear_solver=capi.DBA_LS_DENSE)
+    p = PROBLEMS["rig"]
+    engine.problem_set(p)
+    sg = engine.solve(capi.make_options(max_num_iterations=100, linear_solver=capi.DBA_LS_AUTO))
+    so, xo = oracle.solve(p, capi.make_options(max_num_iterations=100, linear_solver=capi.DBA_LS_DENSE))
+    assert sg.linear_solver_used == capi.DBA_LS_DENSE
+    assert sg.termination == so.termination == capi.DBA_CONVERGENCE
+    assert sg.num_iterations == so.num_iterations
+    assert abs(sg.final_cost - so.final_cost) <= 1e-9 * so.final_cost
+    xg = engine.params_get()
+    for k in ("pts", "ext_rot", "ext_trans"):
+        assert np.max(np.abs(xg[k] - xo[k])) <= 1e-6 * np.max(np.abs(xo[k])), k
+
+
+def test_dense_equals_converged_pcg(engine):
+    """The same LM trace from the exact factorisation and from the PCG driven to 1e-13."""
+    for name in ("rig", "bal"):
+        p = PROBLEMS[name]
+        runs = {}
+        for ls in (capi.DBA_LS_DENSE, capi.DBA_LS_PCG):
+            engine.problem_set(p)
+            s = engine.solve(capi.make_options(max_num_iterations=5, linear_solver=ls, pcg_rel_tolerance=1e-13,
+                                               pcg_max_iterations=3000, **FIXED))
+            runs[ls] = (s, engine.params_get())
+        (sa, xa), (sb, xb) = runs[capi.DBA_LS_DENSE], runs[capi.DBA_LS_PCG]
+        assert sb.linear_solver_used == capi.DBA_LS_PCG and sb.pcg_unconverged_solves == 0
+        np.testing.assert_allclose(sa.trace("cost"), sb.trace("cost"), rtol=1e-8)
+        for k in ("pts", "ext_rot", "ext_trans"):
+            assert np.max(np.abs(xa[k] - xb[k])) <= 1e-7 * np.max(np.abs(xa[k])), (name, k)
+
+
+def test_dense_limits_are_enforced_not_papered_over(engine):
+    """200 cameras x 9 = 1800 reduced unknowns: DENSE is refused (never a silent PCG), AUTO runs
+    the PCG and says so; a PCG that cannot reach its tolerance is counted."""
+    p = synthetic.bal_like(n_cam=200, n_pts=4000, obs_per_point=5, window=30, seed=41)
+    engine.problem_set(p)
+    with pytest.raises(capi.EngineError) as e:
+        engine.solve(capi.make_options(max_num_iterations=2, linear_solver=capi.DBA_LS_DENSE))
+    assert e.value.status == capi.DBA_ERR_UNSUPPORTED
+    s = engine.solve(capi.make_options(max_num_iterations=2, linear_solver=capi.DBA_LS_AUTO, **FIXED))
+    assert s.linear_solver_used == capi.DBA_LS_PCG and s.reduced_system_size == 1800
+    engine.params_reset()
+    s = engine.solve(capi.make_options(max_num_iterations=2, linear_solver=capi.DBA_LS_PCG, pcg_rel_tolerance=1e-14,
+                                       pcg_max_iterations=3, **FIXED))
+    assert s.pcg_unconverged_solves == 2
+    # AUTO honours dense_max_size: a 40-camera problem (360 unknowns) with the limit at 100 runs the PCG
+    engine.problem_set(PROBLEMS["bal"])
+    s = engine.solve(capi.make_options(max_num_iterations=2, linear_solver=capi.DBA_LS_AUTO, dense_max_size=100, **FIXED))
+    assert s.linear_solver_used == capi.DBA_LS_PCG
+    engine.params_reset()
+    s = engine.solve(capi.make_options(max_num_iterations=2, linear_solver=capi.DBA_LS_AUTO, **FIXED))
+    assert s.linear_solver_used == capi.DBA_LS_DENSE
+
+
+@pytest.mark.parametrize("kind", ["rig_long", "teabottle", "many_blocks"])
+def test_dense_schur_shapes(engine, oracle, kind):
+    """Long tracks (a point seen by 300 cameras of a 65-block rig: one point per batch), the
+    teabottle stand-in (50 pose blocks = 300 unknowns, several pair groups) and 120 blocks of
+    6-dof poses (720 unknowns, 7260 block pairs)."""
+    if kind == "rig_long":
+        p = synthetic.arc_rig(n_arc=6, n_ring=60, n_pts=40, obs_per_point=300, seed=17)
+    elif kind == "teabottle":
+        p = synthetic.teabottle_like(n_pts=1500, obs_per_point=8)
+    else:
+        p = synthetic.bal_like(n_cam=120, n_pts=3000, obs_per_point=5, window=25, seed=43, free_intrinsics=0)
+    sg, so = _compare_solve(engine, oracle, p, n_iter=3, linear_solver=capi.DBA_LS_DENSE)
+    assert sg.linear_solver_used == capi.DBA_LS_DENSE
