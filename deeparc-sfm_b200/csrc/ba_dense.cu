@@ -9,10 +9,11 @@
 //                       registers and walks a fixed slice of the points; per batch of points the CTA
 //                       first builds, in shared memory, the compact list of camera blocks each point
 //                       touches and Z_i[A] = Y_i[A] L_i with C_i^-1 = L_i L_i^T, so the elimination
-//                       term of a pair is the 3-deep product Z_i[A] Z_i[B]^T.  F^T F blocks are added
-//                       from the point's observations that carry exactly that pair.  No atomics:
-//                       every pair is owned by one thread, slices are summed in slice order.
-// k_dense_combine       fixed-order sum of the slices into the dense n x n matrix (both triangles)
+//                       term of a pair is the 3-deep product Z_i[A] Z_i[B]^T.  No atomics: every pair is
+//                       owned by one thread, slices are summed in slice order.
+// k_pair_gather         F_A^T F_B of composed (arc, ring) observations, camera-pair-sorted chunks
+//                       (the diagonal blocks F_A^T F_A come from k_camera_gather, mode 2)
+// k_dense_combine       fixed-order sum of all of it into the dense n x n matrix (both triangles)
 // k_dense_cholesky (K9) one CTA: blocked left-looking Cholesky of S + D_c^2 with the right-hand side
 //                       carried as an extra row (so L^-1 rhs falls out of the factorisation), then the
 //                       blocked back substitution; writes the camera step W.x.  A non-positive pivot
@@ -135,34 +136,47 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
       Lp[0] = l00; Lp[1] = l10; Lp[2] = l20; Lp[3] = l11; Lp[4] = l21; Lp[5] = l22;
     }
     __syncthreads();
-    // ---- one work item per (entry, row of the block): Y row = sum F[:, row]^T E, Z row = Y row * L
-    const int n_items = sBase[np] * CB;
-    for (int it = tid; it < n_items; it += kDnThreads) {
-      const int e = it / CB, i = it - e * CB;
+    // ---- one thread per (point, block) entry: Y = sum F^T E over the point's observations that use the
+    // block, Z = Y L  (measured faster than one thread per observation with ordered accumulation
+    // rounds: the rounds cost a block barrier each)
+    const int n_ent = sBase[np];
+    for (int e = tid; e < n_ent; e += kDnThreads) {
       const unsigned int ent = sEnt[e];
       if (ent == 0xffffffffu) continue;
       const int pt = ent >> 16, blk = ent & 0xffffu;
-      double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+      double y[CB][3];
+#pragma unroll
+      for (int i = 0; i < CB; ++i) y[i][0] = y[i][1] = y[i][2] = 0.0;
       for (int o = sSeg[pt]; o < sSeg[pt + 1]; ++o) {
         const int2 ab = D.obs_ab[o];
+        const bool is_a = ab.x == blk;
+        if (!is_a && ab.y != blk) continue;
         const double2* J = D.J + o;
-        double2 F;
-        if (ab.x == blk) F = J[(kPlaneJA + i) * ld];
-        else if (ab.y == blk && i < 6) F = J[(kPlaneJA + CB + i) * ld];
-        else continue;
         const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
-        y0 += F.x * e0.x + F.y * e0.y;
-        y1 += F.x * e1.x + F.y * e1.y;
-        y2 += F.x * e2.x + F.y * e2.y;
+        const int base_pl = is_a ? kPlaneJA : kPlaneJA + CB;
+#pragma unroll
+        for (int i = 0; i < CB; ++i) {
+          if (i < 6 || is_a) {
+            const double2 F = J[(base_pl + i) * ld];
+            y[i][0] += F.x * e0.x + F.y * e0.y;
+            y[i][1] += F.x * e1.x + F.y * e1.y;
+            y[i][2] += F.x * e2.x + F.y * e2.y;
+          }
+        }
       }
       const double* Lp = sL + pt * 6;
-      double* z = sZ + e * ZS + 3 * i;
-      z[0] = y0 * Lp[0] + y1 * Lp[1] + y2 * Lp[2];
-      z[1] = y1 * Lp[3] + y2 * Lp[4];
-      z[2] = y2 * Lp[5];
+      const double l00 = Lp[0], l10 = Lp[1], l20 = Lp[2], l11 = Lp[3], l21 = Lp[4], l22 = Lp[5];
+      double* z = sZ + e * ZS;
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        z[3 * i + 0] = y[i][0] * l00 + y[i][1] * l10 + y[i][2] * l20;
+        z[3 * i + 1] = y[i][1] * l11 + y[i][2] * l21;
+        z[3 * i + 2] = y[i][2] * l22;
+      }
     }
     __syncthreads();
-    // ---- the pair threads: S_AB -= Z_A Z_B^T (+= F_A^T F_B of the observations carrying the pair)
+    // ---- the pair threads: S_AB -= Z_A Z_B^T  (F^T F is added by k_dense_combine from the camera gather
+    // and the camera-pair gather: adding it here would run one lane per matching observation)
     if (has_pair) {
       for (int p = 0; p < np; ++p) {
         const int ia = sLook[p * nbs + A];
@@ -178,47 +192,8 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
         for (int j = 0; j < CB; ++j) {
           const double z0 = zb[3 * j], z1 = zb[3 * j + 1], z2 = zb[3 * j + 2];
 #pragma unroll
-          for (int i = 0; i < CB; ++i) acc[i * CB + j] -= a[3 * i] * z0 + a[3 * i + 1] * z1 + a[3 * i + 2] * z2;
-        }
-        for (int o = sSeg[p]; o < sSeg[p + 1]; ++o) {
-          const int2 ab = D.obs_ab[o];
-          const double2* J = D.J + o;
-          if (A == B) {
-            if (ab.x == A) {
-              double2 F[CB];
-#pragma unroll
-              for (int k = 0; k < CB; ++k) F[k] = J[(kPlaneJA + k) * ld];
-#pragma unroll
-              for (int i = 0; i < CB; ++i)
-#pragma unroll
-                for (int j = 0; j < CB; ++j) acc[i * CB + j] += F[i].x * F[j].x + F[i].y * F[j].y;
-            }
-            if (ab.y == A) {
-              double2 F[6];
-#pragma unroll
-              for (int k = 0; k < 6; ++k) F[k] = J[(kPlaneJA + CB + k) * ld];
-#pragma unroll
-              for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j < 6; ++j) acc[i * CB + j] += F[i].x * F[j].x + F[i].y * F[j].y;
-            }
-          } else if ((ab.x == A && ab.y == B) || (ab.x == B && ab.y == A)) {
-            // rows: block A, columns: block B (block b of an observation has six columns)
-            const bool a_first = ab.x == A;
-            const int pa = a_first ? kPlaneJA : kPlaneJA + CB, pb = a_first ? kPlaneJA + CB : kPlaneJA;
-            const int na = a_first ? CB : 6, nbk = a_first ? 6 : CB;
-            double2 FB[CB];
-#pragma unroll
-            for (int k = 0; k < CB; ++k) FB[k] = k < nbk ? J[(pb + k) * ld] : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int i = 0; i < CB; ++i) {
-              if (i < na) {
-                const double2 fa = J[(pa + i) * ld];
-#pragma unroll
-                for (int j = 0; j < CB; ++j) acc[i * CB + j] += fa.x * FB[j].x + fa.y * FB[j].y;
-              }
-            }
-          }
+          for (int i = 0; i < CB; ++i)
+            acc[i * CB + j] = fma(-a[3 * i + 2], z2, fma(-a[3 * i + 1], z1, fma(-a[3 * i], z0, acc[i * CB + j])));
         }
       }
     }
@@ -231,9 +206,50 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
   }
 }
 
-// S[A-block rows, B-block cols] = sum over slices (slice order) of the pair's partial blocks; mirrored.
+// F_lo^T F_hi of the observations that compose the pose blocks (lo, hi), lo < hi: camera-pair-sorted
+// incidence in chunks (one CTA per chunk, like k_camera_gather); one row of 36 sums per chunk.
+__global__ void __launch_bounds__(128) k_pair_gather(DeviceProblem D, DenseWork Q) {
+  __shared__ double red[4][36];
+  const int4 ch = Q.pair_chunks[blockIdx.x];  // (pair, first entry, last entry, -)
+  double acc[36];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+  const int64_t ld = D.ld;
+  for (int e = ch.y + threadIdx.x; e < ch.z; e += blockDim.x) {
+    const int ent = Q.pair_entries[e];
+    const int o = ent >> 1, swap = ent & 1;  // swap: block b of the observation is the lower-numbered block
+    const double2* J = D.J + o;
+    const int plo = kPlaneJA + (swap ? 6 : 0), phi = kPlaneJA + (swap ? 0 : 6);
+    double2 FH[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) FH[k] = J[(phi + k) * ld];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double2 f = J[(plo + i) * ld];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) acc[i * 6 + j] += f.x * FH[j].x + f.y * FH[j].y;
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 36; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[wid][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 36)
+    Q.pair_chunk_acc[static_cast<int64_t>(blockIdx.x) * 36 + threadIdx.x] =
+        red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+}
+
+// S[A-block rows, B-block cols] = sum over slices (slice order) of the pair's elimination blocks
+//   + F_A^T F_A from the camera gather (diagonal pairs; add_diag = 0 on ranks > 0, whose accumulators
+//     already hold the sum over all ranks) + the chunk rows of the camera-pair gather; mirrored.
 template <int CB>
-__global__ void __launch_bounds__(256) k_dense_combine(DenseWork Q, int nb, int n_slices) {
+__global__ void __launch_bounds__(256) k_dense_combine(DenseWork Q, const double* __restrict__ cam_B, int add_diag, int nb,
+                                                        int n_slices) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(Q.n_pairs) * (CB * CB)) return;
   const int q = static_cast<int>(idx / (CB * CB)), e = static_cast<int>(idx - static_cast<int64_t>(q) * (CB * CB));
@@ -242,6 +258,11 @@ __global__ void __launch_bounds__(256) k_dense_combine(DenseWork Q, int nb, int 
   int A, B;
   pair_decode(q, nb, A, B);
   const int i = e / CB, j = e - i * CB;
+  if (A == B) {
+    if (add_diag) s += cam_B[static_cast<int64_t>(A) * CB * CB + e];
+  } else if (Q.pair_chunk_first && i < 6 && j < 6) {
+    for (int c = Q.pair_chunk_first[q]; c < Q.pair_chunk_first[q + 1]; ++c) s += Q.pair_chunk_acc[static_cast<int64_t>(c) * 36 + i * 6 + j];
+  }
   const int64_t n = static_cast<int64_t>(nb) * CB;
   const int64_t r = static_cast<int64_t>(A) * CB + i, c = static_cast<int64_t>(B) * CB + j;
   Q.S[r * n + c] = s;
@@ -262,6 +283,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __rest
   extern __shared__ __align__(16) unsigned char smem_ch[];
   double* sLjT = reinterpret_cast<double*>(smem_ch);          // [j0][kChLS]: L[j0 + c][k] at [k][c]
   double* sy = sLjT + static_cast<size_t>(n) * kChLS;         // [n + 16] y, then x
+  double* sInv = sy + n + kChNB;                              // [n] 1 / L_kk (no division on the serial chains)
   __shared__ double sD[kChNB][kChNB + 1];
   __shared__ int s_ok;
   const int tid = threadIdx.x;
@@ -294,6 +316,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __rest
     __syncthreads();
     if (active && j0 > 0) {
       const double* lrow = row < n ? S + static_cast<int64_t>(row) * n : sy;
+#pragma unroll 4
       for (int k = 0; k < j0; ++k) {
         const double l = lrow[k];
         const double2* lj = reinterpret_cast<const double2*>(sLjT + k * kChLS);
@@ -305,27 +328,30 @@ __global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __rest
         }
       }
     }
-    // diagonal block rows -> shared memory, factorised by warp 0
-    if (tid < w) {
-#pragma unroll
-      for (int c = 0; c < kChNB; ++c) sD[tid][c] = p[c];
-    }
-    __syncthreads();
+    // diagonal block: lane r of warp 0 keeps row r in registers (p[]), columns travel by shuffle —
+    // no shared-memory round trip on the serial chain
     if (tid < 32) {
-      for (int k = 0; k < w; ++k) {
-        __syncwarp();
-        double d = sD[k][k];
-        const bool good = d > 0.0;
-        d = sqrt(good ? d : 1.0);
-        __syncwarp();
-        if (tid == k) {
-          sD[k][k] = d;
-          if (!good) s_ok = 0;
+      bool good_all = true;
+#pragma unroll
+      for (int k = 0; k < kChNB; ++k) {
+        if (k < w) {
+          const double d = __shfl_sync(0xffffffffu, p[k], k);
+          const bool good = d > 0.0;
+          good_all = good_all && good;
+          const double rs = rsqrt(good ? d : 1.0);
+          if (tid == k) sInv[j0 + k] = rs;
+          p[k] = (tid == k) ? d * rs : p[k] * rs;  // L[r][k] for r > k (rows above the diagonal carry zeros)
+#pragma unroll
+          for (int c = k + 1; c < kChNB; ++c) {
+            const double lck = __shfl_sync(0xffffffffu, p[k], c);
+            if (tid >= c) p[c] -= p[k] * lck;
+          }
         }
-        if (tid > k && tid < w) sD[tid][k] /= d;
-        __syncwarp();
-        if (tid > k && tid < w)
-          for (int c = k + 1; c <= tid; ++c) sD[tid][c] -= sD[tid][k] * sD[c][k];
+      }
+      if (tid == 0 && !good_all) s_ok = 0;
+      if (tid < w) {
+#pragma unroll
+        for (int c = 0; c < kChNB; ++c) sD[tid][c] = p[c];
       }
     }
     __syncthreads();
@@ -337,14 +363,17 @@ __global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __rest
         for (int c = 0; c < kChNB; ++c)
           if (c <= tid) S[static_cast<int64_t>(row) * n + j0 + c] = sD[tid][c];
       } else {
-        // triangular solve of the row against the diagonal block
+        // triangular solve of the row against the diagonal block (the rows that sit in warp 0 were
+        // carried along by the factorisation above)
+        if (tid >= 32) {
 #pragma unroll
-        for (int c = 0; c < kChNB; ++c) {
-          if (c < w) {
-            double v = p[c];
+          for (int c = 0; c < kChNB; ++c) {
+            if (c < w) {
+              double v = p[c];
 #pragma unroll
-            for (int k = 0; k < c; ++k) v -= p[k] * sD[c][k];
-            p[c] = v / sD[c][c];
+              for (int k = 0; k < c; ++k) v -= p[k] * sD[c][k];
+              p[c] = v * sInv[j0 + c];
+            }
           }
         }
         if (row < n) {
@@ -374,15 +403,27 @@ __global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __rest
     const int w = min(kChNB, n - j0);
     __syncthreads();
     if (tid >= j0 && tid < j0 + w) sy[tid] = v;  // current right-hand side of the panel's unknowns
+    if (tid < kChNB * kChNB) {                   // the panel's diagonal block, so that the serial part stays in shared memory
+      const int r = tid / kChNB, c = tid - r * kChNB;
+      if (r < w && c <= r) sD[r][c] = S[static_cast<int64_t>(j0 + r) * n + j0 + c];
+    }
     __syncthreads();
     if (tid < 32) {
-      for (int k = w - 1; k >= 0; --k) {
-        __syncwarp();
-        if (tid == 0) sy[j0 + k] /= S[static_cast<int64_t>(j0 + k) * n + j0 + k];
-        __syncwarp();
-        const double xk = sy[j0 + k];
-        if (tid < k) sy[j0 + tid] -= S[static_cast<int64_t>(j0 + k) * n + j0 + tid] * xk;
+      // lane i: unknown j0 + i; column i of the block (L[k][i], k > i) in registers
+      double col[kChNB];
+#pragma unroll
+      for (int k = 0; k < kChNB; ++k) col[k] = (tid < w && k < w && k > tid) ? sD[k][tid] : 0.0;
+      double yi = tid < w ? sy[j0 + tid] : 0.0;
+      const double inv = tid < w ? sInv[j0 + tid] : 0.0;
+#pragma unroll
+      for (int k = kChNB - 1; k >= 0; --k) {
+        if (k < w) {
+          const double xk = __shfl_sync(0xffffffffu, yi * inv, k);
+          if (tid == k) yi = xk;
+          else if (tid < k) yi -= col[k] * xk;
+        }
       }
+      if (tid < w) sy[j0 + tid] = yi;
     }
     __syncthreads();
     if (tid < j0) {
@@ -391,6 +432,84 @@ __global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __rest
   }
   __syncthreads();
   if (tid < n) x[tid] = sy[tid];
+}
+
+// Small systems (the whole augmented matrix fits in shared memory: n <= kChSmallMax): right-looking
+// L D L^T without square roots, one block barrier per elimination step.  Row n is the right-hand
+// side, so its multipliers are w = D^-1 L^-1 rhs; then the column-oriented back substitution
+// L^T x = w.  Same step as the Cholesky path up to rounding.
+constexpr int kChSmallMax = 152;
+constexpr int kChSmallThreads = 256;  // block barriers dominate this kernel: 8 warps synchronise much faster than 32
+__global__ void __launch_bounds__(kChSmallThreads, 1) k_dense_ldlt_small(const double* __restrict__ S, int n, const double* __restrict__ dc2,
+                                                                     const double* __restrict__ rhs, double* __restrict__ x,
+                                                                     int* __restrict__ fail_flag) {
+  extern __shared__ __align__(16) unsigned char smem_ch[];
+  const int ldm = n | 1;  // odd row stride: a column walk touches every bank
+  double* A = reinterpret_cast<double*>(smem_ch);  // [n + 1][ldm] lower triangle + rhs row
+  double* sw = A + static_cast<size_t>(n + 1) * ldm;  // [n] w, then x
+  __shared__ int s_ok;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_ok = 1;
+  for (int i = tid; i < n * n; i += kChSmallThreads) {
+    const int r = i / n, c = i - r * n;
+    if (c <= r) A[r * ldm + c] = S[i] + (r == c ? dc2[r] : 0.0);
+  }
+  if (tid < n) A[n * ldm + tid] = rhs[tid];
+  __syncthreads();
+  // the trailing block of a step is walked in (threads / 32) x 32 thread tiles: warp ty owns rows k+1+ty (+8, ...),
+  // lane tx columns k+1+tx (+32, ...) up to the diagonal; loads of a row pass are issued together
+  const int tx = tid & 31, ty = tid >> 5;
+  constexpr int kSeg = (kChSmallMax + 31) / 32;
+  for (int k = 0; k < n; ++k) {
+    const double d = A[k * ldm + k];
+    if (!(d > 0.0)) {  // uniform: every thread reads the same pivot
+      if (tid == 0) s_ok = 0;
+      break;
+    }
+    double inv;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(d));
+    inv = inv * (2.0 - d * inv);
+    inv = inv * (2.0 - d * inv);
+    for (int r = k + 1 + ty; r <= n; r += kChSmallThreads / 32) {
+      const double lrk = A[r * ldm + k] * inv;
+      const int jmax = min(r, n - 1);
+      double av[kSeg], cv[kSeg];
+#pragma unroll
+      for (int t = 0; t < kSeg; ++t) {
+        const int j = k + 1 + tx + 32 * t;
+        if (k + 1 + 32 * t <= jmax) {  // warp-uniform
+          const bool in = j <= jmax;
+          av[t] = in ? A[r * ldm + j] : 0.0;
+          cv[t] = in ? A[j * ldm + k] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kSeg; ++t) {
+        const int j = k + 1 + tx + 32 * t;
+        if (k + 1 + 32 * t <= jmax && j <= jmax) A[r * ldm + j] = fma(-lrk, cv[t], av[t]);
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (!s_ok) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = tid; i < n; i += kChSmallThreads) x[i] = nan;
+    if (tid == 0 && fail_flag) *fail_flag = 1;
+    return;
+  }
+  // w_k = A[n][k] / d_k; back substitution with unit-lower L: l_ki = A[k][i] / d_i
+  double v = 0.0, inv_i = 0.0;
+  if (tid < n) {
+    inv_i = 1.0 / A[tid * ldm + tid];
+    v = A[n * ldm + tid] * inv_i;
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    if (tid == k) sw[k] = v;
+    __syncthreads();
+    if (tid < k) v -= A[k * ldm + tid] * inv_i * sw[k];
+  }
+  if (tid < n) x[tid] = v;
 }
 
 }  // namespace
@@ -405,7 +524,7 @@ int dense_slices(const DenseWork& Q) {
 }
 
 template <int CB, int MINB>
-static int launch_schur_dense_t(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st) {
+static int launch_schur_dense_t(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, int add_diag, cudaStream_t st) {
   const size_t smem = DnSmem<CB>::bytes(D.n_blocks);
   static unsigned long long configured = 0;
   int dev = 0;
@@ -417,30 +536,37 @@ static int launch_schur_dense_t(const DeviceProblem& D, const WorkArrays& W, con
   const int groups = (Q.n_pairs + kDnThreads - 1) / kDnThreads;
   const int slices = dense_slices(Q);
   k_schur_dense<CB, MINB><<<dim3(slices, groups), kDnThreads, smem, st>>>(D, W, Q);
+  if (Q.n_pair_chunks > 0) k_pair_gather<<<Q.n_pair_chunks, 128, 0, st>>>(D, Q);
   const int64_t total = static_cast<int64_t>(Q.n_pairs) * CB * CB;
-  k_dense_combine<CB><<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(Q, D.n_blocks, slices);
+  k_dense_combine<CB><<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(Q, W.cam_acc, add_diag, D.n_blocks, slices);
   return 0;
 }
 
-int launch_schur_dense(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st) {
+int launch_schur_dense(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, int add_diag, cudaStream_t st) {
   if (D.n_blocks == 0 || Q.n_pairs == 0) return 0;
-  if (D.cb == 6) return launch_schur_dense_t<6, 2>(D, W, Q, st);
-  if (D.cb == 9) return launch_schur_dense_t<9, 1>(D, W, Q, st);
+  if (D.cb == 6) return launch_schur_dense_t<6, 2>(D, W, Q, add_diag, st);
+  if (D.cb == 9) return launch_schur_dense_t<9, 1>(D, W, Q, add_diag, st);
   return -1;
 }
 
 int launch_dense_cholesky(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st) {
   const int n = D.n_blocks * D.cb;
   if (n == 0) return 0;
-  const size_t smem = sizeof(double) * (static_cast<size_t>(n) * kChLS + n + kChNB);
+  const size_t smem = sizeof(double) * (static_cast<size_t>(n) * kChLS + 2 * static_cast<size_t>(n) + kChNB);
   static unsigned long long configured = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(configured & (1ull << (dev & 63)))) {
     configured |= 1ull << (dev & 63);
     cudaFuncSetAttribute(k_dense_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dense_ldlt_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   const double* rhs = W.cam_acc + static_cast<int64_t>(D.n_blocks) * D.cb * D.cb + 2 * static_cast<int64_t>(n);
+  if (n <= kChSmallMax) {
+    const size_t small = sizeof(double) * (static_cast<size_t>(n + 1) * (n | 1) + n);
+    k_dense_ldlt_small<<<1, kChSmallThreads, small, st>>>(Q.S, n, W.dc2, rhs, W.x, Q.fail_flag);
+    return 0;
+  }
   k_dense_cholesky<<<1, kChThreads, smem, st>>>(Q.S, n, W.dc2, rhs, W.x, Q.fail_flag);
   return 0;
 }

@@ -141,8 +141,9 @@ struct dba_handle {
   bool dense_ok = false;     // the problem fits the dense path (set by dba_problem_set)
   bool use_dense = false;    // linear solver of the running dba_solve
   DenseWork Q{};
-  DevBuf<int> d_dn_batch;
-  DevBuf<double> d_dn_S, d_dn_Spart;
+  DevBuf<int> d_dn_batch, d_dn_pair_entries, d_dn_pair_chunk_first;
+  DevBuf<int4> d_dn_pair_chunks;
+  DevBuf<double> d_dn_S, d_dn_Spart, d_dn_pair_acc;
   int dense_failures = 0, pcg_unconverged = 0;  // per dba_solve
   double* h_scalars = nullptr;  // pinned
   int* h_pcg_state = nullptr;   // pinned
@@ -625,8 +626,8 @@ int dense_solve(dba_handle* h, int* iters_out) {
   const int nplanes = 3 + h->cb + (h->two ? 6 : 0);
   CU(h, cudaMemsetAsync(h->W.pcg_state, 0, 4 * sizeof(int), h->st));
   {
-    Scope s(h, "schur_dense", 16.0 * nplanes * static_cast<double>(h->n_obs), 2);
-    if (launch_schur_dense(D, h->W, h->Q, h->st) != 0) return h->fail(DBA_ERR_UNSUPPORTED, "dense reduced system: unsupported camera block");
+    Scope s(h, "schur_dense", 16.0 * nplanes * static_cast<double>(h->n_obs), h->Q.n_pair_chunks > 0 ? 3 : 2);
+    if (launch_schur_dense(D, h->W, h->Q, /*add_diag=*/h->rank == 0 ? 1 : 0, h->st) != 0) return h->fail(DBA_ERR_UNSUPPORTED, "dense reduced system: unsupported camera block");
   }
   int rc = allreduce(h, h->Q.S, static_cast<size_t>(n) * n, kNcclSum);
   if (rc != DBA_OK) return rc;
@@ -1092,6 +1093,10 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   // dense reduced system (DENSE_SCHUR): eligible when the camera side is small
   const bool dense_ok = cb > 0 && n_ext <= kDnMaxBlocks && n_ext * cb <= kDnMaxSize;
   want(dense_ok ? (static_cast<size_t>(n_pts) + 2) * sizeof(int) : 0);  // dn_batch
+  const size_t dn_pairs = dense_ok ? static_cast<size_t>(n_ext) * (n_ext + 1) / 2 : 0;
+  want((dense_ok && two) ? nl * sizeof(int) : 0);                             // dn_pair_entries
+  want((dense_ok && two) ? (nl / 1024 + dn_pairs + 2) * sizeof(int4) : 0);    // dn_pair_chunks
+  want((dense_ok && two) ? (dn_pairs + 2) * sizeof(int) : 0);                 // dn_pair_chunk_first
   want(3 * sizeof(double) * static_cast<size_t>(h->n_pts));  // the caller's points (pageable) staged for the async copy
   PinnedArena& A = arena_of(h);
   CU(h, cudaStreamSynchronize(h->st));  // the arena may still feed copies of a previous call
@@ -1381,6 +1386,60 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     }
     if (n_pts > 0) s_dn_batch[++n_dn_batches] = n_pts;
   }
+  // composed observations sorted by their (lower, higher) pose-block pair, in chunks of <= 1024:
+  // k_pair_gather sums F_lo^T F_hi per chunk (stable parallel counting sort, as for the camera incidence)
+  int n_dn_pair_chunks = 0;
+  int64_t n_dn_pair_entries = 0;
+  int *s_dn_pair_entries = nullptr, *s_dn_pair_chunk_first = nullptr;
+  int4* s_dn_pair_chunks = nullptr;
+  if (dense_ok && two) {
+    const int np = static_cast<int>(dn_pairs);
+    auto pair_of = [n_ext](int a, int b) { return a * n_ext - a * (a - 1) / 2 + (b - a); };  // a <= b
+    const int nthreads = std::max(1, omp_get_max_threads());
+    std::vector<std::vector<int>> hist(nthreads, std::vector<int>(static_cast<size_t>(np) + 1, 0));
+#pragma omp parallel num_threads(nthreads)
+    {
+      const int t = omp_get_thread_num();
+      const int64_t k0 = nl * t / nthreads, k1 = nl * (t + 1) / nthreads;
+      for (int64_t k = k0; k < k1; ++k) {
+        const int a = s_ab[k].x, b = s_ab[k].y;
+        if (b >= 0 && b != a) hist[t][pair_of(std::min(a, b), std::max(a, b))]++;
+      }
+    }
+    std::vector<int64_t> first(static_cast<size_t>(np) + 1, 0);
+    for (int q = 0; q < np; ++q) {
+      int64_t tot = 0;
+      for (int t = 0; t < nthreads; ++t) {
+        const int c = hist[t][q];
+        hist[t][q] = static_cast<int>(tot);
+        tot += c;
+      }
+      first[q + 1] = first[q] + tot;
+    }
+    n_dn_pair_entries = first[np];
+    s_dn_pair_entries = A.take<int>(static_cast<size_t>(std::max<int64_t>(n_dn_pair_entries, 1)));
+#pragma omp parallel num_threads(nthreads)
+    {
+      const int t = omp_get_thread_num();
+      const int64_t k0 = nl * t / nthreads, k1 = nl * (t + 1) / nthreads;
+      for (int64_t k = k0; k < k1; ++k) {
+        const int a = s_ab[k].x, b = s_ab[k].y;
+        if (b < 0 || b == a) continue;
+        const int q = pair_of(std::min(a, b), std::max(a, b));
+        s_dn_pair_entries[first[q] + hist[t][q]++] = static_cast<int>(2 * k + (b < a ? 1 : 0));
+      }
+    }
+    for (int q = 0; q < np; ++q) n_dn_pair_chunks += static_cast<int>((first[q + 1] - first[q] + 1023) / 1024);
+    s_dn_pair_chunks = A.take<int4>(static_cast<size_t>(std::max(n_dn_pair_chunks, 1)));
+    s_dn_pair_chunk_first = A.take<int>(static_cast<size_t>(np) + 1);
+    int c = 0;
+    for (int q = 0; q < np; ++q) {
+      s_dn_pair_chunk_first[q] = c;
+      for (int64_t e = first[q]; e < first[q + 1]; e += 1024)
+        s_dn_pair_chunks[c++] = make_int4(q, static_cast<int>(e), static_cast<int>(std::min<int64_t>(e + 1024, first[q + 1])), 0);
+    }
+    s_dn_pair_chunk_first[np] = c;
+  }
   mark("tile incidence + columns");
   // ---- device buffers (kept across calls, grow only)
   h->plane_w = 4 + cb + ((two && cb) ? 6 : 0);
@@ -1470,6 +1529,20 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     h->Q.batch_pt = h->d_dn_batch.p;
     h->Q.S = h->d_dn_S.p;
     h->Q.S_part = h->d_dn_Spart.p;
+    if (two && n_dn_pair_chunks > 0) {
+      CU(h, ensure(h->d_dn_pair_entries, static_cast<size_t>(n_dn_pair_entries)));
+      CU(h, ensure(h->d_dn_pair_chunks, static_cast<size_t>(n_dn_pair_chunks)));
+      CU(h, ensure(h->d_dn_pair_chunk_first, dn_pairs + 1));
+      CU(h, ensure(h->d_dn_pair_acc, static_cast<size_t>(n_dn_pair_chunks) * 36));
+      CU(h, up(h->d_dn_pair_entries.p, s_dn_pair_entries, n_dn_pair_entries * sizeof(int)));
+      CU(h, up(h->d_dn_pair_chunks.p, s_dn_pair_chunks, n_dn_pair_chunks * sizeof(int4)));
+      CU(h, up(h->d_dn_pair_chunk_first.p, s_dn_pair_chunk_first, (dn_pairs + 1) * sizeof(int)));
+      h->Q.pair_entries = h->d_dn_pair_entries.p;
+      h->Q.pair_chunks = h->d_dn_pair_chunks.p;
+      h->Q.pair_chunk_first = h->d_dn_pair_chunk_first.p;
+      h->Q.pair_chunk_acc = h->d_dn_pair_acc.p;
+      h->Q.n_pair_chunks = n_dn_pair_chunks;
+    }
   }
   CU(h, ensure(h->d_q_split, nvec * static_cast<size_t>(h->q_split)));
   CU(h, ensure(h->d_vec_partials, nvec / 128 + 2 * static_cast<size_t>(n_ext) + 8192));  // k_partials_to_q: one partial per block

@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(T, MB) k_point_prepare(DeviceProblem D, WorkAr
 // camera block in chunk order: no atomics).
 template <int CB, int MODE>
 __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArrays W) {
-  constexpr int NU = MODE == 1 ? CB * (CB + 1) / 2 : 0;  // mode 2: no block-Jacobi blocks
+  constexpr int NU = CB * (CB + 1) / 2;
   constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
   __shared__ double red[4][NACC];
   const int4 ch = D.cam_chunks[blockIdx.x];  // (block, first entry, last entry, -)
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
       double tp[4];
       load_row<4>(W.tp + 4 * static_cast<int64_t>(pt), tp);
       // M = E C^-1 (2x3), P = I - M E^T (2x2 symmetric)
-      double p00 = 0.0, p01 = 0.0, p11 = 0.0;
+      double p00 = 1.0, p01 = 0.0, p11 = 1.0;  // mode 2: plain F^T F
       if (MODE == 1) {
         const double m00 = e0.x * c0 + e1.x * c1 + e2.x * c2, m01 = e0.x * c1 + e1.x * c3 + e2.x * c4,
                      m02 = e0.x * c2 + e1.x * c4 + e2.x * c5;
@@ -468,15 +468,13 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
       int u = 0;
 #pragma unroll
       for (int i = 0; i < CB; ++i) {
-        if (MODE == 1) {
-          // (P F)_i
-          const double pf0 = p00 * F[i].x + p01 * F[i].y;
-          const double pf1 = p01 * F[i].x + p11 * F[i].y;
+        // (P F)_i
+        const double pf0 = MODE == 1 ? p00 * F[i].x + p01 * F[i].y : F[i].x;
+        const double pf1 = MODE == 1 ? p01 * F[i].x + p11 * F[i].y : F[i].y;
 #pragma unroll
-          for (int j = i; j < CB; ++j) {
-            acc[u] += pf0 * F[j].x + pf1 * F[j].y;
-            ++u;
-          }
+        for (int j = i; j < CB; ++j) {
+          acc[u] += pf0 * F[j].x + pf1 * F[j].y;
+          ++u;
         }
         acc[NU + i] += dot2(F[i], F[i]);
         acc[NU + CB + i] += dot2(F[i], r);
@@ -502,7 +500,7 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
 // one thread per (camera block, accumulator); blocks without observations get zeros.
 template <int CB, int MODE>
 __global__ void __launch_bounds__(128) k_camera_combine(DeviceProblem D, WorkArrays W) {
-  constexpr int NU = MODE == 1 ? CB * (CB + 1) / 2 : 0;
+  constexpr int NU = CB * (CB + 1) / 2;
   constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int nb = D.n_blocks;
@@ -2032,7 +2030,7 @@ static size_t cam_acc_doubles(const DeviceProblem& D) {
 
 template <int CB, int MODE>
 static void launch_camera_gather_t(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
-  constexpr int NACC = MODE == 0 ? CB : (MODE == 1 ? CB * (CB + 1) / 2 : 0) + 3 * CB;
+  constexpr int NACC = MODE == 0 ? CB : CB * (CB + 1) / 2 + 3 * CB;
   if (D.n_chunks > 0) k_camera_gather<CB, MODE><<<D.n_chunks, 128, 0, st>>>(D, W);
   const int n = D.n_blocks * NACC;
   k_camera_combine<CB, MODE><<<(n + 127) / 128, 128, 0, st>>>(D, W);

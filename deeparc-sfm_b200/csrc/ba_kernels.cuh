@@ -154,10 +154,17 @@ struct DenseWork {
   double* S_part = nullptr;       // [slices][n_pairs][cb * cb]
   double* S = nullptr;            // [n][n] reduced matrix without D_c^2, then its Cholesky factor (lower)
   int* fail_flag = nullptr;       // set to 1 when a pivot is not positive
+  // two-pose problems: observations that compose two pose blocks, sorted by the block pair
+  const int* pair_entries = nullptr;      // [n] observation * 2 + (1: block b is the lower-numbered block)
+  const int4* pair_chunks = nullptr;      // [n_pair_chunks] (pair, first entry, last entry, 0), <= 1024 entries each
+  const int* pair_chunk_first = nullptr;  // [n_pairs + 1] pair -> its chunks (NULL: no composed observations)
+  double* pair_chunk_acc = nullptr;       // [n_pair_chunks][36]
+  int n_pair_chunks = 0;
 };
 int dense_slices(const DenseWork& Q);
-// S (both triangles, without D_c^2) from the Jacobian planes and W.cinv; returns 0 on success
-int launch_schur_dense(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st);
+// S (both triangles, without D_c^2) from the Jacobian planes, W.cinv and the F^T F blocks that
+// k_camera_gather (mode 2) left in W.cam_acc (added when add_diag != 0); returns 0 on success
+int launch_schur_dense(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, int add_diag, cudaStream_t st);
 // W.x = (S + D_c^2)^-1 rhs  (rhs = the fourth region of W.cam_acc); NaN and *fail_flag = 1 when not positive definite
 int launch_dense_cholesky(const DeviceProblem& D, const WorkArrays& W, const DenseWork& Q, cudaStream_t st);
 
@@ -182,7 +189,7 @@ int tile_grid(const DeviceProblem& D);
 void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
                           double max_diag, int mode, double* partials, cudaStream_t st);
 // camera-sorted gather into W.cam_acc (zeroed here).  mode 0: diag F^T F only; mode 1: everything;
-// mode 2: everything but the block-Jacobi blocks B (dense reduced system: they are not needed).
+// mode 2: as mode 1 with B = F^T F (no elimination term): the diagonal blocks of the dense reduced system.
 void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st);
 void launch_camera_scales(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // D_c^2, block-Jacobi inverse; partials[3*cta + {0,1,2}] as above for the camera side
