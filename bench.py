@@ -69,13 +69,16 @@ def build_workload(name: str):
     return synthetic.arc_rig(**kw, name=name)
 
 
-def describe(name: str, p, pcg_iters: int, n_gpus: int):
+def describe(name: str, p, pcg_iters: int, n_gpus: int, linear_solver: str = "pcg"):
+    ls_text = ("implicit Schur complement + block-Jacobi PCG (fixed %d iterations per LM iteration, tolerance 0)" % pcg_iters
+               if linear_solver == "pcg" else
+               "DENSE_SCHUR as the reference configures it (sfm.cc:67): explicit reduced system + dense Cholesky, exact step")
     return {
         "workload": f"{name}: synthetic {'BAL-scale' if p.n_ring == 0 else 'DeepArc arc rig'}, "
                     f"{p.n_ext} extrinsics, {p.n_pts} points, {p.n_obs} observations",
         "camera_block": "9-dof [w,t,f,k0,k1]" if p.free_intrinsics else ("2x6-dof composed poses" if (p.obs_pose_b >= 0).any() else "6-dof pose"),
-        "pcg_iterations_per_lm_iteration": pcg_iters,
-        "linear_solver": "implicit Schur complement + block-Jacobi PCG (fixed iterations, tolerance 0)",
+        "pcg_iterations_per_lm_iteration": pcg_iters if linear_solver == "pcg" else None,
+        "linear_solver": ls_text,
         "tolerances": "function/gradient/parameter = 0 (exactly K iterations)",
         "cache": ("inputs larger than L2: Jacobian planes %.0f MB written and re-read per LM iteration vs 126 MB L2; no flush needed"
                   if p.n_obs * 16 * 13 > 2 * 126e6 else
@@ -177,7 +180,9 @@ def main():
     ap.add_argument("--linear-solver", default="pcg", choices=["pcg", "dense"],
                     help="dense = explicit reduced system + device Cholesky (the reference's DENSE_SCHUR); small camera counts only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-budget", type=float, default=40.0, help="seconds of CPU LM iterations")
+    ap.add_argument("--cpu-budget", type=float, default=0.0,
+                    help="seconds of CPU LM iterations per CPU leg (default: 25 for the legs of our arm, 150 for --impl reference)")
+    ap.add_argument("--no-exact-step", action="store_true", help="skip the arc1m DENSE_SCHUR sub-measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -189,17 +194,33 @@ def main():
         if rank != 0:
             return 0
         p = build_workload(args.workload)
-        r = cpu_reference_run(p, steps=max(args.steps, 1), pcg_iters=args.pcg_iters, budget_s=args.cpu_budget)
+        # The reference configures Ceres with DENSE_SCHUR (sfm.cc:67).  For the rigs it was written for
+        # (arc1m, teabottle: 114 / 300 reduced unknowns) that is what this arm times.  For the BAL-scale
+        # workloads the dense reduced matrix is 15 300^2 / 90 000^2 and BASELINE.md 2 specifies the same
+        # implicit-Schur PCG on the CPU: this arm then runs the SAME algorithm as the GPU arm (same K), so
+        # the ratio the driver computes is a kernel/machine ratio and not an algorithm change; the
+        # DENSE_SCHUR time of one iteration is reported beside it.
+        dense_primary = args.linear_solver == "dense" or p.n_ext * (9 if p.free_intrinsics else 6) <= 1008
+        budget = args.cpu_budget if args.cpu_budget > 0 else 150.0
+        r = cpu_reference_run(p, steps=max(args.steps, 1), pcg_iters=args.pcg_iters, budget_s=budget, dense=dense_primary)
+        other = None
+        if not dense_primary and args.workload != "stress50m":
+            other = cpu_reference_run(p, steps=1, pcg_iters=args.pcg_iters, budget_s=1.0, dense=True)
+        ls = "dense" if dense_primary else "pcg"
         line = {
             "impl": "reference", "metric": METRIC, "value": r["iters_per_sec"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": r["steps_done"], "warmup": 0, "ms_per_step": (1e3 / r["iters_per_sec"]) if r["iters_per_sec"] else None,
-            "higher_is_better": True, "scaling": "weak" if args.gpus > 1 else "n/a", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": describe(args.workload, p, args.pcg_iters, 1),
+            "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "n/a", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": describe(args.workload, p, args.pcg_iters, 1, ls),
             "cpu_baseline": {"value": r["iters_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                              "sample": f"{r['steps_done']} full LM iteration(s) of the same problem within a "
-                                       f"{args.cpu_budget:.0f}s budget (requested {args.steps}); {r['linear_solver']}; "
+                                       f"{budget:.0f}s budget (requested {args.steps}); {r['linear_solver']}; "
                                        "oracle/ restatement of the reference's Ceres path (real Ceres not installable)"},
+            "cpu_baseline_dense_schur": None if other is None else {
+                "value": other["iters_per_sec"], "unit": UNIT, "cores": other["cores"], "kind": "port",
+                "sample": f"{other['steps_done']} LM iteration with {other['linear_solver']}"},
             "e2e": {"value": r["iters_per_sec"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "final_cost": r["final_cost"], "initial_cost": r["initial_cost"],
             "gpu_launches": 0,
         }
         print(json.dumps(line))
@@ -267,6 +288,29 @@ def main():
     value = steps_done / loop_s if loop_s > 0 else 0.0
     launches = int(s.kernel_launches)
     accepted = int(s.num_successful_steps)
+
+    # ---- multi-GPU parity, driver-visible: rank 0 solves the SAME problem with the same options on
+    # its GPU alone; the N-rank cost trace and parameters must equal the 1-GPU ones to 1e-9
+    parity_vs_1gpu = None
+    if world > 1:
+        x_n = eng.params_get()  # collective
+        if rank == 0:
+            one = capi.Engine(device=local_rank)
+            one.problem_set(p)
+            s1 = one.solve(opts)
+            x1 = one.params_get()
+            one.close()
+            cost_rel = float(np.max(np.abs(s.trace("cost") - s1.trace("cost")) / np.abs(s1.trace("cost"))))
+            par_rel = max(float(np.max(np.abs(x_n[k] - x1[k])) / max(float(np.max(np.abs(x1[k]))), 1e-300)) for k in x1)
+            same_accepts = bool(np.array_equal(s.trace("step_is_successful"), s1.trace("step_is_successful")))
+            parity_vs_1gpu = {"cost_trace_max_rel": cost_rel, "params_max_rel": par_rel, "same_accept_pattern": same_accepts,
+                              "final_cost_n_gpu": s.final_cost, "final_cost_1_gpu": s1.final_cost, "tolerance": 1e-9,
+                              "ok": bool(cost_rel <= 1e-9 and par_rel <= 1e-9 and same_accepts),
+                              "what": f"same {args.workload} problem, same options, {world} ranks vs rank 0's GPU alone"}
+            if not parity_vs_1gpu["ok"]:
+                sys.stderr.write(f"bench.py: MULTI-GPU PARITY FAILED: {parity_vs_1gpu}\n")
+        eng.params_reset()
+        barrier()
 
     # ---- same run with per-kernel CUDA events (roofline of the dominant kernel)
     eng.params_reset()
@@ -387,21 +431,57 @@ def main():
     jac_obs_s_in_solve = obs_per_s(stats.get("jacobian"))
     jac_obs_s = obs_per_s(jac_alone) or jac_obs_s_in_solve
 
-    cpu = None
+    cpu = cpu_same = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(p, steps=1, pcg_iters=args.pcg_iters, budget_s=args.cpu_budget)
-        cpu = {"value": r["iters_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
-               "sample": f"{r['steps_done']} full LM iteration of the same problem ({r['loop_seconds']:.1f}s), "
-                         f"{r['linear_solver']}; oracle/ restatement of the reference's Ceres path"}
+        budget = args.cpu_budget if args.cpu_budget > 0 else 25.0
+        def leg(dense):
+            r = cpu_reference_run(p, steps=1, pcg_iters=args.pcg_iters, budget_s=budget, dense=dense)
+            return {"value": r["iters_per_sec"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                    "sample": f"{r['steps_done']} full LM iteration of the same problem ({r['loop_seconds']:.1f}s), "
+                              f"{r['linear_solver']}; oracle/ restatement of the reference's Ceres path"}
+        # the reference's configured solver (DENSE_SCHUR) and the algorithm the GPU arm actually runs
+        cpu = leg(dense=True) if args.workload != "stress50m" else None
+        cpu_same = leg(dense=(args.linear_solver == "dense"))
+        if cpu is None:
+            cpu = cpu_same
+
+    # ---- exact-step mode on the reference's own rig shape (BASELINE configs[2], arc1m): DENSE_SCHUR
+    # as sfm.cc:67 configures Ceres = explicit reduced system + device Cholesky, no PCG
+    exact = None
+    if world == 1 and not args.no_exact_step and args.workload == "bal5m":
+        from deeparc_sfm_b200 import capi as _capi
+        pa = build_workload("arc1m")
+        e2 = _capi.Engine(device=local_rank)
+        e2.problem_set(pa)
+        od = solve_options(_capi, args.steps, args.pcg_iters, "dense")
+        e2.solve(solve_options(_capi, 3, args.pcg_iters, "dense"))
+        e2.params_reset()
+        torch.cuda.synchronize()
+        sd = e2.solve(od)
+        t0 = time.perf_counter()
+        e2.problem_set(pa)
+        sd2 = e2.solve(od)
+        e2.params_get()
+        t_e2e = time.perf_counter() - t0
+        e2.close()
+        nd = sd.num_iterations - 1
+        exact = {"workload": describe("arc1m", pa, args.pcg_iters, 1, "dense")["workload"],
+                 "linear_solver": "DENSE_SCHUR (DBA_LS_DENSE): k_schur_dense + k_dense_ldlt_small, 114 reduced unknowns",
+                 "value": nd / sd.loop_device_time_in_seconds if sd.loop_device_time_in_seconds > 0 else 0.0, "unit": UNIT,
+                 "steps": nd, "ms_per_step": 1e3 * sd.loop_device_time_in_seconds / max(nd, 1),
+                 "e2e": (sd2.num_iterations - 1) / t_e2e, "initial_cost": sd.initial_cost, "final_cost": sd.final_cost,
+                 "accepted_steps": int(sd.num_successful_steps), "linear_solver_failures": int(sd.linear_solver_failures)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done, "warmup": max(args.warmup, 3),
         "ms_per_step": 1e3 * loop_s / max(steps_done, 1), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": describe(args.workload, p, args.pcg_iters, world),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": describe(args.workload, p, args.pcg_iters, world, args.linear_solver),
         "clocks": dict(clocks, sampled="timed solve + identical solves repeated for 1 s") if clocks else None, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(steps_done, 1),
                                   "d2h_bytes_per_step": d2h / max(steps_done, 1), "seconds": e2e_s,
                                   "includes": "dba_problem_set (host sort + H2D) + dba_solve + dba_params_get (D2H)"},
         "gpu_launches": launches, "roofline": roof, "lm_iteration_model": lm_model, "cpu_baseline": cpu,
+        "cpu_baseline_same_algorithm": cpu_same, "exact_step": exact, "parity_vs_1gpu": parity_vs_1gpu,
+        "residual_tolerance": "tests: |dr| <= 1e-10 |r| + 64 eps |predicted px| (>= 99 % within the pure 1e-10 relative bound)",
         "jacobian_obs_per_sec": jac_obs_s, "jacobian_obs_per_sec_in_solve": jac_obs_s_in_solve, "accepted_steps": accepted, "final_cost": s.final_cost,
         "initial_cost": s.initial_cost, "ms_per_step_with_event_timers": 1e3 * loop2_s / max(steps_done, 1),
         "kernels": kernels,

@@ -348,6 +348,10 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # 200 cameras x 9 = 1800 reduced unknowns: the arm runs the algorithm the GPU arm times (implicit Schur
+    # PCG, same K) and says so; the DENSE_SCHUR time of one iteration is reported beside it
+    assert "PCG" in d["config"]["linear_solver"] and "PCG" in d["cpu_baseline"]["sample"]
+    assert d["cpu_baseline_dense_schur"]["value"] > 0 and "DENSE_SCHUR" in d["cpu_baseline_dense_schur"]["sample"]
 
 
 def test_bench_fails_loudly_without_a_device():
