@@ -311,6 +311,19 @@ int oracle_solve(const dba_problem* p, const dba_solve_options* o, dba_summary* 
       problem.SetParameterBlockConstant(blk[6]);
       problem.SetParameterBlockConstant(blk[7]);
     }
+    // implicit-Schur PCG mode only (a shim extension, used as the same-algorithm CPU baseline and for the
+    // fixed-K parity test): the preconditioner blocks are per camera, as in the GPU engine — rotation and
+    // translation of one extrinsic together, plus focal / distortion of its intrinsic when those are free
+    problem.SetParameterBlockPreconditionerGroup(blk[4], hp.pose_a[i]);
+    problem.SetParameterBlockPreconditionerGroup(blk[5], hp.pose_a[i]);
+    if (two) {
+      problem.SetParameterBlockPreconditionerGroup(blk[6], hp.pose_b[i]);
+      problem.SetParameterBlockPreconditionerGroup(blk[7], hp.pose_b[i]);
+    }
+    if (hp.free_intrinsics) {
+      problem.SetParameterBlockPreconditionerGroup(blk[2], hp.pose_a[i]);
+      if (hp.nd[it] > 0) problem.SetParameterBlockPreconditionerGroup(blk[3], hp.pose_a[i]);
+    }
     if (hp.freeze_camera) {  // sfm.cc:54-57
       for (size_t j = 1; j < blk.size(); ++j) problem.SetParameterBlockConstant(blk[j]);
     } else {                 // sfm.cc:58-63

@@ -228,6 +228,9 @@ class Problem {
   void AddParameterBlock(double* values, int size);
   void SetParameterBlockConstant(double* values);
   void SetParameterBlockVariable(double* values);
+  // (shim extension, not upstream) blocks with the same id >= 0 form one diagonal block of the
+  // block-Jacobi preconditioner of the implicit-Schur PCG mode; see mini_ceres.cc::SolveImplicit.
+  void SetParameterBlockPreconditionerGroup(double* values, int group);
   int NumResidualBlocks() const;
   int NumParameterBlocks() const;
 

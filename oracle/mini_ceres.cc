@@ -35,6 +35,7 @@ struct ParamRecord {
   double* user;
   int size;
   bool constant;
+  int group = -1;  // shim extension: preconditioner group of the implicit-Schur PCG (-1: the block alone)
 };
 
 struct ResidualRecord {
@@ -102,6 +103,17 @@ void Problem::SetParameterBlockConstant(double* values) {
   }
   impl_->params[it->second].constant = true;
 }
+// (shim extension) parameter blocks with the same group id >= 0 form ONE diagonal block of the
+// block-Jacobi preconditioner of the implicit-Schur PCG (SolveImplicit); no effect on DENSE_SCHUR.
+void Problem::SetParameterBlockPreconditionerGroup(double* values, int group) {
+  auto it = impl_->index_of.find(values);
+  if (it == impl_->index_of.end()) {
+    std::fprintf(stderr, "mini-ceres: SetParameterBlockPreconditionerGroup on an unknown block\n");
+    std::abort();
+  }
+  impl_->params[it->second].group = group;
+}
+
 void Problem::SetParameterBlockVariable(double* values) {
   auto it = impl_->index_of.find(values);
   if (it != impl_->index_of.end()) impl_->params[it->second].constant = false;
@@ -119,6 +131,7 @@ double Now() {
 // ---- reduced program ----------------------------------------------------------
 struct FreeBlock {
   double* user;
+  int group = -1;  // preconditioner group (shim extension)
   int size;
   int offset;     // offset in x (problem order)
   bool is_e;      // eliminated in the Schur complement
@@ -162,7 +175,7 @@ void Preprocess(internal::ProblemImpl* pi, bool want_schur, Program* prog) {
     const auto& pr = pi->params[i];
     if (!used[i] || pr.constant || pr.size == 0) continue;
     free_of[i] = static_cast<int>(prog->blocks.size());
-    prog->blocks.push_back(FreeBlock{pr.user, pr.size, offset, false, 0, 0});
+    prog->blocks.push_back(FreeBlock{pr.user, pr.group, pr.size, offset, false, 0, 0});
     offset += pr.size;
     prog->max_block = std::max(prog->max_block, pr.size);
   }
@@ -809,13 +822,36 @@ bool SolveImplicit(const Program& prog, const std::vector<double>& jac,
     ete_off[e + 1] = ete_off[e] + static_cast<size_t>(s) * s;
   }
   std::vector<double> ete_inv(ete_off[ne_blocks], 0.0);
-  // block-diagonal of S (per f block, size^2), b
-  std::vector<size_t> m_off(prog.num_f + 1, 0);
-  for (int f = 0; f < prog.num_f; ++f) {
-    const int s = prog.blocks[prog.f_block_ids[f]].size;
-    m_off[f + 1] = m_off[f] + static_cast<size_t>(s) * s;
+  // block-diagonal of S, b.  One diagonal block per PRECONDITIONER GROUP: the f-blocks that carry the
+  // same group id (the rotation / translation [/ focal / distortion] blocks of one camera when the
+  // caller says so, as the GPU engine's 6- or 9-dof camera blocks) or, without a group, the
+  // parameter block alone (what Ceres' SCHUR_JACOBI does with the reference's parameter blocks).
+  std::vector<int> g_of(prog.num_f, -1), f_goff(prog.num_f, 0), g_size;
+  std::vector<std::vector<int>> g_members;
+  {
+    std::unordered_map<int, int> seen;
+    for (int f = 0; f < prog.num_f; ++f) {
+      const FreeBlock& fb = prog.blocks[prog.f_block_ids[f]];
+      int g;
+      auto it = fb.group >= 0 ? seen.find(fb.group) : seen.end();
+      if (it != seen.end()) {
+        g = it->second;
+      } else {
+        g = static_cast<int>(g_size.size());
+        g_size.push_back(0);
+        g_members.emplace_back();
+        if (fb.group >= 0) seen.emplace(fb.group, g);
+      }
+      g_of[f] = g;
+      f_goff[f] = g_size[g];
+      g_size[g] += fb.size;
+      g_members[g].push_back(f);
+    }
   }
-  std::vector<double> M(m_off[prog.num_f], 0.0), b(nf, 0.0);
+  const int ng = static_cast<int>(g_size.size());
+  std::vector<size_t> m_off(ng + 1, 0);
+  for (int g = 0; g < ng; ++g) m_off[g + 1] = m_off[g] + static_cast<size_t>(g_size[g]) * g_size[g];
+  std::vector<double> M(m_off[ng], 0.0), b(nf, 0.0);
   bool ok = true;
   std::vector<std::vector<double>> Mp(nt), bp(nt);
 #pragma omp parallel num_threads(nt)
@@ -864,28 +900,51 @@ bool SolveImplicit(const Program& prog, const std::vector<double>& jac,
           for (int i = 0; i < es; ++i) t -= E[k * es + i] * ig[i];
           rr[k] = t;
         }
-        for (size_t s = 0; s < rb.user.size(); ++s) {
+        // F^T E and (F^T E) C^-1 of every f slot of this residual block
+        const int nslot = static_cast<int>(rb.user.size());
+        const int mb2 = prog.max_block * es;
+        fte.assign(static_cast<size_t>(nslot) * mb2, 0.0);
+        tmp.assign(static_cast<size_t>(nslot) * mb2, 0.0);
+        for (int s = 0; s < nslot; ++s) {
+          const int fid = rb.free_id[s];
+          if (fid < 0 || prog.blocks[fid].is_e) continue;
+          const int fs = prog.blocks[fid].size;
+          const double* F = jac.data() + rb.jac_off[s];
+          double* ft = fte.data() + static_cast<size_t>(s) * mb2;
+          double* tp = tmp.data() + static_cast<size_t>(s) * mb2;
+          for (int i = 0; i < fs; ++i)
+            for (int j = 0; j < es; ++j)
+              for (int k = 0; k < rb.nres; ++k) ft[i * es + j] += F[k * fs + i] * E[k * es + j];
+          for (int i = 0; i < fs; ++i)
+            for (int j = 0; j < es; ++j)
+              for (int k = 0; k < es; ++k) tp[i * es + j] += ft[i * es + k] * inv[k * es + j];
+        }
+        for (int s = 0; s < nslot; ++s) {
           const int fid = rb.free_id[s];
           if (fid < 0 || prog.blocks[fid].is_e) continue;
           const FreeBlock& fb = prog.blocks[fid];
           const double* F = jac.data() + rb.jac_off[s];
           const int fs = fb.size;
-          fte.assign(fs * es, 0.0);
-          tmp.assign(fs * es, 0.0);
-          for (int i = 0; i < fs; ++i)
-            for (int j = 0; j < es; ++j)
-              for (int k = 0; k < rb.nres; ++k) fte[i * es + j] += F[k * fs + i] * E[k * es + j];
-          for (int i = 0; i < fs; ++i)
-            for (int j = 0; j < es; ++j)
-              for (int k = 0; k < es; ++k) tmp[i * es + j] += fte[i * es + k] * inv[k * es + j];
-          double* Mb = Ml + m_off[fb.ef_index];
+          const int g = g_of[fb.ef_index], gs = g_size[g], oi = f_goff[fb.ef_index];
+          double* Mg = Ml + m_off[g];
+          const double* tps = tmp.data() + static_cast<size_t>(s) * mb2;
+          for (int s2 = 0; s2 < nslot; ++s2) {
+            const int fid2 = rb.free_id[s2];
+            if (fid2 < 0 || prog.blocks[fid2].is_e) continue;
+            const FreeBlock& fb2 = prog.blocks[fid2];
+            if (g_of[fb2.ef_index] != g) continue;
+            const double* F2 = jac.data() + rb.jac_off[s2];
+            const int fs2 = fb2.size, oj = f_goff[fb2.ef_index];
+            const double* ft2 = fte.data() + static_cast<size_t>(s2) * mb2;
+            for (int i = 0; i < fs; ++i)
+              for (int j = 0; j < fs2; ++j) {
+                double acc = 0.0;
+                for (int k = 0; k < rb.nres; ++k) acc += F[k * fs + i] * F2[k * fs2 + j];
+                for (int k = 0; k < es; ++k) acc -= tps[i * es + k] * ft2[j * es + k];
+                Mg[(oi + i) * gs + oj + j] += acc;
+              }
+          }
           for (int i = 0; i < fs; ++i) {
-            for (int j = 0; j < fs; ++j) {
-              double acc = 0.0;
-              for (int k = 0; k < rb.nres; ++k) acc += F[k * fs + i] * F[k * fs + j];
-              for (int k = 0; k < es; ++k) acc -= tmp[i * es + k] * fte[j * es + k];
-              Mb[i * fs + j] += acc;
-            }
             double acc = 0.0;
             for (int k = 0; k < rb.nres; ++k) acc += F[k * fs + i] * rr[k];
             bl[fb.ef_offset + i] += acc;
@@ -904,12 +963,20 @@ bool SolveImplicit(const Program& prog, const std::vector<double>& jac,
         const FreeBlock& fb = prog.blocks[fid];
         const double* F = jac.data() + rb.jac_off[s];
         const int fs = fb.size;
-        double* Mb = Ml + m_off[fb.ef_index];
-        for (int i = 0; i < fs; ++i) {
-          for (int j = 0; j < fs; ++j)
-            for (int k = 0; k < rb.nres; ++k) Mb[i * fs + j] += F[k * fs + i] * F[k * fs + j];
-          for (int k = 0; k < rb.nres; ++k) bl[fb.ef_offset + i] += F[k * fs + i] * res[k];
+        const int g = g_of[fb.ef_index], gs = g_size[g], oi = f_goff[fb.ef_index];
+        double* Mg = Ml + m_off[g];
+        for (size_t s2 = 0; s2 < rb.user.size(); ++s2) {
+          const int fid2 = rb.free_id[s2];
+          if (fid2 < 0 || g_of[prog.blocks[fid2].ef_index] != g) continue;
+          const FreeBlock& fb2 = prog.blocks[fid2];
+          const double* F2 = jac.data() + rb.jac_off[s2];
+          const int fs2 = fb2.size, oj = f_goff[fb2.ef_index];
+          for (int i = 0; i < fs; ++i)
+            for (int j = 0; j < fs2; ++j)
+              for (int k = 0; k < rb.nres; ++k) Mg[(oi + i) * gs + oj + j] += F[k * fs + i] * F2[k * fs2 + j];
         }
+        for (int i = 0; i < fs; ++i)
+          for (int k = 0; k < rb.nres; ++k) bl[fb.ef_offset + i] += F[k * fs + i] * res[k];
       }
     }
   }
@@ -918,22 +985,36 @@ bool SolveImplicit(const Program& prog, const std::vector<double>& jac,
     for (size_t i = 0; i < M.size(); ++i) M[i] += Mp[t][i];
     for (int i = 0; i < nf; ++i) b[i] += bp[t][i];
   }
-  // + D_f^2, invert the diagonal blocks
+  // + D_f^2, invert the diagonal blocks (one per group)
   std::vector<double> Minv(M.size(), 0.0);
-  for (int f = 0; f < prog.num_f; ++f) {
-    const FreeBlock& fb = prog.blocks[prog.f_block_ids[f]];
-    double* Mb = M.data() + m_off[f];
-    for (int i = 0; i < fb.size; ++i) Mb[i * fb.size + i] += D[fb.offset + i] * D[fb.offset + i];
-    if (!InvertSPD(Mb, fb.size, Minv.data() + m_off[f])) return false;
+  for (int g = 0; g < ng; ++g) {
+    double* Mg = M.data() + m_off[g];
+    const int gs = g_size[g];
+    for (int f : g_members[g]) {
+      const FreeBlock& fb = prog.blocks[prog.f_block_ids[f]];
+      for (int i = 0; i < fb.size; ++i) Mg[(f_goff[f] + i) * gs + f_goff[f] + i] += D[fb.offset + i] * D[fb.offset + i];
+    }
+    if (!InvertSPD(Mg, gs, Minv.data() + m_off[g])) return false;
   }
   auto apply_minv = [&](const std::vector<double>& r, std::vector<double>* z) {
-    for (int f = 0; f < prog.num_f; ++f) {
-      const FreeBlock& fb = prog.blocks[prog.f_block_ids[f]];
-      const double* Mi = Minv.data() + m_off[f];
-      for (int i = 0; i < fb.size; ++i) {
+    std::vector<double> rg, zg;
+    for (int g = 0; g < ng; ++g) {
+      const int gs = g_size[g];
+      rg.assign(gs, 0.0);
+      zg.assign(gs, 0.0);
+      for (int f : g_members[g]) {
+        const FreeBlock& fb = prog.blocks[prog.f_block_ids[f]];
+        for (int i = 0; i < fb.size; ++i) rg[f_goff[f] + i] = r[fb.ef_offset + i];
+      }
+      const double* Mi = Minv.data() + m_off[g];
+      for (int i = 0; i < gs; ++i) {
         double acc = 0.0;
-        for (int j = 0; j < fb.size; ++j) acc += Mi[i * fb.size + j] * r[fb.ef_offset + j];
-        (*z)[fb.ef_offset + i] = acc;
+        for (int j = 0; j < gs; ++j) acc += Mi[i * gs + j] * rg[j];
+        zg[i] = acc;
+      }
+      for (int f : g_members[g]) {
+        const FreeBlock& fb = prog.blocks[prog.f_block_ids[f]];
+        for (int i = 0; i < fb.size; ++i) (*z)[fb.ef_offset + i] = zg[f_goff[f] + i];
       }
     }
   };
