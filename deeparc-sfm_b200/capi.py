@@ -28,6 +28,7 @@ DBA_ERR_NUMERIC = -7
 
 DBA_LS_AUTO, DBA_LS_PCG, DBA_LS_DENSE = 0, 1, 2
 DBA_CONVERGENCE, DBA_NO_CONVERGENCE, DBA_FAILURE = 0, 1, 2
+DBA_LOSS_NONE, DBA_LOSS_CAUCHY = 0, 1
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -57,7 +58,7 @@ class DbaSolveOptions(C.Structure):
                 ("max_num_consecutive_invalid_steps", C.c_int32), ("linear_solver", C.c_int32),
                 ("pcg_max_iterations", C.c_int32), ("pcg_min_iterations", C.c_int32),
                 ("pcg_rel_tolerance", C.c_double), ("dense_max_size", C.c_int32),
-                ("progress_to_stdout", C.c_int32)]
+                ("progress_to_stdout", C.c_int32), ("loss_type", C.c_int32), ("loss_scale", C.c_double)]
 
 
 class DbaIteration(C.Structure):
@@ -109,6 +110,8 @@ def default_options_struct() -> DbaSolveOptions:
     o.pcg_rel_tolerance = 1e-12
     o.dense_max_size = 768
     o.progress_to_stdout = 0
+    o.loss_type = DBA_LOSS_NONE
+    o.loss_scale = 0.5
     return o
 
 

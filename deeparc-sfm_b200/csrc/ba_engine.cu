@@ -360,7 +360,7 @@ int setup_peer_windows(dba_handle* h, size_t nvec) {
   h->win_slot_cap = 0;
   if (ok < 0.5) return DBA_OK;
 
-  const size_t data_bytes = 2 * static_cast<size_t>(h->world) * slot_len * sizeof(double);
+  const size_t data_bytes = 2 * static_cast<size_t>(h->world) * slot_len * sizeof(uint4);
   const size_t bytes = data_bytes + flag_bytes;
   cudaIpcMemHandle_t mine{};
   if (cudaMalloc(&h->win_local, bytes) != cudaSuccess || cudaMemsetAsync(h->win_local, 0, bytes, h->st) != cudaSuccess ||
@@ -404,10 +404,8 @@ int setup_peer_windows(dba_handle* h, size_t nvec) {
   if (const char* t = std::getenv("DBA_P2P_TIMEOUT_MS")) pw.timeout_ns = std::max(1LL, std::atoll(t)) * 1000 * 1000;
   for (int r = 0; r < h->world; ++r) {
     char* base = static_cast<char*>(r == h->rank ? h->win_local : h->win_peer[r]);
-    pw.data[r] = reinterpret_cast<double*>(base);
-    pw.flags[r] = reinterpret_cast<unsigned long long*>(base + data_bytes);
+    pw.ll[r] = reinterpret_cast<uint4*>(base);
   }
-  pw.go = pw.flags[h->rank] + kMaxPeers;
   h->p2p_ready = true;
   return DBA_OK;
 }
@@ -820,7 +818,13 @@ void dba_destroy(dba_handle* h) {
   for (cudaEvent_t e : h->ev_solve)
     if (e) cudaEventDestroy(e);
   close_peer_windows(h);
-  if (h->comm) nccl_api().CommDestroy(h->comm);  // (a barrier in practice: peers have unmapped before the window goes)
+  if (h->comm && h->win_local && h->d_scalars_red.p) {
+    // explicit barrier (dba_destroy is collective): every peer has closed its mapping of this rank's
+    // window before the exported memory is freed
+    if (nccl_api().AllReduce(h->d_scalars_red.p, h->d_scalars_red.p, 1, kNcclFloat64, kNcclSum, h->comm, h->st) == 0)
+      cudaStreamSynchronize(h->st);
+  }
+  if (h->comm) nccl_api().CommDestroy(h->comm);
   if (h->win_local) cudaFree(h->win_local);
   delete h->upload;
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -1704,6 +1708,7 @@ int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, dou
   const bool per_obs = residuals || jac_pt || jac_pose_a || jac_pose_b || jac_intr;
   if (per_obs && h->world > 1)
     return h->fail(DBA_ERR_UNSUPPORTED, "per-observation outputs need a single-GPU handle");
+  h->D.loss_type = 0;  // dba_eval reports the raw functor (no loss), like Problem::Evaluate with apply_loss_function = false
   const DeviceProblem& D0 = h->D;
   const ParamSet& P = h->P[h->cur];
   const bool want_jac = jac_pt || jac_pose_a || jac_pose_b || jac_intr;
@@ -1797,6 +1802,7 @@ int dba_filter_mse(dba_handle* h, double* mse) {
   if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
   if (h->world > 1) return h->fail(DBA_ERR_UNSUPPORTED, "per-observation outputs need a single-GPU handle");
   CU(h, cudaSetDevice(h->device));
+  h->D.loss_type = 0;  // the filter re-evaluates the plain functor (DeepArcManager.cc:335-347)
   const ParamSet& P = h->P[h->cur];
   DevBuf<double> d;
   CU(h, d.alloc(std::max<int64_t>(h->n_obs, 1)));
@@ -1821,6 +1827,7 @@ int dba_filter(dba_handle* h, double error_boundary, const double* centre, doubl
   if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
   if (h->world > 1) return h->fail(DBA_ERR_UNSUPPORTED, "per-observation outputs need a single-GPU handle");
   CU(h, cudaSetDevice(h->device));
+  h->D.loss_type = 0;
   const ParamSet& P = h->P[h->cur];
   const int64_t n = h->n_obs;
   const int n_pts = h->n_pts;
@@ -1882,6 +1889,8 @@ void dba_solve_options_default(dba_solve_options* o) {
   o->pcg_rel_tolerance = 1e-12;
   o->dense_max_size = 768;
   o->progress_to_stdout = 0;
+  o->loss_type = DBA_LOSS_NONE;
+  o->loss_scale = 0.5;  // the value in the reference's commented-out CauchyLoss (sfm.cc:49)
 }
 
 int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
@@ -1913,6 +1922,20 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     }
   }
   sum->linear_solver_used = (h->use_dense || !h->cb) ? DBA_LS_DENSE : DBA_LS_PCG;
+  // robust loss (reference sfm.cc:49, commented out there): applied inside the Jacobian / cost kernels
+  if (o.loss_type != DBA_LOSS_NONE && o.loss_type != DBA_LOSS_CAUCHY) return h->fail(DBA_ERR_INVALID_ARGUMENT, "unknown loss_type %d", o.loss_type);
+  if (o.loss_type == DBA_LOSS_CAUCHY && !(o.loss_scale > 0.0)) return h->fail(DBA_ERR_INVALID_ARGUMENT, "loss_scale must be positive");
+  h->D.loss_type = o.loss_type;
+  h->D.loss_b = o.loss_scale * o.loss_scale;
+  h->D.loss_c = o.loss_type ? 1.0 / h->D.loss_b : 0.0;
+  // the matrix-free product recomputes the UNcorrected Jacobian from the camera rows: with a loss
+  // the product reads the (corrected) planes instead
+  struct MfGuard {
+    dba_handle* h;
+    int saved;
+    ~MfGuard() { h->mf = saved; }
+  } mf_guard{h, h->mf};
+  if (o.loss_type != DBA_LOSS_NONE) h->mf = 0;
   h->dense_failures = 0;
   h->pcg_unconverged = 0;
   h->pcg_pending = false;

@@ -165,9 +165,20 @@ __device__ __forceinline__ double jacobian_obs(const DeviceProblem& D, int64_t o
   observation_jacobian(A, B, I, X, xy.x, xy.y, CB > 0, j);
   double2* J = D.J + o;
   const int64_t ld = D.ld;
+  // robust loss (Ceres corrector.cc; Cauchy has rho'' < 0, so residuals and Jacobian are simply
+  // scaled by sqrt(rho')): cost term rho(s), planes of the corrected r~, J~
+  double cost_term = j.r0 * j.r0 + j.r1 * j.r1;
+  double lw = 1.0;
+  if (D.loss_type == 1) {
+    const double sum = 1.0 + cost_term * D.loss_c;
+    lw = sqrt(fmax(DBL_MIN, 1.0 / sum));
+    cost_term = D.loss_b * log(sum);
+    j.r0 *= lw;
+    j.r1 *= lw;
+  }
   J[kPlaneR * ld] = make_double2(j.r0, j.r1);
   {
-    const double s0 = sp ? sp[0] : 1.0, s1 = sp ? sp[1] : 1.0, s2 = sp ? sp[2] : 1.0;
+    const double s0 = (sp ? sp[0] : 1.0) * lw, s1 = (sp ? sp[1] : 1.0) * lw, s2 = (sp ? sp[2] : 1.0) * lw;
     J[(kPlaneJp + 0) * ld] = make_double2(j.Jp[0][0] * s0, j.Jp[1][0] * s0);
     J[(kPlaneJp + 1) * ld] = make_double2(j.Jp[0][1] * s1, j.Jp[1][1] * s1);
     J[(kPlaneJp + 2) * ld] = make_double2(j.Jp[0][2] * s2, j.Jp[1][2] * s2);
@@ -175,10 +186,10 @@ __device__ __forceinline__ double jacobian_obs(const DeviceProblem& D, int64_t o
   if (CB >= 6) {
     double s[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s[k] = 1.0;
+    for (int k = 0; k < 9; ++k) s[k] = lw;
     if (scA) {
 #pragma unroll
-      for (int k = 0; k < CB; ++k) s[k] = scA[k];
+      for (int k = 0; k < CB; ++k) s[k] = scA[k] * lw;
 #pragma unroll
       for (int k = 0; k < 6; ++k) s[k] *= A.free_;  // constant pose: its six columns vanish
     }
@@ -198,10 +209,10 @@ __device__ __forceinline__ double jacobian_obs(const DeviceProblem& D, int64_t o
     if (TWO) {
       const int pb = kPlaneJA + CB;
       if (B) {
-        double sb[6] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+        double sb[6] = {lw, lw, lw, lw, lw, lw};
         if (scB) {
 #pragma unroll
-          for (int k = 0; k < 6; ++k) sb[k] = scB[k] * B->free_;
+          for (int k = 0; k < 6; ++k) sb[k] = scB[k] * B->free_ * lw;
         }
         double2 FB[6];
 #pragma unroll
@@ -217,7 +228,7 @@ __device__ __forceinline__ double jacobian_obs(const DeviceProblem& D, int64_t o
       }
     }
   }
-  return j.r0 * j.r0 + j.r1 * j.r1;
+  return cost_term;
 }
 
 // One thread per observation (point-sorted).  Reads 16 B (xy) + 8 B (indices) + L1/L2-resident
@@ -323,6 +334,7 @@ __global__ void __launch_bounds__(256) k_cost(DeviceProblem D, ParamSet P, doubl
     project<false>(P.intr_rows[idx.x], f.cam, xy.x, xy.y, pr);
     c = pr.r0 * pr.r0 + pr.r1 * pr.r1;
     if (mse_out) mse_out[o] = c / 2.0;
+    if (D.loss_type == 1) c = D.loss_b * log(1.0 + c * D.loss_c);
   }
   c = block_sum(c, red);
   if (threadIdx.x == 0 && partial_cost) partial_cost[blockIdx.x] = c;
@@ -1440,13 +1452,13 @@ __global__ void __launch_bounds__(256) k_pcg_direction(DeviceProblem D, WorkArra
   if (i < n) W.p[i] = W.z[i] + W.pcg_scal[3] * W.p[i];
 }
 
-// system-scope flag accesses of the peer exchange
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// 16-byte records of the LL exchange: one vector store / one volatile vector load
+__device__ __forceinline__ void ll_store(uint4* p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ll_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ long long global_ns() {
@@ -1546,10 +1558,14 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
         q *= Tm[9 + lane];
       }
       if (exchange) {
-        // push this rank's share of q into slot `rank` of every window (own window included)
+        // push this rank's share of q into slot `rank` of every window (own window included) as a
+        // self-validating record {low half, seq, high half, seq}: the flag travels with the data, so the
+        // exchange needs no fence, no separate flag and no grid-wide barrier (NCCL's LL protocol)
         const long long off = buf_off + static_cast<long long>(pw.rank) * pw.slot_len + i;
+        const unsigned int sq = static_cast<unsigned int>(pw.seq);
+        const uint4 rec = make_uint4(static_cast<unsigned int>(__double2loint(q)), sq, static_cast<unsigned int>(__double2hiint(q)), sq);
 #pragma unroll 1
-        for (int r = 0; r < pw.world; ++r) pw.data[r][off] = q;
+        for (int r = 0; r < pw.world; ++r) ll_store(pw.ll[r] + off, rec);
       } else {
         const double p = W.p[i];
         q += W.dc2[i] * p;
@@ -1559,45 +1575,33 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
     }
   }
   if (exchange) {
-    __threadfence_system();  // the pushed values are visible system-wide before any flag is raised
-    grid.sync();
-    if (blockIdx.x == 0) {
-      if (tid < pw.world && tid != pw.rank) st_release_sys(pw.flags[tid] + pw.rank, pw.seq);
-      int ok = 1;
-      if (tid < pw.world && tid != pw.rank) {
-        const long long t0 = global_ns();
-        while (ld_acquire_sys(pw.flags[pw.rank] + tid) < pw.seq) {
-          if (global_ns() - t0 > pw.timeout_ns) {
-            ok = 0;
-            break;
-          }
-          __nanosleep(100);
-        }
-      }
-      ok = __syncthreads_and(ok);
-      if (tid == 0) {
-        if (!ok) {
-          W.pcg_state[2] = 1;
-          W.pcg_state[1] = 1;
-        }
-        st_release_sys(pw.go, ok ? pw.seq : ~0ull);
-        *s_flag = ok;
-      }
-    } else if (tid == 0) {
-      unsigned long long g;
-      while ((g = ld_acquire_sys(pw.go)) < pw.seq) __nanosleep(50);
-      *s_flag = g != ~0ull;
-    }
-    __syncthreads();
-    if (!*s_flag) return;  // every CTA takes the same exit: no grid.sync is left half-attended
-    // q = sum of the slots in rank order (the same order on every rank) + D_c^2 p
-    const double* mine = pw.data[pw.rank] + buf_off;
+    // q = sum of the slots in rank order (the same order on every rank) + D_c^2 p; a record is consumed
+    // as soon as both halves carry this exchange's sequence number.  A peer that never delivers raises
+    // the error flag after the timeout; the launch still runs to its end (every grid.sync is attended).
+    const uint4* mine = pw.ll[pw.rank] + buf_off;
+    const unsigned int sq = static_cast<unsigned int>(pw.seq);
     for (int blk = gwarp; blk < nb; blk += n_warps) {
       if (lane < CB) {
         const int64_t i = static_cast<int64_t>(blk) * CB + lane;
         double q = 0.0;
 #pragma unroll 1
-        for (int r = 0; r < pw.world; ++r) q += __ldcg(mine + static_cast<long long>(r) * pw.slot_len + i);
+        for (int r = 0; r < pw.world; ++r) {
+          const uint4* src = mine + static_cast<long long>(r) * pw.slot_len + i;
+          uint4 rec = ll_load(src);
+          if (rec.y != sq || rec.w != sq) {
+            const long long t0 = global_ns();
+            do {
+              rec = ll_load(src);
+              if (*reinterpret_cast<volatile int*>(W.pcg_state + 2)) break;  // somebody already gave up: do not wait again
+              if (global_ns() - t0 > pw.timeout_ns) {
+                W.pcg_state[2] = 1;
+                W.pcg_state[1] = 1;
+                break;
+              }
+            } while (rec.y != sq || rec.w != sq);
+          }
+          q += __hiloint2double(static_cast<int>(rec.z), static_cast<int>(rec.x));
+        }
         const double p = W.p[i];
         q += W.dc2[i] * p;
         W.q[i] = q;

@@ -75,6 +75,9 @@ struct DeviceProblem {
   const int* part_blk;              // [n_partials] camera block of partial g (rows staged by k_jacobian_tile)
   const ushort2* obs_lc;            // [n_obs] tile-local camera block (= partial) of block a / block b (0xffff: none)
   int intr_is_pose;                 // every observation uses intrinsic == block a (per-camera intrinsics)
+  // robust loss of the running solve (dba_solve_options.loss_type): 0 none, 1 Cauchy with b = a^2, c = 1 / b
+  int loss_type;
+  double loss_b, loss_c;
 };
 
 __host__ __device__ constexpr int mf_row_len(int cb) { return cb == 9 ? 24 : 20; }  // multiples of 4 doubles (256-bit loads)
@@ -125,20 +128,19 @@ struct WorkArrays {
 };
 
 // Peer windows of the fused PCG tail (multi-GPU): every rank owns one window in its HBM,
-//   data  [2 buffers][world slots][slot_len] doubles   slot s = camera-space vector pushed by rank s
-//   flags [world] u64 | go u64                         flags[s] = last exchange whose slot s is complete
+//   ll [2 buffers][world slots][slot_len] 16-byte records   slot s = camera-space vector pushed by rank s
 // mapped into the other ranks through CUDA IPC, so a rank PUSHES its partial q = S p straight into
-// the HBM of every peer over NVLink (plain stores), raises the flags, waits for its own flags and
-// sums the slots in rank order (bit-identical on every rank, no NCCL call on the PCG path).
+// the HBM of every peer over NVLink.  A record is {low half, seq, high half, seq} of one double: each
+// 8-byte half validates itself (NCCL's LL protocol), so the receiver simply polls the record it
+// needs — no fence, no flag round trip, no grid-wide barrier around the exchange — and adds the
+// slots in rank order (bit-identical on every rank, no NCCL call on the PCG path).
 constexpr int kMaxPeers = 8;
 struct PeerWin {
   int world = 1, rank = 0;
   unsigned long long seq = 0;   // number of this exchange (1, 2, ...), identical on every rank
-  long long slot_len = 0;       // doubles per slot
+  long long slot_len = 0;       // records per slot
   long long timeout_ns = 0;     // give up waiting for a peer after this long (error flag, no hang)
-  double* data[kMaxPeers] = {};
-  unsigned long long* flags[kMaxPeers] = {};
-  unsigned long long* go = nullptr;  // local: CTA 0 publishes `seq` (all slots in) or ~0 (timeout)
+  uint4* ll[kMaxPeers] = {};
 };
 
 // Explicit reduced system + Cholesky (ba_dense.cu): DENSE_SCHUR for small camera counts.

@@ -112,6 +112,14 @@ typedef enum dba_linear_solver {
                        DBA_ERR_UNSUPPORTED — it never substitutes the PCG silently.      */
 } dba_linear_solver;
 
+typedef enum dba_loss {
+  DBA_LOSS_NONE = 0,   /* cost = 1/2 sum |r|^2 (as shipped)                                    */
+  DBA_LOSS_CAUCHY = 1  /* cost = 1/2 sum rho(|r|^2); residuals and Jacobians of every observation
+                          are rescaled by sqrt(rho') inside the Jacobian kernel (Ceres' corrector;
+                          rho'' < 0 for Cauchy, so the rank-one term vanishes).  The implicit Schur
+                          product then runs on the materialised planes.                          */
+} dba_loss;
+
 typedef struct dba_solve_options {
   int32_t max_num_iterations;             /* reference: 100 (sfm.cc:111,121)            */
   double max_solver_time_in_seconds;      /* reference: 3600                            */
@@ -133,6 +141,9 @@ typedef struct dba_solve_options {
   int32_t dense_max_size;                 /* DBA_LS_AUTO picks DBA_LS_DENSE up to this many
                                              reduced unknowns (default 768)             */
   int32_t progress_to_stdout;             /* reference: true (sfm.cc:68)                */
+  int32_t loss_type;                      /* dba_loss.  The reference passes NULL (sfm.cc:48) and
+                                             keeps `new ceres::CauchyLoss(0.5)` in a comment (:49) */
+  double loss_scale;                      /* a of CauchyLoss(a): rho(s) = a^2 log(1 + s / a^2)  */
 } dba_solve_options;
 
 typedef enum dba_termination {

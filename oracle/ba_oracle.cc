@@ -302,7 +302,9 @@ int oracle_solve(const dba_problem* p, const dba_solve_options* o, dba_summary* 
     const bool two = hp.pose_b[i] >= 0;
     ceres::CostFunction* c = MakeReprojectionCost(hp.obs_xy[2 * i], hp.obs_xy[2 * i + 1], hp.nf[it], hp.nd[it], two);
     std::vector<double*> blk = hp.Blocks(i);
-    problem.AddResidualBlock(c, NULL, blk);  // sfm.cc:48, no loss
+    // sfm.cc:48 passes NULL; sfm.cc:49 keeps `new ceres::CauchyLoss(0.5)` in a comment
+    ceres::LossFunction* loss = (o && o->loss_type == DBA_LOSS_CAUCHY) ? new ceres::CauchyLoss(o->loss_scale) : NULL;
+    problem.AddResidualBlock(c, loss, blk);
     if (hp.ext_const[hp.pose_a[i]]) {        // gauge rule, resolved by the caller into a mask
       problem.SetParameterBlockConstant(blk[4]);
       problem.SetParameterBlockConstant(blk[5]);

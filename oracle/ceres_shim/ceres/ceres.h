@@ -33,6 +33,7 @@
 #include <set>
 #include <string>
 #include <utility>
+#include <limits>
 #include <vector>
 
 #include "Eigen/Core"
@@ -64,9 +65,28 @@ class CostFunction {
   int num_residuals_;
 };
 
+// [Ceres-upstream loss_function.h]  rho(s) of the squared residual norm s: out = {rho, rho', rho''}.
+// The reference passes NULL (sfm.cc:48) and carries `new ceres::CauchyLoss(0.5)` in a comment (:49).
 class LossFunction {
  public:
   virtual ~LossFunction() {}
+  virtual void Evaluate(double sq_norm, double out[3]) const = 0;
+};
+
+// [Ceres-upstream loss_function.cc]  rho(s) = b log(1 + s / b), b = a^2
+class CauchyLoss : public LossFunction {
+ public:
+  explicit CauchyLoss(double a) : b_(a * a), c_(1.0 / b_) {}
+  void Evaluate(double s, double rho[3]) const override {
+    const double sum = 1.0 + s * c_;
+    const double inv = 1.0 / sum;
+    rho[0] = b_ * std::log(sum);
+    rho[1] = std::max(std::numeric_limits<double>::min(), inv);
+    rho[2] = -c_ * (inv * inv);
+  }
+
+ private:
+  const double b_, c_;
 };
 
 // Evaluates the functor with Jet<double,Stride> in ceil(active/Stride) passes

@@ -41,6 +41,7 @@ struct ParamRecord {
 struct ResidualRecord {
   CostFunction* cost;
   std::vector<double*> params;
+  LossFunction* loss = nullptr;
 };
 
 class ProblemImpl {
@@ -49,6 +50,7 @@ class ProblemImpl {
   std::unordered_map<double*, int> index_of;
   std::vector<ResidualRecord> residuals;
   std::set<CostFunction*> owned;
+  std::set<LossFunction*> owned_loss;
 
   int Intern(double* p, int size) {
     auto it = index_of.find(p);
@@ -72,15 +74,12 @@ class ProblemImpl {
 Problem::Problem() : impl_(new internal::ProblemImpl) {}
 Problem::~Problem() {
   for (CostFunction* c : impl_->owned) delete c;
+  for (LossFunction* l : impl_->owned_loss) delete l;
   delete impl_;
 }
 
 void* Problem::AddResidualBlock(CostFunction* cost_function, LossFunction* loss_function,
                                 const std::vector<double*>& parameter_blocks) {
-  if (loss_function != NULL) {
-    std::fprintf(stderr, "mini-ceres: loss functions are not supported (reference passes NULL)\n");
-    std::abort();
-  }
   const std::vector<int32_t>& sizes = cost_function->parameter_block_sizes();
   if (sizes.size() != parameter_blocks.size()) {
     std::fprintf(stderr, "mini-ceres: cost function expects %zu parameter blocks, got %zu\n",
@@ -88,8 +87,9 @@ void* Problem::AddResidualBlock(CostFunction* cost_function, LossFunction* loss_
     std::abort();
   }
   for (size_t i = 0; i < sizes.size(); ++i) impl_->Intern(parameter_blocks[i], sizes[i]);
-  impl_->residuals.push_back(internal::ResidualRecord{cost_function, parameter_blocks});
+  impl_->residuals.push_back(internal::ResidualRecord{cost_function, parameter_blocks, loss_function});
   impl_->owned.insert(cost_function);
+  if (loss_function != NULL) impl_->owned_loss.insert(loss_function);  // TAKE_OWNERSHIP, possibly shared
   return &impl_->residuals.back();
 }
 
@@ -141,6 +141,7 @@ struct FreeBlock {
 
 struct RBlock {
   const CostFunction* cost;
+  const LossFunction* loss = nullptr;
   int nres;
   int row;                     // first residual row
   std::vector<double*> user;   // user pointers, one per cost-function slot
@@ -187,6 +188,7 @@ void Preprocess(internal::ProblemImpl* pi, bool want_schur, Program* prog) {
   for (const auto& rr : pi->residuals) {
     RBlock rb;
     rb.cost = rr.cost;
+    rb.loss = rr.loss;
     rb.nres = rr.cost->num_residuals();
     rb.user = rr.params;
     rb.e_slot = -1;
@@ -202,6 +204,11 @@ void Preprocess(internal::ProblemImpl* pi, bool want_schur, Program* prog) {
       rr.cost->Evaluate(rr.params.data(), r.data(), NULL);
       double c = 0.0;
       for (double v : r) c += v * v;
+      if (rr.loss != NULL) {
+        double rho[3];
+        rr.loss->Evaluate(c, rho);
+        c = rho[0];
+      }
       prog->fixed_cost += 0.5 * c;
       continue;
     }
@@ -321,7 +328,46 @@ bool Evaluate(const Program& prog, const double* x, bool want_jac, double* cost,
 #pragma omp atomic write
         ok = false;
       }
-      for (int k = 0; k < rb.nres; ++k) total += res[k] * res[k];
+      double sq = 0.0;
+      for (int k = 0; k < rb.nres; ++k) sq += res[k] * res[k];
+      if (rb.loss == NULL) {
+        total += sq;
+        continue;
+      }
+      // robust loss [Ceres-upstream residual_block.cc + corrector.cc]: cost 1/2 rho(s); the residuals
+      // and Jacobians handed to the linear solver are corrected so that J~^T J~ is the Gauss-Newton
+      // (Triggs) approximation of the robustified Hessian
+      double rho[3];
+      rb.loss->Evaluate(sq, rho);
+      total += rho[0];
+      const double sqrt_rho1 = std::sqrt(rho[1]);
+      double residual_scaling, alpha_sq_norm;
+      if (sq == 0.0 || rho[2] <= 0.0) {
+        residual_scaling = sqrt_rho1;
+        alpha_sq_norm = 0.0;
+      } else {
+        const double D = 1.0 + 2.0 * sq * rho[2] / rho[1];
+        const double alpha = 1.0 - std::sqrt(D);
+        residual_scaling = sqrt_rho1 / (1 - alpha);
+        alpha_sq_norm = alpha / sq;
+      }
+      if (want_jac) {
+        for (int s = 0; s < ns; ++s) {
+          if (jj[s] == NULL) continue;
+          const int bs = prog.blocks[rb.free_id[s]].size;
+          double* J = jj[s];
+          if (alpha_sq_norm == 0.0) {
+            for (int i = 0; i < rb.nres * bs; ++i) J[i] *= sqrt_rho1;
+          } else {
+            for (int c = 0; c < bs; ++c) {
+              double r_dot_j = 0.0;
+              for (int k = 0; k < rb.nres; ++k) r_dot_j += J[k * bs + c] * res[k];
+              for (int k = 0; k < rb.nres; ++k) J[k * bs + c] = sqrt_rho1 * (J[k * bs + c] - alpha_sq_norm * res[k] * r_dot_j);
+            }
+          }
+        }
+      }
+      for (int k = 0; k < rb.nres; ++k) res[k] *= residual_scaling;
     }
   }
   *cost = 0.5 * total;

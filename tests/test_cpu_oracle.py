@@ -172,6 +172,41 @@ def test_minimizer_reaches_scipy_optimum(oracle):
     assert s.termination == capi.DBA_CONVERGENCE
 
 
+def test_cauchy_loss_reaches_scipy_optimum(oracle):
+    """The robust loss the reference keeps in a comment (`new ceres::CauchyLoss(0.5)`, sfm.cc:49): the
+    oracle's corrector restatement minimises 1/2 sum a^2 log(1 + |r|^2 / a^2) — the same optimum and cost
+    as scipy's loss='cauchy' applied to the per-observation residual norm."""
+    p = synthetic.bal_like(n_cam=6, n_pts=60, obs_per_point=4, window=6, seed=43, free_intrinsics=0)
+    rng = np.random.default_rng(9)
+    bad = rng.choice(p.n_obs, size=12, replace=False)
+    p.obs_xy[bad] += rng.normal(0.0, 40.0, size=(12, 2))  # gross outliers
+    a = 2.0
+    kw = dict(max_num_iterations=400, function_tolerance=1e-15, gradient_tolerance=1e-14, parameter_tolerance=1e-14,
+              linear_solver=capi.DBA_LS_DENSE)
+    s, x = oracle.solve(p, capi.make_options(loss_type=capi.DBA_LOSS_CAUCHY, loss_scale=a, **kw))
+    s_plain, _ = oracle.solve(p, capi.make_options(**kw))
+    free_ext = np.flatnonzero(p.ext_const == 0)
+
+    def fun(z):
+        q = p.copy()
+        q.pts = z[:3 * p.n_pts].reshape(-1, 3)
+        rest = z[3 * p.n_pts:].reshape(-1, 6)
+        q.ext_rot = p.ext_rot.copy()
+        q.ext_trans = p.ext_trans.copy()
+        q.ext_rot[free_ext] = rest[:, :3]
+        q.ext_trans[free_ext] = rest[:, 3:]
+        return np.linalg.norm(oracle.eval(q)["residuals"], axis=1)
+
+    z0 = np.concatenate([x["pts"].reshape(-1), np.concatenate([x["ext_rot"][free_ext], x["ext_trans"][free_ext]], axis=1).reshape(-1)])
+    r = fun(z0)
+    cost_at_x = 0.5 * np.sum(a * a * np.log1p(r * r / (a * a)))
+    assert abs(s.final_cost - cost_at_x) <= 1e-10 * cost_at_x            # the reported cost is 1/2 sum rho
+    ref = scipy.optimize.least_squares(fun, z0, method="trf", loss="cauchy", f_scale=a, xtol=1e-15, ftol=1e-15, gtol=1e-12,
+                                       max_nfev=300)
+    assert abs(ref.cost - s.final_cost) <= 1e-7 * s.final_cost            # scipy cannot improve on the oracle's optimum
+    assert s.final_cost < 0.5 * s_plain.final_cost                        # and the outliers no longer dominate
+
+
 def test_dense_and_implicit_schur_agree(oracle):
     p = synthetic.bal_like(n_cam=20, n_pts=400, window=8, seed=42)
     kw = dict(max_num_iterations=5, function_tolerance=0.0, gradient_tolerance=0.0, parameter_tolerance=0.0)
