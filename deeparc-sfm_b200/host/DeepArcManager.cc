@@ -16,6 +16,11 @@
 #include <stdexcept>
 #include <unordered_map>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "ba_client.hh"
 #include "rotation_conv.hh"
 
@@ -26,7 +31,7 @@ namespace {
 // ~10x faster than iostream extraction, which matters at 5-50 M observation lines.
 class Tokens {
  public:
-  explicit Tokens(const std::string& data) : p_(data.c_str()) {}  // the caller keeps `data` alive
+  explicit Tokens(const char* data) : p_(data) {}  // NUL-terminated image; the caller keeps it alive
   const char* pos() const { return p_; }
   void seek(const char* p) { p_ = p; }
   bool nextDouble(double* v) {
@@ -191,28 +196,237 @@ int DeepArcManager::ringSlot(int ring_position, int arc_size) {
 // and linked by all host cores (at 5-50 M observation lines the reference's
 // iostream loader takes longer than the GPU solve by two orders of magnitude); the small sections
 // and any file the strict parallel parser does not accept go through the serial tokenizer.
+namespace {
+// The file image: mmap'ed (no copy; the kernel reads ahead while the parser threads run), or read
+// into memory when the size is an exact number of pages (the text tokenizer wants a NUL after the
+// last byte, which the zero-filled tail of the last mapped page provides otherwise).
+struct FileImage {
+  const char* data = nullptr;
+  size_t size = 0;
+  void* map = nullptr;
+  size_t map_len = 0;
+  std::string owned;
+  bool open(const std::string& filename) {
+    const int fd = ::open(filename.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (::fstat(fd, &st) != 0) {
+      ::close(fd);
+      return false;
+    }
+    size = static_cast<size_t>(st.st_size);
+    const size_t page = static_cast<size_t>(::sysconf(_SC_PAGESIZE));
+    if (size > 0 && size % page != 0) {
+      void* m = ::mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+      if (m != MAP_FAILED) {
+        ::madvise(m, size, MADV_SEQUENTIAL | MADV_WILLNEED);
+        map = m;
+        map_len = size;
+        data = static_cast<const char*>(m);
+        ::close(fd);
+        return true;
+      }
+    }
+    owned.resize(size);
+    size_t got = 0;
+    while (got < size) {
+      const ssize_t n = ::read(fd, &owned[got], size - got);
+      if (n <= 0) break;
+      got += static_cast<size_t>(n);
+    }
+    owned.resize(got);
+    size = got;
+    data = owned.c_str();
+    ::close(fd);
+    return true;
+  }
+  ~FileImage() {
+    if (map) ::munmap(map, map_len);
+  }
+};
+
+// ---- binary side format (".deeparcb").  The text format keeps six decimals
+// (DeepArcManager.cc:428), so a text round trip is lossy; this one stores the scene bit for bit and
+// loads at memcpy speed.  Little-endian, all sections 8-byte aligned:
+//   char magic[8] = "DEEPARCB"; u32 version = 1; u32 reserved;
+//   i64 n_obs; i32 n_intr, n_arc, n_ring (0: non-shared), n_pts, n_ext, pad;
+//   i32 col0[n_obs] (pos_arc | intrinsic id)  i32 col1[n_obs] (pos_ring | extrinsic id)  i32 point[n_obs]  (+pad)
+//   f64 xy[n_obs][2]
+//   per intrinsic: f64 cx, cy, f0, f1, k0, k1; i32 nf, nd      per extrinsic: f64 t[3], aa[3]
+//   f64 xyz[n_pts][3]; i32 rgb[n_pts][3] (+pad)
+constexpr char kBinMagic[8] = {'D', 'E', 'E', 'P', 'A', 'R', 'C', 'B'};
+struct BinHeader {
+  char magic[8];
+  uint32_t version, reserved;
+  int64_t n_obs;
+  int32_t n_intr, n_arc, n_ring, n_pts, n_ext, pad;
+};
+struct BinIntrinsic {
+  double cx, cy, f0, f1, k0, k1;
+  int32_t nf, nd;
+};
+struct BinExtrinsic {
+  double t[3], aa[3];
+};
+inline size_t pad8(size_t n) { return (n + 7) & ~size_t{7}; }
+}  // namespace
+
+// DeepArcManager.cc:26-74.  The two O(n) sections (observations, points) are parsed, allocated
+// and linked by all host cores (at 5-50 M observation lines the reference's
+// iostream loader takes longer than the GPU solve by two orders of magnitude); the small sections
+// and any file the strict parallel parser does not accept go through the serial tokenizer.
+// A file that starts with the binary magic is loaded by readBinary.
 bool DeepArcManager::read(std::string filename) {
-  std::FILE* fp = std::fopen(filename.c_str(), "rb");
-  if (!fp) {
+  FileImage img;
+  if (!img.open(filename)) {
     std::cout << "Cannot read " << filename << std::endl;
     throw "Cannot read input file";
   }
-  std::string data;
-  std::fseek(fp, 0, SEEK_END);
-  const long size = std::ftell(fp);
-  std::fseek(fp, 0, SEEK_SET);
-  if (size > 0) {
-    data.resize(static_cast<size_t>(size));
-    const size_t got = std::fread(&data[0], 1, data.size(), fp);
-    data.resize(got);
+  if (img.size >= sizeof(BinHeader) && std::memcmp(img.data, kBinMagic, 8) == 0) {
+    if (!readBinary(img.data, img.size)) throw "Corrupt binary deeparc file";
+    return true;
   }
-  std::fclose(fp);
   const char* serial = std::getenv("DEEPARC_SERIAL_IO");
   const bool parallel = !(serial && serial[0] == '1');
-  if (parallel && readText(data, true)) return true;
+  if (parallel && readText(img.data, img.size, true)) return true;
   if (parallel) clearScene();  // the strict parser met a token it does not take: start over
-  readText(data, false);
+  readText(img.data, img.size, false);
   return true;
+}
+
+bool DeepArcManager::readBinary(const char* data, size_t size) {
+  BinHeader h;
+  std::memcpy(&h, data, sizeof h);
+  if (h.version != 1 || h.n_obs < 0 || h.n_intr < 0 || h.n_pts < 0 || h.n_ext < 0) return false;
+  const size_t n = static_cast<size_t>(h.n_obs);
+  size_t off = sizeof(BinHeader);
+  const size_t o_col0 = off, o_col1 = o_col0 + 4 * n, o_pid = o_col1 + 4 * n;
+  off = pad8(o_pid + 4 * n);
+  const size_t o_xy = off;
+  off += 16 * n;
+  const size_t o_intr = off;
+  off += sizeof(BinIntrinsic) * static_cast<size_t>(h.n_intr);
+  const size_t o_ext = off;
+  off += sizeof(BinExtrinsic) * static_cast<size_t>(h.n_ext);
+  const size_t o_xyz = off;
+  off += 24 * static_cast<size_t>(h.n_pts);
+  const size_t o_rgb = off;
+  off += 12 * static_cast<size_t>(h.n_pts);
+  if (off > size) return false;
+  share_extrinsic_ = h.n_ring != 0;
+  arc_size_ = h.n_arc;
+  ring_size_ = h.n_ring;
+  const int32_t* col0 = reinterpret_cast<const int32_t*>(data + o_col0);
+  const int32_t* col1 = reinterpret_cast<const int32_t*>(data + o_col1);
+  const int32_t* pid = reinterpret_cast<const int32_t*>(data + o_pid);
+  const double* xy = reinterpret_cast<const double*>(data + o_xy);
+  params_.assign(n, nullptr);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < h.n_obs; ++i) params_[i] = new ParameterBlock(col0[i], col1[i], pid[i], new Point2d(xy[2 * i], xy[2 * i + 1]));
+  for (int i = 0; i < h.n_intr; ++i) {
+    BinIntrinsic b;
+    std::memcpy(&b, data + o_intr + sizeof b * static_cast<size_t>(i), sizeof b);
+    Intrinsic* in = new Intrinsic();
+    in->id(i);
+    in->center(static_cast<int>(b.cx), static_cast<int>(b.cy));  // same entry point as the text loader (already integral)
+    double f[2] = {b.f0, b.f1}, k[2] = {b.k0, b.k1};
+    in->focal(b.nf, f);
+    in->distrotion(b.nd, k);
+    intrinsics_.push_back(in);
+  }
+  for (int i = 0; i < h.n_ext; ++i) {
+    BinExtrinsic b;
+    std::memcpy(&b, data + o_ext + sizeof b * static_cast<size_t>(i), sizeof b);
+    Extrinsic* ex = new Extrinsic();
+    ex->id(i);
+    ex->translation(b.t[0], b.t[1], b.t[2]);
+    ex->rotation(b.aa);
+    extrinsics_.push_back(ex);
+  }
+  const double* xyz = reinterpret_cast<const double*>(data + o_xyz);
+  const int32_t* rgb = reinterpret_cast<const int32_t*>(data + o_rgb);
+  point3d_.assign(static_cast<size_t>(h.n_pts), nullptr);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < h.n_pts; ++i)
+    point3d_[i] = new Point3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);
+  if (share_extrinsic_)
+    buildHemisphere();
+  else
+    buildCameras();
+  linkBlocks(share_extrinsic_ ? arc_size_ : 0);
+  return true;
+}
+
+// Same scene as write(), bit for bit (the observation columns are the ones write() emits:
+// intrinsic()->id() and ring()->id() / extrinsic()->id(), points re-indexed; DeepArcManager.cc:430-449).
+void DeepArcManager::writeBinary(std::string filename) {
+  const int64_t n_pts = static_cast<int64_t>(point3d_.size()), n_obs = static_cast<int64_t>(params_.size());
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_pts; ++i) point3d_[i]->id(static_cast<int>(i));
+  BinHeader h;
+  std::memset(&h, 0, sizeof h);
+  std::memcpy(h.magic, kBinMagic, 8);
+  h.version = 1;
+  h.n_obs = n_obs;
+  h.n_intr = static_cast<int32_t>(intrinsics_.size());
+  h.n_arc = share_extrinsic_ ? arc_size_ : static_cast<int32_t>(camera_.size());
+  h.n_ring = share_extrinsic_ ? ring_size_ : 0;
+  h.n_pts = static_cast<int32_t>(n_pts);
+  h.n_ext = static_cast<int32_t>(extrinsics_.size());
+  const size_t n = static_cast<size_t>(n_obs);
+  std::vector<char> buf(sizeof h + pad8(12 * n) + 16 * n + sizeof(BinIntrinsic) * intrinsics_.size() +
+                        sizeof(BinExtrinsic) * extrinsics_.size() + 24 * static_cast<size_t>(n_pts) + pad8(12 * static_cast<size_t>(n_pts)), 0);
+  char* p = buf.data();
+  std::memcpy(p, &h, sizeof h);
+  int32_t* col0 = reinterpret_cast<int32_t*>(p + sizeof h);
+  int32_t* col1 = col0 + n;
+  int32_t* pid = col1 + n;
+  double* xy = reinterpret_cast<double*>(p + sizeof h + pad8(12 * n));
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_obs; ++i) {
+    ParameterBlock* b = params_[i];
+    col0[i] = b->intrinsic()->id();
+    col1[i] = share_extrinsic_ ? b->ring()->id() : b->extrinsic()->id();
+    pid[i] = b->point3d()->id();
+    xy[2 * i] = b->point2d()->x();
+    xy[2 * i + 1] = b->point2d()->y();
+  }
+  char* q = reinterpret_cast<char*>(xy + 2 * n);
+  for (Intrinsic* in : intrinsics_) {
+    BinIntrinsic b;
+    std::memset(&b, 0, sizeof b);
+    b.cx = in->center()[0];
+    b.cy = in->center()[1];
+    b.nf = in->focal_size();
+    b.nd = in->distrotion_size();
+    b.f0 = in->focal()[0];
+    b.f1 = in->focal()[1];
+    b.k0 = in->distrotion()[0];
+    b.k1 = in->distrotion()[1];
+    std::memcpy(q, &b, sizeof b);
+    q += sizeof b;
+  }
+  for (Extrinsic* ex : extrinsics_) {
+    BinExtrinsic b;
+    for (int j = 0; j < 3; ++j) {
+      b.t[j] = ex->translation()[j];
+      b.aa[j] = ex->rotation()[j];
+    }
+    std::memcpy(q, &b, sizeof b);
+    q += sizeof b;
+  }
+  double* xyz = reinterpret_cast<double*>(q);
+  int32_t* rgb = reinterpret_cast<int32_t*>(q + 24 * static_cast<size_t>(n_pts));
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n_pts; ++i) {
+    Point3d* pt = point3d_[i];
+    for (int j = 0; j < 3; ++j) xyz[3 * i + j] = pt->position()[j];
+    rgb[3 * i] = pt->r();
+    rgb[3 * i + 1] = pt->g();
+    rgb[3 * i + 2] = pt->b();
+  }
+  std::ofstream of(filename, std::ios::binary);
+  of.write(buf.data(), static_cast<std::streamsize>(buf.size()));
 }
 
 void DeepArcManager::clearScene() {
@@ -234,7 +448,7 @@ void DeepArcManager::clearScene() {
   hemisphere_.clear();
 }
 
-bool DeepArcManager::readText(const std::string& data, bool parallel) {
+bool DeepArcManager::readText(const char* data, size_t size, bool parallel) {
   const bool timing = std::getenv("DBA_TIMING") != nullptr;
   double t_mark = omp_get_wtime();
   auto mark = [&](const char* what) {
@@ -244,7 +458,7 @@ bool DeepArcManager::readText(const std::string& data, bool parallel) {
     t_mark = t;
   };
   Tokens tok(data);
-  const char* const end = data.c_str() + data.size();
+  const char* const end = data + size;
 
   double version = 0.0;
   int n_block = 0, n_intrinsic = 0, n_arc = 0, n_ring = 0, n_point = 0;

@@ -31,6 +31,9 @@ class DeepArcManager {
   void write(std::string filename);
   std::vector<std::vector<double> > getCameraCenter();
 
+  // ---- binary side format (lossless, memcpy-speed; read() recognises it by its magic) ----
+  void writeBinary(std::string filename);
+
   // ---- additions used by the GPU boundary (gather / scatter) ---------------------------
   std::vector<Intrinsic*>* intrinsics() { return &intrinsics_; }
   std::vector<Extrinsic*>* extrinsics() { return &extrinsics_; }
@@ -48,7 +51,8 @@ class DeepArcManager {
   std::vector<Point3d*> point3d_;
 
   static int ringSlot(int ring_position, int arc_size);
-  bool readText(const std::string& data, bool parallel);  // false: the strict parallel parser gave up
+  bool readText(const char* data, size_t size, bool parallel);  // false: the strict parallel parser gave up
+  bool readBinary(const char* data, size_t size);
   void clearScene();
   void linkBlocks(int arc_size);
   void buildHemisphere();

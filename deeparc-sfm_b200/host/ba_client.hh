@@ -49,6 +49,10 @@ void check(int status, const char* what);
 void solve(DeepArcManager& deeparcManager, int max_iteration = 1000, int max_second = 3600,
            bool freeze_camera = false);
 
+// Optional robust loss for the following solve() calls (the reference builds its problem with a NULL
+// loss, sfm.cc:48, and keeps `new ceres::CauchyLoss(0.5)` in a comment, :49): scale <= 0 switches it off.
+void solve_set_cauchy_loss(double scale);
+
 // Last summary of solve() / of the hemisphere fit, for drivers that want more than stdout.
 const dba_summary& last_solve_summary();
 const std::vector<dba_iteration>& last_solve_iterations();

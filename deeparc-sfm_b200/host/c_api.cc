@@ -101,6 +101,7 @@ int dam_manager_filter(void* h, double error_boundary, double* centre, double ra
   return guarded([&] { static_cast<DeepArcManager*>(h)->filterPoint3d(error_boundary, centre, radius); });
 }
 void dam_manager_write(void* h, const char* path) { static_cast<DeepArcManager*>(h)->write(path); }
+void dam_manager_write_binary(void* h, const char* path) { static_cast<DeepArcManager*>(h)->writeBinary(path); }
 void dam_manager_write_ply(void* h, const char* path) { static_cast<DeepArcManager*>(h)->writePly(path); }
 int dam_manager_camera_centers(void* h, double* out, int capacity) {
   std::vector<std::vector<double> > c = static_cast<DeepArcManager*>(h)->getCameraCenter();

@@ -5,6 +5,8 @@
 // arguments this binary behaves the same (same default paths), and accepts optional overrides:
 //   sfm [--input F] [--output F] [--ply-init F] [--ply-adjust PREFIX] [--ply-clear F]
 //       [--max-iter N] [--max-seconds S] [--filter-boundary E] [--max-outer N]
+//       [--cauchy-loss A]      robust loss CauchyLoss(A) (commented out in the reference, sfm.cc:49)
+//       [--output-binary F]    additionally write the lossless binary side format (read() accepts it as --input)
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -25,6 +27,7 @@ int main(int argc, char** argv) {
               ply_adjust = PLY_ADJUST;
   int max_iter = 100, max_seconds = 3600, max_outer = 1 << 30;
   double boundary = 5.0;
+  std::string output_binary;
   for (int i = 1; i + 1 < argc; i += 2) {
     const std::string k = argv[i], v = argv[i + 1];
     if (k == "--input") input = v;
@@ -36,6 +39,8 @@ int main(int argc, char** argv) {
     else if (k == "--max-seconds") max_seconds = std::atoi(v.c_str());
     else if (k == "--filter-boundary") boundary = std::atof(v.c_str());
     else if (k == "--max-outer") max_outer = std::atoi(v.c_str());
+    else if (k == "--cauchy-loss") solve_set_cauchy_loss(std::atof(v.c_str()));
+    else if (k == "--output-binary") output_binary = v;
     else {
       std::cerr << "unknown option " << k << "\n";
       return 2;
@@ -88,6 +93,7 @@ int main(int argc, char** argv) {
     std::cout << "TOTAL REPEAT: " << step << "\n";
     deeparcManager.writePly(ply_clear);
     deeparcManager.write(output);
+    if (!output_binary.empty()) deeparcManager.writeBinary(output_binary);
     deeparc::engine_release();
   } catch (const char* msg) {
     std::cerr << "sfm: " << msg << "\n";

@@ -13,6 +13,7 @@
 namespace {
 dba_summary g_summary;
 std::vector<dba_iteration> g_iterations;
+double g_cauchy_scale = 0.0;  // <= 0: no loss, as the reference ships (sfm.cc:48)
 
 void print_full_report(const dba_summary& s, const deeparc::FlatProblem& f, bool freeze) {
   std::printf("\nSolver Summary (deeparc B200 engine)\n\n");
@@ -36,6 +37,7 @@ void print_full_report(const dba_summary& s, const deeparc::FlatProblem& f, bool
 }
 }  // namespace
 
+void solve_set_cauchy_loss(double scale) { g_cauchy_scale = scale; }
 const dba_summary& last_solve_summary() { return g_summary; }
 const std::vector<dba_iteration>& last_solve_iterations() { return g_iterations; }
 
@@ -57,6 +59,10 @@ void solve(DeepArcManager& deeparcManager, int max_iteration, int max_second, bo
   options.max_solver_time_in_seconds = max_second;  // sfm.cc:71
   options.pcg_rel_tolerance = 1e-13;
   options.pcg_max_iterations = 4000;
+  if (g_cauchy_scale > 0.0) {                     // sfm.cc:49 (commented out in the reference)
+    options.loss_type = DBA_LOSS_CAUCHY;
+    options.loss_scale = g_cauchy_scale;
+  }
   // (sfm.cc:70 num_threads has no meaning here)
   g_iterations.assign(static_cast<size_t>(max_iteration) + 2, dba_iteration());
   std::memset(&g_summary, 0, sizeof g_summary);

@@ -252,6 +252,11 @@ class HostMirror(_ManagerApi):
         self.lib = C.CDLL(path)
         self._bind_manager(self.lib, "dam_")
         self.lib.dam_last_error.restype = C.c_char_p
+        self.lib.dam_manager_write_binary.argtypes = [C.c_void_p, C.c_char_p]
+        self.lib.dam_manager_write_binary.restype = None
+
+    def write_binary(self, h, path):
+        self.lib.dam_manager_write_binary(h, path.encode())
 
     def last_error(self) -> str:
         return self.lib.dam_last_error().decode()

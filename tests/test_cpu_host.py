@@ -121,6 +121,44 @@ def test_host_mirror_reads_and_writes_like_the_reference(reference, tmp_path, na
     reference.free(hr), H.free(hh)
 
 
+@pytest.mark.parametrize("kind", ["rig", "bal"])
+def test_binary_side_format_is_lossless(tmp_path, kind):
+    """the text format keeps six decimals (reference src/DeepArcManager.cc:428), so a
+    text round trip moves every parameter; the binary side format (writeBinary, recognised by read()
+    through its magic, loaded from the mmap'ed image) reproduces the scene bit for bit, and writing
+    text from either copy gives the same bytes."""
+    H = oracle_lib.HostMirror()
+    p = _make(kind)
+    f = str(tmp_path / "a.deeparc")
+    synthetic.write_deeparc(p, f)
+    h = H.read(f)
+    a = H.export(h)
+    H.write_binary(h, f + "b")
+    H.write(h, f + ".txt1")
+    hb = H.read(f + "b")
+    b = H.export(hb)
+    assert H.counts(h) == H.counts(hb) and H.is_shared(h) == H.is_shared(hb)
+    for k in ("obs_xy", "obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr", "pts", "ext_rot", "ext_trans", "intr_center",
+              "intr_focal", "intr_dist", "intr_nf", "intr_nd", "ext_const", "pts_rgb"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    H.write(hb, f + ".txt2")
+    assert filecmp.cmp(f + ".txt1", f + ".txt2", shallow=False)
+    H.write_binary(hb, f + "b2")
+    assert filecmp.cmp(f + "b", f + "b2", shallow=False)
+    # the text round trip is lossy, which is what the side format is for
+    ht = H.read(f + ".txt1")
+    t = H.export(ht)
+    assert not np.array_equal(t.pts, a.pts) and np.allclose(t.pts, a.pts, atol=1e-6)
+    assert np.array_equal(H.camera_centers(h), H.camera_centers(hb))
+    for x in (h, hb, ht):
+        H.free(x)
+    # a truncated binary file is refused, not half-loaded
+    raw = open(f + "b", "rb").read()
+    open(f + "b3", "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(Exception):
+        H.read(f + "b3")
+
+
 def test_host_mirror_standalone_roundtrip(tmp_path):
     """Without the reference build: read -> write -> read reproduces the scene to the 6 decimals
     of the text format; ids, modes and the gauge mask survive."""
