@@ -201,6 +201,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.dba_last_error.restype = C.c_char_p
     lib.dba_problem_set.argtypes = [C.c_void_p, C.POINTER(DbaProblem)]
     lib.dba_params_reset.argtypes = [C.c_void_p]
+    lib.dba_problem_update.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.dba_eval.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp]
     lib.dba_solve_options_default.argtypes = [C.POINTER(DbaSolveOptions)]
     lib.dba_solve_options_default.restype = None
@@ -275,6 +276,31 @@ class Engine:
     def problem_set(self, p: Problem):
         self.problem = ProblemMarshal(p)
         self._check(self.lib.dba_problem_set(self.h, C.byref(self.problem.struct)))
+
+    def problem_update(self, obs_remove=None, pt_remove=None, freeze_camera: int = 0):
+        """Drops flagged observations / points on the engine side (no second upload); returns (n_obs, n_pts)."""
+        o = None if obs_remove is None else np.ascontiguousarray(obs_remove, dtype=np.uint8)
+        t = None if pt_remove is None else np.ascontiguousarray(pt_remove, dtype=np.uint8)
+        n_obs, n_pts = C.c_int64(0), C.c_int32(0)
+        self._check(self.lib.dba_problem_update(self.h, None if o is None else o.ctypes.data, None if t is None else t.ctypes.data,
+                                                int(freeze_camera), C.byref(n_obs), C.byref(n_pts)))
+        # keep the marshalled problem in step with the engine (shapes of later eval / filter / params_get calls)
+        p = self.problem.p
+        keep_pt = np.ones(p.n_pts, bool) if t is None else (t == 0)
+        keep_ob = (np.ones(p.n_obs, bool) if o is None else (o == 0)) & keep_pt[p.obs_pt]
+        new_pt = np.cumsum(keep_pt) - 1
+        q = p.copy()
+        for k in ("obs_xy", "obs_pose_a", "obs_pose_b", "obs_intr"):
+            setattr(q, k, getattr(p, k)[keep_ob])
+        q.obs_pt = new_pt[p.obs_pt[keep_ob]].astype(np.int32)
+        q.pts = p.pts[keep_pt]
+        if p.pts_rgb is not None:
+            q.pts_rgb = p.pts_rgb[keep_pt]
+        q.obs_col0 = q.obs_col1 = None
+        q.freeze_camera = int(freeze_camera)
+        self.problem = ProblemMarshal(q)
+        assert (n_obs.value, n_pts.value) == (q.n_obs, q.n_pts)
+        return n_obs.value, n_pts.value
 
     def params_reset(self):
         self._check(self.lib.dba_params_reset(self.h))

@@ -137,6 +137,18 @@ struct dba_handle {
   DevBuf<double> d_sp, d_sc, d_cinv, d_tp, d_dp, d_cam_acc, d_minv, d_dc2, d_x, d_r, d_z, d_p, d_q;
   DevBuf<double> d_cam_chunk_acc;
   DevBuf<double> d_partA, d_partB, d_scalars, d_scalars_red, d_pcg_scal, d_full_pts, d_vec_partials;
+  // retained for dba_problem_update: the point-sorted observation arrays of the last dba_problem_set
+  // (they live in the pinned staging arena until the next upload) and the small constant tables
+  struct Keep {
+    bool valid = false;
+    const double2* xy = nullptr;
+    const int2* ip = nullptr;  // (intrinsic, local point)
+    const int2* ab = nullptr;  // (block a, block b or -1)
+    std::vector<double> center;
+    std::vector<int32_t> nf, nd;
+    std::vector<uint8_t> ext_const;
+    int free_intrinsics = 0;
+  } keep;
   // explicit reduced system + device Cholesky (DENSE_SCHUR) for small camera counts
   bool dense_ok = false;     // the problem fits the dense path (set by dba_problem_set)
   bool use_dense = false;    // linear solver of the running dba_solve
@@ -906,6 +918,7 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   if (!h || !p) return DBA_ERR_INVALID_ARGUMENT;
   CU(h, cudaSetDevice(h->device));
   h->have_problem = false;
+  h->keep.valid = false;
   if (p->n_obs < 0 || p->n_pts < 0 || p->n_ext < 0 || p->n_intr < 0)
     return h->fail(DBA_ERR_INVALID_ARGUMENT, "negative size");
   if (p->n_obs > 0 && (!p->obs_xy || !p->obs_pt || !p->obs_pose_a || !p->obs_intr))
@@ -1677,8 +1690,133 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.vec_partials = h->d_vec_partials.p;
   W.counters = h->d_counters.p;
   h->Q.fail_flag = h->d_pcg_state.p + 3;
+  h->keep.valid = h->world == 1;
+  h->keep.xy = s_xy;
+  h->keep.ip = s_ip;
+  h->keep.ab = s_ab;
+  h->keep.center.assign(p->intr_center, p->intr_center + 2 * static_cast<size_t>(n_intr));
+  h->keep.nf.assign(p->intr_nf, p->intr_nf + n_intr);
+  h->keep.nd.assign(p->intr_nd, p->intr_nd + n_intr);
+  h->keep.ext_const = ext_const;
+  h->keep.free_intrinsics = p->free_intrinsics;
   h->have_problem = true;
   return dba_params_reset(h);
+}
+
+// Device-resident outer loop (reference sfm.cc:118-127: solve, filterPoint3d, solve, ...): drops the
+// observations / points a dba_filter call flagged and rebuilds the index structures from the
+// point-sorted arrays the engine kept from the last upload — the caller does not gather, validate,
+// sort or upload the scene again, and the parameters continue from their current device values.
+int dba_problem_update(dba_handle* h, const uint8_t* obs_remove, const uint8_t* pt_remove, int32_t freeze_camera,
+                       int64_t* n_obs_out, int32_t* n_pts_out) {
+  if (!h) return DBA_ERR_INVALID_ARGUMENT;
+  if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
+  if (h->world > 1) return h->fail(DBA_ERR_UNSUPPORTED, "dba_problem_update needs a single-GPU handle");
+  if (!h->keep.valid) return h->fail(DBA_ERR_NO_PROBLEM, "the retained problem image is gone: call dba_problem_set");
+  CU(h, cudaSetDevice(h->device));
+  const int64_t n = h->n_obs;
+  const int n_pts = h->n_pts, n_ext = h->n_ext, n_intr = h->n_intr;
+  const int c = h->cur;
+  // current parameters: the scatter-back source, read once
+  std::vector<double> pts(3 * static_cast<size_t>(n_pts)), rot(3 * static_cast<size_t>(n_ext)), trans(3 * static_cast<size_t>(n_ext)),
+      focal(2 * static_cast<size_t>(n_intr)), dist(2 * static_cast<size_t>(n_intr));
+  if (n_pts) CU(h, cudaMemcpyAsync(pts.data(), h->d_pts[c].p, pts.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  if (n_ext) {
+    CU(h, cudaMemcpyAsync(rot.data(), h->d_rot[c].p, rot.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaMemcpyAsync(trans.data(), h->d_trans[c].p, trans.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  }
+  if (n_intr) {
+    CU(h, cudaMemcpyAsync(focal.data(), h->d_focal[c].p, focal.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaMemcpyAsync(dist.data(), h->d_dist[c].p, dist.size() * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+  }
+  // surviving points, re-indexed in order
+  std::vector<int> new_pt(static_cast<size_t>(n_pts) + 1, 0);
+  for (int i = 0; i < n_pts; ++i) new_pt[i + 1] = new_pt[i] + ((pt_remove && pt_remove[i]) ? 0 : 1);
+  const int n_pts_new = new_pt[n_pts];
+  // surviving observations in sorted order (two-pass chunked compaction on all host cores)
+  const int2* ip = h->keep.ip;
+  const int2* ab = h->keep.ab;
+  const double2* xy = h->keep.xy;
+  const int64_t* perm = h->perm.data();
+  auto gone = [&](int64_t k) { return (obs_remove && obs_remove[perm[k]]) || (pt_remove && pt_remove[ip[k].y]); };
+  const int n_chunk = std::max(1, omp_get_max_threads() * 4);
+  std::vector<int64_t> first(static_cast<size_t>(n_chunk) + 1, 0);
+#pragma omp parallel for schedule(static, 1)
+  for (int ch = 0; ch < n_chunk; ++ch) {
+    int64_t cnt = 0;
+    for (int64_t k = n * ch / n_chunk; k < n * (ch + 1) / n_chunk; ++k) cnt += gone(k) ? 0 : 1;
+    first[ch + 1] = cnt;
+  }
+  for (int ch = 0; ch < n_chunk; ++ch) first[ch + 1] += first[ch];
+  const int64_t n_new = first[n_chunk];
+  std::vector<double> nxy(2 * static_cast<size_t>(n_new));
+  std::vector<int32_t> npt(static_cast<size_t>(n_new)), na(static_cast<size_t>(n_new)), nb(static_cast<size_t>(n_new)), nin(static_cast<size_t>(n_new));
+  std::vector<int64_t> old_caller(static_cast<size_t>(n_new));
+#pragma omp parallel for schedule(static, 1)
+  for (int ch = 0; ch < n_chunk; ++ch) {
+    int64_t w = first[ch];
+    for (int64_t k = n * ch / n_chunk; k < n * (ch + 1) / n_chunk; ++k) {
+      if (gone(k)) continue;
+      nxy[2 * w] = xy[k].x;
+      nxy[2 * w + 1] = xy[k].y;
+      npt[w] = new_pt[ip[k].y];
+      nin[w] = ip[k].x;
+      na[w] = ab[k].x;
+      nb[w] = ab[k].y;
+      old_caller[w] = perm[k];
+      ++w;
+    }
+  }
+  // caller order of the survivors: rank of the old caller index among the kept ones
+  const int64_t n_caller = h->n_obs_global;
+  std::vector<int64_t> caller_rank(static_cast<size_t>(n_caller) + 1, 0);
+  {
+    std::vector<uint8_t> kept(static_cast<size_t>(n_caller), 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t w = 0; w < n_new; ++w) kept[old_caller[w]] = 1;
+    for (int64_t i = 0; i < n_caller; ++i) caller_rank[i + 1] = caller_rank[i] + kept[i];
+  }
+  CU(h, cudaStreamSynchronize(h->st));  // parameters have arrived
+  std::vector<double> npts(3 * static_cast<size_t>(n_pts_new));
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n_pts; ++i)
+    if (new_pt[i + 1] != new_pt[i])
+      for (int k2 = 0; k2 < 3; ++k2) npts[3 * static_cast<size_t>(new_pt[i]) + k2] = pts[3 * static_cast<size_t>(i) + k2];
+  // the small tables move out of the handle: dba_problem_set rewrites them
+  std::vector<double> center = h->keep.center;
+  std::vector<int32_t> nf = h->keep.nf, nd = h->keep.nd;
+  std::vector<uint8_t> ext_const = h->keep.ext_const;
+  dba_problem q;
+  std::memset(&q, 0, sizeof q);
+  q.n_obs = n_new;
+  q.n_pts = n_pts_new;
+  q.n_ext = n_ext;
+  q.n_intr = n_intr;
+  q.obs_xy = nxy.data();
+  q.obs_pt = npt.data();
+  q.obs_pose_a = na.data();
+  q.obs_pose_b = nb.data();
+  q.obs_intr = nin.data();
+  q.pts = npts.data();
+  q.ext_rot = rot.data();
+  q.ext_trans = trans.data();
+  q.intr_center = center.data();
+  q.intr_focal = focal.data();
+  q.intr_dist = dist.data();
+  q.intr_nf = nf.data();
+  q.intr_nd = nd.data();
+  q.ext_const = ext_const.data();
+  q.freeze_camera = freeze_camera;
+  q.free_intrinsics = h->keep.free_intrinsics;
+  const int rc = dba_problem_set(h, &q);
+  if (rc != DBA_OK) return rc;
+  // observation outputs (dba_eval, dba_filter) stay in the CALLER's order: position among the survivors
+#pragma omp parallel for schedule(static)
+  for (int64_t w = 0; w < n_new; ++w) h->perm[w] = caller_rank[old_caller[w]];
+  h->n_obs_global = n_new;
+  if (n_obs_out) *n_obs_out = n_new;
+  if (n_pts_out) *n_pts_out = n_pts_new;
+  return DBA_OK;
 }
 
 int dba_params_reset(dba_handle* h) {

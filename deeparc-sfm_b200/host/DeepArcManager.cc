@@ -174,6 +174,7 @@ std::string deeparc_format_fixed6(double v) {
 DeepArcManager::DeepArcManager() : arc_size_(0), ring_size_(0), share_extrinsic_(false) {}
 
 DeepArcManager::~DeepArcManager() {
+  if (deeparc::resident().manager == this) deeparc::resident_invalidate();  // the engine's copy describes objects that go away now
   for (ParameterBlock* b : params_) delete b;
   for (Point3d* p : point3d_) delete p;
   for (Intrinsic* i : intrinsics_) delete i;
@@ -430,6 +431,7 @@ void DeepArcManager::writeBinary(std::string filename) {
 }
 
 void DeepArcManager::clearScene() {
+  if (deeparc::resident().manager == this) deeparc::resident_invalidate();
   for (ParameterBlock* b : params_) {
     if (b) b->point3d_unlinked(nullptr);
     delete b;
@@ -801,11 +803,20 @@ void DeepArcManager::filterPoint3d(double error_boundary, double* hemisphere_cen
   // pointer-graph surgery, which leaves the same survivors in the same order.
   std::vector<uint8_t> obs_gone(params_.size(), 0), pt_gone;
   if (!params_.empty()) {
-    deeparc::FlatProblem flat;
-    deeparc::flatten(*this, /*freeze_camera=*/false, &flat);
-    dba_problem view = flat.view();
     dba_handle* h = deeparc::engine();
-    deeparc::check(dba_problem_set(h, &view), "dba_problem_set");
+    deeparc::Resident& res = deeparc::resident();
+    const bool on_device = deeparc::resident_usable(*this) && !res.pending;
+    if (!on_device) {
+      // the engine does not hold this scene (first call, or the scene was edited): gather and upload it
+      deeparc::resident_invalidate();
+      deeparc::flatten(*this, /*freeze_camera=*/false, &res.flat);
+      dba_problem view = res.flat.view();
+      deeparc::check(dba_problem_set(h, &view), "dba_problem_set");
+      res.manager = this;
+      res.freeze_camera = 0;
+      res.valid = true;
+    }
+    deeparc::FlatProblem& flat = res.flat;
     pt_gone.assign(flat.point_of.size(), 0);
     deeparc::check(dba_filter(h, error_boundary, hemisphere_center, hemisphere_radius, obs_gone.data(), pt_gone.data(), nullptr, nullptr),
                    "dba_filter");
@@ -813,6 +824,10 @@ void DeepArcManager::filterPoint3d(double error_boundary, double* hemisphere_cen
       if (obs_gone[i]) params_[i]->require_remove(true);  // QUIRK: "<" as written (:348)
     for (size_t i = 0; i < flat.point_of.size(); ++i)
       if (pt_gone[i]) flat.point_of[i]->require_remove(true);
+    // the next solve() lets the engine drop them (dba_problem_update) instead of uploading the scene again
+    res.obs_remove = obs_gone;
+    res.pt_remove = pt_gone;
+    res.pending = true;
   } else {
     for (Point3d* p : point3d_) p->require_remove(true);  // nothing observes them: all empty (:368-378)
   }

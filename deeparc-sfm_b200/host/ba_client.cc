@@ -85,6 +85,7 @@ void flatten(DeepArcManager& m, bool freeze_camera, FlatProblem* out) {
     }
   }
   const int64_t n = static_cast<int64_t>(blocks.size());
+  f.block_of = blocks;
   f.obs_xy.resize(2 * static_cast<size_t>(n));
   f.obs_pt.resize(static_cast<size_t>(n));
   f.obs_pose_a.resize(static_cast<size_t>(n));
@@ -145,6 +146,74 @@ void scatter(const FlatProblem& f, const std::vector<double>& pts, const std::ve
 
 namespace {
 dba_handle* g_engine = nullptr;
+Resident g_resident;
+}
+
+Resident& resident() { return g_resident; }
+void resident_invalidate() { g_resident = Resident(); }
+
+void resident_compact() {
+  Resident& r = g_resident;
+  if (!r.pending) return;
+  FlatProblem& f = r.flat;
+  const size_t n = f.block_of.size(), np = f.point_of.size();
+  std::vector<int> new_pt(np + 1, 0);
+  for (size_t i = 0; i < np; ++i) new_pt[i + 1] = new_pt[i] + (r.pt_remove[i] ? 0 : 1);
+  size_t w = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (r.obs_remove[i] || r.pt_remove[f.obs_pt[i]]) continue;
+    f.block_of[w] = f.block_of[i];
+    f.obs_pt[w] = new_pt[f.obs_pt[i]];
+    ++w;
+  }
+  f.block_of.resize(w);
+  f.obs_pt.resize(w);
+  size_t wp = 0;
+  for (size_t i = 0; i < np; ++i) {
+    if (r.pt_remove[i]) continue;
+    f.point_of[wp] = f.point_of[i];
+    for (int k = 0; k < 3; ++k) f.pts[3 * wp + k] = f.pts[3 * i + k];
+    ++wp;
+  }
+  f.point_of.resize(wp);
+  f.pts.resize(3 * wp);
+  r.pending = false;
+  r.obs_remove.clear();
+  r.pt_remove.clear();
+}
+
+bool resident_usable(DeepArcManager& m) {
+  Resident& r = g_resident;
+  const char* env = std::getenv("DEEPARC_RESIDENT");
+  if (env && env[0] == '0') return false;
+  if (!r.valid || r.manager != &m || !g_engine) return false;
+  const FlatProblem& f = r.flat;
+  const std::vector<ParameterBlock*>& blocks = *m.parameters();
+  const std::vector<Point3d*>& points = *m.point3ds();
+  if (*m.extrinsics() != f.ext_of || *m.intrinsics() != f.intr_of) return false;
+  // object sequences: the scene must hold exactly the survivors, in order
+  size_t w = 0;
+  for (size_t i = 0; i < f.block_of.size(); ++i) {
+    if (r.pending && (r.obs_remove[i] || r.pt_remove[f.obs_pt[i]])) continue;
+    if (w >= blocks.size() || blocks[w] != f.block_of[i]) return false;
+    ++w;
+  }
+  if (w != blocks.size()) return false;
+  size_t wp = 0;
+  for (size_t i = 0; i < f.point_of.size(); ++i) {
+    if (r.pending && r.pt_remove[i]) continue;
+    if (wp >= points.size() || points[wp] != f.point_of[i]) return false;
+    // parameters unchanged since the last scatter (sampled)
+    if (i % 61 == 0)
+      for (int k = 0; k < 3; ++k)
+        if (points[wp]->position()[k] != f.pts[3 * i + k]) return false;
+    ++wp;
+  }
+  if (wp != points.size()) return false;
+  for (size_t i = 0; i < f.ext_of.size(); ++i)
+    for (int k = 0; k < 3; ++k)
+      if (f.ext_of[i]->rotation()[k] != f.ext_rot[3 * i + k] || f.ext_of[i]->translation()[k] != f.ext_trans[3 * i + k]) return false;
+  return true;
 }
 
 dba_handle* engine() {
@@ -167,6 +236,7 @@ dba_handle* engine() {
 void engine_release() {
   if (g_engine) dba_destroy(g_engine);
   g_engine = nullptr;
+  g_resident = Resident();
 }
 
 void check(int status, const char* what) {

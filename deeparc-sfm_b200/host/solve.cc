@@ -18,7 +18,7 @@ double g_cauchy_scale = 0.0;  // <= 0: no loss, as the reference ships (sfm.cc:4
 void print_full_report(const dba_summary& s, const deeparc::FlatProblem& f, bool freeze) {
   std::printf("\nSolver Summary (deeparc B200 engine)\n\n");
   std::printf("Observations       %12zu\nPoints             %12zu\nExtrinsics         %12zu\nIntrinsics         %12zu (constant)\n",
-              f.obs_pt.size(), f.point_of.size(), f.ext_of.size(), f.intr_of.size());
+              f.block_of.size(), f.point_of.size(), f.ext_of.size(), f.intr_of.size());
   std::printf("Camera parameters  %12s\n", freeze ? "constant" : "6 per free extrinsic");
   std::printf("Linear solver      %s, reduced system %d\n",
               s.linear_solver_used == DBA_LS_DENSE ? "explicit Schur + dense Cholesky" : "implicit Schur + block-Jacobi PCG",
@@ -42,11 +42,34 @@ const dba_summary& last_solve_summary() { return g_summary; }
 const std::vector<dba_iteration>& last_solve_iterations() { return g_iterations; }
 
 void solve(DeepArcManager& deeparcManager, int max_iteration, int max_second, bool freeze_camera) {
-  deeparc::FlatProblem flat;
-  deeparc::flatten(deeparcManager, freeze_camera, &flat);  // sfm.cc:36-65
   dba_handle* h = deeparc::engine();
-  dba_problem view = flat.view();
-  deeparc::check(dba_problem_set(h, &view), "dba_problem_set");
+  deeparc::Resident& res = deeparc::resident();
+  if (deeparc::resident_usable(deeparcManager)) {
+    // the engine still holds this scene (left there by the previous solve() / filterPoint3d()): drop what
+    // the filter removed and switch the freeze flag on the device side, no gather / sort / upload
+    if (res.pending || res.freeze_camera != (freeze_camera ? 1 : 0)) {
+      deeparc::check(dba_problem_update(h, res.pending ? res.obs_remove.data() : nullptr, res.pending ? res.pt_remove.data() : nullptr,
+                                        freeze_camera ? 1 : 0, nullptr, nullptr),
+                     "dba_problem_update");
+      deeparc::resident_compact();
+      res.freeze_camera = freeze_camera ? 1 : 0;
+      res.flat.freeze_camera = res.freeze_camera;
+    }
+  } else {
+    deeparc::resident_invalidate();
+    deeparc::flatten(deeparcManager, freeze_camera, &res.flat);  // sfm.cc:36-65
+    dba_problem view = res.flat.view();
+    deeparc::check(dba_problem_set(h, &view), "dba_problem_set");
+    res.manager = &deeparcManager;
+    res.freeze_camera = freeze_camera ? 1 : 0;
+    res.valid = true;
+    // the observation arrays live on the device now; the maps stay for the scatter-back and the filter
+    std::vector<double>().swap(res.flat.obs_xy);
+    std::vector<int32_t>().swap(res.flat.obs_pose_a);
+    std::vector<int32_t>().swap(res.flat.obs_pose_b);
+    std::vector<int32_t>().swap(res.flat.obs_intr);
+  }
+  deeparc::FlatProblem& flat = res.flat;
 
   dba_solve_options options;
   dba_solve_options_default(&options);            // Ceres defaults (not overridden at sfm.cc:66-71)
@@ -71,8 +94,9 @@ void solve(DeepArcManager& deeparcManager, int max_iteration, int max_second, bo
   deeparc::check(dba_solve(h, &options, &g_summary), "dba_solve");  // sfm.cc:73
   g_iterations.resize(static_cast<size_t>(g_summary.num_iterations));
 
-  std::vector<double> pts(flat.pts.size()), rot(flat.ext_rot.size()), trans(flat.ext_trans.size());
-  deeparc::check(dba_params_get(h, pts.data(), rot.data(), trans.data(), nullptr, nullptr), "dba_params_get");
-  deeparc::scatter(flat, pts, rot, trans);
+  // scatter-back; the resident image remembers the values so that a later call can tell whether the
+  // scene graph was edited behind the engine's back
+  deeparc::check(dba_params_get(h, flat.pts.data(), flat.ext_rot.data(), flat.ext_trans.data(), nullptr, nullptr), "dba_params_get");
+  deeparc::scatter(flat, flat.pts, flat.ext_rot, flat.ext_trans);
   print_full_report(g_summary, flat, freeze_camera);  // sfm.cc:74
 }

@@ -227,6 +227,17 @@ const char* dba_last_error(const dba_handle* h); /* h may be NULL: last create e
  * shard of this rank.  May be called again with a new problem on the same handle.   */
 int dba_problem_set(dba_handle* h, const dba_problem* p);
 
+/* The outer loop of main() (sfm.cc:118-127: solve, filterPoint3d, solve, ...) without a second
+ * upload: removes the observations / points flagged by dba_filter (arrays in the shapes and the
+ * caller's order of the last dba_problem_set / dba_problem_update; either may be NULL) and rebuilds
+ * the device structures from the point-sorted image the engine kept.  Observations of removed points
+ * go with them; surviving points / observations keep their relative order and are re-indexed
+ * 0 .. n-1, exactly as a fresh dba_problem_set of the filtered scene would index them.  Parameters
+ * continue from their current device values.  freeze_camera may change (sfm.cc:111 vs :121).
+ * Single-GPU handles only.                                                                  */
+int dba_problem_update(dba_handle* h, const uint8_t* obs_remove, const uint8_t* pt_remove, int32_t freeze_camera,
+                       int64_t* n_obs_out, int32_t* n_pts_out);
+
 /* Restores the parameters uploaded by the last dba_problem_set (device-side copy). */
 int dba_params_reset(dba_handle* h);
 

@@ -254,9 +254,10 @@ def test_reference_solve_equals_oracle_solve(oracle, reference, tmp_path):
     after = reference.export(h)
     so, xo = oracle.solve(flat, capi.make_options(max_num_iterations=6, function_tolerance=0.0, gradient_tolerance=0.0,
                                                   parameter_tolerance=0.0, linear_solver=capi.DBA_LS_DENSE))
-    np.testing.assert_allclose(sr.trace("cost"), so.trace("cost"), rtol=1e-12)
+    # (two OpenMP runs of the same code differ by the order of their thread-private partial sums)
+    np.testing.assert_allclose(sr.trace("cost"), so.trace("cost"), rtol=1e-10)
     for k in ("pts", "ext_rot", "ext_trans"):
-        assert np.max(np.abs(getattr(after, k) - xo[k])) <= 1e-12 * np.max(np.abs(xo[k]))
+        assert np.max(np.abs(getattr(after, k) - xo[k])) <= 1e-10 * np.max(np.abs(xo[k]))
     reference.free(h)
 
 

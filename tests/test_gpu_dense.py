@@ -105,3 +105,67 @@ def test_dense_schur_shapes(engine, oracle, kind):
         p = synthetic.bal_like(n_cam=120, n_pts=3000, obs_per_point=5, window=25, seed=43, free_intrinsics=0)
     sg, so = _compare_solve(engine, oracle, p, n_iter=3, linear_solver=capi.DBA_LS_DENSE)
     assert sg.linear_solver_used == capi.DBA_LS_DENSE
+
+
+# ------------------------------------------------------ device-resident outer loop (dba_problem_update)
+def _filtered_copy(p, x, obs_remove, pt_remove, freeze):
+    """What a caller that re-gathers the scene would upload after the filter: survivors in their
+    original order, points re-indexed, parameters = the values the first solve left."""
+    keep_pt = pt_remove == 0
+    keep_ob = (obs_remove == 0) & keep_pt[p.obs_pt]
+    new_pt = np.cumsum(keep_pt) - 1
+    q = p.copy()
+    for k in ("obs_xy", "obs_pose_a", "obs_pose_b", "obs_intr"):
+        setattr(q, k, getattr(p, k)[keep_ob])
+    q.obs_pt = new_pt[p.obs_pt[keep_ob]].astype(np.int32)
+    q.pts = x["pts"][keep_pt]
+    q.ext_rot, q.ext_trans = x["ext_rot"].copy(), x["ext_trans"].copy()
+    q.intr_focal, q.intr_dist = x["intr_focal"].copy(), x["intr_dist"].copy()
+    q.pts_rgb = None
+    q.obs_col0 = q.obs_col1 = None
+    q.freeze_camera = freeze
+    return q
+
+
+@pytest.mark.parametrize("name", ["rig", "plain", "bal"])
+def test_problem_update_equals_reupload_bit_for_bit(engine, name):
+    """The reference's outer loop (sfm.cc:111-127): points-only solve, filterPoint3d, full solve, filter, ...
+    With dba_problem_update the engine drops the flagged observations / points itself and keeps the
+    parameters on the device; the following solve is bit-identical to the one after gathering and
+    uploading the filtered scene again — same structures, same summation order."""
+    p = PROBLEMS[name].copy()
+    rng = np.random.default_rng(21)
+    order = rng.permutation(p.n_obs)  # a scene graph in file order, not point-sorted
+    for k in ("obs_xy", "obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr"):
+        setattr(p, k, getattr(p, k)[order].copy())
+    p.freeze_camera = 1
+    opts = capi.make_options(max_num_iterations=3, linear_solver=capi.DBA_LS_AUTO, **FIXED)
+    engine.problem_set(p)
+    engine.solve(opts)
+    x1 = engine.params_get()
+    mse = engine.filter_mse()
+    boundary = float(np.quantile(mse, 0.15))
+    centre = x1["pts"].mean(axis=0)
+    rho = 2.0 * float(np.quantile(((x1["pts"] - centre) ** 2).sum(axis=1), 0.9))
+    obs_rm, pt_rm = engine.filter(boundary, centre, rho)
+    assert 0 < obs_rm.sum() < p.n_obs and 0 < pt_rm.sum() < p.n_pts
+    # path A: engine-side compaction, cameras released for the second solve
+    n_obs, n_pts = engine.problem_update(obs_rm, pt_rm, freeze_camera=0)
+    ca = engine.eval(residuals=True)
+    sa = engine.solve(opts)
+    xa = engine.params_get()
+    fa = engine.filter(boundary, centre, rho)  # caller-order outputs of the compacted problem
+    # path B: the caller gathers the filtered scene and uploads it
+    q = _filtered_copy(p, x1, obs_rm, pt_rm, 0)
+    assert (q.n_obs, q.n_pts) == (n_obs, n_pts)
+    engine.problem_set(q)
+    cb = engine.eval(residuals=True)
+    sb = engine.solve(opts)
+    xb = engine.params_get()
+    fb = engine.filter(boundary, centre, rho)
+    assert ca["cost"] == cb["cost"] and np.array_equal(ca["residuals"], cb["residuals"])
+    assert np.array_equal(sa.trace("cost"), sb.trace("cost")) and sa.num_iterations == sb.num_iterations
+    for k in xa:
+        assert np.array_equal(xa[k], xb[k]), k
+    assert np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1])
+    assert sa.final_cost < sa.initial_cost
