@@ -221,7 +221,8 @@ struct PinnedArena {
   }
 };
 struct dba_upload_state {
-  PinnedArena arena;
+  PinnedArena arena;     // staging of dba_problem_set; its observation arrays stay valid for dba_problem_update
+  PinnedArena readback;  // staging of dba_params_get (separate: it must not overwrite the retained image)
 };
 
 namespace {
@@ -2312,7 +2313,8 @@ int dba_params_get(dba_handle* h, double* pts, double* ext_rot, double* ext_tran
   if (pts) {
     // device -> pinned arena (one asynchronous copy at link rate) -> the caller's buffer (all host cores)
     const size_t total = 3 * static_cast<size_t>(h->world == 1 ? h->n_pts : h->n_pts_global);
-    PinnedArena& A = arena_of(h);
+    arena_of(h);
+    PinnedArena& A = h->upload->readback;
     CU(h, cudaStreamSynchronize(h->st));
     CU(h, A.reserve(std::max(A.cap, total * sizeof(double) + 512)));
     double* stage = A.take<double>(std::max<size_t>(total, 1));
