@@ -798,15 +798,21 @@ int dba_create(dba_handle** out, const dba_config* cfg) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), S_TOTAL * sizeof(double));
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void**>(&h->h_pcg_state), 4 * sizeof(int));
+  auto release = [&]() {  // error exits of dba_create: nothing allocated so far may leak
+    if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    if (h->h_pcg_state) cudaFreeHost(h->h_pcg_state);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+  };
   if (e != cudaSuccess) {
     g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
-    delete h;
+    release();
     return DBA_ERR_CUDA;
   }
   if (h->world > 1) {
     if (!cfg->nccl_unique_id || !nccl_api().load()) {
       g_create_error = "world_size > 1 needs NCCL (libnccl.so.2) and a unique id";
-      delete h;
+      release();
       return DBA_ERR_NCCL;
     }
     NcclUniqueId id;
@@ -814,7 +820,7 @@ int dba_create(dba_handle** out, const dba_config* cfg) {
     int rc = nccl_api().CommInitRank(&h->comm, h->world, id, h->rank);
     if (rc != 0) {
       g_create_error = std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(rc);
-      delete h;
+      release();
       return DBA_ERR_NCCL;
     }
   }

@@ -318,8 +318,17 @@ const char* reason_text(int r) {
 int hemisphere_fit_device(const double* centres_host, int n, double centre_io[3], double* rho_io,
                           const dba_solve_options* o, dba_summary* s, cudaStream_t st, std::string* err,
                           int64_t* launches) {
-  auto fail = [&](cudaError_t e, const char* what) {
+  double* d_pos = nullptr;
+  HemiResult* d_res = nullptr;
+  dba_iteration* d_it = nullptr;
+  auto fail = [&](cudaError_t e, const char* what) {  // every error exit releases what was allocated so far
     *err = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaFree(d_pos);
+    cudaFree(d_res);
+    cudaFree(d_it);
+    d_pos = nullptr;
+    d_res = nullptr;
+    d_it = nullptr;
     return DBA_ERR_CUDA;
   };
   dba_iteration* it_buf = s->iterations;
@@ -329,9 +338,7 @@ int hemisphere_fit_device(const double* centres_host, int n, double centre_io[3]
   s->iterations_capacity = cap;
   s->linear_solver_used = DBA_LS_DENSE;
   s->reduced_system_size = 4;
-  double* d_pos = nullptr;
-  HemiResult* d_res = nullptr;
-  dba_iteration* d_it = nullptr;
+  s->termination = DBA_FAILURE;  // until the kernel has reported
   cudaError_t e;
   const int dev_cap = std::max(cap, 1);
   if ((e = cudaMalloc(&d_pos, sizeof(double) * 3 * std::max(n, 1))) != cudaSuccess) return fail(e, "cudaMalloc");

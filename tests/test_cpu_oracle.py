@@ -261,6 +261,29 @@ def test_reference_solve_equals_oracle_solve(oracle, reference, tmp_path):
     reference.free(h)
 
 
+def test_real_ceres_pins_the_restatement(oracle, tmp_path):
+    """SURVEY 8c-iv / BASELINE.md 2: when a real ceres-solver install exists, `make -C oracle WITH_CERES=1
+    ref_ceres` builds the reference's UNMODIFIED solve() against it; this test then pins the mini-Ceres
+    restatement: the scene the reference's solve() leaves (Ceres defaults, 100 iterations, as sfm.cc:121
+    calls it) equals the oracle's to 1e-6.  Skipped in this image (no Ceres / Eigen / glog, no network)."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libdeeparc_ref_ceres.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libdeeparc_ref_ceres.so not built: needs a ceres-solver install (make -C oracle WITH_CERES=1 ref_ceres)")
+    real = oracle_lib.Reference(path)
+    assert real.lib.ref_is_real_ceres() == 1
+    p = synthetic.arc_rig(n_arc=3, n_ring=4, n_pts=250, obs_per_point=6, seed=44)
+    f = str(tmp_path / "rig.deeparc")
+    synthetic.write_deeparc(p, f)
+    h = real.read(f)
+    flat = real.export(h)
+    real.solve(h, 100, 3600, False)
+    after = real.export(h)
+    so, xo = oracle.solve(flat, capi.make_options(max_num_iterations=100, linear_solver=capi.DBA_LS_DENSE))
+    for k in ("pts", "ext_rot", "ext_trans"):
+        assert np.max(np.abs(getattr(after, k) - xo[k])) <= 1e-6 * np.max(np.abs(xo[k])), k
+    real.free(h)
+
+
 # ------------------------------------------------------------------------------ hemisphere
 def test_hemisphere_fit_closed_form(oracle):
     """|c - p|^2 - rho is linear in (c, rho - |c|^2): the LM fit must land on the lstsq answer."""
