@@ -129,6 +129,7 @@ struct dba_handle {
   DevBuf<int2> d_obs_ip;
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
   DevBuf<unsigned int> d_counters;
+  DevBuf<unsigned long long> d_trace;  // DBA_TAIL_TRACE=1
   DevBuf<int4> d_cam_chunks;
   DevBuf<uint8_t> d_ext_const;
   DevBuf<double> d_center, d_pts[3], d_rot[3], d_trans[3], d_focal[3], d_dist[3];  // [2] = initial copy
@@ -1696,6 +1697,14 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   W.mf_T = h->d_mf_T.p;
   W.vec_partials = h->d_vec_partials.p;
   W.counters = h->d_counters.p;
+  W.trace = nullptr;
+  if (std::getenv("DBA_TAIL_TRACE")) {
+    CU(h, ensure(h->d_trace, 16));
+    unsigned long long init[16] = {0};
+    init[10] = ~0ull;
+    CU(h, cudaMemcpy(h->d_trace.p, init, sizeof init, cudaMemcpyHostToDevice));
+    W.trace = h->d_trace.p;
+  }
   h->Q.fail_flag = h->d_pcg_state.p + 3;
   h->keep.valid = h->world == 1;
   h->keep.xy = s_xy;
@@ -2111,6 +2120,20 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     sum->total_time_in_seconds = now_s() - t_start;
     sum->device_time_in_seconds = ms * 1e-3;
     sum->kernel_launches = h->launches - launches0;
+    if (h->W.trace) {
+      unsigned long long tr[16];
+      if (cudaMemcpy(tr, h->W.trace, sizeof tr, cudaMemcpyDeviceToHost) == cudaSuccess && tr[0] > 0) {
+        const double n = static_cast<double>(tr[0]);
+        std::fprintf(stderr,
+                     "[dba tail trace] rank %d launches %llu  us/launch: product %.1f | sync1 %.1f (CTA spread %.1f) | sums+push %.1f | "
+                     "exchange %.1f | sync2 %.1f | phase2 %.1f | sync3 %.1f | phase3 %.1f\n",
+                     h->rank, tr[0], tr[1] / n * 1e-3, tr[2] / n * 1e-3, tr[9] / n * 1e-3, tr[3] / n * 1e-3, tr[4] / n * 1e-3, tr[5] / n * 1e-3,
+                     tr[6] / n * 1e-3, tr[7] / n * 1e-3, tr[8] / n * 1e-3);
+        unsigned long long init[16] = {0};
+        init[10] = ~0ull;
+        cudaMemcpy(h->W.trace, init, sizeof init, cudaMemcpyHostToDevice);
+      }
+    }
     sum->linear_solver_failures = h->dense_failures;
     sum->pcg_unconverged_solves = h->pcg_unconverged;
     std::snprintf(sum->message, sizeof sum->message, "%s", msg);

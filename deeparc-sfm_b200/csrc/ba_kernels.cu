@@ -101,6 +101,11 @@ __device__ __forceinline__ double sum_partials(const volatile double* part, int 
 }
 
 __device__ __forceinline__ double dot2(const double2 a, const double2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // camera row -> registers with 256-bit loads (sm_100 LDG.256: one L1 tag lookup per 32 B of a row
 // instead of one per 16 B; rows are 32-byte aligned and a multiple of 32 bytes long)
@@ -977,6 +982,14 @@ template <int CB, bool MF>
 __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArrays& W, double tol2, int min_iter, int n_split,
                                          const PeerWin& pw, double* red, int* s_flag);
 
+// Measured in round 2 and not kept (device timestamps, DBA_TAIL_TRACE=1, bal5m, 1 GPU: product 157 us, wait
+// for the slowest CTA 14, per-camera sums 17, dot-product phases + two grid barriers 9, launch + drain 9):
+//  * all K iterations in one cooperative launch (grid barrier instead of launch + drain): the extra loop level
+//    costs 416 bytes of spills inside the tile loop at the 64-register cap, product 157 -> 250 us;
+//  * contiguous tile range per CTA with one shared-memory accumulator row per (range, camera): 30x fewer
+//    partial rows and per-camera sums 17 -> 9 us, but the product loses 9 us (18 KB less L1 per CTA, wider
+//    arrival spread): net zero;
+//  * four warps per camera in the per-camera sums: same 17 us (latency of the dependent loads, not list length).
 // Persistent CTAs (grid = resident CTAs), each walking tiles blockIdx.x, += gridDim.x.  Everything a
 // tile needs from HBM is fetched one tile ahead with cp.async into the other stage buffer, so the
 // only exposed latency per tile is the L1/L2-resident camera-row load.
@@ -985,6 +998,7 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
                                                       const IntrRow* __restrict__ intr_rows, int fuse_tail, double tol2,
                                                       int min_iter, PeerWin pw) {
   if (W.pcg_state[1]) return;
+  const long long t_start = W.trace ? global_ns() : 0;
   using L = MfSmem<CB, TWO, T>;
   constexpr int S = L::S, PS = L::PS, ROW = mf_row_len(CB);
   extern __shared__ __align__(16) unsigned char smem_mf[];
@@ -1235,7 +1249,22 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
   // ---- epilogue (cooperative launch only): the rest of the PCG iteration in the same kernel —
   // per-camera sum of the partials just written, the cross-rank exchange, x / r / z / p updates
   if (fuse_tail) {
+    long long t_done = 0;
+    if (W.trace && tid == 0) {
+      t_done = global_ns();
+      atomicMin(W.trace + 10, static_cast<unsigned long long>(t_done));
+      atomicMax(W.trace + 11, static_cast<unsigned long long>(t_done));
+    }
     cooperative_groups::this_grid().sync();  // every partial of every tile is in memory
+    if (W.trace && tid == 0 && blockIdx.x == 0) {
+      const long long t = global_ns();
+      W.trace[0] += 1;
+      W.trace[1] += static_cast<unsigned long long>(t_done - t_start);
+      W.trace[2] += static_cast<unsigned long long>(t - t_done);
+      W.trace[9] += W.trace[11] - W.trace[10];
+      W.trace[10] = ~0ull;
+      W.trace[11] = 0ull;
+    }
     pcg_tail<CB, true>(D, W, tol2, min_iter, fuse_tail, pw, reinterpret_cast<double*>(smem_mf), reinterpret_cast<int*>(smem_mf + 512));
   }
 }
@@ -1461,11 +1490,6 @@ __device__ __forceinline__ uint4 ll_load(const uint4* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ long long global_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // PCG iteration tail in ONE cooperative launch (grid = co-resident CTAs, grid.sync between the
 // phases): per camera block q = T^T sum(partials) + D_c^2 p and p.q | alpha, x, r, z = M^-1 r and
@@ -1495,6 +1519,15 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
   const bool exchange = pw.world > 1;
   const long long buf_off = static_cast<long long>(pw.seq & 1ull) * pw.world * pw.slot_len;
   double acc_dot = 0.0;
+  const bool tracer = W.trace && blockIdx.x == 0 && tid == 0;
+  long long t_prev = tracer ? global_ns() : 0;
+  auto stamp = [&](int slot) {
+    if (tracer) {
+      const long long t = global_ns();
+      W.trace[slot] += static_cast<unsigned long long>(t - t_prev);
+      t_prev = t;
+    }
+  };
   // ---- phase 1
   // streams rows [r0, r1) of the camera-grouped partial buffer: one contiguous run of (r1 - r0) * CB
   // doubles, fully coalesced 8-byte loads, kM loads (= one chunk of 32 * kM elements, a whole number
@@ -1574,6 +1607,7 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
       }
     }
   }
+  stamp(3);
   if (exchange) {
     // q = sum of the slots in rank order (the same order on every rank) + D_c^2 p; a record is consumed
     // as soon as both halves carry this exchange's sequence number.  A peer that never delivers raises
@@ -1611,7 +1645,9 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
   }
   acc_dot = block_sum(acc_dot, red);
   if (tid == 0) W.vec_partials[blockIdx.x] = acc_dot;
+  stamp(4);
   grid.sync();
+  stamp(5);
   // ---- phase 2
   const double pq = sum_partials(W.vec_partials, gridDim.x, red);
   const double rz = W.pcg_scal[0];
@@ -1639,7 +1675,9 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
   }
   acc_dot = block_sum(acc_dot, red);
   if (tid == 0) W.vec_partials[gridDim.x + blockIdx.x] = acc_dot;
+  stamp(6);
   grid.sync();
+  stamp(7);
   if (breakdown) {
     if (blockIdx.x == 0 && tid == 0) {
       W.pcg_state[1] = 1;  // keep the current x
@@ -1669,6 +1707,7 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
       }
     }
   }
+  stamp(8);
   if (blockIdx.x == 0 && tid == 0) {
     const int it = W.pcg_state[0] + 1;
     W.pcg_state[0] = it;

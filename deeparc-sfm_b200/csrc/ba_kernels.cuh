@@ -125,6 +125,11 @@ struct WorkArrays {
   double* mf_T;      // [n_blocks][9 + cb]  J_l row-major, then sc * free
   double* vec_partials;    // per-CTA partials of the PCG vector kernels
   unsigned int* counters;  // [4] "last block" arrival counters
+  // DBA_TAIL_TRACE=1: device-timestamp accumulators of the fused PCG launch (NULL otherwise), ns:
+  //   [0] launches  [1] product (kernel start -> CTA 0 done)  [2] grid sync 1 (incl. waiting for the slowest CTA)
+  //   [3] phase 1 (per-camera sums + push)  [4] exchange wait + slot sum  [5] grid sync 2  [6] phase 2
+  //   [7] grid sync 3  [8] phase 3  [9] spread of the CTAs' product-done times  [10] min  [11] max (scratch)
+  unsigned long long* trace;
 };
 
 // Peer windows of the fused PCG tail (multi-GPU): every rank owns one window in its HBM,
