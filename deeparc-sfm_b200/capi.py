@@ -15,7 +15,8 @@ import numpy as np
 from .synthetic import Problem
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdeeparc_ba.so")
+# DBA_LIB=checked selects the build with device-side index assertions (make CHECKED=1)
+LIB_PATH = os.path.join(_HERE, "lib", "libdeeparc_ba_checked.so" if os.environ.get("DBA_LIB") == "checked" else "libdeeparc_ba.so")
 
 DBA_OK = 0
 DBA_ERR_INVALID_ARGUMENT = -1

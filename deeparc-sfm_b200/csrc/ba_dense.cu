@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
   const int b1 = static_cast<int>(static_cast<int64_t>(Q.n_batches) * (blockIdx.x + 1) / gridDim.x);
   for (int b = b0; b < b1; ++b) {
     const int p0 = Q.batch_pt[b], np = Q.batch_pt[b + 1] - p0;
+    DBA_CHECK(np > 0 && np <= kDnPtsCap && p0 >= 0 && p0 + np <= D.n_pts);
     // ---- the batch's points: segments, entry capacities, cleared lookup
     for (int i = tid; i < (np * nbs) / 2; i += kDnThreads) reinterpret_cast<unsigned int*>(sLook)[i] = 0u;
     if (tid <= np) sSeg[tid] = D.pt_first[p0 + tid];
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
     // ---- one thread per point: compact list of the camera blocks it touches; L with C^-1 = L L^T
     if (tid < np) {
       const int base = sBase[tid], cap = sBase[tid + 1] - base;
+      DBA_CHECK(base >= 0 && base + cap <= kDnEntCap);
       int cnt = 0;
       unsigned short* look = sLook + tid * nbs;
       for (int o = sSeg[tid]; o < sSeg[tid + 1]; ++o) {
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
         for (int slot = 0; slot < 2; ++slot) {
           const int blk = slot ? ab.y : ab.x;
           if (blk < 0 || look[blk]) continue;
+          DBA_CHECK(blk < nb && cnt < cap);
           look[blk] = static_cast<unsigned short>(++cnt);
           sEnt[base + cnt - 1] = (static_cast<unsigned int>(tid) << 16) | static_cast<unsigned int>(blk);
         }
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
         if (!ia) continue;
         const int ib = (A == B) ? ia : sLook[p * nbs + B];
         if (!ib) continue;
+        DBA_CHECK(sBase[p] + ia - 1 < sBase[p + 1] && sBase[p] + ib - 1 < sBase[p + 1]);
         const double* za = sZ + (sBase[p] + ia - 1) * ZS;
         const double* zb = sZ + (sBase[p] + ib - 1) * ZS;
         double a[3 * CB];
@@ -217,7 +221,8 @@ __global__ void __launch_bounds__(128) k_pair_gather(DeviceProblem D, DenseWork 
   const int64_t ld = D.ld;
   for (int e = ch.y + threadIdx.x; e < ch.z; e += blockDim.x) {
     const int ent = Q.pair_entries[e];
-    const int o = ent >> 1, swap = ent & 1;  // swap: block b of the observation is the lower-numbered block
+    const int o = ent >> 1, swap = ent & 1;
+    DBA_CHECK(o >= 0 && o < D.n_obs && D.obs_ab[o].y >= 0);  // swap: block b of the observation is the lower-numbered block
     const double2* J = D.J + o;
     const int plo = kPlaneJA + (swap ? 6 : 0), phi = kPlaneJA + (swap ? 0 : 6);
     double2 FH[6];

@@ -299,6 +299,9 @@ __global__ void __launch_bounds__(kJacThreads, MINB) k_jacobian_tile(DeviceProbl
     const int2 idx = D.obs_ip[o];
     const int2 ab = D.obs_ab[o];
     const ushort2 lc = D.obs_lc[o];
+    DBA_CHECK(idx.y >= 0 && idx.y < D.n_pts && idx.x >= 0 && idx.x < D.n_intr);
+    DBA_CHECK(ab.x >= 0 && ab.x < D.n_ext && ab.y >= -1 && ab.y < D.n_ext);
+    DBA_CHECK(CB == 0 || (lc.x < tm.n_parts && (ab.y < 0 || lc.y < tm.n_parts)));
     const double* Xp = P.pts + 3 * static_cast<int64_t>(idx.y);
     const double X[3] = {Xp[0], Xp[1], Xp[2]};
     const double* sp = unit_scale ? nullptr : W.sp + 3 * static_cast<int64_t>(idx.y);
@@ -381,6 +384,7 @@ __global__ void __launch_bounds__(T, MB) k_point_prepare(DeviceProblem D, WorkAr
   const int pt = pt0 + tid;
   if (pt < pt1) {
     const int a = D.pt_first[pt] - obs0, b = D.pt_first[pt + 1] - obs0;
+    DBA_CHECK(a >= 0 && a <= b && b <= obs1 - obs0 && b <= T);
     double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = a; i < b; ++i) {
 #pragma unroll
@@ -448,6 +452,8 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
     const int ent = D.cam_entries[e];
     const int o = ent >> 1;
     const int slot = ent & 1;
+    DBA_CHECK(o >= 0 && o < D.n_obs && (slot == 0 || D.two));
+    DBA_CHECK((slot ? D.obs_ab[o].y : D.obs_ab[o].x) == ch.x);
     const double2* J = D.J + o;
     const int base = kPlaneJA + (slot ? D.cb : 0);
     double2 F[CB];
@@ -811,11 +817,13 @@ __global__ void __launch_bounds__(T, 1024 / T) k_spmv_tile(DeviceProblem D, Work
     for (int i = i0; i < i1; ++i) {
       const unsigned int it = s_items[i];
       const int lo = it & 0x7fffu;
+      DBA_CHECK(lo < n_tile && i < tm.n_items);
       const int row = TWO ? 3 + (it >> 15) * CB + k0 : 3 + k0;  // slot-B items: planes 3+CB.. (CB == 6 there)
       a0 += sJ[row * L::kStride + lo].x;
       a1 += sJ[(row + 1) * L::kStride + lo].x;
       a2 += sJ[(row + 2) * L::kStride + lo].x;
     }
+    DBA_CHECK(D.part_dst[tm.g0 + lc] >= 0 && D.part_dst[tm.g0 + lc] < D.n_partials);
     double* out = W.partials_q + static_cast<int64_t>(D.part_dst[tm.g0 + lc]) * CB + k0;
     out[0] = a0;
     out[1] = a1;
@@ -1082,6 +1090,8 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
     const bool active = blk_a >= 0;
     const bool has_b = TWO && blk_b >= 0;
     const int lp = lplo >> 16, lo = lplo & 0xffffu;
+    DBA_CHECK(!active || (blk_a < D.n_blocks && blk_b < D.n_blocks && lp < tm.n_pts && lo < tm.n_obs && tid < T));
+    DBA_CHECK(tm.n_pts <= L::PM && tm.n_parts <= L::MP && tm.n_obs <= T);
     // ---- phase 1: geometry of this observation, u = F p, v = E^T u
     // (xa, xb: the vector the rotation derivative crosses with: R X, or X itself in Ceres' small-angle branch)
     double G[2][3], E[2][3], GA[2][3];
@@ -1170,6 +1180,7 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
     // observation; the Jacobi scale of the point columns is applied here, once per point)
     if (tid < tm.n_pts) {
       const int sa = seg[tid] - tm.obs0, sb = seg[tid + 1] - tm.obs0;
+      DBA_CHECK(sa >= 0 && sa <= sb && sb <= tm.n_obs);
       double z0 = 0.0, z1 = 0.0, z2 = 0.0;
       for (int i = sa; i < sb; ++i) {
         z0 += sV[0 * S + i];
@@ -1228,6 +1239,7 @@ __global__ void __launch_bounds__(T, MINB) k_spmv_mf(DeviceProblem D, WorkArrays
     for (int wk = tid; wk < n_work; wk += T) {
       const int lc = wk / CB, k = wk - lc * CB;
       const int i0 = s_first[lc], i1 = s_first[lc + 1];
+      DBA_CHECK(i0 >= 0 && i0 <= i1 && i1 <= (TWO ? tm.n_items : tm.n_obs) && s_dst[lc] >= 0 && s_dst[lc] < D.n_partials);
       double a0 = 0.0;
       if (TWO) {
         for (int i = i0; i < i1; ++i) {
@@ -1749,6 +1761,7 @@ __global__ void __launch_bounds__(T, MB) k_back_substitute(DeviceProblem D, Work
   int lp = 0;
   if (active) {
     lp = D.obs_ip[o].y - pt0;
+    DBA_CHECK(lp >= 0 && lp < pt1 - pt0 && lp < T);
     const double2* J = D.J + o;
     const int64_t ld = D.ld;
     r = J[kPlaneR * ld];
@@ -1897,6 +1910,7 @@ __global__ void __launch_bounds__(256) k_filter_flags(DeviceProblem D, const dou
   const int pt = blockIdx.x * blockDim.x + threadIdx.x;
   if (pt >= D.n_pts) return;
   const int a = D.pt_first[pt], b = D.pt_first[pt + 1];
+  DBA_CHECK(a >= 0 && a <= b && b <= D.n_obs);
   int kept = 0;
   for (int o = a; o < b; ++o) kept += (mse[o] < boundary) ? 0 : 1;
   bool gone = kept == 0;

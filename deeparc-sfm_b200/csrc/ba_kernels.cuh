@@ -14,6 +14,26 @@
 
 #include "ba_math.cuh"
 
+// Checked build (`make CHECKED=1` -> lib/libdeeparc_ba_checked.so): device-side assertions on every
+// data-dependent index of the tile / product / gather / dense kernels.  compute-sanitizer is closed on the
+// GPU pool this was developed on (profiles/r02_sanitizer.md); these checks are the substitute, run over
+// scripts/sanitize_probe.py.  A failed check prints the site and traps (the launch fails with an error).
+#ifdef DBA_CHECKED
+#include <cstdio>
+#define DBA_CHECK(cond)                                                                        \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      printf("DBA_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, \
+             static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));                     \
+      __trap();                                                                                \
+    }                                                                                          \
+  } while (0)
+#else
+#define DBA_CHECK(cond) \
+  do {                  \
+  } while (0)
+#endif
+
 namespace dba {
 
 constexpr int kTile = 256;       // default tile capacity (observations per tile == threads per tile CTA);

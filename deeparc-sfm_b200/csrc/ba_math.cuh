@@ -114,7 +114,7 @@ __host__ __device__ __forceinline__ void rotation_derivative(const PoseRow& P, c
 struct Projection {
   double r0, r1;      // residual
   double G[2][3];     // d r / d p (camera-frame point)
-  double df[2];       // d r / d f   (nf = 1: both rows; nf = 2: d r0/d fx only, r1 entry 0)
+  double df[2];       // d r / d f   (nf = 1: both rows; nf = 2: (d r0/d fx, d r1/d fy))
   double dk0[2], dk1[2];
 };
 
@@ -140,8 +140,11 @@ __host__ __device__ __forceinline__ void project(const IntrRow& I, const double 
     out.G[1][0] = r1u * iz;
     out.G[1][1] = r1v * iz;
     out.G[1][2] = -(r1u * u + r1v * v) * iz;
+    // nf = 1: d r / d f.  nf = 2: the diagonal of the 2x2 focal Jacobian (d r0/d fx, d r1/d fy); its
+    // off-diagonal entries are identically zero.  (Free intrinsics need nf = 1, so the solver only ever
+    // sees the first meaning; dba_eval reports both.)
     out.df[0] = d * u;
-    out.df[1] = (I.nf == 2.0) ? 0.0 : d * v;
+    out.df[1] = d * v;
     // coefficients that are not parameters of this intrinsic (nd < 1, nd < 2) have no column
     const double m0 = I.nd >= 1.0 ? rr : 0.0, m1 = I.nd >= 2.0 ? rr * rr : 0.0;
     out.dk0[0] = I.fx * u * m0;

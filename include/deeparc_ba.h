@@ -224,7 +224,11 @@ const char* dba_last_error(const dba_handle* h); /* h may be NULL: last create e
 
 /* Replaces the Problem construction loop of solve() (sfm.cc:36-65): copies the SoA
  * arrays to the device, validates indices, sorts observations by point, builds the
- * shard of this rank.  May be called again with a new problem on the same handle.   */
+ * shard of this rank.  May be called again with a new problem on the same handle.
+ * Limits (DBA_ERR_UNSUPPORTED beyond them; the reference has none): a point may carry at
+ * most 1024 observations (512 when observations compose two poses and cameras are free) —
+ * a point and its observations are processed by one thread block; fewer than 2^30
+ * observations per handle; free_intrinsics as described at dba_problem.                 */
 int dba_problem_set(dba_handle* h, const dba_problem* p);
 
 /* The outer loop of main() (sfm.cc:118-127: solve, filterPoint3d, solve, ...) without a second
@@ -249,8 +253,9 @@ int dba_params_reset(dba_handle* h);
  *   jac_pt     [n_obs][2][3]  d r / d point
  *   jac_pose_a [n_obs][2][6]  d r / d (rot_a, trans_a)
  *   jac_pose_b [n_obs][2][6]  d r / d (rot_b, trans_b); zero rows where pose_b == -1
- *   jac_intr   [n_obs][2][3]  d r / d (f, k0, k1)  (nf = 1 layout; for nf = 2 column 0
- *                             is d/d fx and the d/d fy column is not reported)
+ *   jac_intr   [n_obs][2][3]  d r / d (f, k0, k1).  nf = 2: column 0 holds the diagonal of the
+ *                             2x2 focal Jacobian, (d r0 / d fx, d r1 / d fy); the off-diagonal
+ *                             entries d r0 / d fy and d r1 / d fx are identically zero
  * Jacobians are UNSCALED and ignore constancy masks (raw derivatives).  Single-GPU
  * handles only for the per-observation outputs.                                       */
 int dba_eval(dba_handle* h, double* cost, double* residuals, double* jac_pt, double* jac_pose_a,

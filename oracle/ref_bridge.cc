@@ -170,7 +170,9 @@ int ref_eval(const dba_problem* p, double* cost, double* residuals, double* jac_
         }
     if (jac_intr)
       for (int k = 0; k < 2; ++k) {
-        jac_intr[6 * i + 3 * k + 0] = J2[nf * k + 0];
+        // nf = 2: column 0 carries the diagonal of the 2x2 focal Jacobian, (d r0/d fx, d r1/d fy);
+        // its off-diagonal entries d r0/d fy, d r1/d fx are identically zero (snavely...hh:53-55, :71-72)
+        jac_intr[6 * i + 3 * k + 0] = J2[nf * k + (nf == 2 ? k : 0)];
         jac_intr[6 * i + 3 * k + 1] = nd >= 1 ? J3[nd * k + 0] : 0.0;
         jac_intr[6 * i + 3 * k + 2] = nd >= 2 ? J3[nd * k + 1] : 0.0;
       }
