@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../include/deeparc_ba.h"
+#include "ba_build.cuh"
 #include "ba_kernels.cuh"
 #include "nccl_dyn.h"
 
@@ -130,6 +131,14 @@ struct dba_handle {
   DevBuf<int> d_tile_obs, d_tile_pt, d_pt_first, d_cam_entries, d_cam_chunk_first, d_nf, d_nd, d_pcg_state;
   DevBuf<unsigned int> d_counters;
   DevBuf<unsigned long long> d_trace;  // DBA_TAIL_TRACE=1
+  // device-side problem construction (ba_build.cu): raw shard arrays and scratch
+  DevBuf<double> d_raw_xy;
+  DevBuf<int> d_raw_pt, d_raw_a, d_raw_b, d_raw_in, d_bld_a, d_bld_flags, d_bld_np, d_bld_g0, d_bld_key, d_bld_id, d_bld_key2, d_bld_id2,
+      d_bld_first, d_bld_cnt;
+  DevBuf<unsigned char> d_bld_temp;
+  std::vector<double2> keep_xy_v;
+  std::vector<int2> keep_ip_v, keep_ab_v;
+  int build_mode = 0;  // how the last dba_problem_set built its index structures: 0 host cores, 1 device
   DevBuf<int4> d_cam_chunks;
   DevBuf<uint8_t> d_ext_const;
   DevBuf<double> d_center, d_pts[3], d_rot[3], d_trans[3], d_focal[3], d_dist[3];  // [2] = initial copy
@@ -421,6 +430,247 @@ int setup_peer_windows(dba_handle* h, size_t nvec) {
     pw.ll[r] = reinterpret_cast<uint4*>(base);
   }
   h->p2p_ready = true;
+  return DBA_OK;
+}
+
+// ---- pieces of dba_problem_set shared by the host build and the device build (ba_build.cu)
+struct BuildSizes {
+  int64_t nl = 0, ld = 64, n_entries = 0;
+  int n_pts = 0, n_tiles = 0, tile_cap = 256, n_chunks = 0, n_partials = 0;
+  size_t n_cols = 0;
+  int mf_w = 2, two = 0, cb = 0, intr_is_pose = 1;
+  bool dense_ok = false;
+  int n_dn_batches = 0;
+};
+
+// every device buffer of the problem at its size (grow only), solver switches from the environment, peer
+// windows, dense-solver work space; nothing here depends on where the index arrays were built
+int ensure_work_buffers(dba_handle* h, const BuildSizes& z) {
+  const int64_t nl = z.nl, n_entries = z.n_entries;
+  const int n_pts = z.n_pts, n_tiles = z.n_tiles, n_chunks = z.n_chunks, n_partials = z.n_partials, two = z.two, cb = z.cb;
+  const int n_ext = h->n_ext, n_intr = h->n_intr;
+  h->plane_w = 4 + cb + ((two && cb) ? 6 : 0);
+  h->j_planes = h->plane_w;
+  CU(h, ensure(h->d_obs_xy, nl));
+  CU(h, ensure(h->d_obs_ip, nl));
+  CU(h, ensure(h->d_obs_ab, nl));
+  CU(h, ensure(h->d_obs_lp, nl));
+  CU(h, ensure(h->d_tile_obs, n_tiles + 1));
+  CU(h, ensure(h->d_tile_pt, n_tiles + 1));
+  CU(h, ensure(h->d_pt_first, n_pts + 1));
+  CU(h, ensure(h->d_cam_entries, n_entries));
+  CU(h, ensure(h->d_cam_chunks, n_chunks));
+  CU(h, ensure(h->d_cam_chunk_first, n_ext + 1));
+  CU(h, ensure(h->d_tile_meta, n_tiles));
+  CU(h, ensure(h->d_part_first_rel, n_entries + n_tiles + 1));
+  CU(h, ensure(h->d_items, n_entries));
+  CU(h, ensure(h->d_cam_part_first, n_ext + 1));
+  CU(h, ensure(h->d_part_dst, n_partials));
+  CU(h, ensure(h->d_part_blk, n_partials));
+  CU(h, ensure(h->d_obs_lc, nl));
+  CU(h, ensure(h->d_mf_cols, std::max<size_t>(z.n_cols * z.mf_w, 1)));
+  CU(h, ensure(h->d_items_mf, (two && cb) ? n_entries : 1));
+  CU(h, ensure(h->d_part_first, n_entries + n_tiles + 1));
+  CU(h, ensure(h->d_mf_rows, static_cast<size_t>(n_ext) * mf_row_len(cb)));
+  CU(h, ensure(h->d_mf_T, static_cast<size_t>(n_ext) * (9 + cb)));
+  {
+    const char* env = std::getenv("DBA_SPMV");
+    // default: matrix-free for single-pose problems; composed two-pose rigs (two row fetches, 128
+    // registers) measured faster on the plane product (arc1m: 360 vs 304 LM it/s)
+    h->mf = two ? 0 : 1;
+    if (env && std::strcmp(env, "planes") == 0) h->mf = 0;
+    if (env && std::strcmp(env, "mf") == 0) h->mf = 1;
+    const char* ef = std::getenv("DBA_PCG_FUSED");
+    h->fuse_pcg = !(ef && std::strcmp(ef, "0") == 0);
+    const char* et = std::getenv("DBA_MF_TAIL");
+    h->mf_tail = !(et && std::strcmp(et, "0") == 0);
+    const char* es = std::getenv("DBA_SPECULATE");
+    h->speculate = !(es && std::strcmp(es, "0") == 0);
+  }
+  CU(h, ensure(h->d_partials_q, static_cast<size_t>(n_partials) * std::max(cb, 1)));
+  CU(h, ensure(h->d_J, z.ld * h->j_planes));
+  CU(h, ensure(h->d_ext_const, n_ext));
+  CU(h, ensure(h->d_center, 2 * n_intr));
+  CU(h, ensure(h->d_nf, n_intr));
+  CU(h, ensure(h->d_nd, n_intr));
+  for (int s = 0; s < 3; ++s) {
+    CU(h, ensure(h->d_pts[s], 3 * static_cast<size_t>(n_pts)));
+    CU(h, ensure(h->d_rot[s], 3 * n_ext));
+    CU(h, ensure(h->d_trans[s], 3 * n_ext));
+    CU(h, ensure(h->d_focal[s], 2 * n_intr));
+    CU(h, ensure(h->d_dist[s], 2 * n_intr));
+  }
+  for (int s = 0; s < 2; ++s) {
+    CU(h, ensure(h->d_pose_rows[s], n_ext));
+    CU(h, ensure(h->d_intr_rows[s], n_intr));
+  }
+  const size_t nvec = static_cast<size_t>(n_ext) * std::max(cb, 1);
+  CU(h, ensure(h->d_sp, 3 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_cinv, 6 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_tp, 4 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_dp, 3 * static_cast<size_t>(n_pts)));
+  CU(h, ensure(h->d_sc, nvec));
+  CU(h, ensure(h->d_cam_acc, nvec * (std::max(cb, 1) + 3)));
+  CU(h, ensure(h->d_cam_chunk_acc, static_cast<size_t>(std::max(n_chunks, 1)) * (std::max(cb, 1) * (std::max(cb, 1) + 1) / 2 + 3 * std::max(cb, 1))));
+  CU(h, ensure(h->d_minv, nvec * std::max(cb, 1)));
+  CU(h, ensure(h->d_dc2, nvec));
+  CU(h, ensure(h->d_x, nvec));
+  CU(h, ensure(h->d_r, nvec));
+  CU(h, ensure(h->d_z, nvec));
+  CU(h, ensure(h->d_p, nvec));
+  CU(h, ensure(h->d_q, nvec));
+  h->q_split = (n_ext >= 296 || !cb) ? 1 : std::min(32, (592 + std::max(n_ext, 1) - 1) / std::max(n_ext, 1));
+  if (h->world > 1 && cb) {
+    int rc = setup_peer_windows(h, nvec);
+    if (rc != DBA_OK) return rc;
+  }
+  h->dense_ok = z.dense_ok;
+  h->Q = DenseWork{};
+  if (z.dense_ok) {
+    h->Q.n_batches = z.n_dn_batches;
+    h->Q.n_pairs = n_ext * (n_ext + 1) / 2;
+    CU(h, ensure(h->d_dn_batch, static_cast<size_t>(z.n_dn_batches) + 1));
+    CU(h, ensure(h->d_dn_S, nvec * nvec));
+    CU(h, ensure(h->d_dn_Spart, static_cast<size_t>(dense_slices(h->Q)) * h->Q.n_pairs * cb * cb));
+    h->Q.batch_pt = h->d_dn_batch.p;
+    h->Q.S = h->d_dn_S.p;
+    h->Q.S_part = h->d_dn_Spart.p;
+  }
+  CU(h, ensure(h->d_q_split, nvec * static_cast<size_t>(h->q_split)));
+  CU(h, ensure(h->d_vec_partials, nvec / 128 + 2 * static_cast<size_t>(n_ext) + 8192));  // k_partials_to_q: one partial per block
+  CU(h, ensure(h->d_counters, 4));
+  // largest user: apply_step_and_evaluate keeps three ranges side by side (tiles | point update | cost)
+  const size_t n_part = static_cast<size_t>((nl + 255) / 256) + 3 * static_cast<size_t>(n_tiles) + 3 +
+                        2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256) + 256;
+  CU(h, ensure(h->d_partA, n_part));
+  CU(h, ensure(h->d_partB, 3 * static_cast<size_t>((std::max(n_ext, n_intr) + 63) / 64) + 64));
+  CU(h, ensure(h->d_scalars, S_TOTAL));
+  CU(h, ensure(h->d_scalars_red, S_TOTAL));
+  CU(h, ensure(h->d_pcg_scal, 8));
+  CU(h, ensure(h->d_pcg_state, 4));
+  CU(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * sizeof(unsigned int), h->st));
+  CU(h, cudaMemsetAsync(h->d_scalars.p, 0, S_TOTAL * sizeof(double), h->st));
+  CU(h, cudaMemsetAsync(h->d_x.p, 0, std::max<size_t>(nvec, 1) * sizeof(double), h->st));
+  CU(h, cudaMemsetAsync(h->d_pcg_state.p, 0, 4 * sizeof(int), h->st));
+  if (h->world > 1) CU(h, ensure(h->d_full_pts, 3 * static_cast<size_t>(h->n_pts_global)));  // dba_params_get
+  return DBA_OK;
+}
+
+// camera-side parameters and constant tables of the caller (slot 2 = pristine copy for dba_params_reset);
+// also what dba_problem_update needs to keep
+int upload_params(dba_handle* h, const dba_problem* p) {
+  const int n_ext = h->n_ext, n_intr = h->n_intr;
+  auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->st);
+  };
+  std::vector<uint8_t>& ext_const = h->keep.ext_const;
+  ext_const.assign(std::max(n_ext, 1), 0);
+  h->any_const = false;
+  if (p->ext_const)
+    for (int i = 0; i < n_ext; ++i) {
+      ext_const[i] = p->ext_const[i] ? 1 : 0;
+      h->any_const |= ext_const[i] != 0;
+    }
+  CU(h, up(h->d_ext_const.p, ext_const.data(), n_ext));
+  CU(h, up(h->d_center.p, p->intr_center, 2 * sizeof(double) * n_intr));
+  CU(h, up(h->d_nf.p, p->intr_nf, sizeof(int) * n_intr));
+  CU(h, up(h->d_nd.p, p->intr_nd, sizeof(int) * n_intr));
+  CU(h, up(h->d_rot[2].p, p->ext_rot, 3 * sizeof(double) * n_ext));
+  CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * n_ext));
+  CU(h, up(h->d_focal[2].p, p->intr_focal, 2 * sizeof(double) * n_intr));
+  CU(h, up(h->d_dist[2].p, p->intr_dist, 2 * sizeof(double) * n_intr));
+  h->keep.center.assign(p->intr_center, p->intr_center + 2 * static_cast<size_t>(n_intr));
+  h->keep.nf.assign(p->intr_nf, p->intr_nf + n_intr);
+  h->keep.nd.assign(p->intr_nd, p->intr_nd + n_intr);
+  h->keep.free_intrinsics = p->free_intrinsics;
+  return DBA_OK;
+}
+
+// DeviceProblem / ParamSet / WorkArrays point at the buffers
+int bind_problem(dba_handle* h, const BuildSizes& z) {
+  h->n_cam_entries = z.n_entries;
+  DeviceProblem& D = h->D;
+  D.n_obs = z.nl;
+  D.ld = z.ld;
+  D.n_pts = z.n_pts;
+  D.n_ext = h->n_ext;
+  D.n_intr = h->n_intr;
+  D.n_tiles = z.n_tiles;
+  D.tile = z.tile_cap;
+  D.cb = z.cb;
+  D.two = z.two;
+  D.n_blocks = h->n_ext;
+  D.obs_xy = h->d_obs_xy.p;
+  D.obs_ip = h->d_obs_ip.p;
+  D.tile_obs = h->d_tile_obs.p;
+  D.tile_pt = h->d_tile_pt.p;
+  D.pt_first = h->d_pt_first.p;
+  D.cam_entries = h->d_cam_entries.p;
+  D.cam_chunks = h->d_cam_chunks.p;
+  D.cam_chunk_first = h->d_cam_chunk_first.p;
+  D.n_chunks = z.n_chunks;
+  D.J = h->d_J.p;
+  D.tile_meta = h->d_tile_meta.p;
+  D.obs_ab = h->d_obs_ab.p;
+  D.obs_lp = h->d_obs_lp.p;
+  D.part_first_rel = h->d_part_first_rel.p;
+  D.items = h->d_items.p;
+  D.cam_part_first = h->d_cam_part_first.p;
+  D.n_partials = z.n_partials;
+  D.mf_cols = h->d_mf_cols.p;
+  D.items_mf = h->d_items_mf.p;
+  D.part_dst = h->d_part_dst.p;
+  D.part_blk = h->d_part_blk.p;
+  D.obs_lc = h->d_obs_lc.p;
+  D.intr_is_pose = z.intr_is_pose;
+  D.part_first = h->d_part_first.p;
+  for (int s = 0; s < 2; ++s) {
+    ParamSet& P = h->P[s];
+    P.pts = h->d_pts[s].p;
+    P.ext_rot = h->d_rot[s].p;
+    P.ext_trans = h->d_trans[s].p;
+    P.focal = h->d_focal[s].p;
+    P.dist = h->d_dist[s].p;
+    P.center = h->d_center.p;
+    P.nf = h->d_nf.p;
+    P.nd = h->d_nd.p;
+    P.pose_rows = h->d_pose_rows[s].p;
+    P.intr_rows = h->d_intr_rows[s].p;
+  }
+  WorkArrays& W = h->W;
+  W.sp = h->d_sp.p;
+  W.sc = h->d_sc.p;
+  W.cinv = h->d_cinv.p;
+  W.tp = h->d_tp.p;
+  W.dp = h->d_dp.p;
+  W.cam_acc = h->d_cam_acc.p;
+  W.cam_chunk_acc = h->d_cam_chunk_acc.p;
+  W.minv = h->d_minv.p;
+  W.dc2 = h->d_dc2.p;
+  W.x = h->d_x.p;
+  W.r = h->d_r.p;
+  W.z = h->d_z.p;
+  W.p = h->d_p.p;
+  W.q = h->d_q.p;
+  W.scalars = h->d_scalars.p;
+  W.pcg_state = h->d_pcg_state.p;
+  W.pcg_scal = h->d_pcg_scal.p;
+  W.partials_q = h->d_partials_q.p;
+  W.q_split = h->d_q_split.p;
+  W.mf_rows = h->d_mf_rows.p;
+  W.mf_T = h->d_mf_T.p;
+  W.vec_partials = h->d_vec_partials.p;
+  W.counters = h->d_counters.p;
+  W.trace = nullptr;
+  if (std::getenv("DBA_TAIL_TRACE")) {
+    CU(h, ensure(h->d_trace, 16));
+    unsigned long long init[16] = {0};
+    init[10] = ~0ull;
+    CU(h, cudaMemcpy(h->d_trace.p, init, sizeof init, cudaMemcpyHostToDevice));
+    W.trace = h->d_trace.p;
+  }
+  h->Q.fail_flag = h->d_pcg_state.p + 3;
   return DBA_OK;
 }
 
@@ -919,6 +1169,337 @@ struct OmpThreadScope {
   ~OmpThreadScope() { omp_set_num_threads(saved); }
 };
 
+// ------------------------------------------------------------------- device-side problem construction
+// SURVEY 8 f-3.  Point-sorted, single-pose input only; *handled = 0 leaves everything to the host build.
+// With several ranks every rank stages and builds ONLY its shard (the host build hands every rank the whole
+// problem and each builds its shard with cores / world threads).
+static int problem_set_device(dba_handle* h, const dba_problem* p, int* handled) {
+  *handled = 0;
+  const int64_t n = p->n_obs;
+  const int n_ext = p->n_ext, n_intr = p->n_intr;
+  if (n <= 0 || p->n_pts <= 0 || n_ext <= 0) return DBA_OK;
+  const bool timing = std::getenv("DBA_TIMING") != nullptr;
+  double t_mark = now_s();
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    const double t = now_s();
+    std::fprintf(stderr, "[dba_problem_set/device] %-26s %8.2f ms\n", what, 1e3 * (t - t_mark));
+    t_mark = t;
+  };
+  for (int i = 0; i < n_intr; ++i)
+    if (p->intr_nf[i] < 1 || p->intr_nf[i] > 2 || p->intr_nd[i] < 0 || p->intr_nd[i] > 2)
+      return h->fail(DBA_ERR_INVALID_ARGUMENT, "intrinsic %d: nf must be 1|2 and nd 0|1|2", i);
+  const int freeze = p->freeze_camera != 0;
+  const int free_intr = (!freeze && p->free_intrinsics) ? 1 : 0;
+  if (free_intr) {
+    if (n_ext != n_intr) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs one intrinsic per extrinsic");
+    for (int i = 0; i < n_intr; ++i)
+      if (p->intr_nf[i] != 1 || p->intr_nd[i] != 2) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs nf=1, nd=2");
+  }
+  const int cb = freeze ? 0 : (free_intr ? 9 : 6);
+  // shard of this rank, assuming sorted input (verified on the device below): same cuts as dba_shard_plan
+  auto cut_pt = [&](int r) -> int {
+    if (r <= 0) return 0;
+    if (r >= h->world) return p->n_pts;
+    const int64_t target = n * r / h->world;
+    return target <= 0 ? 0 : std::min(p->obs_pt[target - 1] + 1, p->n_pts);
+  };
+  auto first_obs_of = [&](int pt) -> int64_t {  // lower bound in the (sorted) point column
+    return std::lower_bound(p->obs_pt, p->obs_pt + n, pt) - p->obs_pt;
+  };
+  int pt_lo = cut_pt(h->rank);
+  for (int r = 1; r < h->rank; ++r) pt_lo = std::max(pt_lo, cut_pt(r));
+  int pt_hi = std::max(cut_pt(h->rank + 1), pt_lo);
+  if (h->rank + 1 == h->world) pt_hi = p->n_pts;
+  if (pt_lo < 0 || pt_hi > p->n_pts) return DBA_OK;  // garbage point ids: let the host path report them
+  const int64_t obs_lo = h->world > 1 ? first_obs_of(pt_lo) : 0, obs_hi = h->world > 1 ? first_obs_of(pt_hi) : n;
+  const int64_t nl = obs_hi - obs_lo;
+  const int n_pts = pt_hi - pt_lo;
+  if (nl >= (int64_t{1} << 30)) return DBA_OK;
+  // ---- stage the raw shard through the pinned arena (all host cores of this rank), one DMA per array
+  OmpThreadScope omp_scope(h->world);
+  PinnedArena& A = arena_of(h);
+  CU(h, cudaStreamSynchronize(h->st));
+  const bool have_b = p->obs_pose_b != nullptr;
+  CU(h, A.reserve(pad256(nl * 16) + (have_b ? 4 : 3) * pad256(nl * 4) + pad256(static_cast<size_t>(n_pts) * 24) +
+                  pad256((static_cast<size_t>(n_pts) + 2) * 4) + 8192));
+  double* s_xy = A.take<double>(static_cast<size_t>(std::max<int64_t>(2 * nl, 1)));
+  int* s_pt = A.take<int>(static_cast<size_t>(std::max<int64_t>(nl, 1)));
+  int* s_a = A.take<int>(static_cast<size_t>(std::max<int64_t>(nl, 1)));
+  int* s_b = have_b ? A.take<int>(static_cast<size_t>(std::max<int64_t>(nl, 1))) : nullptr;
+  int* s_in = A.take<int>(static_cast<size_t>(std::max<int64_t>(nl, 1)));
+  double* s_pts = A.take<double>(static_cast<size_t>(std::max(3 * n_pts, 1)));
+  int* s_first = A.take<int>(static_cast<size_t>(n_pts) + 2);
+  int* s_flags = A.take<int>(8);
+  auto stage = [&](void* dst, const void* src, size_t bytes) {
+    const int64_t chunks = static_cast<int64_t>((bytes + (1 << 20) - 1) >> 20);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < chunks; ++c) {
+      const size_t a = static_cast<size_t>(c) << 20, b = std::min(bytes, a + (size_t{1} << 20));
+      std::memcpy(static_cast<char*>(dst) + a, static_cast<const char*>(src) + a, b - a);
+    }
+  };
+  auto up = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->st);
+  };
+  CU(h, ensure(h->d_raw_xy, 2 * nl));
+  CU(h, ensure(h->d_raw_pt, nl));
+  CU(h, ensure(h->d_raw_a, nl));
+  CU(h, ensure(h->d_raw_b, have_b ? nl : 1));
+  CU(h, ensure(h->d_raw_in, nl));
+  CU(h, ensure(h->d_bld_a, nl));
+  CU(h, ensure(h->d_bld_flags, 8));
+  stage(s_pt, p->obs_pt + obs_lo, nl * 4);
+  CU(h, up(h->d_raw_pt.p, s_pt, nl * 4));
+  stage(s_a, p->obs_pose_a + obs_lo, nl * 4);
+  CU(h, up(h->d_raw_a.p, s_a, nl * 4));
+  if (have_b) {
+    stage(s_b, p->obs_pose_b + obs_lo, nl * 4);
+    CU(h, up(h->d_raw_b.p, s_b, nl * 4));
+  }
+  stage(s_in, p->obs_intr + obs_lo, nl * 4);
+  CU(h, up(h->d_raw_in.p, s_in, nl * 4));
+  stage(s_xy, p->obs_xy + 2 * obs_lo, nl * 16);
+  CU(h, up(h->d_raw_xy.p, s_xy, nl * 16));
+  mark("stage + enqueue raw shard");
+  // ---- per-observation records, validation, CSR offsets of the points
+  h->n_ext = n_ext;
+  h->n_intr = n_intr;
+  CU(h, ensure(h->d_obs_xy, nl));
+  CU(h, ensure(h->d_obs_ip, nl));
+  CU(h, ensure(h->d_obs_ab, nl));
+  CU(h, ensure(h->d_pt_first, n_pts + 1));
+  CU(h, cudaMemsetAsync(h->d_bld_flags.p, 0, 8 * sizeof(int), h->st));
+  const int prev_pt = obs_lo > 0 ? p->obs_pt[obs_lo - 1] : -1;
+  bld_observations(nl, h->d_raw_xy.p, h->d_raw_pt.p, h->d_raw_a.p, have_b ? h->d_raw_b.p : nullptr, h->d_raw_in.p, pt_lo, n_pts, n_ext,
+                   n_intr, prev_pt, h->d_obs_xy.p, h->d_obs_ip.p, h->d_obs_ab.p, h->d_bld_a.p, h->d_bld_flags.p, h->st);
+  bld_lower_bound(h->d_raw_pt.p, nl, pt_lo, n_pts, h->d_pt_first.p, h->st);
+  CU(h, cudaMemcpyAsync(s_first, h->d_pt_first.p, (static_cast<size_t>(n_pts) + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaMemcpyAsync(s_flags, h->d_bld_flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+  CU(h, cudaStreamSynchronize(h->st));
+  CU(h, cudaGetLastError());
+  int flags = s_flags[0];
+  // ranks take the same road: one of them meeting unsorted / composed / out-of-range input sends all to the host build
+  double not_ok = (flags & (1 | 2 | 4)) ? 1.0 : 0.0;
+  if (h->world > 1) {
+    CU(h, ensure(h->d_scalars_red, S_TOTAL));
+    CU(h, cudaMemcpyAsync(h->d_scalars_red.p, &not_ok, sizeof not_ok, cudaMemcpyHostToDevice, h->st));
+    int rc = nccl_api().AllReduce(h->d_scalars_red.p, h->d_scalars_red.p, 1, kNcclFloat64, kNcclMax, h->comm, h->st);
+    if (rc != 0) return h->fail(DBA_ERR_NCCL, "ncclAllReduce: %s", nccl_api().GetErrorString(rc));
+    CU(h, cudaMemcpyAsync(&not_ok, h->d_scalars_red.p, sizeof not_ok, cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+  }
+  if (not_ok > 0.5) return DBA_OK;  // not handled here
+  if (free_intr && (flags & 8)) return h->fail(DBA_ERR_UNSUPPORTED, "free_intrinsics needs obs_intr == obs_pose_a");
+  mark("records + point offsets");
+  // ---- tiles of whole points (host: O(#tiles) binary searches in the offsets), dense-solver batches
+  const int* first = s_first;
+  int max_track = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_track)
+  for (int i = 0; i < n_pts; ++i) max_track = std::max(max_track, first[i + 1] - first[i]);
+  if (h->world > 1) {  // the tile capacity follows the longest track of the WHOLE problem, as in the host build
+    double mt = max_track;
+    CU(h, cudaMemcpyAsync(h->d_scalars_red.p, &mt, sizeof mt, cudaMemcpyHostToDevice, h->st));
+    int rc = nccl_api().AllReduce(h->d_scalars_red.p, h->d_scalars_red.p, 1, kNcclFloat64, kNcclMax, h->comm, h->st);
+    if (rc != 0) return h->fail(DBA_ERR_NCCL, "ncclAllReduce: %s", nccl_api().GetErrorString(rc));
+    CU(h, cudaMemcpyAsync(&mt, h->d_scalars_red.p, sizeof mt, cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+    max_track = static_cast<int>(mt);
+  }
+  if (max_track > kMaxTile)
+    return h->fail(DBA_ERR_UNSUPPORTED, "a point has %d observations; tracks longer than %d are not implemented", max_track, kMaxTile);
+  int tile_cap = max_track <= 256 ? 256 : (max_track <= 512 ? 512 : 1024);
+  if (tile_cap == 256 && !freeze && n / std::max(h->world, 1) >= int64_t{512} * 148 * 4) tile_cap = 512;
+  if (const char* env = std::getenv("DBA_TILE")) {
+    const int forced = std::atoi(env);
+    if ((forced == 512 || forced == 1024) && forced >= tile_cap) tile_cap = forced;
+    if (forced == 256 && max_track <= 256) tile_cap = 256;
+  }
+  std::vector<TileMeta> tile_meta;
+  tile_meta.reserve(static_cast<size_t>(nl / 200 + 16));
+  {
+    const int max_pts = max_tile_points(tile_cap);
+    for (int sp = 0; sp < n_pts;) {
+      const int limit = first[sp] + tile_cap;
+      int end = static_cast<int>(std::upper_bound(first + sp + 1, first + n_pts + 1, limit) - first) - 1;
+      end = std::max(std::min(end, sp + max_pts), sp + 1);
+      TileMeta m{};
+      m.obs0 = first[sp];
+      m.n_obs = first[end] - first[sp];
+      m.pt0 = sp;
+      m.n_pts = end - sp;
+      tile_meta.push_back(m);
+      sp = end;
+    }
+  }
+  const int n_tiles = static_cast<int>(tile_meta.size());
+  const bool dense_ok = cb > 0 && n_ext <= kDnMaxBlocks && n_ext * cb <= kDnMaxSize;
+  std::vector<int> dn_batch;
+  if (dense_ok) {
+    int start = 0, ents = 0;
+    dn_batch.push_back(0);
+    for (int i = 0; i < n_pts; ++i) {
+      const int c = std::min(2 * (first[i + 1] - first[i]), n_ext);
+      if (i > start && (i - start >= kDnPtsCap || ents + c > kDnEntCap)) {
+        dn_batch.push_back(i);
+        start = i;
+        ents = 0;
+      }
+      ents += c;
+    }
+    if (n_pts > 0) dn_batch.push_back(n_pts);
+  }
+  std::vector<int> tile_obs(static_cast<size_t>(n_tiles) + 1), tile_pt(static_cast<size_t>(n_tiles) + 1);
+  for (int t = 0; t < n_tiles; ++t) {
+    tile_obs[t] = tile_meta[t].obs0;
+    tile_pt[t] = tile_meta[t].pt0;
+  }
+  tile_obs[n_tiles] = static_cast<int>(nl);
+  tile_pt[n_tiles] = n_pts;
+  mark("tiles");
+  // ---- sizes known so far; the partial count comes from the device count pass
+  h->freeze = freeze;
+  h->free_intr = free_intr;
+  h->cb = cb;
+  h->two = 0;
+  h->n_obs_global = n;
+  h->n_pts_global = p->n_pts;
+  h->pt_lo = pt_lo;
+  h->n_pts = n_pts;
+  h->n_obs = nl;
+  BuildSizes z;
+  z.nl = nl;
+  z.ld = std::max<int64_t>(((nl + 63) / 64) * 64, 64);
+  z.n_entries = cb ? nl : 0;
+  z.n_pts = n_pts;
+  z.n_tiles = n_tiles;
+  z.tile_cap = tile_cap;
+  z.n_cols = cb ? static_cast<size_t>(n_tiles) * tile_cap : 0;
+  z.mf_w = cb == 9 ? 2 : 4;
+  z.two = 0;
+  z.cb = cb;
+  z.intr_is_pose = (flags & 8) ? 0 : 1;
+  z.dense_ok = dense_ok;
+  z.n_dn_batches = dense_ok ? static_cast<int>(dn_batch.size()) - 1 : 0;
+  CU(h, ensure(h->d_tile_meta, n_tiles));
+  CU(h, ensure(h->d_tile_obs, n_tiles + 1));
+  CU(h, ensure(h->d_tile_pt, n_tiles + 1));
+  CU(h, cudaMemcpyAsync(h->d_tile_meta.p, tile_meta.data(), sizeof(TileMeta) * n_tiles, cudaMemcpyHostToDevice, h->st));
+  CU(h, cudaMemcpyAsync(h->d_tile_obs.p, tile_obs.data(), sizeof(int) * (n_tiles + 1), cudaMemcpyHostToDevice, h->st));
+  CU(h, cudaMemcpyAsync(h->d_tile_pt.p, tile_pt.data(), sizeof(int) * (n_tiles + 1), cudaMemcpyHostToDevice, h->st));
+  const size_t temp_bytes = bld_temp_bytes(nl, static_cast<int>(std::min<int64_t>(nl, INT32_MAX)), n_tiles, n_ext);
+  CU(h, ensure(h->d_bld_temp, temp_bytes));
+  int n_partials = 0, n_chunks = 0;
+  if (cb) {
+    DeviceBuild B{};
+    B.obs_ab = h->d_obs_ab.p;
+    B.obs_ip = h->d_obs_ip.p;
+    B.tile_meta = h->d_tile_meta.p;
+    CU(h, ensure(h->d_bld_np, n_tiles + 1));
+    CU(h, ensure(h->d_bld_g0, n_tiles + 1));
+    CU(h, cudaMemsetAsync(h->d_bld_np.p, 0, sizeof(int) * (n_tiles + 1), h->st));
+    B.tile_np = h->d_bld_np.p;
+    bld_tiles(B, cb, tile_cap, n_tiles, /*fill=*/false, h->st);
+    if (bld_exclusive_sum(h->d_bld_temp.p, temp_bytes, h->d_bld_np.p, h->d_bld_g0.p, n_tiles + 1, h->st) != 0)
+      return h->fail(DBA_ERR_CUDA, "device scan failed");
+    CU(h, cudaMemcpyAsync(s_flags + 1, h->d_bld_g0.p + n_tiles, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+    n_partials = s_flags[1];
+    z.n_partials = n_partials;
+    // camera-sorted incidence first (its chunk count is the other size the buffers depend on)
+    CU(h, ensure(h->d_cam_entries, nl));
+    CU(h, ensure(h->d_bld_key, std::max<int64_t>(nl, n_partials)));
+    CU(h, ensure(h->d_bld_id, std::max<int64_t>(nl, n_partials)));
+    CU(h, ensure(h->d_bld_key2, std::max<int64_t>(nl, n_partials)));
+    CU(h, ensure(h->d_bld_first, n_ext + 2));
+    CU(h, ensure(h->d_bld_cnt, n_ext + 2));
+    CU(h, ensure(h->d_cam_chunk_first, n_ext + 1));
+    int key_bits = 1;
+    while ((1 << key_bits) < n_ext && key_bits < 31) ++key_bits;
+    bld_iota2(nl, h->d_bld_id.p, h->st);
+    if (bld_sort_pairs(h->d_bld_temp.p, temp_bytes, h->d_bld_a.p, h->d_bld_key2.p, h->d_bld_id.p, h->d_cam_entries.p, static_cast<int>(nl),
+                       key_bits, h->st) != 0)
+      return h->fail(DBA_ERR_CUDA, "device sort failed");
+    bld_lower_bound(h->d_bld_key2.p, nl, 0, n_ext, h->d_bld_first.p, h->st);
+    CU(h, cudaMemsetAsync(h->d_bld_cnt.p, 0, sizeof(int) * (n_ext + 2), h->st));
+    bld_chunk_counts(n_ext, h->d_bld_first.p, h->d_bld_cnt.p, h->st);
+    if (bld_exclusive_sum(h->d_bld_temp.p, temp_bytes, h->d_bld_cnt.p, h->d_cam_chunk_first.p, n_ext + 1, h->st) != 0)
+      return h->fail(DBA_ERR_CUDA, "device scan failed");
+    CU(h, cudaMemcpyAsync(s_flags + 2, h->d_cam_chunk_first.p + n_ext, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CU(h, cudaStreamSynchronize(h->st));
+    n_chunks = s_flags[2];
+    z.n_chunks = n_chunks;
+  }
+  {
+    const int rc = ensure_work_buffers(h, z);  // (buffers filled above are large enough already: grow only)
+    if (rc != DBA_OK) return rc;
+  }
+  if (cb) {
+    bld_chunks(n_ext, h->d_bld_first.p, h->d_cam_chunk_first.p, h->d_cam_chunks.p, h->st);
+    // tile incidence: items, partial offsets, blocks, local indices, matrix-free columns
+    DeviceBuild B{};
+    B.obs_ab = h->d_obs_ab.p;
+    B.obs_ip = h->d_obs_ip.p;
+    B.tile_meta = h->d_tile_meta.p;
+    B.tile_np = h->d_bld_np.p;
+    B.tile_g0 = h->d_bld_g0.p;
+    B.items = h->d_items.p;
+    B.part_first_rel = h->d_part_first_rel.p;
+    B.part_first = h->d_part_first.p;
+    B.part_blk = h->d_part_blk.p;
+    B.part_key = h->d_bld_key.p;
+    B.part_id = h->d_bld_id.p;
+    B.obs_lc = h->d_obs_lc.p;
+    B.obs_lp = h->d_obs_lp.p;
+    B.mf_cols = h->d_mf_cols.p;
+    bld_tiles(B, cb, tile_cap, n_tiles, /*fill=*/true, h->st);
+    // partials grouped by camera block: stable sort by block; row of partial g = its rank
+    CU(h, ensure(h->d_bld_id2, std::max(n_partials, 1)));
+    int key_bits = 1;
+    while ((1 << key_bits) < n_ext && key_bits < 31) ++key_bits;
+    if (n_partials > 0 && bld_sort_pairs(h->d_bld_temp.p, temp_bytes, h->d_bld_key.p, h->d_bld_key2.p, h->d_bld_id.p, h->d_bld_id2.p, n_partials,
+                                         key_bits, h->st) != 0)
+      return h->fail(DBA_ERR_CUDA, "device sort failed");
+    bld_scatter_pos(n_partials, h->d_bld_id2.p, h->d_part_dst.p, h->st);
+    bld_lower_bound(h->d_bld_key2.p, n_partials, 0, n_ext, h->d_cam_part_first.p, h->st);
+  } else {
+    // points only: the tile kernels still want the tile-local point of every observation
+    DeviceBuild B{};
+    B.obs_ip = h->d_obs_ip.p;
+    B.tile_meta = h->d_tile_meta.p;
+    B.obs_lc = h->d_obs_lc.p;
+    B.obs_lp = h->d_obs_lp.p;
+    bld_tiles_plain(B, n_tiles, h->st);
+  }
+  if (dense_ok) CU(h, cudaMemcpyAsync(h->d_dn_batch.p, dn_batch.data(), sizeof(int) * dn_batch.size(), cudaMemcpyHostToDevice, h->st));
+  // points of the shard and the camera-side parameters
+  stage(s_pts, p->pts + 3 * static_cast<size_t>(pt_lo), static_cast<size_t>(n_pts) * 24);
+  CU(h, up(h->d_pts[2].p, s_pts, static_cast<size_t>(n_pts) * 24));
+  {
+    const int rc = upload_params(h, p);
+    if (rc != DBA_OK) return rc;
+  }
+  h->perm.resize(static_cast<size_t>(nl));
+  int64_t* perm = h->perm.data();
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nl; ++k) perm[k] = obs_lo + k;
+  CU(h, cudaStreamSynchronize(h->st));
+  CU(h, cudaGetLastError());
+  mark("device build + params");
+  {
+    const int rc = bind_problem(h, z);
+    if (rc != DBA_OK) return rc;
+  }
+  // dba_problem_update reads the point-sorted observation image from the arena: for sorted single-pose input
+  // that is the raw shard itself, re-packed lazily by dba_problem_update from the device copies
+  h->keep.valid = false;
+  h->build_mode = 1;
+  h->have_problem = true;
+  *handled = 1;
+  return dba_params_reset(h);
+}
+
 // ------------------------------------------------------------------- problem upload
 // Host side of the upload: every O(n_obs) step is a parallel pass (OpenMP over the host cores)
 // writing straight into the pinned staging arena, copied with a handful of large async memcpys.
@@ -937,6 +1518,20 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   if (p->n_obs >= (int64_t{1} << 30)) return h->fail(DBA_ERR_UNSUPPORTED, "more than 2^30 observations per handle");
   const int64_t n = p->n_obs;
   const int n_ext = p->n_ext, n_intr = p->n_intr;
+  h->build_mode = 0;
+  {
+    // device-side construction, the default: every rank stages and builds only its shard, and a
+    // single GPU builds a 5M-observation problem in half the time of the 16-core host build.  Point-sorted
+    // single-pose input only; otherwise (or when any rank says so) the host build below runs.
+    // DBA_BUILD=host forces the host build.
+    const char* env = std::getenv("DBA_BUILD");
+    const bool want_device = env ? std::strcmp(env, "host") != 0 : true;
+    if (want_device) {
+      int handled = 0;
+      const int rc = problem_set_device(h, p, &handled);
+      if (rc != DBA_OK || handled) return rc;
+    }
+  }
 
   OmpThreadScope omp_scope(h->world);
   const bool timing = std::getenv("DBA_TIMING") != nullptr;
@@ -1466,94 +2061,29 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
     s_dn_pair_chunk_first[np] = c;
   }
   mark("tile incidence + columns");
-  // ---- device buffers (kept across calls, grow only)
-  h->plane_w = 4 + cb + ((two && cb) ? 6 : 0);
-  h->j_planes = h->plane_w;
-  CU(h, ensure(h->d_obs_xy, nl));
-  CU(h, ensure(h->d_obs_ip, nl));
-  CU(h, ensure(h->d_obs_ab, nl));
-  CU(h, ensure(h->d_obs_lp, nl));
-  CU(h, ensure(h->d_tile_obs, n_tiles + 1));
-  CU(h, ensure(h->d_tile_pt, n_tiles + 1));
-  CU(h, ensure(h->d_pt_first, n_pts + 1));
-  CU(h, ensure(h->d_cam_entries, n_entries));
-  CU(h, ensure(h->d_cam_chunks, n_chunks));
-  CU(h, ensure(h->d_cam_chunk_first, n_ext + 1));
-  CU(h, ensure(h->d_tile_meta, n_tiles));
-  CU(h, ensure(h->d_part_first_rel, n_entries + n_tiles + 1));
-  CU(h, ensure(h->d_items, n_entries));
-  CU(h, ensure(h->d_cam_part_first, n_ext + 1));
-  CU(h, ensure(h->d_part_dst, n_partials));
-  CU(h, ensure(h->d_part_blk, n_partials));
-  CU(h, ensure(h->d_obs_lc, nl));
-  CU(h, ensure(h->d_mf_cols, std::max<size_t>(n_cols * mf_w, 1)));
-  CU(h, ensure(h->d_items_mf, (two && cb) ? n_entries : 1));
-  CU(h, ensure(h->d_part_first, n_entries + n_tiles + 1));
-  CU(h, ensure(h->d_mf_rows, static_cast<size_t>(n_ext) * mf_row_len(cb)));
-  CU(h, ensure(h->d_mf_T, static_cast<size_t>(n_ext) * (9 + cb)));
+  // ---- device buffers (kept across calls, grow only), host-built arrays -> device, binding
+  BuildSizes z;
+  z.nl = nl;
+  z.ld = ld;
+  z.n_entries = n_entries;
+  z.n_pts = n_pts;
+  z.n_tiles = n_tiles;
+  z.tile_cap = tile_cap;
+  z.n_chunks = n_chunks;
+  z.n_partials = n_partials;
+  z.n_cols = n_cols;
+  z.mf_w = mf_w;
+  z.two = two;
+  z.cb = cb;
+  z.intr_is_pose = intr_is_pose;
+  z.dense_ok = dense_ok;
+  z.n_dn_batches = n_dn_batches;
   {
-    const char* env = std::getenv("DBA_SPMV");
-    // default: matrix-free for single-pose problems; composed two-pose rigs (two row fetches, 128
-    // registers) measured faster on the plane product (arc1m: 360 vs 304 LM it/s)
-    h->mf = two ? 0 : 1;
-    if (env && std::strcmp(env, "planes") == 0) h->mf = 0;
-    if (env && std::strcmp(env, "mf") == 0) h->mf = 1;
-    const char* ef = std::getenv("DBA_PCG_FUSED");
-    h->fuse_pcg = !(ef && std::strcmp(ef, "0") == 0);
-    const char* et = std::getenv("DBA_MF_TAIL");
-    h->mf_tail = !(et && std::strcmp(et, "0") == 0);
-    const char* es = std::getenv("DBA_SPECULATE");
-    h->speculate = !(es && std::strcmp(es, "0") == 0);
-  }
-  CU(h, ensure(h->d_partials_q, static_cast<size_t>(n_partials) * std::max(cb, 1)));
-  CU(h, ensure(h->d_J, ld * h->j_planes));
-  CU(h, ensure(h->d_ext_const, n_ext));
-  CU(h, ensure(h->d_center, 2 * n_intr));
-  CU(h, ensure(h->d_nf, n_intr));
-  CU(h, ensure(h->d_nd, n_intr));
-  for (int s = 0; s < 3; ++s) {
-    CU(h, ensure(h->d_pts[s], 3 * static_cast<size_t>(n_pts)));
-    CU(h, ensure(h->d_rot[s], 3 * n_ext));
-    CU(h, ensure(h->d_trans[s], 3 * n_ext));
-    CU(h, ensure(h->d_focal[s], 2 * n_intr));
-    CU(h, ensure(h->d_dist[s], 2 * n_intr));
-  }
-  for (int s = 0; s < 2; ++s) {
-    CU(h, ensure(h->d_pose_rows[s], n_ext));
-    CU(h, ensure(h->d_intr_rows[s], n_intr));
-  }
-  const size_t nvec = static_cast<size_t>(n_ext) * std::max(cb, 1);
-  CU(h, ensure(h->d_sp, 3 * static_cast<size_t>(n_pts)));
-  CU(h, ensure(h->d_cinv, 6 * static_cast<size_t>(n_pts)));
-  CU(h, ensure(h->d_tp, 4 * static_cast<size_t>(n_pts)));
-  CU(h, ensure(h->d_dp, 3 * static_cast<size_t>(n_pts)));
-  CU(h, ensure(h->d_sc, nvec));
-  CU(h, ensure(h->d_cam_acc, nvec * (std::max(cb, 1) + 3)));
-  CU(h, ensure(h->d_cam_chunk_acc, static_cast<size_t>(std::max(n_chunks, 1)) * (std::max(cb, 1) * (std::max(cb, 1) + 1) / 2 + 3 * std::max(cb, 1))));
-  CU(h, ensure(h->d_minv, nvec * std::max(cb, 1)));
-  CU(h, ensure(h->d_dc2, nvec));
-  CU(h, ensure(h->d_x, nvec));
-  CU(h, ensure(h->d_r, nvec));
-  CU(h, ensure(h->d_z, nvec));
-  CU(h, ensure(h->d_p, nvec));
-  CU(h, ensure(h->d_q, nvec));
-  h->q_split = (n_ext >= 296 || !cb) ? 1 : std::min(32, (592 + std::max(n_ext, 1) - 1) / std::max(n_ext, 1));
-  if (h->world > 1 && cb) {
-    int rc = setup_peer_windows(h, nvec);
+    const int rc = ensure_work_buffers(h, z);
     if (rc != DBA_OK) return rc;
   }
-  h->dense_ok = dense_ok;
-  h->Q = DenseWork{};
   if (dense_ok) {
-    h->Q.n_batches = n_dn_batches;
-    h->Q.n_pairs = n_ext * (n_ext + 1) / 2;
-    CU(h, ensure(h->d_dn_batch, static_cast<size_t>(n_dn_batches) + 1));
-    CU(h, ensure(h->d_dn_S, nvec * nvec));
-    CU(h, ensure(h->d_dn_Spart, static_cast<size_t>(dense_slices(h->Q)) * h->Q.n_pairs * cb * cb));
     CU(h, up(h->d_dn_batch.p, s_dn_batch, (static_cast<size_t>(n_dn_batches) + 1) * sizeof(int)));
-    h->Q.batch_pt = h->d_dn_batch.p;
-    h->Q.S = h->d_dn_S.p;
-    h->Q.S_part = h->d_dn_Spart.p;
     if (two && n_dn_pair_chunks > 0) {
       CU(h, ensure(h->d_dn_pair_entries, static_cast<size_t>(n_dn_pair_entries)));
       CU(h, ensure(h->d_dn_pair_chunks, static_cast<size_t>(n_dn_pair_chunks)));
@@ -1569,23 +2099,6 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
       h->Q.n_pair_chunks = n_dn_pair_chunks;
     }
   }
-  CU(h, ensure(h->d_q_split, nvec * static_cast<size_t>(h->q_split)));
-  CU(h, ensure(h->d_vec_partials, nvec / 128 + 2 * static_cast<size_t>(n_ext) + 8192));  // k_partials_to_q: one partial per block
-  CU(h, ensure(h->d_counters, 4));
-  // largest user: apply_step_and_evaluate keeps three ranges side by side (tiles | point update | cost)
-  const size_t n_part = static_cast<size_t>((nl + 255) / 256) + 3 * static_cast<size_t>(n_tiles) + 3 +
-                        2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256) + 256;
-  CU(h, ensure(h->d_partA, n_part));
-  CU(h, ensure(h->d_partB, 3 * static_cast<size_t>((std::max(n_ext, n_intr) + 63) / 64) + 64));
-  CU(h, ensure(h->d_scalars, S_TOTAL));
-  CU(h, ensure(h->d_scalars_red, S_TOTAL));
-  CU(h, ensure(h->d_pcg_scal, 8));
-  CU(h, ensure(h->d_pcg_state, 4));
-  CU(h, cudaMemsetAsync(h->d_counters.p, 0, 4 * sizeof(unsigned int), h->st));
-  CU(h, cudaMemsetAsync(h->d_scalars.p, 0, S_TOTAL * sizeof(double), h->st));
-  CU(h, cudaMemsetAsync(h->d_x.p, 0, std::max<size_t>(nvec, 1) * sizeof(double), h->st));
-  CU(h, cudaMemsetAsync(h->d_pcg_state.p, 0, 4 * sizeof(int), h->st));
-
   CU(h, up(h->d_obs_lp.p, s_lp, nl * sizeof(unsigned short)));
   CU(h, up(h->d_tile_obs.p, s_tile_obs, (n_tiles + 1) * sizeof(int)));
   CU(h, up(h->d_tile_pt.p, s_tile_pt, (n_tiles + 1) * sizeof(int)));
@@ -1603,118 +2116,21 @@ int dba_problem_set(dba_handle* h, const dba_problem* p) {
   if (cb) CU(h, up(h->d_mf_cols.p, s_mf_cols, n_cols * mf_w * sizeof(int)));
   if (two && cb) CU(h, up(h->d_items_mf.p, s_items_mf, n_entries * sizeof(int)));
   if (cb) CU(h, up(h->d_part_first.p, s_part_first, (n_entries + n_tiles + 1) * sizeof(int)));
-  std::vector<uint8_t> ext_const(std::max(n_ext, 1), 0);
-  h->any_const = false;
-  if (p->ext_const)
-    for (int i = 0; i < n_ext; ++i) {
-      ext_const[i] = p->ext_const[i] ? 1 : 0;
-      h->any_const |= ext_const[i] != 0;
-    }
-  CU(h, up(h->d_ext_const.p, ext_const.data(), n_ext));
-  CU(h, up(h->d_center.p, p->intr_center, 2 * sizeof(double) * n_intr));
-  CU(h, up(h->d_nf.p, p->intr_nf, sizeof(int) * n_intr));
-  CU(h, up(h->d_nd.p, p->intr_nd, sizeof(int) * n_intr));
-  // slot 2 = pristine copy for dba_params_reset, slot 0 = current
-  if (h->world > 1) CU(h, ensure(h->d_full_pts, 3 * static_cast<size_t>(h->n_pts_global)));  // dba_params_get
-  CU(h, up(h->d_rot[2].p, p->ext_rot, 3 * sizeof(double) * n_ext));
-  CU(h, up(h->d_trans[2].p, p->ext_trans, 3 * sizeof(double) * n_ext));
-  CU(h, up(h->d_focal[2].p, p->intr_focal, 2 * sizeof(double) * n_intr));
-  CU(h, up(h->d_dist[2].p, p->intr_dist, 2 * sizeof(double) * n_intr));
+  {
+    const int rc = upload_params(h, p);
+    if (rc != DBA_OK) return rc;
+  }
   mark("alloc + enqueue copies");
   CU(h, cudaStreamSynchronize(h->st));  // caller buffers and local staging may go away now
   mark("copies complete");
-  h->n_cam_entries = n_entries;
-
-  DeviceProblem& D = h->D;
-  D.n_obs = nl;
-  D.ld = ld;
-  D.n_pts = n_pts;
-  D.n_ext = n_ext;
-  D.n_intr = n_intr;
-  D.n_tiles = n_tiles;
-  D.tile = tile_cap;
-  D.cb = cb;
-  D.two = two;
-  D.n_blocks = n_ext;
-  D.obs_xy = h->d_obs_xy.p;
-  D.obs_ip = h->d_obs_ip.p;
-  D.tile_obs = h->d_tile_obs.p;
-  D.tile_pt = h->d_tile_pt.p;
-  D.pt_first = h->d_pt_first.p;
-  D.cam_entries = h->d_cam_entries.p;
-  D.cam_chunks = h->d_cam_chunks.p;
-  D.cam_chunk_first = h->d_cam_chunk_first.p;
-  D.n_chunks = n_chunks;
-  D.J = h->d_J.p;
-  D.tile_meta = h->d_tile_meta.p;
-  D.obs_ab = h->d_obs_ab.p;
-  D.obs_lp = h->d_obs_lp.p;
-  D.part_first_rel = h->d_part_first_rel.p;
-  D.items = h->d_items.p;
-  D.cam_part_first = h->d_cam_part_first.p;
-  D.n_partials = n_partials;
-  D.mf_cols = h->d_mf_cols.p;
-  D.items_mf = h->d_items_mf.p;
-  D.part_dst = h->d_part_dst.p;
-  D.part_blk = h->d_part_blk.p;
-  D.obs_lc = h->d_obs_lc.p;
-  D.intr_is_pose = intr_is_pose;
-  D.part_first = h->d_part_first.p;
-  for (int s = 0; s < 2; ++s) {
-    ParamSet& P = h->P[s];
-    P.pts = h->d_pts[s].p;
-    P.ext_rot = h->d_rot[s].p;
-    P.ext_trans = h->d_trans[s].p;
-    P.focal = h->d_focal[s].p;
-    P.dist = h->d_dist[s].p;
-    P.center = h->d_center.p;
-    P.nf = h->d_nf.p;
-    P.nd = h->d_nd.p;
-    P.pose_rows = h->d_pose_rows[s].p;
-    P.intr_rows = h->d_intr_rows[s].p;
+  {
+    const int rc = bind_problem(h, z);
+    if (rc != DBA_OK) return rc;
   }
-  WorkArrays& W = h->W;
-  W.sp = h->d_sp.p;
-  W.sc = h->d_sc.p;
-  W.cinv = h->d_cinv.p;
-  W.tp = h->d_tp.p;
-  W.dp = h->d_dp.p;
-  W.cam_acc = h->d_cam_acc.p;
-  W.cam_chunk_acc = h->d_cam_chunk_acc.p;
-  W.minv = h->d_minv.p;
-  W.dc2 = h->d_dc2.p;
-  W.x = h->d_x.p;
-  W.r = h->d_r.p;
-  W.z = h->d_z.p;
-  W.p = h->d_p.p;
-  W.q = h->d_q.p;
-  W.scalars = h->d_scalars.p;
-  W.pcg_state = h->d_pcg_state.p;
-  W.pcg_scal = h->d_pcg_scal.p;
-  W.partials_q = h->d_partials_q.p;
-  W.q_split = h->d_q_split.p;
-  W.mf_rows = h->d_mf_rows.p;
-  W.mf_T = h->d_mf_T.p;
-  W.vec_partials = h->d_vec_partials.p;
-  W.counters = h->d_counters.p;
-  W.trace = nullptr;
-  if (std::getenv("DBA_TAIL_TRACE")) {
-    CU(h, ensure(h->d_trace, 16));
-    unsigned long long init[16] = {0};
-    init[10] = ~0ull;
-    CU(h, cudaMemcpy(h->d_trace.p, init, sizeof init, cudaMemcpyHostToDevice));
-    W.trace = h->d_trace.p;
-  }
-  h->Q.fail_flag = h->d_pcg_state.p + 3;
   h->keep.valid = h->world == 1;
   h->keep.xy = s_xy;
   h->keep.ip = s_ip;
   h->keep.ab = s_ab;
-  h->keep.center.assign(p->intr_center, p->intr_center + 2 * static_cast<size_t>(n_intr));
-  h->keep.nf.assign(p->intr_nf, p->intr_nf + n_intr);
-  h->keep.nd.assign(p->intr_nd, p->intr_nd + n_intr);
-  h->keep.ext_const = ext_const;
-  h->keep.free_intrinsics = p->free_intrinsics;
   h->have_problem = true;
   return dba_params_reset(h);
 }
@@ -1728,8 +2144,25 @@ int dba_problem_update(dba_handle* h, const uint8_t* obs_remove, const uint8_t* 
   if (!h) return DBA_ERR_INVALID_ARGUMENT;
   if (!h->have_problem) return h->fail(DBA_ERR_NO_PROBLEM, "no problem set");
   if (h->world > 1) return h->fail(DBA_ERR_UNSUPPORTED, "dba_problem_update needs a single-GPU handle");
-  if (!h->keep.valid) return h->fail(DBA_ERR_NO_PROBLEM, "the retained problem image is gone: call dba_problem_set");
   CU(h, cudaSetDevice(h->device));
+  if (!h->keep.valid && h->build_mode == 1) {
+    // the device build keeps the point-sorted image on the device only: read it back once
+    const size_t nk = static_cast<size_t>(h->n_obs);
+    h->keep_xy_v.resize(nk);
+    h->keep_ip_v.resize(nk);
+    h->keep_ab_v.resize(nk);
+    if (nk) {
+      CU(h, cudaMemcpyAsync(h->keep_xy_v.data(), h->d_obs_xy.p, nk * sizeof(double2), cudaMemcpyDeviceToHost, h->st));
+      CU(h, cudaMemcpyAsync(h->keep_ip_v.data(), h->d_obs_ip.p, nk * sizeof(int2), cudaMemcpyDeviceToHost, h->st));
+      CU(h, cudaMemcpyAsync(h->keep_ab_v.data(), h->d_obs_ab.p, nk * sizeof(int2), cudaMemcpyDeviceToHost, h->st));
+      CU(h, cudaStreamSynchronize(h->st));
+    }
+    h->keep.xy = h->keep_xy_v.data();
+    h->keep.ip = h->keep_ip_v.data();
+    h->keep.ab = h->keep_ab_v.data();
+    h->keep.valid = true;
+  }
+  if (!h->keep.valid) return h->fail(DBA_ERR_NO_PROBLEM, "the retained problem image is gone: call dba_problem_set");
   const int64_t n = h->n_obs;
   const int n_pts = h->n_pts, n_ext = h->n_ext, n_intr = h->n_intr;
   const int c = h->cur;

@@ -169,3 +169,59 @@ def test_problem_update_equals_reupload_bit_for_bit(engine, name):
         assert np.array_equal(xa[k], xb[k]), k
     assert np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1])
     assert sa.final_cost < sa.initial_cost
+
+
+# ------------------------------------------------------------ device-side problem construction
+@pytest.mark.parametrize("name,freeze,ls", [("bal", 0, capi.DBA_LS_PCG), ("bal", 0, capi.DBA_LS_DENSE), ("plain", 0, capi.DBA_LS_PCG),
+                                            ("plain", 1, capi.DBA_LS_AUTO), ("nd1", 0, capi.DBA_LS_PCG), ("small_angle", 0, capi.DBA_LS_DENSE)])
+def test_device_build_equals_host_build(engine, monkeypatch, name, freeze, ls):
+    """DBA_BUILD=device builds the per-observation records, point offsets, tile incidence, partial grouping and
+    camera-sorted chunks on the GPU (ba_build.cu) instead of the host cores.  Same structures up to the order
+    of a tile's camera blocks, which no sum depends on: residuals, traces, parameters and filter decisions are
+    bit-identical; the engine-side compaction (dba_problem_update) works from the device-built image too."""
+    p = PROBLEMS[name].copy()
+    p.freeze_camera = freeze
+    opts = capi.make_options(max_num_iterations=4, linear_solver=ls, pcg_rel_tolerance=0.0, pcg_max_iterations=15, **FIXED)
+    runs = {}
+    for mode in ("host", "device"):
+        monkeypatch.setenv("DBA_BUILD", mode)
+        engine.problem_set(p)
+        e = engine.eval(residuals=True, jacobians=True)
+        s = engine.solve(opts)
+        x = engine.params_get()
+        mse = engine.filter_mse()
+        fl = engine.filter(float(np.quantile(mse, 0.2)))
+        n2 = engine.problem_update(fl[0], fl[1], freeze_camera=0)
+        s2 = engine.solve(opts)
+        runs[mode] = (e, s, x, mse, fl, n2, s2, engine.params_get())
+    monkeypatch.delenv("DBA_BUILD", raising=False)
+    (ea, sa, xa, ma, fa, na, sa2, xa2), (eb, sb, xb, mb, fb, nb2, sb2, xb2) = runs["host"], runs["device"]
+    for k in ("residuals", "jac_pt", "jac_pose_a", "jac_intr"):
+        assert np.array_equal(ea[k], eb[k]), k
+    assert ea["cost"] == eb["cost"]
+    assert np.array_equal(sa.trace("cost"), sb.trace("cost")) and sa.kernel_launches == sb.kernel_launches
+    for k in xa:
+        assert np.array_equal(xa[k], xb[k]), k
+    assert np.array_equal(ma, mb) and np.array_equal(fa[0], fb[0]) and np.array_equal(fa[1], fb[1]) and na == nb2
+    assert np.array_equal(sa2.trace("cost"), sb2.trace("cost"))
+    for k in xa2:
+        assert np.array_equal(xa2[k], xb2[k]), k
+
+
+def test_device_build_falls_back_for_unsorted_and_composed_input(engine, oracle, monkeypatch):
+    """Anything the device build does not take (observations not sorted by point, composed arc o ring poses,
+    an index out of range) goes through the host build, with the same results / the same error."""
+    monkeypatch.setenv("DBA_BUILD", "device")
+    p = PROBLEMS["plain"].copy()
+    perm = np.random.default_rng(4).permutation(p.n_obs)
+    for k in ("obs_xy", "obs_pt", "obs_pose_a", "obs_pose_b", "obs_intr"):
+        setattr(p, k, getattr(p, k)[perm].copy())
+    _compare_solve(engine, oracle, p, n_iter=3)
+    _compare_solve(engine, oracle, PROBLEMS["rig"], n_iter=3, linear_solver=capi.DBA_LS_DENSE)
+    q = PROBLEMS["plain"].copy()
+    q.obs_pose_a = q.obs_pose_a.copy()
+    q.obs_pose_a[5] = q.n_ext + 3
+    with pytest.raises(capi.EngineError) as e:
+        engine.problem_set(q)
+    assert e.value.status == capi.DBA_ERR_INVALID_ARGUMENT
+    monkeypatch.delenv("DBA_BUILD", raising=False)
