@@ -12,8 +12,8 @@ Jacobian evaluation.  Tolerances are 0 so exactly K iterations run.
 
   value   LM iterations/s, problem resident in HBM, CUDA events around iterations 1..K
           (dba_summary.loop_device_time_in_seconds), max over ranks
-  e2e     the same metric through the C ABI with HOST buffers: dba_problem_set (host sort +
-          host->device copies) + dba_solve (K iterations incl. the initial evaluation) +
+  e2e     the same metric through the C ABI with HOST buffers: dba_problem_set (host->device
+          copies + device-side build of the index structures) + dba_solve (K iterations incl. the initial evaluation) +
           dba_params_get (device->host), wall clock around the three calls
   roofline  dominant kernel (the implicit Schur product): model bytes / mean CUDA-event duration,
           against MEASURED_PEAKS.json hbm_gbs
@@ -480,7 +480,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": describe(args.workload, p, args.pcg_iters, world, args.linear_solver),
         "clocks": dict(clocks, sampled="timed solve + identical solves repeated for 1 s") if clocks else None, "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d / max(steps_done, 1),
                                   "d2h_bytes_per_step": d2h / max(steps_done, 1), "seconds": e2e_s,
-                                  "includes": "dba_problem_set (host sort + H2D) + dba_solve + dba_params_get (D2H)"},
+                                  "includes": "dba_problem_set (H2D + device-side build) + dba_solve + dba_params_get (D2H)"},
         "gpu_launches": launches, "roofline": roof, "lm_iteration_model": lm_model, "cpu_baseline": cpu,
         "cpu_baseline_same_algorithm": cpu_same, "exact_step": exact, "parity_vs_1gpu": parity_vs_1gpu,
         "residual_tolerance": "tests: |dr| <= 1e-10 |r| + 64 eps |predicted px| (>= 99 % within the pure 1e-10 relative bound)",
