@@ -115,6 +115,7 @@ struct dba_handle {
   // the planes / cost partials / camera rows currently describe the CANDIDATE (speculative evaluation)
   bool pcg_pending = false;  // h_pcg_state is in flight (valid after the next stream synchronisation)
   bool jacobian_at_candidate = false;
+  int mf_front = 1;   // DBA_MF_FRONT=0: the camera-side gather reads the Jacobian planes instead of recomputing (single-pose problems)
   int mf_tail = 1;    // DBA_MF_TAIL=0: PCG tail as a separate launch (k_pcg_fused) instead of the k_spmv_mf epilogue
   int speculate = 1;  // DBA_SPECULATE=0: always evaluate candidates with the residual-only kernel
   bool p2p_ready = false;
@@ -484,6 +485,8 @@ int ensure_work_buffers(dba_handle* h, const BuildSizes& z) {
     h->fuse_pcg = !(ef && std::strcmp(ef, "0") == 0);
     const char* et = std::getenv("DBA_MF_TAIL");
     h->mf_tail = !(et && std::strcmp(et, "0") == 0);
+    const char* efr = std::getenv("DBA_MF_FRONT");
+    h->mf_front = !(efr && std::strcmp(efr, "0") == 0);
     const char* es = std::getenv("DBA_SPECULATE");
     h->speculate = !(es && std::strcmp(es, "0") == 0);
   }
@@ -705,7 +708,7 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
       if (h->cb) {
         {
           Scope s(h, "camera_gather", 0.0, 2);
-          launch_camera_gather(D, h->W, 0, h->st);
+          launch_camera_gather(D, h->W, 0, h->st, h->mf_front ? &P : nullptr);
         }
         int rc = allreduce(h, h->W.cam_acc, static_cast<size_t>(D.n_blocks) * h->cb * (h->cb + 3), kNcclSum);
         if (rc != DBA_OK) return rc;
@@ -753,7 +756,7 @@ int prepare_step(dba_handle* h, double radius, const dba_solve_options& o) {
       // gather: Jc + Jp + r planes at sector granularity, plus C^-1 and t per observation
       // (the dense reduced system does not need the block-Jacobi blocks: mode 2)
       Scope s(h, "camera_gather", 0.0, 2);
-      launch_camera_gather(D, h->W, h->use_dense ? 2 : 1, h->st);
+      launch_camera_gather(D, h->W, h->use_dense ? 2 : 1, h->st, h->mf_front ? &h->P[h->cur] : nullptr);
     }
     int rc = allreduce(h, h->W.cam_acc, static_cast<size_t>(D.n_blocks) * h->cb * (h->cb + 3), kNcclSum);
     if (rc != DBA_OK) return rc;

@@ -120,6 +120,20 @@ __device__ __forceinline__ void load_row(const double* __restrict__ row, double 
 }
 
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+// cp.async (LDGSTS) helpers: per-thread 4/8/16-byte asynchronous copies global -> shared
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ------------------------------------------------------------------------- pose rows
 __global__ void k_pose_rows(ParamSet P, const uint8_t* __restrict__ ext_const, int freeze_all, int n_ext, int n_intr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -438,6 +452,65 @@ __global__ void __launch_bounds__(T, MB) k_point_prepare(DeviceProblem D, WorkAr
 //   mode 1: B = F^T (I - E C^-1 E^T) F (upper), diag(F^T F), g = F^T r, rhs = -F^T (r - E t)
 // then reduces across the CTA into one row of sums per chunk (k_camera_combine adds the rows of a
 // camera block in chunk order: no atomics).
+// accumulation of one observation into the chunk sums (shared by the plane-reading and the recomputing kernel)
+template <int CB, int MODE>
+__device__ __forceinline__ void gather_accumulate(const double2 (&F)[CB], const double2 r, const double2 e0, const double2 e1,
+                                                  const double2 e2, const double (&c)[6], const double (&t)[3],
+                                                  double (&acc)[MODE == 0 ? CB : CB * (CB + 1) / 2 + 3 * CB]) {
+  constexpr int NU = CB * (CB + 1) / 2;
+  if (MODE == 0) {
+#pragma unroll
+    for (int k = 0; k < CB; ++k) acc[k] += dot2(F[k], F[k]);
+    return;
+  }
+  const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3], c4 = c[4], c5 = c[5];
+  // M = E C^-1 (2x3), P = I - M E^T (2x2 symmetric)
+  double p00 = 1.0, p01 = 0.0, p11 = 1.0;  // mode 2: plain F^T F
+  if (MODE == 1) {
+    const double m00 = e0.x * c0 + e1.x * c1 + e2.x * c2, m01 = e0.x * c1 + e1.x * c3 + e2.x * c4,
+                 m02 = e0.x * c2 + e1.x * c4 + e2.x * c5;
+    const double m10 = e0.y * c0 + e1.y * c1 + e2.y * c2, m11 = e0.y * c1 + e1.y * c3 + e2.y * c4,
+                 m12 = e0.y * c2 + e1.y * c4 + e2.y * c5;
+    p00 = 1.0 - (m00 * e0.x + m01 * e1.x + m02 * e2.x);
+    p01 = -(m00 * e0.y + m01 * e1.y + m02 * e2.y);
+    p11 = 1.0 - (m10 * e0.y + m11 * e1.y + m12 * e2.y);
+  }
+  // rr = r - E t
+  const double t0 = t[0], t1 = t[1], t2 = t[2];
+  const double rr0 = r.x - (e0.x * t0 + e1.x * t1 + e2.x * t2);
+  const double rr1 = r.y - (e0.y * t0 + e1.y * t1 + e2.y * t2);
+  int u = 0;
+#pragma unroll
+  for (int i = 0; i < CB; ++i) {
+    // (P F)_i
+    const double pf0 = MODE == 1 ? p00 * F[i].x + p01 * F[i].y : F[i].x;
+    const double pf1 = MODE == 1 ? p01 * F[i].x + p11 * F[i].y : F[i].y;
+#pragma unroll
+    for (int j = i; j < CB; ++j) {
+      acc[u] += pf0 * F[j].x + pf1 * F[j].y;
+      ++u;
+    }
+    acc[NU + i] += dot2(F[i], F[i]);
+    acc[NU + CB + i] += dot2(F[i], r);
+    acc[NU + 2 * CB + i] -= F[i].x * rr0 + F[i].y * rr1;
+  }
+}
+
+// CTA-wide sum of the per-thread accumulators into the chunk's row (fixed order: warp tree, then warps 0..3)
+template <int NACC>
+__device__ __forceinline__ void gather_store(double (&acc)[NACC], double (*red)[NACC], double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    const double s = warp_sum(acc[k]);
+    if (lane == 0) red[wid][k] = s;
+  }
+  __syncthreads();
+  // one row of sums per chunk; k_camera_combine adds the rows of a camera block in chunk order
+  // (no atomics: the accumulators, hence the whole solve, are bit-reproducible)
+  for (int k = threadIdx.x; k < NACC; k += blockDim.x) out[k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+}
+
 template <int CB, int MODE>
 __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArrays W) {
   constexpr int NU = CB * (CB + 1) / 2;
@@ -459,63 +532,151 @@ __global__ void __launch_bounds__(128) k_camera_gather(DeviceProblem D, WorkArra
     double2 F[CB];
 #pragma unroll
     for (int k = 0; k < CB; ++k) F[k] = (slot && k >= 6) ? make_double2(0.0, 0.0) : J[(base + k) * ld];
-    if (MODE == 0) {
-#pragma unroll
-      for (int k = 0; k < CB; ++k) acc[k] += dot2(F[k], F[k]);
-    } else {
-      const double2 r = J[kPlaneR * ld];
-      const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
+    double2 r = make_double2(0.0, 0.0), e0 = r, e1 = r, e2 = r;
+    double c[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, t[3] = {0.0, 0.0, 0.0};
+    if (MODE != 0) {
+      r = J[kPlaneR * ld];
+      e0 = J[(kPlaneJp + 0) * ld];
+      e1 = J[(kPlaneJp + 1) * ld];
+      e2 = J[(kPlaneJp + 2) * ld];
       const int pt = D.obs_ip[o].y;
       // the kernel is bound by L1 tag lookups (one per gathered sector): C^-1 in three 16-byte
       // loads, t in one 32-byte load
       const double2* ci2 = reinterpret_cast<const double2*>(W.cinv + 6 * static_cast<int64_t>(pt));
       const double2 ca = ci2[0], cbb = ci2[1], cc = ci2[2];
-      const double c0 = ca.x, c1 = ca.y, c2 = cbb.x, c3 = cbb.y, c4 = cc.x, c5 = cc.y;
+      c[0] = ca.x; c[1] = ca.y; c[2] = cbb.x; c[3] = cbb.y; c[4] = cc.x; c[5] = cc.y;
       double tp[4];
       load_row<4>(W.tp + 4 * static_cast<int64_t>(pt), tp);
-      // M = E C^-1 (2x3), P = I - M E^T (2x2 symmetric)
-      double p00 = 1.0, p01 = 0.0, p11 = 1.0;  // mode 2: plain F^T F
-      if (MODE == 1) {
-        const double m00 = e0.x * c0 + e1.x * c1 + e2.x * c2, m01 = e0.x * c1 + e1.x * c3 + e2.x * c4,
-                     m02 = e0.x * c2 + e1.x * c4 + e2.x * c5;
-        const double m10 = e0.y * c0 + e1.y * c1 + e2.y * c2, m11 = e0.y * c1 + e1.y * c3 + e2.y * c4,
-                     m12 = e0.y * c2 + e1.y * c4 + e2.y * c5;
-        p00 = 1.0 - (m00 * e0.x + m01 * e1.x + m02 * e2.x);
-        p01 = -(m00 * e0.y + m01 * e1.y + m02 * e2.y);
-        p11 = 1.0 - (m10 * e0.y + m11 * e1.y + m12 * e2.y);
-      }
-      // rr = r - E t
-      const double t0 = tp[0], t1 = tp[1], t2 = tp[2];
-      const double rr0 = r.x - (e0.x * t0 + e1.x * t1 + e2.x * t2);
-      const double rr1 = r.y - (e0.y * t0 + e1.y * t1 + e2.y * t2);
-      int u = 0;
+      t[0] = tp[0]; t[1] = tp[1]; t[2] = tp[2];
+    }
+    gather_accumulate<CB, MODE>(F, r, e0, e1, e2, c, t, acc);
+  }
+  gather_store<NACC>(acc, red, W.cam_chunk_acc + static_cast<int64_t>(blockIdx.x) * NACC);
+}
+
+// The same sums with the Jacobian of every observation RECOMPUTED from the camera row (shared by the whole
+// chunk: one CTA = one chunk of ONE camera block), the observation's pixel and its point, instead of being
+// gathered from the point-sorted planes: 13 half-used sectors per observation (the planes in camera order)
+// become xy + indices + X, sp, C^-1, t.  Single-pose problems; same expressions as jacobian_obs, so the
+// values are those of the planes.
+template <int CB, int MODE>
+__global__ void __launch_bounds__(128) k_camera_gather_mf(DeviceProblem D, ParamSet P, WorkArrays W) {
+  constexpr int NU = CB * (CB + 1) / 2;
+  constexpr int NACC = MODE == 0 ? CB : NU + 3 * CB;
+  constexpr int T = 128;
+  constexpr int NPT = MODE == 0 ? 3 : 16;  // staged doubles per observation: X | sp | C^-1 | t (4)
+  __shared__ double red[4][NACC];
+  __shared__ PoseRow sA;
+  __shared__ IntrRow sI;
+  __shared__ double sSc[CB];
+  __shared__ __align__(16) double stage[2][NPT][T];
+  const int tid = threadIdx.x;
+  const int4 ch = D.cam_chunks[blockIdx.x];  // (block, first entry, last entry, -)
+  if (tid < 20) reinterpret_cast<double*>(&sA)[tid] = reinterpret_cast<const double*>(P.pose_rows + ch.x)[tid];
+  if (tid >= 32 && tid < 40 && D.intr_is_pose)
+    reinterpret_cast<double*>(&sI)[tid - 32] = reinterpret_cast<const double*>(P.intr_rows + ch.x)[tid - 32];
+  if (tid >= 64 && tid < 64 + CB) sSc[tid - 64] = MODE == 0 ? 1.0 : W.sc[static_cast<int64_t>(ch.x) * CB + (tid - 64)];
+  // Three dependent levels of gathered loads per observation (incidence entry -> pixel + indices -> point
+  // data) at 8 resident warps per SM: software pipeline.  Entries are read three iterations ahead, pixel
+  // and indices two ahead, and the point data lands one iteration ahead in this thread's own shared-memory
+  // slot through cp.async (no registers held, no barrier: a thread reads only what it copied itself).
+  auto load_entry = [&](int e) { return e < ch.z ? (D.cam_entries[e] >> 1) : -1; };
+  struct Obs {
+    double2 xy;
+    int2 idx;
+  };
+  auto load_obs = [&](int o) {
+    Obs b;
+    b.xy = make_double2(0.0, 0.0);
+    b.idx = make_int2(0, -1);
+    if (o >= 0) {
+      DBA_CHECK(o < D.n_obs && !D.two && D.obs_ab[o].x == ch.x);
+      b.xy = D.obs_xy[o];
+      b.idx = D.obs_ip[o];
+    }
+    return b;
+  };
+  auto issue_point = [&](int buf, int pt) {
+    if (pt >= 0) {
+      const double* Xp = P.pts + 3 * static_cast<int64_t>(pt);
 #pragma unroll
-      for (int i = 0; i < CB; ++i) {
-        // (P F)_i
-        const double pf0 = MODE == 1 ? p00 * F[i].x + p01 * F[i].y : F[i].x;
-        const double pf1 = MODE == 1 ? p01 * F[i].x + p11 * F[i].y : F[i].y;
+      for (int k = 0; k < 3; ++k) cp_async8(&stage[buf][k][tid], Xp + k);
+      if (MODE != 0) {
+        const double* sp = W.sp + 3 * static_cast<int64_t>(pt);
 #pragma unroll
-        for (int j = i; j < CB; ++j) {
-          acc[u] += pf0 * F[j].x + pf1 * F[j].y;
-          ++u;
-        }
-        acc[NU + i] += dot2(F[i], F[i]);
-        acc[NU + CB + i] += dot2(F[i], r);
-        acc[NU + 2 * CB + i] -= F[i].x * rr0 + F[i].y * rr1;
+        for (int k = 0; k < 3; ++k) cp_async8(&stage[buf][3 + k][tid], sp + k);
+        const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cp_async8(&stage[buf][6 + k][tid], ci + k);
+        const double* tp = W.tp + 4 * static_cast<int64_t>(pt);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cp_async8(&stage[buf][12 + k][tid], tp + k);
       }
     }
-  }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    cp_async_commit();
+  };
+  int e = ch.y + tid;
+  int o1 = load_entry(e + T), o2 = load_entry(e + 2 * T);
+  Obs b0 = load_obs(load_entry(e));
+  Obs b1 = load_obs(o1);
+  issue_point(0, b0.idx.y);
+  __syncthreads();  // camera row in shared memory
+  double acc[NACC];
 #pragma unroll
-  for (int k = 0; k < NACC; ++k) {
-    const double s = warp_sum(acc[k]);
-    if (lane == 0) red[wid][k] = s;
+  for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+  for (int it = 0; e < ch.z; ++it, e += T) {
+    const int buf = it & 1;
+    const int o3 = load_entry(e + 3 * T);
+    const Obs b2 = load_obs(o2);
+    issue_point(buf ^ 1, b1.idx.y);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // this iteration's point data landed
+    const double X[3] = {stage[buf][0][tid], stage[buf][1][tid], stage[buf][2][tid]};
+    ObsJacobian j;
+    observation_jacobian(sA, nullptr, D.intr_is_pose ? sI : P.intr_rows[b0.idx.x], X, b0.xy.x, b0.xy.y, true, j);
+    double lw = 1.0;
+    if (D.loss_type == 1) {
+      lw = sqrt(fmax(DBL_MIN, 1.0 / (1.0 + (j.r0 * j.r0 + j.r1 * j.r1) * D.loss_c)));
+      j.r0 *= lw;
+      j.r1 *= lw;
+    }
+    const double2 r = make_double2(j.r0, j.r1);
+    double2 e0 = r, e1 = r, e2 = r;
+    double c[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, t[3] = {0.0, 0.0, 0.0};
+    double s[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s[k] = lw;
+    if (MODE != 0) {
+      const double s0 = stage[buf][3][tid] * lw, s1 = stage[buf][4][tid] * lw, s2 = stage[buf][5][tid] * lw;
+      e0 = make_double2(j.Jp[0][0] * s0, j.Jp[1][0] * s0);
+      e1 = make_double2(j.Jp[0][1] * s1, j.Jp[1][1] * s1);
+      e2 = make_double2(j.Jp[0][2] * s2, j.Jp[1][2] * s2);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c[k] = stage[buf][6 + k][tid];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = stage[buf][12 + k][tid];
+#pragma unroll
+      for (int k = 0; k < CB; ++k) s[k] = sSc[k] * lw;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s[k] *= sA.free_;  // constant pose: its six columns vanish
+    }
+    double2 F[CB];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      F[k] = make_double2(j.JwA[0][k] * s[k], j.JwA[1][k] * s[k]);
+      F[3 + k] = make_double2(j.JtA[0][k] * s[3 + k], j.JtA[1][k] * s[3 + k]);
+    }
+    if (CB == 9) {
+      F[6] = make_double2(j.df[0] * s[6], j.df[1] * s[6]);
+      F[7] = make_double2(j.dk0[0] * s[7], j.dk0[1] * s[7]);
+      F[8] = make_double2(j.dk1[0] * s[8], j.dk1[1] * s[8]);
+    }
+    gather_accumulate<CB, MODE>(F, r, e0, e1, e2, c, t, acc);
+    b0 = b1;
+    b1 = b2;
+    o2 = o3;
   }
-  __syncthreads();
-  // one row of sums per chunk; k_camera_combine adds the rows of a camera block in chunk order
-  // (no atomics: the accumulators, hence the whole solve, are bit-reproducible)
-  for (int k = threadIdx.x; k < NACC; k += blockDim.x)
-    W.cam_chunk_acc[static_cast<int64_t>(blockIdx.x) * NACC + k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+  cp_async_wait_all();
+  gather_store<NACC>(acc, red, W.cam_chunk_acc + static_cast<int64_t>(blockIdx.x) * NACC);
 }
 
 // Fixed-order sum of the chunk rows of every camera block into the accumulator layout
@@ -657,7 +818,6 @@ __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArr
 // History: fp64 RED to L2 serialises at ~150 cycles per cache line on B200 (3.65 ms per
 // product); a camera-sorted second pass over a copy of Jc took 0.33 ms.
 // --- TMA (cp.async.bulk) + mbarrier helpers: 1-D bulk copies global -> shared, sm_90+ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -944,18 +1104,6 @@ __device__ __forceinline__ void project_G(double fx, double fy, double k0, doubl
   G[1][2] = -(r1u * uu + r1v * vv) * iz;
 }
 
-// cp.async (LDGSTS) helpers: per-thread 4/8/16-byte asynchronous copies global -> shared
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Shared-memory plan of k_spmv_mf.  Two stage buffers (tile k computes while tile k+1 lands):
 //   cols [T] column records | ptd [12][PS] X, sp, C^-1 of the tile's points (<= kMaxTilePoints by construction)
@@ -2086,23 +2234,29 @@ static size_t cam_acc_doubles(const DeviceProblem& D) {
 }
 
 template <int CB, int MODE>
-static void launch_camera_gather_t(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st) {
+static void launch_camera_gather_t(const DeviceProblem& D, const WorkArrays& W, const ParamSet* P, cudaStream_t st) {
   constexpr int NACC = MODE == 0 ? CB : CB * (CB + 1) / 2 + 3 * CB;
-  if (D.n_chunks > 0) k_camera_gather<CB, MODE><<<D.n_chunks, 128, 0, st>>>(D, W);
+  if (D.n_chunks > 0) {
+    if (P) k_camera_gather_mf<CB, MODE><<<D.n_chunks, 128, 0, st>>>(D, *P, W);
+    else k_camera_gather<CB, MODE><<<D.n_chunks, 128, 0, st>>>(D, W);
+  }
   const int n = D.n_blocks * NACC;
   k_camera_combine<CB, MODE><<<(n + 127) / 128, 128, 0, st>>>(D, W);
 }
-void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st) {
+// recompute != nullptr: the Jacobian is recomputed from these parameters instead of read from the planes
+// (single-pose problems only)
+void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st, const ParamSet* recompute) {
   if (D.cb == 0 || D.n_blocks == 0) return;
+  const ParamSet* P = (recompute && !D.two) ? recompute : nullptr;
   if (mode == 0) cudaMemsetAsync(W.cam_acc, 0, cam_acc_doubles(D) * sizeof(double), st);  // mode 0 fills diagF only
   if (D.cb == 6) {
-    if (mode == 0) launch_camera_gather_t<6, 0>(D, W, st);
-    else if (mode == 1) launch_camera_gather_t<6, 1>(D, W, st);
-    else launch_camera_gather_t<6, 2>(D, W, st);
+    if (mode == 0) launch_camera_gather_t<6, 0>(D, W, P, st);
+    else if (mode == 1) launch_camera_gather_t<6, 1>(D, W, P, st);
+    else launch_camera_gather_t<6, 2>(D, W, P, st);
   } else {
-    if (mode == 0) launch_camera_gather_t<9, 0>(D, W, st);
-    else if (mode == 1) launch_camera_gather_t<9, 1>(D, W, st);
-    else launch_camera_gather_t<9, 2>(D, W, st);
+    if (mode == 0) launch_camera_gather_t<9, 0>(D, W, P, st);
+    else if (mode == 1) launch_camera_gather_t<9, 1>(D, W, P, st);
+    else launch_camera_gather_t<9, 2>(D, W, P, st);
   }
 }
 

@@ -217,7 +217,7 @@ void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double ra
                           double max_diag, int mode, double* partials, cudaStream_t st);
 // camera-sorted gather into W.cam_acc (zeroed here).  mode 0: diag F^T F only; mode 1: everything;
 // mode 2: as mode 1 with B = F^T F (no elimination term): the diagonal blocks of the dense reduced system.
-void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st);
+void launch_camera_gather(const DeviceProblem& D, const WorkArrays& W, int mode, cudaStream_t st, const ParamSet* recompute = nullptr);
 void launch_camera_scales(const DeviceProblem& D, const WorkArrays& W, cudaStream_t st);
 // D_c^2, block-Jacobi inverse; partials[3*cta + {0,1,2}] as above for the camera side
 int camera_finalize_grid(const DeviceProblem& D);
