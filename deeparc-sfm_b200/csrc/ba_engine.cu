@@ -115,6 +115,7 @@ struct dba_handle {
   // the planes / cost partials / camera rows currently describe the CANDIDATE (speculative evaluation)
   bool pcg_pending = false;  // h_pcg_state is in flight (valid after the next stream synchronisation)
   bool jacobian_at_candidate = false;
+  bool planeless = false;  // this solve keeps no camera planes: gather, product and back-substitution recompute F (set per dba_solve)
   int mf_front = 1;   // DBA_MF_FRONT=0: the camera-side gather reads the Jacobian planes instead of recomputing (single-pose problems)
   int mf_tail = 1;    // DBA_MF_TAIL=0: PCG tail as a separate launch (k_pcg_fused) instead of the k_spmv_mf epilogue
   int speculate = 1;  // DBA_SPECULATE=0: always evaluate candidates with the residual-only kernel
@@ -688,8 +689,8 @@ void fill_ones(dba_handle* h, double* p, size_t n) {
 int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
   const DeviceProblem& D = h->D;
   const ParamSet& P = h->P[h->cur];
-  const int nplanes = 4 + h->cb + (h->two && h->cb ? 6 : 0);
-  // read xy(16)+idx(8), write r + Jp + Jc planes
+  const int nplanes = h->planeless ? 4 : 4 + h->cb + (h->two && h->cb ? 6 : 0);
+  // read xy(16)+idx(8), write r + Jp + Jc planes (no Jc planes when every consumer recomputes F)
   const double k1_bytes = (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs);
   {
     Scope s(h, "pose_rows");
@@ -699,7 +700,7 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
     if (jacobi_scaling) {
       {
         Scope s(h, "jacobian", k1_bytes);
-        launch_jacobian(D, P, h->W, h->cb, h->two, /*unit_scale=*/1, nullptr, h->st);
+        launch_jacobian(D, P, h->W, h->planeless ? 0 : h->cb, h->planeless ? 0 : h->two, /*unit_scale=*/1, nullptr, h->st);
       }
       {
         Scope s(h, "point_prepare", bytes_per_obs_planes(h, 4));
@@ -722,7 +723,7 @@ int evaluate_jacobian(dba_handle* h, bool first, bool jacobi_scaling) {
   }
   {
     Scope s(h, "jacobian", k1_bytes);
-    launch_jacobian(D, P, h->W, h->cb, h->two, /*unit_scale=*/0, h->d_partA.p, h->st);
+    launch_jacobian(D, P, h->W, h->planeless ? 0 : h->cb, h->planeless ? 0 : h->two, /*unit_scale=*/0, h->d_partA.p, h->st);
   }
   {
     Scope s(h, "reduce");
@@ -931,7 +932,7 @@ int apply_step_and_evaluate(dba_handle* h, bool speculate) {
   const DeviceProblem& D = h->D;
   const ParamSet& cur = h->P[h->cur];
   const ParamSet& cand = h->P[1 - h->cur];
-  const int nplanes = 4 + h->cb + (h->two && h->cb ? 6 : 0);
+  const int nplanes = h->planeless ? 4 : 4 + h->cb + (h->two && h->cb ? 6 : 0);
   const int gp = update_points_grid(D), gc = update_cameras_grid(D);
   // three disjoint partial ranges of d_partA so that ONE launch reduces everything at the end
   double* pa_model = h->d_partA.p;
@@ -939,7 +940,7 @@ int apply_step_and_evaluate(dba_handle* h, bool speculate) {
   double* pa_cost = pa_upd + ((2 * gp + 31) / 32) * 32;
   {
     Scope s(h, "back_substitute", (8.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs));
-    launch_back_substitute(D, h->W, pa_model, h->st);
+    launch_back_substitute(D, h->W, pa_model, h->st, h->planeless ? &cur : nullptr);
   }
   {
     Scope s(h, "param_update", 0.0, 2);
@@ -953,7 +954,7 @@ int apply_step_and_evaluate(dba_handle* h, bool speculate) {
   if (speculate) {
     {
       Scope s(h, "jacobian", (24.0 + 16.0 * nplanes) * static_cast<double>(h->n_obs));
-      launch_jacobian(D, cand, h->W, h->cb, h->two, /*unit_scale=*/0, pa_cost, h->st);
+      launch_jacobian(D, cand, h->W, h->planeless ? 0 : h->cb, h->planeless ? 0 : h->two, /*unit_scale=*/0, pa_cost, h->st);
     }
     if (h->mf && h->cb) {
       Scope s(h, "mf_rows");
@@ -2526,6 +2527,7 @@ int dba_solve(dba_handle* h, const dba_solve_options* opt, dba_summary* sum) {
     ~MfGuard() { h->mf = saved; }
   } mf_guard{h, h->mf};
   if (o.loss_type != DBA_LOSS_NONE) h->mf = 0;
+  h->planeless = h->mf && h->mf_front && h->cb > 0 && !h->two && !h->use_dense;
   h->dense_failures = 0;
   h->pcg_unconverged = 0;
   h->pcg_pending = false;

@@ -1512,6 +1512,154 @@ __global__ void __launch_bounds__(128) k_mf_direction(DeviceProblem D, WorkArray
   for (int k = 3; k < CB; ++k) row[k] = ps[k];
 }
 
+// x~ = T x into the p~ slots of the camera rows (after the PCG; the next PCG's init refills them with p~)
+template <int CB>
+__global__ void __launch_bounds__(128) k_mf_step(DeviceProblem D, WorkArrays W) {
+  constexpr int ROW = mf_row_len(CB), PO = CB == 9 ? 15 : 12;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= D.n_blocks) return;
+  const double* Tm = W.mf_T + static_cast<int64_t>(b) * (9 + CB);
+  double xs[CB];
+#pragma unroll
+  for (int k = 0; k < CB; ++k) xs[k] = W.x[static_cast<int64_t>(b) * CB + k] * Tm[9 + k];
+  double* row = W.mf_rows + static_cast<int64_t>(b) * ROW + PO;
+  row[0] = Tm[0] * xs[0] + Tm[1] * xs[1] + Tm[2] * xs[2];
+  row[1] = Tm[3] * xs[0] + Tm[4] * xs[1] + Tm[5] * xs[2];
+  row[2] = Tm[6] * xs[0] + Tm[7] * xs[1] + Tm[8] * xs[2];
+#pragma unroll
+  for (int k = 3; k < CB; ++k) row[k] = xs[k];
+}
+
+// K7 without the camera planes (single-pose, matrix-free solves): u = F x of every observation from the
+// camera row (with x~ = T x in its p~ slots, k_mf_step) and the point, as phase 1 of k_spmv_mf; the point
+// side (E, r) still comes from the planes.  Lets the Jacobian kernel skip the camera planes altogether.
+template <int CB, int T, int MB>
+__global__ void __launch_bounds__(T, MB) k_back_substitute_mf(DeviceProblem D, WorkArrays W, const double* __restrict__ pts,
+                                                               const IntrRow* __restrict__ intr_rows,
+                                                               double* __restrict__ partial_model) {
+  constexpr int ROW = mf_row_len(CB);
+  extern __shared__ __align__(16) unsigned char smem_bs[];
+  double(*v)[T] = reinterpret_cast<double(*)[T]>(smem_bs);  // [3][T]
+  double(*y)[T] = v + 3;                                     // [3][T]
+  double(*sPt)[T] = v + 6;                                   // [9][T] C^-1 (6), t (3) of this thread's point
+  int(*sSeg)[T] = reinterpret_cast<int(*)[T]>(v + 15);       // [2][T] first observation of the point, of the next
+  __shared__ double red[32];
+  const int t = blockIdx.x;
+  const int obs0 = D.tile_obs[t];
+  [[maybe_unused]] const int obs1 = D.tile_obs[t + 1];
+  const int pt0 = D.tile_pt[t], pt1 = D.tile_pt[t + 1];
+  const int tid = threadIdx.x;
+  // the point-side inputs of phase 2 do not depend on anything computed here: in flight (cp.async into this
+  // thread's own slots) while the observation side runs, instead of a second chain of dependent loads
+  const int pt = pt0 + tid;
+  if (pt < pt1) {
+    cp_async4(&sSeg[0][tid], D.pt_first + pt);
+    cp_async4(&sSeg[1][tid], D.pt_first + pt + 1);
+    const double* ci = W.cinv + 6 * static_cast<int64_t>(pt);
+    const double* tp = W.tp + 4 * static_cast<int64_t>(pt);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cp_async8(&sPt[k][tid], ci + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cp_async8(&sPt[6 + k][tid], tp + k);
+  }
+  cp_async_commit();
+  // threads map to the tile's observations in camera-block order (the column records of k_spmv_mf): a
+  // warp's row loads hit few distinct rows
+  int blk, intr = 0;
+  unsigned int lplo;
+  if (CB == 9) {
+    const int2 c = reinterpret_cast<const int2*>(D.mf_cols)[static_cast<int64_t>(t) * T + tid];
+    blk = c.x;
+    lplo = static_cast<unsigned int>(c.y);
+  } else {
+    const int4 c = reinterpret_cast<const int4*>(D.mf_cols)[static_cast<int64_t>(t) * T + tid];
+    blk = c.x;
+    lplo = static_cast<unsigned int>(c.z);
+    intr = c.w;
+  }
+  const bool active = blk >= 0;
+  const int lp = lplo >> 16, lo = lplo & 0xffffu;
+  double2 e0, e1, e2, r;
+  double u0 = 0.0, u1 = 0.0;
+  if (active) {
+    DBA_CHECK(lp < pt1 - pt0 && lo < obs1 - obs0 && blk < D.n_blocks);
+    const double2* J = D.J + obs0 + lo;
+    const int64_t ld = D.ld;
+    r = J[kPlaneR * ld];
+    e0 = J[(kPlaneJp + 0) * ld];
+    e1 = J[(kPlaneJp + 1) * ld];
+    e2 = J[(kPlaneJp + 2) * ld];
+    double ra[ROW];
+    load_row<ROW>(W.mf_rows + static_cast<int64_t>(blk) * ROW, ra);
+    double fx, fy, k0, k1;
+    if (CB == 9) {
+      fx = fy = ra[12];
+      k0 = ra[13];
+      k1 = ra[14];
+    } else {
+      const double2* ir = reinterpret_cast<const double2*>(intr_rows + intr);
+      const double2 f2 = __ldg(ir), k2 = __ldg(ir + 2);
+      fx = f2.x; fy = f2.y; k0 = k2.x; k1 = k2.y;
+    }
+    const double* Xp = pts + 3 * static_cast<int64_t>(pt0 + lp);
+    const double X[3] = {Xp[0], Xp[1], Xp[2]};
+    double qa[3], xa[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) qa[k] = ra[3 * k] * X[0] + ra[3 * k + 1] * X[1] + ra[3 * k + 2] * X[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xa[k] = X[k] + mf_row_sel(ra[9]) * (qa[k] - X[k]);
+    const double cam[3] = {qa[0] + ra[9], qa[1] + ra[10], qa[2] + ra[11]};
+    double G[2][3], uu, vv, rr, dd;
+    project_G(fx, fy, k0, k1, cam, G, uu, vv, rr, dd);
+    constexpr int PO = CB == 9 ? 15 : 12;  // x~ offset in the row
+    double dc[3];
+    dc[0] = ra[PO + 1] * xa[2] - ra[PO + 2] * xa[1] + ra[PO + 3];
+    dc[1] = ra[PO + 2] * xa[0] - ra[PO + 0] * xa[2] + ra[PO + 4];
+    dc[2] = ra[PO + 0] * xa[1] - ra[PO + 1] * xa[0] + ra[PO + 5];
+    u0 = G[0][0] * dc[0] + G[0][1] * dc[1] + G[0][2] * dc[2];
+    u1 = G[1][0] * dc[0] + G[1][1] * dc[1] + G[1][2] * dc[2];
+    if (CB == 9) {
+      const double sI = dd * ra[21] + fx * rr * (ra[22] + rr * ra[23]);
+      u0 += uu * sI;
+      u1 += vv * sI;
+    }
+    v[0][lo] = e0.x * u0 + e0.y * u1;
+    v[1][lo] = e1.x * u0 + e1.y * u1;
+    v[2][lo] = e2.x * u0 + e2.y * u1;
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (pt < pt1) {
+    const int a = sSeg[0][tid] - obs0, b = sSeg[1][tid] - obs0;
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+    for (int i = a; i < b; ++i) {
+      z0 += v[0][i];
+      z1 += v[1][i];
+      z2 += v[2][i];
+    }
+    const double d0 = -sPt[6][tid] - (sPt[0][tid] * z0 + sPt[1][tid] * z1 + sPt[2][tid] * z2);
+    const double d1 = -sPt[7][tid] - (sPt[1][tid] * z0 + sPt[3][tid] * z1 + sPt[4][tid] * z2);
+    const double d2 = -sPt[8][tid] - (sPt[2][tid] * z0 + sPt[4][tid] * z1 + sPt[5][tid] * z2);
+    double* dp = W.dp + 3 * static_cast<int64_t>(pt);
+    dp[0] = d0;
+    dp[1] = d1;
+    dp[2] = d2;
+    y[0][tid] = d0;
+    y[1][tid] = d1;
+    y[2][tid] = d2;
+  }
+  __syncthreads();
+  double m = 0.0;
+  if (active) {
+    const double y0 = y[0][lp], y1 = y[1][lp], y2 = y[2][lp];
+    const double jd0 = u0 + e0.x * y0 + e1.x * y1 + e2.x * y2;
+    const double jd1 = u1 + e0.y * y0 + e1.y * y1 + e2.y * y2;
+    m = jd0 * (r.x + 0.5 * jd0) + jd1 * (r.y + 0.5 * jd1);
+  }
+  m = block_sum(m, red);
+  if (tid == 0) partial_model[t] = m;
+}
+
 // --------------------------------------------------------------------------- K6 PCG
 // Block-Jacobi PCG vector work, multi-CTA (one thread per unknown), deterministic: every
 // global scalar is a fixed-order sum of per-CTA partials done by the last CTA to finish
@@ -2483,8 +2631,35 @@ static void launch_back_substitute_t(const DeviceProblem& D, const WorkArrays& W
   } else go(integral_constant<int, 1024>(), integral_constant<int, 1>());
 }
 
-void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st) {
+template <int CB>
+static void launch_back_substitute_mf_t(const DeviceProblem& D, const WorkArrays& W, const ParamSet& P, double* partial_model,
+                                        cudaStream_t st) {
+  k_mf_step<CB><<<(D.n_blocks + 127) / 128, 128, 0, st>>>(D, W);
+  auto go = [&](auto tag, auto mb) {
+    constexpr int T = decltype(tag)::value;
+    constexpr int MB = decltype(mb)::value;
+    constexpr size_t smem = 16 * T * sizeof(double);
+    static unsigned long long configured = 0;  // per device: function attributes are
+    if (first_use_on_device(&configured)) {
+      cudaFuncSetAttribute(k_back_substitute_mf<CB, T, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    }
+    k_back_substitute_mf<CB, T, MB><<<D.n_tiles, T, smem, st>>>(D, W, P.pts, P.intr_rows, partial_model);
+  };
+  using std::integral_constant;
+  if (D.tile == 256) go(integral_constant<int, 256>(), integral_constant<int, 2>());
+  else if (D.tile == 512) go(integral_constant<int, 512>(), integral_constant<int, 2>());
+  else go(integral_constant<int, 1024>(), integral_constant<int, 1>());
+}
+
+// recompute != nullptr (single-pose, matrix-free solves): u = F x from the camera rows instead of the camera planes
+void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st,
+                            const ParamSet* recompute) {
   if (D.n_tiles == 0) return;
+  if (recompute && D.cb > 0 && !D.two) {
+    if (D.cb == 6) launch_back_substitute_mf_t<6>(D, W, *recompute, partial_model, st);
+    else launch_back_substitute_mf_t<9>(D, W, *recompute, partial_model, st);
+    return;
+  }
   if (D.cb == 0)
     launch_back_substitute_t<0, false>(D, W, partial_model, st);
   else if (D.cb == 6 && !D.two)

@@ -252,7 +252,8 @@ void launch_pcg_direction(const DeviceProblem& D, const WorkArrays& W, cudaStrea
 int launch_pcg_fused(const DeviceProblem& D, const WorkArrays& W, int mf, double tol2, int min_iter, int n_split,
                      const PeerWin& pw, cudaStream_t st);
 // dp = -t - C^-1 E^T F x ; partial_model[tile] = sum (J d).(r + J d / 2)
-void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st);
+void launch_back_substitute(const DeviceProblem& D, const WorkArrays& W, double* partial_model, cudaStream_t st,
+                            const ParamSet* recompute = nullptr);
 // candidate = current + scale * step; partials[2*cta + {0,1}] = {sum step^2, sum x^2}
 int update_points_grid(const DeviceProblem& D);
 int update_cameras_grid(const DeviceProblem& D);
