@@ -323,10 +323,18 @@ class Engine:
         self._check(self.lib.dba_solve(self.h, C.byref(o), C.byref(s.struct)))
         return s
 
-    def params_get(self):
+    def params_get(self, out=None):
+        """Current parameters in caller order.  `out`: a dict returned by an earlier call, written in place
+        (a caller that keeps its result buffers, as the C++ host mirror does, pays no page faults here)."""
         q = self.problem.p
-        out = {"pts": np.zeros_like(q.pts), "ext_rot": np.zeros_like(q.ext_rot), "ext_trans": np.zeros_like(q.ext_trans),
-               "intr_focal": np.zeros_like(q.intr_focal), "intr_dist": np.zeros_like(q.intr_dist)}
+        if out is None:
+            out = {"pts": np.zeros_like(q.pts), "ext_rot": np.zeros_like(q.ext_rot), "ext_trans": np.zeros_like(q.ext_trans),
+                   "intr_focal": np.zeros_like(q.intr_focal), "intr_dist": np.zeros_like(q.intr_dist)}
+        else:
+            for k, ref in (("pts", q.pts), ("ext_rot", q.ext_rot), ("ext_trans", q.ext_trans), ("intr_focal", q.intr_focal),
+                           ("intr_dist", q.intr_dist)):
+                if out[k].shape != ref.shape or out[k].dtype != np.float64 or not out[k].flags.c_contiguous:
+                    raise ValueError(f"params_get(out=): {k} does not match the problem")
         self._check(self.lib.dba_params_get(self.h, _ptr(out["pts"]), _ptr(out["ext_rot"]), _ptr(out["ext_trans"]),
                                             _ptr(out["intr_focal"]), _ptr(out["intr_dist"])))
         return out

@@ -1254,18 +1254,23 @@ static int problem_set_device(dba_handle* h, const dba_problem* p, int* handled)
   CU(h, ensure(h->d_raw_in, nl));
   CU(h, ensure(h->d_bld_a, nl));
   CU(h, ensure(h->d_bld_flags, 8));
-  stage(s_pt, p->obs_pt + obs_lo, nl * 4);
-  CU(h, up(h->d_raw_pt.p, s_pt, nl * 4));
-  stage(s_a, p->obs_pose_a + obs_lo, nl * 4);
-  CU(h, up(h->d_raw_a.p, s_a, nl * 4));
-  if (have_b) {
-    stage(s_b, p->obs_pose_b + obs_lo, nl * 4);
-    CU(h, up(h->d_raw_b.p, s_b, nl * 4));
-  }
-  stage(s_in, p->obs_intr + obs_lo, nl * 4);
-  CU(h, up(h->d_raw_in.p, s_in, nl * 4));
-  stage(s_xy, p->obs_xy + 2 * obs_lo, nl * 16);
-  CU(h, up(h->d_raw_xy.p, s_xy, nl * 16));
+  // copy into the pinned arena and DMA in pieces, the largest array first: the link is busy from the first
+  // 16 MB on, and only the last small piece is still in flight when the host cores are done
+  auto stage_up = [&](void* dev, void* pinned, const void* src, size_t bytes) -> cudaError_t {
+    constexpr size_t kPiece = size_t{16} << 20;
+    for (size_t a = 0; a < bytes; a += kPiece) {
+      const size_t len = std::min(kPiece, bytes - a);
+      stage(static_cast<char*>(pinned) + a, static_cast<const char*>(src) + a, len);
+      const cudaError_t e = up(static_cast<char*>(dev) + a, static_cast<char*>(pinned) + a, len);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  CU(h, stage_up(h->d_raw_xy.p, s_xy, p->obs_xy + 2 * obs_lo, nl * 16));
+  CU(h, stage_up(h->d_raw_pt.p, s_pt, p->obs_pt + obs_lo, nl * 4));
+  CU(h, stage_up(h->d_raw_a.p, s_a, p->obs_pose_a + obs_lo, nl * 4));
+  if (have_b) CU(h, stage_up(h->d_raw_b.p, s_b, p->obs_pose_b + obs_lo, nl * 4));
+  CU(h, stage_up(h->d_raw_in.p, s_in, p->obs_intr + obs_lo, nl * 4));
   mark("stage + enqueue raw shard");
   // ---- per-observation records, validation, CSR offsets of the points
   h->n_ext = n_ext;

@@ -225,3 +225,30 @@ def test_device_build_falls_back_for_unsorted_and_composed_input(engine, oracle,
         engine.problem_set(q)
     assert e.value.status == capi.DBA_ERR_INVALID_ARGUMENT
     monkeypatch.delenv("DBA_BUILD", raising=False)
+
+
+# ------------------------------------------------------------ plane-less front half of matrix-free solves
+@pytest.mark.parametrize("name,ls", [("bal", capi.DBA_LS_PCG), ("plain", capi.DBA_LS_PCG), ("small_angle", capi.DBA_LS_PCG),
+                                     ("nd1", capi.DBA_LS_PCG), ("bal", capi.DBA_LS_DENSE)])
+def test_recomputed_front_half_equals_plane_reader(engine, monkeypatch, name, ls):
+    """Single-pose PCG solves keep no camera planes: the camera-side gather (k_camera_gather_mf) and the
+    back-substitution (k_back_substitute_mf) recompute F from the camera row, the Jacobian kernel writes r and E
+    only.  DBA_MF_FRONT=0 restores the plane readers: same algorithm, so the traces agree to rounding
+    (the recomputed F differs from the stored one by an ulp or two: fused multiply-adds contract differently,
+    and F x goes through the geometric form of the product)."""
+    p = PROBLEMS[name]
+    opts = capi.make_options(max_num_iterations=5, linear_solver=ls, pcg_rel_tolerance=0.0, pcg_max_iterations=25, **FIXED)
+    runs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DBA_MF_FRONT", mode)
+        engine.problem_set(p)
+        s = engine.solve(opts)
+        runs[mode] = (s, engine.params_get())
+    monkeypatch.delenv("DBA_MF_FRONT", raising=False)
+    engine.problem_set(p)  # leave the engine in its default mode
+    (sa, xa), (sb, xb) = runs["0"], runs["1"]
+    assert np.array_equal(sa.trace("step_is_successful"), sb.trace("step_is_successful"))
+    np.testing.assert_allclose(sb.trace("cost"), sa.trace("cost"), rtol=1e-11)
+    np.testing.assert_allclose(sb.trace("gradient_max_norm"), sa.trace("gradient_max_norm"), rtol=1e-9)
+    for k in xa:
+        np.testing.assert_allclose(xb[k], xa[k], rtol=1e-8, atol=1e-10, err_msg=k)
