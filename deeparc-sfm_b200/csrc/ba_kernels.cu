@@ -1146,6 +1146,11 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
 //    partial rows and per-camera sums 17 -> 9 us, but the product loses 9 us (18 KB less L1 per CTA, wider
 //    arrival spread): net zero;
 //  * four warps per camera in the per-camera sums: same 17 us (latency of the dependent loads, not list length).
+//  * tiles handed out through an atomic counter instead of the static round robin (first tiles static, the draw
+//    issued before phase 4, published through shared memory after it): the wait for the slowest CTA drops
+//    18 -> 4 us (spread of the CTAs' finish times 26 -> 6 us), but a drawn index is not warp-uniform, so the tile
+//    records leave the uniform registers: 28 -> 56 bytes of spills (68 / 100 with the records in a shared-memory
+//    ring), product 157 -> 168..176 us: net +15 us per launch.
 // Persistent CTAs (grid = resident CTAs), each walking tiles blockIdx.x, += gridDim.x.  Everything a
 // tile needs from HBM is fetched one tile ahead with cp.async into the other stage buffer, so the
 // only exposed latency per tile is the L1/L2-resident camera-row load.
