@@ -1151,6 +1151,10 @@ __device__ __forceinline__ void pcg_tail(const DeviceProblem& D, const WorkArray
 //    18 -> 4 us (spread of the CTAs' finish times 26 -> 6 us), but a drawn index is not warp-uniform, so the tile
 //    records leave the uniform registers: 28 -> 56 bytes of spills (68 / 100 with the records in a shared-memory
 //    ring), product 157 -> 168..176 us: net +15 us per launch.
+//  * two observations per thread (T / 2 threads per tile at 128 registers, a pair of one camera shares its row
+//    fill and is added in registers before the reduce-by-camera): shared-memory wavefronts 26.3 M -> 20.8 M,
+//    instructions -10 %, barrier stalls 8.5 -> 3.8 per issue — and 16 instead of 32 warps per SM, 128 B of spills:
+//    issue utilisation 31.6 -> 27 %, product 157 -> 168 us.
 // Persistent CTAs (grid = resident CTAs), each walking tiles blockIdx.x, += gridDim.x.  Everything a
 // tile needs from HBM is fetched one tile ahead with cp.async into the other stage buffer, so the
 // only exposed latency per tile is the L1/L2-resident camera-row load.
