@@ -5,12 +5,12 @@
 //
 //   S = F^T F + D_c^2 - sum_points Y_i C_i^-1 Y_i^T,   Y_i[A] = sum_{o in i, o uses A} F_{o,A}^T E_o
 //
-// k_schur_dense   (K4)  one THREAD per camera-block pair (A <= B) keeps the CB x CB block S_AB in
-//                       registers and walks a fixed slice of the points; per batch of points the CTA
-//                       first builds, in shared memory, the compact list of camera blocks each point
-//                       touches and Z_i[A] = Y_i[A] L_i with C_i^-1 = L_i L_i^T, so the elimination
-//                       term of a pair is the 3-deep product Z_i[A] Z_i[B]^T.  No atomics: every pair is
-//                       owned by one thread, slices are summed in slice order.
+// k_dense_z      (K4a)  one CTA per batch of points: the compact list of camera blocks each point touches
+//                       and Z_i[A] = Y_i[A] L_i with C_i^-1 = L_i L_i^T, written to a global image
+// k_dense_pairs  (K4b)  one THREAD per camera-block pair (A <= B) keeps the CB x CB block S_AB in
+//                       registers and walks a fixed slice of the batches: the elimination term of a
+//                       pair is the 3-deep product Z_i[A] Z_i[B]^T.  No atomics: every pair is owned by
+//                       one thread, slices are summed in slice order.
 // k_pair_gather         F_A^T F_B of composed (arc, ring) observations, camera-pair-sorted chunks
 //                       (the diagonal blocks F_A^T F_A come from k_camera_gather, mode 2)
 // k_dense_combine       fixed-order sum of all of it into the dense n x n matrix (both triangles)
@@ -28,6 +28,7 @@ namespace dba {
 namespace {
 
 constexpr int kDnThreads = 256;  // pair threads per CTA == pairs per pair group
+constexpr int kDnIncObs = 512;   // observations of a batch that the incidence path of k_dense_z stages (else: one thread per entry)
 
 // packed upper-triangular pair index -> (A, B), A <= B, row-major over A
 __device__ __forceinline__ void pair_decode(int q, int nb, int& A, int& B) {
@@ -40,27 +41,273 @@ __device__ __forceinline__ void pair_decode(int q, int nb, int& A, int& B) {
   B = a + rem;
 }
 
+// Shared-memory plan of k_dense_z: per-point segments, entry capacities, the compact entry list and the
+// per-point block lookup of one batch.
+struct DzSmem {
+  static constexpr size_t oL = 0;                                               // [points][6] L with C^-1 = L L^T
+  static constexpr size_t oBase = oL + sizeof(double) * kDnPtsCap * 6;          // capacity-based entry base of each point
+  static constexpr size_t oSeg = oBase + sizeof(int) * (kDnPtsCap + 4);         // first observation of each point
+  static constexpr size_t oCnt = oSeg + sizeof(int) * (kDnPtsCap + 4);          // distinct blocks of each point, then their exclusive scan
+  static constexpr size_t oEnt = oCnt + sizeof(int) * (kDnPtsCap + 4);          // entry -> (point << 16 | block), 0xffffffff = unused
+  static constexpr size_t oMul = oEnt + sizeof(unsigned int) * kDnEntCap;       // incidences seen so far of each entry
+  static constexpr size_t oInc = oMul + sizeof(int) * kDnEntCap;                // (observation, slot) -> entry | rank << 16
+  static constexpr size_t oLook = oInc + sizeof(unsigned int) * 2 * kDnIncObs;  // [point][block] -> entry index + 1 within the point
+  __host__ __device__ static size_t look_bytes(int nb) { return (sizeof(unsigned short) * kDnPtsCap * ((nb + 1) & ~1) + 15) / 16 * 16; }
+  // + the Z tile [kDnEntCap][3 CB + 1] of the incidence path behind the lookup
+  static size_t bytes(int nb, int cb) { return oLook + look_bytes(nb) + sizeof(double) * kDnEntCap * (3 * cb + 1); }
+};
+template <int CB>
+__host__ __device__ constexpr int dn_zs() { return 3 * CB; }  // doubles per entry of the global Z image
+
+// K4a: one CTA per batch of points.  Compact list of the camera blocks each point touches, Y = sum F^T E over the
+// point's observations that use the block, Z = Y L with C^-1 = L L^T — written to the global Z image of the batch,
+// entries compacted (Q.Z, Q.Zent, Q.Zcount).  One thread per INCIDENCE (observation, pose slot): consecutive lanes
+// read consecutive observations of the planes, form (F^T E) L in registers and add it to the entry's row of a
+// shared-memory Z tile in rounds — round r takes the r-th incidence of every entry, so no two threads meet in a
+// row and each row is summed in observation order (bit-reproducible).  (One thread per entry scanning its point's
+// observations, as the fused kernel of the first version did, spends its time on serial scattered plane loads:
+// 393 us on arc1m; it remains the path for batches of more than kDnIncObs observations.)
+template <int CB>
+__global__ void __launch_bounds__(kDnThreads) k_dense_z(DeviceProblem D, WorkArrays W, DenseWork Q) {
+  using L = DzSmem;
+  constexpr int ZS = dn_zs<CB>();
+  extern __shared__ __align__(16) unsigned char smem_dz[];
+  double* sL = reinterpret_cast<double*>(smem_dz + L::oL);
+  int* sBase = reinterpret_cast<int*>(smem_dz + L::oBase);
+  int* sSeg = reinterpret_cast<int*>(smem_dz + L::oSeg);
+  int* sCnt = reinterpret_cast<int*>(smem_dz + L::oCnt);
+  unsigned int* sEnt = reinterpret_cast<unsigned int*>(smem_dz + L::oEnt);
+  int* sMul = reinterpret_cast<int*>(smem_dz + L::oMul);
+  unsigned int* sInc = reinterpret_cast<unsigned int*>(smem_dz + L::oInc);
+  unsigned short* sLook = reinterpret_cast<unsigned short*>(smem_dz + L::oLook);
+  __shared__ int s_rounds;
+  const int tid = threadIdx.x;
+  const int nb = D.n_blocks, nbs = (nb + 1) & ~1;
+  constexpr int ZT = 3 * CB + 1;  // odd row stride of the Z tile
+  double* sZt = reinterpret_cast<double*>(smem_dz + L::oLook + L::look_bytes(nb));
+  const int64_t ld = D.ld;
+  const int b = blockIdx.x;
+  const int p0 = Q.batch_pt[b], np = Q.batch_pt[b + 1] - p0;
+  DBA_CHECK(np > 0 && np <= kDnPtsCap && p0 >= 0 && p0 + np <= D.n_pts);
+  // ---- the batch's points: segments, entry capacities, cleared lookup
+  for (int i = tid; i < (np * nbs) / 2; i += kDnThreads) reinterpret_cast<unsigned int*>(sLook)[i] = 0u;
+  for (int i = tid; i < kDnEntCap; i += kDnThreads) sMul[i] = 0;
+  for (int i = tid; i < kDnEntCap * ZT; i += kDnThreads) sZt[i] = 0.0;
+  if (tid == 0) s_rounds = 0;
+  if (tid <= np) sSeg[tid] = D.pt_first[p0 + tid];
+  __syncthreads();
+  if (tid < 32) {
+    // exclusive scan of the capacities min(2 k_i, nb) (np <= kDnPtsCap = 2 per lane)
+    int c[kDnPtsCap / 32], tot = 0;
+#pragma unroll
+    for (int j = 0; j < kDnPtsCap / 32; ++j) {
+      const int p = tid * (kDnPtsCap / 32) + j;
+      c[j] = p < np ? min(2 * (sSeg[p + 1] - sSeg[p]), nb) : 0;
+      tot += c[j];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += v;
+    }
+    int run = incl - tot;
+#pragma unroll
+    for (int j = 0; j < kDnPtsCap / 32; ++j) {
+      const int p = tid * (kDnPtsCap / 32) + j;
+      if (p <= np) sBase[p] = run;
+      run += c[j];
+    }
+    if (tid == 31 && np == kDnPtsCap) sBase[np] = run;
+  }
+  __syncthreads();
+  // ---- one thread per point: compact list of the camera blocks it touches; L with C^-1 = L L^T
+  if (tid < np) {
+    const int base = sBase[tid], cap = sBase[tid + 1] - base;
+    DBA_CHECK(base >= 0 && base + cap <= kDnEntCap);
+    int cnt = 0, max_rank = 0;
+    unsigned short* look = sLook + tid * nbs;
+    const int o_first = sSeg[0];
+    const bool stage_inc = sSeg[np] - o_first <= kDnIncObs;
+    for (int o = sSeg[tid]; o < sSeg[tid + 1]; ++o) {
+      const int2 ab = D.obs_ab[o];
+#pragma unroll
+      for (int slot = 0; slot < 2; ++slot) {
+        const int blk = slot ? ab.y : ab.x;
+        unsigned int inc = 0xffffffffu;
+        if (blk >= 0) {
+          if (!look[blk]) {
+            DBA_CHECK(blk < nb && cnt < cap);
+            look[blk] = static_cast<unsigned short>(++cnt);
+            sEnt[base + cnt - 1] = (static_cast<unsigned int>(tid) << 16) | static_cast<unsigned int>(blk);
+          }
+          const int e = base + look[blk] - 1;
+          const int rank = sMul[e]++;  // entries of a point are touched by its own thread only
+          max_rank = max(max_rank, rank);
+          inc = static_cast<unsigned int>(e) | (static_cast<unsigned int>(rank) << 16);
+        }
+        if (stage_inc) sInc[2 * (o - o_first) + slot] = inc;
+      }
+    }
+    for (int e = cnt; e < cap; ++e) sEnt[base + e] = 0xffffffffu;
+    sCnt[tid] = cnt;
+    if (stage_inc) atomicMax(&s_rounds, max_rank + 1);
+    const double* ci = W.cinv + 6 * static_cast<int64_t>(p0 + tid);
+    double l00 = 0.0, l10 = 0.0, l20 = 0.0, l11 = 0.0, l21 = 0.0, l22 = 0.0;
+    if (ci[0] > 0.0) {  // a point whose C was not positive definite carries C^-1 = 0 (flagged by k_point_prepare)
+      l00 = sqrt(ci[0]);
+      l10 = ci[1] / l00;
+      l20 = ci[2] / l00;
+      l11 = sqrt(fmax(ci[3] - l10 * l10, 0.0));
+      l21 = l11 > 0.0 ? (ci[4] - l20 * l10) / l11 : 0.0;
+      l22 = sqrt(fmax(ci[5] - l20 * l20 - l21 * l21, 0.0));
+    }
+    double* Lp = sL + tid * 6;
+    Lp[0] = l00; Lp[1] = l10; Lp[2] = l20; Lp[3] = l11; Lp[4] = l21; Lp[5] = l22;
+  }
+  __syncthreads();
+  // ---- compact entry index of each point: exclusive scan of the distinct-block counts
+  if (tid < 32) {
+    int c[kDnPtsCap / 32], tot = 0;
+#pragma unroll
+    for (int j = 0; j < kDnPtsCap / 32; ++j) {
+      const int p = tid * (kDnPtsCap / 32) + j;
+      c[j] = p < np ? sCnt[p] : 0;
+      tot += c[j];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += v;
+    }
+    int run = incl - tot;
+#pragma unroll
+    for (int j = 0; j < kDnPtsCap / 32; ++j) {
+      const int p = tid * (kDnPtsCap / 32) + j;
+      if (p < np) sCnt[p] = run;
+      run += c[j];
+    }
+    if (tid == 31) Q.Zcount[b] = run;  // lane 31 ends with the total
+  }
+  __syncthreads();
+  const int n_ent = sBase[np];
+  double* Zb = Q.Z + static_cast<int64_t>(b) * kDnEntCap * ZS;
+  unsigned int* Eb = Q.Zent + static_cast<int64_t>(b) * kDnEntCap;
+  const int o_first = sSeg[0], n_inc = 2 * (sSeg[np] - o_first);
+  if (n_inc <= 2 * kDnIncObs) {
+    // ---- one thread per incidence, chunks of kDnThreads in observation order, rounds by rank within the entry
+    const int rounds = s_rounds;
+    for (int i0 = 0; i0 < n_inc; i0 += kDnThreads) {
+      const int i = i0 + tid;
+      const unsigned int inc = i < n_inc ? sInc[i] : 0xffffffffu;
+      const int e = inc & 0xffffu, rank = inc >> 16;
+      double zc[3 * CB];
+      if (inc != 0xffffffffu) {
+        const int o = o_first + (i >> 1), slot = i & 1;
+        const double2* J = D.J + o;
+        const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
+        const int base_pl = slot ? kPlaneJA + CB : kPlaneJA;
+        const double* Lp = sL + (sEnt[e] >> 16) * 6;
+        const double l00 = Lp[0], l10 = Lp[1], l20 = Lp[2], l11 = Lp[3], l21 = Lp[4], l22 = Lp[5];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+          double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+          if (k < 6 || !slot) {
+            const double2 F = J[(base_pl + k) * ld];
+            y0 = F.x * e0.x + F.y * e0.y;
+            y1 = F.x * e1.x + F.y * e1.y;
+            y2 = F.x * e2.x + F.y * e2.y;
+          }
+          zc[3 * k + 0] = y0 * l00 + y1 * l10 + y2 * l20;
+          zc[3 * k + 1] = y1 * l11 + y2 * l21;
+          zc[3 * k + 2] = y2 * l22;
+        }
+      }
+      for (int r = 0; r < rounds; ++r) {
+        if (inc != 0xffffffffu && rank == r) {
+          double* z = sZt + e * ZT;
+#pragma unroll
+          for (int k = 0; k < 3 * CB; ++k) z[k] += zc[k];
+        }
+        __syncthreads();
+      }
+    }
+    // compacted write-out (the point's entries are the first of its capacity)
+    for (int idx = tid; idx < n_ent * ZS; idx += kDnThreads) {
+      const int e = idx / ZS, k = idx - e * ZS;
+      const unsigned int ent = sEnt[e];
+      if (ent == 0xffffffffu) continue;
+      const int pt = ent >> 16;
+      const int ce = sCnt[pt] + (e - sBase[pt]);
+      DBA_CHECK(ce >= 0 && ce < kDnEntCap);
+      Zb[static_cast<int64_t>(ce) * ZS + k] = sZt[e * ZT + k];
+      if (k == 0) Eb[ce] = ent;
+    }
+    return;
+  }
+  // ---- (large batches) one thread per (point, block) entry: Y = sum F^T E over the point's observations that use
+  // the block, Z = Y L
+  for (int e = tid; e < n_ent; e += kDnThreads) {
+    const unsigned int ent = sEnt[e];
+    if (ent == 0xffffffffu) continue;
+    const int pt = ent >> 16, blk = ent & 0xffffu;
+    double y[CB][3];
+#pragma unroll
+    for (int i = 0; i < CB; ++i) y[i][0] = y[i][1] = y[i][2] = 0.0;
+    for (int o = sSeg[pt]; o < sSeg[pt + 1]; ++o) {
+      const int2 ab = D.obs_ab[o];
+      const bool is_a = ab.x == blk;
+      if (!is_a && ab.y != blk) continue;
+      const double2* J = D.J + o;
+      const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
+      const int base_pl = is_a ? kPlaneJA : kPlaneJA + CB;
+#pragma unroll
+      for (int i = 0; i < CB; ++i) {
+        if (i < 6 || is_a) {
+          const double2 F = J[(base_pl + i) * ld];
+          y[i][0] += F.x * e0.x + F.y * e0.y;
+          y[i][1] += F.x * e1.x + F.y * e1.y;
+          y[i][2] += F.x * e2.x + F.y * e2.y;
+        }
+      }
+    }
+    const double* Lp = sL + pt * 6;
+    const double l00 = Lp[0], l10 = Lp[1], l20 = Lp[2], l11 = Lp[3], l21 = Lp[4], l22 = Lp[5];
+    const int ce = sCnt[pt] + (e - sBase[pt]);  // compact index: the point's entries are the first of its capacity
+    DBA_CHECK(ce >= 0 && ce < kDnEntCap);
+    double* z = Zb + static_cast<int64_t>(ce) * ZS;
+#pragma unroll
+    for (int i = 0; i < CB; ++i) {
+      z[3 * i + 0] = y[i][0] * l00 + y[i][1] * l10 + y[i][2] * l20;
+      z[3 * i + 1] = y[i][1] * l11 + y[i][2] * l21;
+      z[3 * i + 2] = y[i][2] * l22;
+    }
+    Eb[ce] = ent;
+  }
+}
+
+// Shared-memory plan of k_dense_pairs: the batch's Z entries (odd stride: entries of different blocks on
+// different banks), the entry list and the per-point block lookup.
 template <int CB>
 struct DnSmem {
-  static constexpr int ZS = (3 * CB) | 1;  // odd stride (19 / 27 doubles): entries of different blocks on different banks
+  static constexpr int ZS = (3 * CB) | 1;
   static constexpr size_t oZ = 0;
-  static constexpr size_t oL = oZ + sizeof(double) * kDnEntCap * ZS;
-  static constexpr size_t oBase = oL + sizeof(double) * kDnPtsCap * 6;
-  static constexpr size_t oSeg = oBase + sizeof(int) * (kDnPtsCap + 4);
-  static constexpr size_t oEnt = oSeg + sizeof(int) * (kDnPtsCap + 4);          // entry -> (point << 16 | block), 0xffffffff = unused
-  static constexpr size_t oLook = oEnt + sizeof(unsigned int) * kDnEntCap;      // [point][block] -> entry index + 1 within the point
+  static constexpr size_t oEnt = oZ + sizeof(double) * kDnEntCap * ZS;
+  static constexpr size_t oLook = oEnt + sizeof(unsigned int) * kDnEntCap;      // [point][block] -> entry index + 1 within the batch
   static size_t bytes(int nb) { return oLook + sizeof(unsigned short) * kDnPtsCap * ((nb + 1) & ~1); }
 };
 
+// K4b: one THREAD per camera-block pair (A <= B) keeps S_AB in registers and walks a fixed slice of the batches:
+// per batch the CTA copies the Z entries (one coalesced stream) and rebuilds the block lookup, then
+// S_AB -= Z_A Z_B^T over the batch's points.  (F^T F is added by k_dense_combine from the camera gather and the
+// camera-pair gather: adding it here would run one lane per matching observation.)
 template <int CB, int MINB>
-__global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem D, WorkArrays W, DenseWork Q) {
+__global__ void __launch_bounds__(kDnThreads, MINB) k_dense_pairs(DeviceProblem D, DenseWork Q) {
   using L = DnSmem<CB>;
-  constexpr int ZS = L::ZS;
+  constexpr int ZS = L::ZS, ZG = dn_zs<CB>();
   extern __shared__ __align__(16) unsigned char smem_dn[];
   double* sZ = reinterpret_cast<double*>(smem_dn + L::oZ);
-  double* sL = reinterpret_cast<double*>(smem_dn + L::oL);
-  int* sBase = reinterpret_cast<int*>(smem_dn + L::oBase);
-  int* sSeg = reinterpret_cast<int*>(smem_dn + L::oSeg);
   unsigned int* sEnt = reinterpret_cast<unsigned int*>(smem_dn + L::oEnt);
   unsigned short* sLook = reinterpret_cast<unsigned short*>(smem_dn + L::oLook);
   const int tid = threadIdx.x;
@@ -72,126 +319,35 @@ __global__ void __launch_bounds__(kDnThreads, MINB) k_schur_dense(DeviceProblem 
   double acc[CB * CB];
 #pragma unroll
   for (int k = 0; k < CB * CB; ++k) acc[k] = 0.0;
-  const int64_t ld = D.ld;
   const int b0 = static_cast<int>(static_cast<int64_t>(Q.n_batches) * blockIdx.x / gridDim.x);
   const int b1 = static_cast<int>(static_cast<int64_t>(Q.n_batches) * (blockIdx.x + 1) / gridDim.x);
   for (int b = b0; b < b1; ++b) {
-    const int p0 = Q.batch_pt[b], np = Q.batch_pt[b + 1] - p0;
-    DBA_CHECK(np > 0 && np <= kDnPtsCap && p0 >= 0 && p0 + np <= D.n_pts);
-    // ---- the batch's points: segments, entry capacities, cleared lookup
+    const int np = Q.batch_pt[b + 1] - Q.batch_pt[b];
+    const int n_ent = Q.Zcount[b];
+    DBA_CHECK(np > 0 && np <= kDnPtsCap && n_ent >= 0 && n_ent <= kDnEntCap);
+    const double* Zb = Q.Z + static_cast<int64_t>(b) * kDnEntCap * ZG;
+    const unsigned int* Eb = Q.Zent + static_cast<int64_t>(b) * kDnEntCap;
     for (int i = tid; i < (np * nbs) / 2; i += kDnThreads) reinterpret_cast<unsigned int*>(sLook)[i] = 0u;
-    if (tid <= np) sSeg[tid] = D.pt_first[p0 + tid];
-    __syncthreads();
-    if (tid < 32) {
-      // exclusive scan of the capacities min(2 k_i, nb) (np <= kDnPtsCap = 2 per lane)
-      int c[kDnPtsCap / 32], tot = 0;
-#pragma unroll
-      for (int j = 0; j < kDnPtsCap / 32; ++j) {
-        const int p = tid * (kDnPtsCap / 32) + j;
-        c[j] = p < np ? min(2 * (sSeg[p + 1] - sSeg[p]), nb) : 0;
-        tot += c[j];
-      }
-      int incl = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= o) incl += v;
-      }
-      int run = incl - tot;
-#pragma unroll
-      for (int j = 0; j < kDnPtsCap / 32; ++j) {
-        const int p = tid * (kDnPtsCap / 32) + j;
-        if (p <= np) sBase[p] = run;
-        run += c[j];
-      }
-      if (tid == 31 && np == kDnPtsCap) sBase[np] = run;
+    for (int i = tid; i < n_ent * ZG; i += kDnThreads) {
+      const int e = i / ZG, k = i - e * ZG;
+      sZ[e * ZS + k] = Zb[i];
     }
+    for (int e = tid; e < n_ent; e += kDnThreads) sEnt[e] = Eb[e];
     __syncthreads();
-    // ---- one thread per point: compact list of the camera blocks it touches; L with C^-1 = L L^T
-    if (tid < np) {
-      const int base = sBase[tid], cap = sBase[tid + 1] - base;
-      DBA_CHECK(base >= 0 && base + cap <= kDnEntCap);
-      int cnt = 0;
-      unsigned short* look = sLook + tid * nbs;
-      for (int o = sSeg[tid]; o < sSeg[tid + 1]; ++o) {
-        const int2 ab = D.obs_ab[o];
-#pragma unroll
-        for (int slot = 0; slot < 2; ++slot) {
-          const int blk = slot ? ab.y : ab.x;
-          if (blk < 0 || look[blk]) continue;
-          DBA_CHECK(blk < nb && cnt < cap);
-          look[blk] = static_cast<unsigned short>(++cnt);
-          sEnt[base + cnt - 1] = (static_cast<unsigned int>(tid) << 16) | static_cast<unsigned int>(blk);
-        }
-      }
-      for (int e = cnt; e < cap; ++e) sEnt[base + e] = 0xffffffffu;
-      const double* ci = W.cinv + 6 * static_cast<int64_t>(p0 + tid);
-      double l00 = 0.0, l10 = 0.0, l20 = 0.0, l11 = 0.0, l21 = 0.0, l22 = 0.0;
-      if (ci[0] > 0.0) {  // a point whose C was not positive definite carries C^-1 = 0 (flagged by k_point_prepare)
-        l00 = sqrt(ci[0]);
-        l10 = ci[1] / l00;
-        l20 = ci[2] / l00;
-        l11 = sqrt(fmax(ci[3] - l10 * l10, 0.0));
-        l21 = l11 > 0.0 ? (ci[4] - l20 * l10) / l11 : 0.0;
-        l22 = sqrt(fmax(ci[5] - l20 * l20 - l21 * l21, 0.0));
-      }
-      double* Lp = sL + tid * 6;
-      Lp[0] = l00; Lp[1] = l10; Lp[2] = l20; Lp[3] = l11; Lp[4] = l21; Lp[5] = l22;
-    }
-    __syncthreads();
-    // ---- one thread per (point, block) entry: Y = sum F^T E over the point's observations that use the
-    // block, Z = Y L.  41 % of the kernel's stall samples sit on these scattered plane loads, but both
-    // coalesced alternatives measured 2x slower on arc1m (0.77 -> 1.5 ms): one thread per observation with
-    // W = F^T E in registers and ordered accumulation rounds, block-wide (a barrier per round) or per warp
-    // over runs of whole points (__syncwarp per round) — next to the 36 pair accumulators the 36 doubles of
-    // W do not fit 128 registers and are re-read from local memory in every round.
-    const int n_ent = sBase[np];
     for (int e = tid; e < n_ent; e += kDnThreads) {
       const unsigned int ent = sEnt[e];
-      if (ent == 0xffffffffu) continue;
-      const int pt = ent >> 16, blk = ent & 0xffffu;
-      double y[CB][3];
-#pragma unroll
-      for (int i = 0; i < CB; ++i) y[i][0] = y[i][1] = y[i][2] = 0.0;
-      for (int o = sSeg[pt]; o < sSeg[pt + 1]; ++o) {
-        const int2 ab = D.obs_ab[o];
-        const bool is_a = ab.x == blk;
-        if (!is_a && ab.y != blk) continue;
-        const double2* J = D.J + o;
-        const double2 e0 = J[(kPlaneJp + 0) * ld], e1 = J[(kPlaneJp + 1) * ld], e2 = J[(kPlaneJp + 2) * ld];
-        const int base_pl = is_a ? kPlaneJA : kPlaneJA + CB;
-#pragma unroll
-        for (int i = 0; i < CB; ++i) {
-          if (i < 6 || is_a) {
-            const double2 F = J[(base_pl + i) * ld];
-            y[i][0] += F.x * e0.x + F.y * e0.y;
-            y[i][1] += F.x * e1.x + F.y * e1.y;
-            y[i][2] += F.x * e2.x + F.y * e2.y;
-          }
-        }
-      }
-      const double* Lp = sL + pt * 6;
-      const double l00 = Lp[0], l10 = Lp[1], l20 = Lp[2], l11 = Lp[3], l21 = Lp[4], l22 = Lp[5];
-      double* z = sZ + e * ZS;
-#pragma unroll
-      for (int i = 0; i < CB; ++i) {
-        z[3 * i + 0] = y[i][0] * l00 + y[i][1] * l10 + y[i][2] * l20;
-        z[3 * i + 1] = y[i][1] * l11 + y[i][2] * l21;
-        z[3 * i + 2] = y[i][2] * l22;
-      }
+      DBA_CHECK((ent >> 16) < static_cast<unsigned int>(np) && (ent & 0xffffu) < static_cast<unsigned int>(nb));
+      sLook[(ent >> 16) * nbs + (ent & 0xffffu)] = static_cast<unsigned short>(e + 1);
     }
     __syncthreads();
-    // ---- the pair threads: S_AB -= Z_A Z_B^T  (F^T F is added by k_dense_combine from the camera gather
-    // and the camera-pair gather: adding it here would run one lane per matching observation)
     if (has_pair) {
       for (int p = 0; p < np; ++p) {
         const int ia = sLook[p * nbs + A];
         if (!ia) continue;
         const int ib = (A == B) ? ia : sLook[p * nbs + B];
         if (!ib) continue;
-        DBA_CHECK(sBase[p] + ia - 1 < sBase[p + 1] && sBase[p] + ib - 1 < sBase[p + 1]);
-        const double* za = sZ + (sBase[p] + ia - 1) * ZS;
-        const double* zb = sZ + (sBase[p] + ib - 1) * ZS;
+        const double* za = sZ + (ia - 1) * ZS;
+        const double* zb = sZ + (ib - 1) * ZS;
         double a[3 * CB];
 #pragma unroll
         for (int k = 0; k < 3 * CB; ++k) a[k] = za[k];
@@ -539,11 +695,13 @@ static int launch_schur_dense_t(const DeviceProblem& D, const WorkArrays& W, con
   cudaGetDevice(&dev);
   if (!(configured & (1ull << (dev & 63)))) {
     configured |= 1ull << (dev & 63);
-    cudaFuncSetAttribute(k_schur_dense<CB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dense_pairs<CB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dense_z<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   }
   const int groups = (Q.n_pairs + kDnThreads - 1) / kDnThreads;
   const int slices = dense_slices(Q);
-  k_schur_dense<CB, MINB><<<dim3(slices, groups), kDnThreads, smem, st>>>(D, W, Q);
+  if (Q.n_batches > 0) k_dense_z<CB><<<Q.n_batches, kDnThreads, DzSmem::bytes(D.n_blocks, CB), st>>>(D, W, Q);
+  k_dense_pairs<CB, MINB><<<dim3(slices, groups), kDnThreads, smem, st>>>(D, Q);
   if (Q.n_pair_chunks > 0) k_pair_gather<<<Q.n_pair_chunks, 128, 0, st>>>(D, Q);
   const int64_t total = static_cast<int64_t>(Q.n_pairs) * CB * CB;
   k_dense_combine<CB><<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(Q, W.cam_acc, add_diag, D.n_blocks, slices);

@@ -167,7 +167,9 @@ struct dba_handle {
   DenseWork Q{};
   DevBuf<int> d_dn_batch, d_dn_pair_entries, d_dn_pair_chunk_first;
   DevBuf<int4> d_dn_pair_chunks;
-  DevBuf<double> d_dn_S, d_dn_Spart, d_dn_pair_acc;
+  DevBuf<double> d_dn_S, d_dn_Spart, d_dn_pair_acc, d_dn_Z;
+  DevBuf<unsigned int> d_dn_Zent;
+  DevBuf<int> d_dn_Zcount;
   int dense_failures = 0, pcg_unconverged = 0;  // per dba_solve
   double* h_scalars = nullptr;  // pinned
   int* h_pcg_state = nullptr;   // pinned
@@ -547,7 +549,7 @@ int ensure_work_buffers(dba_handle* h, const BuildSizes& z) {
   const size_t n_part = static_cast<size_t>((nl + 255) / 256) + 3 * static_cast<size_t>(n_tiles) + 3 +
                         2 * static_cast<size_t>((3 * static_cast<int64_t>(n_pts) + 255) / 256) + 256;
   CU(h, ensure(h->d_partA, n_part));
-  CU(h, ensure(h->d_partB, 3 * static_cast<size_t>((std::max(n_ext, n_intr) + 63) / 64) + 64));
+  CU(h, ensure(h->d_partB, 3 * static_cast<size_t>((std::max(n_ext, n_intr) + 5) / 6) + 64));  // k_camera_finalize: 7 or 10 blocks per CTA
   CU(h, ensure(h->d_scalars, S_TOTAL));
   CU(h, ensure(h->d_scalars_red, S_TOTAL));
   CU(h, ensure(h->d_pcg_scal, 8));
@@ -891,8 +893,16 @@ int dense_solve(dba_handle* h, int* iters_out) {
   const int n = D.n_blocks * h->cb;
   const int nplanes = 3 + h->cb + (h->two ? 6 : 0);
   CU(h, cudaMemsetAsync(h->W.pcg_state, 0, 4 * sizeof(int), h->st));
+  if (!h->Q.Z && h->Q.n_batches > 0) {  // the Z image exists only for handles that solve densely
+    CU(h, ensure(h->d_dn_Z, static_cast<size_t>(h->Q.n_batches) * kDnEntCap * 3 * h->cb));
+    CU(h, ensure(h->d_dn_Zent, static_cast<size_t>(h->Q.n_batches) * kDnEntCap));
+    CU(h, ensure(h->d_dn_Zcount, static_cast<size_t>(h->Q.n_batches)));
+    h->Q.Z = h->d_dn_Z.p;
+    h->Q.Zent = h->d_dn_Zent.p;
+    h->Q.Zcount = h->d_dn_Zcount.p;
+  }
   {
-    Scope s(h, "schur_dense", 16.0 * nplanes * static_cast<double>(h->n_obs), h->Q.n_pair_chunks > 0 ? 3 : 2);
+    Scope s(h, "schur_dense", 16.0 * nplanes * static_cast<double>(h->n_obs), h->Q.n_pair_chunks > 0 ? 4 : 3);
     if (launch_schur_dense(D, h->W, h->Q, /*add_diag=*/h->rank == 0 ? 1 : 0, h->st) != 0) return h->fail(DBA_ERR_UNSUPPORTED, "dense reduced system: unsupported camera block");
   }
   int rc = allreduce(h, h->Q.S, static_cast<size_t>(n) * n, kNcclSum);

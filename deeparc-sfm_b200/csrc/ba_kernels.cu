@@ -721,16 +721,21 @@ __global__ void k_camera_scales(DeviceProblem D, WorkArrays W) {
   }
 }
 
-// One thread per camera block: D_c^2 = clamp(diag F^T F)/radius, M = B + D_c^2, M^-1 by
-// Cholesky, camera part of the gradient norms.
+// CB threads per camera block (thread c owns column c of the inverse): D_c^2 = clamp(diag F^T F)/radius,
+// M = B + D_c^2, Cholesky of M (every thread of the block's group, redundantly: 165 flops), M^-1 = L^-T L^-1
+// column c, camera part of the gradient norms (thread 0 of the group).  The kernel is one serial chain per
+// thread and replicated on every rank: a column per thread makes the chain 4x shorter than a camera per thread.
+constexpr int kFinThreads = 64;
 template <int CB, bool MINV>
-__global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArrays W, double radius, double min_diag,
-                                                         double max_diag, double* __restrict__ partials) {
+__global__ void __launch_bounds__(kFinThreads) k_camera_finalize(DeviceProblem D, WorkArrays W, double radius, double min_diag,
+                                                                  double max_diag, double* __restrict__ partials) {
+  constexpr int kCams = kFinThreads / CB;  // camera blocks per CTA
   __shared__ double red[32];
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int grp = threadIdx.x / CB, c = threadIdx.x - grp * CB;
+  const int b = blockIdx.x * kCams + grp;
   const int nb = D.n_blocks;
   double gsq = 0.0, gmax = 0.0, bad = 0.0;
-  if (b < nb) {
+  if (grp < kCams && b < nb) {
     const double* Bm = W.cam_acc + static_cast<int64_t>(b) * CB * CB;
     const double* diagF = W.cam_acc + static_cast<int64_t>(nb) * CB * CB + static_cast<int64_t>(b) * CB;
     const double* gc = diagF + static_cast<int64_t>(nb) * CB;
@@ -738,41 +743,40 @@ __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArr
 #pragma unroll
     for (int i = 0; i < CB; ++i) {
       const double d2 = fmin(fmax(diagF[i], min_diag), max_diag) / radius;
-      W.dc2[static_cast<int64_t>(b) * CB + i] = d2;
+      if (c == 0) {
+        W.dc2[static_cast<int64_t>(b) * CB + i] = d2;
+        const double g = gc[i] / W.sc[static_cast<int64_t>(b) * CB + i];
+        gsq += g * g;
+        gmax = fmax(gmax, fabs(g));
+      }
 #pragma unroll
       for (int j = 0; j < CB; ++j) L[i][j] = Bm[i * CB + j] + (i == j ? d2 : 0.0);
-      const double g = gc[i] / W.sc[static_cast<int64_t>(b) * CB + i];
-      gsq += g * g;
-      gmax = fmax(gmax, fabs(g));
     }
-    // in-place lower Cholesky
-    bool ok = true;
     if (MINV) {
+      // in-place lower Cholesky
+      bool ok = true;
 #pragma unroll
-    for (int j = 0; j < CB; ++j) {
-      double d = L[j][j];
+      for (int j = 0; j < CB; ++j) {
+        double d = L[j][j];
 #pragma unroll
-      for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
-      if (!(d > 0.0)) {
-        ok = false;
-        d = 1.0;
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        if (!(d > 0.0)) {
+          ok = false;
+          d = 1.0;
+        }
+        d = sqrt(d);
+        L[j][j] = d;
+        const double id = 1.0 / d;
+#pragma unroll
+        for (int i = j + 1; i < CB; ++i) {
+          double s = L[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+          L[i][j] = s * id;
+        }
       }
-      d = sqrt(d);
-      L[j][j] = d;
-      const double id = 1.0 / d;
-#pragma unroll
-      for (int i = j + 1; i < CB; ++i) {
-        double s = L[i][j];
-#pragma unroll
-        for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-        L[i][j] = s * id;
-      }
-    }
-    if (!ok) bad = 1.0;
-    // M^-1 = L^-T L^-1, column by column
-    double* Mi = W.minv + static_cast<int64_t>(b) * CB * CB;
-#pragma unroll
-    for (int c = 0; c < CB; ++c) {
+      if (!ok && c == 0) bad = 1.0;
+      // column c of M^-1 = L^-T L^-1
       double y[CB];
 #pragma unroll
       for (int i = 0; i < CB; ++i) {
@@ -788,9 +792,9 @@ __global__ void __launch_bounds__(64) k_camera_finalize(DeviceProblem D, WorkArr
         for (int k = i + 1; k < CB; ++k) s -= L[k][i] * y[k];
         y[i] = s / L[i][i];
       }
+      double* Mi = W.minv + static_cast<int64_t>(b) * CB * CB;
 #pragma unroll
       for (int i = 0; i < CB; ++i) Mi[i * CB + c] = ok ? y[i] : (i == c ? 1.0 : 0.0);
-    }
     }
   }
   gsq = block_sum(gsq, red);
@@ -2423,18 +2427,21 @@ void launch_camera_scales(const DeviceProblem& D, const WorkArrays& W, cudaStrea
   k_camera_scales<<<(n + 255) / 256, 256, 0, st>>>(D, W);
 }
 
-int camera_finalize_grid(const DeviceProblem& D) { return (D.n_blocks + 63) / 64; }
+int camera_finalize_grid(const DeviceProblem& D) {
+  const int per_cta = kFinThreads / (D.cb > 0 ? D.cb : 6);
+  return (D.n_blocks + per_cta - 1) / per_cta;
+}
 
 void launch_camera_finalize(const DeviceProblem& D, const WorkArrays& W, double radius, double min_diag,
                             double max_diag, double* partials, int with_minv, cudaStream_t st) {
   if (D.cb == 0 || D.n_blocks == 0) return;
   const int grid = camera_finalize_grid(D);
   if (D.cb == 6) {
-    if (with_minv) k_camera_finalize<6, true><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
-    else k_camera_finalize<6, false><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+    if (with_minv) k_camera_finalize<6, true><<<grid, kFinThreads, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+    else k_camera_finalize<6, false><<<grid, kFinThreads, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
   } else {
-    if (with_minv) k_camera_finalize<9, true><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
-    else k_camera_finalize<9, false><<<grid, 64, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+    if (with_minv) k_camera_finalize<9, true><<<grid, kFinThreads, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
+    else k_camera_finalize<9, false><<<grid, kFinThreads, 0, st>>>(D, W, radius, min_diag, max_diag, partials);
   }
 }
 

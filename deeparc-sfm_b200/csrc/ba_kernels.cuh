@@ -178,6 +178,9 @@ struct DenseWork {
                                   // min(2 k_i, n_blocks) over a batch <= kDnEntCap, points <= kDnPtsCap)
   int n_batches = 0;
   int n_pairs = 0;                // n_blocks (n_blocks + 1) / 2 camera-block pairs A <= B
+  double* Z = nullptr;            // [n_batches][kDnEntCap][3 cb] Z entries of each batch, compacted (k_dense_z -> k_dense_pairs)
+  unsigned int* Zent = nullptr;   // [n_batches][kDnEntCap] entry -> (point in batch << 16 | block)
+  int* Zcount = nullptr;          // [n_batches] entries of each batch
   double* S_part = nullptr;       // [slices][n_pairs][cb * cb]
   double* S = nullptr;            // [n][n] reduced matrix without D_c^2, then its Cholesky factor (lower)
   int* fail_flag = nullptr;       // set to 1 when a pivot is not positive
