@@ -598,19 +598,28 @@ __global__ void __launch_bounds__(kChThreads, 1) k_dense_cholesky(double* __rest
   if (tid < n) x[tid] = sy[tid];
 }
 
-// Small systems (the whole augmented matrix fits in shared memory: n <= kChSmallMax): right-looking
-// L D L^T without square roots, one block barrier per elimination step.  Row n is the right-hand
-// side, so its multipliers are w = D^-1 L^-1 rhs; then the column-oriented back substitution
-// L^T x = w.  Same step as the Cholesky path up to rounding.
+// Small systems (the whole augmented matrix fits in shared memory: n <= kChSmallMax): blocked right-looking
+// L D L^T without square roots, panels of 8 columns.  Row n is the right-hand side, so its multipliers are
+// w = D^-1 L^-1 rhs; then the column-oriented back substitution L^T x = w.  Same step as the Cholesky path up
+// to rounding.  The kernel is ONE SM running a chain of dependent steps, so what counts is the length of the
+// chain, not the flops: per panel every thread factors the 8 x 8 diagonal block by itself in registers (85
+// multiply-adds, no communication) and solves its own row against it, then one rank-8 update of the trailing
+// block in 4 x 4 register tiles — two block barriers per panel, 2 n / 8 in all, and the matrix passes through
+// shared memory once per panel.  (The unblocked version — a barrier and a read-modify-write of the whole
+// trailing block per column — took 156 us for n = 114.)
 constexpr int kChSmallMax = 152;
-constexpr int kChSmallThreads = 256;  // block barriers dominate this kernel: 8 warps synchronise much faster than 32
+constexpr int kChSmallThreads = 256;
+constexpr int kLdNB = 8;
+constexpr int kLdPS = kLdNB + 1;  // odd row stride of the panel buffers
 __global__ void __launch_bounds__(kChSmallThreads, 1) k_dense_ldlt_small(const double* __restrict__ S, int n, const double* __restrict__ dc2,
                                                                      const double* __restrict__ rhs, double* __restrict__ x,
                                                                      int* __restrict__ fail_flag) {
   extern __shared__ __align__(16) unsigned char smem_ch[];
   const int ldm = n | 1;  // odd row stride: a column walk touches every bank
-  double* A = reinterpret_cast<double*>(smem_ch);  // [n + 1][ldm] lower triangle + rhs row
-  double* sw = A + static_cast<size_t>(n + 1) * ldm;  // [n] w, then x
+  double* A = reinterpret_cast<double*>(smem_ch);          // [n + 1][ldm] lower triangle + rhs row; column k ends as l_rk d_k
+  double* sw = A + static_cast<size_t>(n + 1) * ldm;       // [n] w, then x
+  double* sP = sw + n;                                     // [n + 1][kLdPS] multipliers l_rc of the current panel
+  double* sQ = sP + static_cast<size_t>(n + 1) * kLdPS;    // [n + 1][kLdPS] l_rc d_c of the current panel
   __shared__ int s_ok;
   const int tid = threadIdx.x;
   if (tid == 0) s_ok = 1;
@@ -620,41 +629,99 @@ __global__ void __launch_bounds__(kChSmallThreads, 1) k_dense_ldlt_small(const d
   }
   if (tid < n) A[n * ldm + tid] = rhs[tid];
   __syncthreads();
-  // the trailing block of a step is walked in (threads / 32) x 32 thread tiles: warp ty owns rows k+1+ty (+8, ...),
-  // lane tx columns k+1+tx (+32, ...) up to the diagonal; loads of a row pass are issued together
-  const int tx = tid & 31, ty = tid >> 5;
-  constexpr int kSeg = (kChSmallMax + 31) / 32;
-  for (int k = 0; k < n; ++k) {
-    const double d = A[k * ldm + k];
-    if (!(d > 0.0)) {  // uniform: every thread reads the same pivot
-      if (tid == 0) s_ok = 0;
-      break;
+  bool ok = true;
+  for (int k0 = 0; k0 < n; k0 += kLdNB) {
+    const int w = min(kLdNB, n - k0);
+    // ---- the diagonal block, factored by every thread in registers (padded with the identity beyond w)
+    double B[kLdNB][kLdNB], inv[kLdNB];
+#pragma unroll
+    for (int i = 0; i < kLdNB; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) B[i][j] = (i < w) ? A[(k0 + i) * ldm + k0 + j] : (i == j ? 1.0 : 0.0);
+#pragma unroll
+    for (int c = 0; c < kLdNB; ++c) {
+      const double d = B[c][c];
+      if (!(d > 0.0)) ok = false;
+      double iv;
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(iv) : "d"(d));
+      iv = iv * (2.0 - d * iv);
+      iv = iv * (2.0 - d * iv);
+      inv[c] = iv;
+#pragma unroll
+      for (int i = c + 1; i < kLdNB; ++i) {
+        const double l = B[i][c] * iv;
+#pragma unroll
+        for (int j = c + 1; j <= i; ++j) B[i][j] = fma(-l, B[j][c], B[i][j]);
+      }
     }
-    double inv;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(inv) : "d"(d));
-    inv = inv * (2.0 - d * inv);
-    inv = inv * (2.0 - d * inv);
-    for (int r = k + 1 + ty; r <= n; r += kChSmallThreads / 32) {
-      const double lrk = A[r * ldm + k] * inv;
-      const int jmax = min(r, n - 1);
-      double av[kSeg], cv[kSeg];
+    if (!ok) break;  // uniform: every thread factors the same block
+    // ---- this thread's row against the block: a'_rc = a_rc - sum_{m<c} l_rm a'_{cm},  l_rc = a'_rc / d_c
+    const int r = k0 + w + tid;  // rows below the block (the block's own rows are B itself)
+    if (r <= n) {
+      double a[kLdNB], l[kLdNB];
 #pragma unroll
-      for (int t = 0; t < kSeg; ++t) {
-        const int j = k + 1 + tx + 32 * t;
-        if (k + 1 + 32 * t <= jmax) {  // warp-uniform
-          const bool in = j <= jmax;
-          av[t] = in ? A[r * ldm + j] : 0.0;
-          cv[t] = in ? A[j * ldm + k] : 0.0;
+      for (int c = 0; c < kLdNB; ++c) a[c] = c < w ? A[r * ldm + k0 + c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < kLdNB; ++c) {
+        double v = a[c];
+#pragma unroll
+        for (int m = 0; m < c; ++m) v = fma(-l[m], B[c][m], v);
+        a[c] = v;
+        l[c] = v * inv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < kLdNB; ++c) {
+        if (c < w) A[r * ldm + k0 + c] = a[c];
+        sP[r * kLdPS + c] = l[c];
+        sQ[r * kLdPS + c] = a[c];
+      }
+    }
+    if (tid < w) {  // the block's own rows: updated entries back into A (row k0 + tid, columns k0 .. k0 + tid)
+#pragma unroll
+      for (int i = 0; i < kLdNB; ++i)
+        if (i == tid) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) A[(k0 + i) * ldm + k0 + j] = B[i][j];
         }
+    }
+    __syncthreads();
+    // ---- rank-w update of the trailing block (rows k0 + w .. n, columns k0 + w .. min(row, n - 1)), 4 x 4 tiles
+    const int base = k0 + w, m = n + 1 - base;  // trailing rows (the right-hand side row included)
+    const int mt = (m + 3) >> 2, n_tiles = mt * (mt + 1) / 2;
+    for (int t = tid; t < n_tiles; t += kChSmallThreads) {
+      int tr = static_cast<int>((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+      while ((tr + 1) * (tr + 2) / 2 <= t) ++tr;
+      while (tr * (tr + 1) / 2 > t) --tr;
+      const int tj = t - tr * (tr + 1) / 2;
+      const int r0 = base + 4 * tr, j0 = base + 4 * tj;
+      double acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll
+      for (int c = 0; c < kLdNB; ++c) {
+        double lr[4], qj[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lr[i] = (r0 + i <= n) ? sP[(r0 + i) * kLdPS + c] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) qj[j] = (j0 + j < n) ? sQ[(j0 + j) * kLdPS + c] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(lr[i], qj[j], acc[i][j]);
       }
 #pragma unroll
-      for (int t = 0; t < kSeg; ++t) {
-        const int j = k + 1 + tx + 32 * t;
-        if (k + 1 + 32 * t <= jmax && j <= jmax) A[r * ldm + j] = fma(-lrk, cv[t], av[t]);
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int rr = r0 + i, jj = j0 + j;
+          if (rr <= n && jj < n && jj <= rr) A[rr * ldm + jj] -= acc[i][j];
+        }
     }
     __syncthreads();
   }
+  if (!ok && tid == 0) s_ok = 0;
   __syncthreads();
   if (!s_ok) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
@@ -662,7 +729,8 @@ __global__ void __launch_bounds__(kChSmallThreads, 1) k_dense_ldlt_small(const d
     if (tid == 0 && fail_flag) *fail_flag = 1;
     return;
   }
-  // w_k = A[n][k] / d_k; back substitution with unit-lower L: l_ki = A[k][i] / d_i
+  // w_k = A[n][k] / d_k; back substitution with unit-lower L: l_ki = A[k][i] / d_i  (one barrier per unknown;
+  // eight unknowns per barrier with the 8 x 8 triangle solved by every thread measured slower: 68 vs 62 us)
   double v = 0.0, inv_i = 0.0;
   if (tid < n) {
     inv_i = 1.0 / A[tid * ldm + tid];
@@ -725,11 +793,11 @@ int launch_dense_cholesky(const DeviceProblem& D, const WorkArrays& W, const Den
   if (!(configured & (1ull << (dev & 63)))) {
     configured |= 1ull << (dev & 63);
     cudaFuncSetAttribute(k_dense_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_dense_ldlt_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_dense_ldlt_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);  // (+ 1 KB static <= 227 KB)
   }
   const double* rhs = W.cam_acc + static_cast<int64_t>(D.n_blocks) * D.cb * D.cb + 2 * static_cast<int64_t>(n);
   if (n <= kChSmallMax) {
-    const size_t small = sizeof(double) * (static_cast<size_t>(n + 1) * (n | 1) + n);
+    const size_t small = sizeof(double) * (static_cast<size_t>(n + 1) * (n | 1) + n + 2 * static_cast<size_t>(n + 1) * 9);
     k_dense_ldlt_small<<<1, kChSmallThreads, small, st>>>(Q.S, n, W.dc2, rhs, W.x, Q.fail_flag);
     return 0;
   }
