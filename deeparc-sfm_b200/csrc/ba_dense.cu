@@ -437,6 +437,10 @@ __global__ void __launch_bounds__(256) k_dense_combine(DenseWork Q, const double
 // One CTA of 1024 threads, thread t <-> row j0 + t of the current panel (panel width 16).  Row n is
 // the right-hand side, so after the last panel it holds y = L^-1 rhs.  The factor overwrites the
 // lower triangle of S.
+// (Measured and not kept: the right-looking panel scheme of k_dense_ldlt_small — diagonal block factored per thread
+// in registers, rank-8 trailing update in 4 x 4 tiles — on the L2-resident matrix: every panel then pays two round
+// trips to L2 per tile, n = 306: 0.60 ms against 0.48 ms for this left-looking version.  The matrix has to sit in
+// shared memory for that scheme to pay: beyond n = 152 that takes a thread-block cluster.)
 constexpr int kChNB = 16;
 constexpr int kChLS = 18;  // row stride of the staged panel rows: 16-byte aligned rows, spread over the banks
 constexpr int kChThreads = 1024;
