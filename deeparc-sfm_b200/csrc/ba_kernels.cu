@@ -2325,9 +2325,32 @@ static bool jac_tiled() {
 }
 int jacobian_partials(const DeviceProblem& D) { return (jac_tiled() && D.obs_lc) ? D.n_tiles : cost_grid(D); }
 
+// the variant without camera planes (points-only solves, plane-less matrix-free solves) is light enough for more
+// resident CTAs, and the kernel is bound by waves x depth of its load chain (DBA_JAC0_MINB = 3..8; measured on
+// bal5m: 3: 206 us, 4: 168 us)
+static int jac0_minb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("DBA_JAC0_MINB");
+    v = e ? std::atoi(e) : 4;
+    if (v != 3 && v != 4 && v != 5 && v != 6 && v != 8) v = 4;
+  }
+  return v;
+}
 template <int CB, bool TWO>
 static void launch_jacobian_t(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, int unit_scale, double* partial_cost,
                               cudaStream_t st) {
+  if constexpr (CB == 0) {
+    if (jac_tiled() && D.obs_lc) {
+      switch (jac0_minb()) {
+        case 3: k_jacobian_tile<0, false, 3><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost); return;
+        case 5: k_jacobian_tile<0, false, 5><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost); return;
+        case 6: k_jacobian_tile<0, false, 6><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost); return;
+        case 8: k_jacobian_tile<0, false, 8><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost); return;
+        default: k_jacobian_tile<0, false, 4><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost); return;
+      }
+    }
+  }
   if (jac_tiled() && D.obs_lc) {
     const int mb = jac_minb();
     if (mb == 2) k_jacobian_tile<CB, TWO, 2><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost);
@@ -2385,7 +2408,13 @@ void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double ra
   using std::integral_constant;
   if (D.tile == 256) go(integral_constant<int, 256>(), integral_constant<int, 1>());
   else if (D.tile == 512) {
-    if (tile_minb() == 3) go(integral_constant<int, 512>(), integral_constant<int, 3>());
+    static int prep4 = -1;  // four resident 512-thread CTAs (32 registers, 120 B of spills): 131 vs 139 us on bal5m (DBA_PREP_MINB=3 restores three)
+    if (prep4 < 0) {
+      const char* e = std::getenv("DBA_PREP_MINB");
+      prep4 = (e && std::atoi(e) != 4) ? 0 : 1;
+    }
+    if (prep4) go(integral_constant<int, 512>(), integral_constant<int, 4>());
+    else if (tile_minb() == 3) go(integral_constant<int, 512>(), integral_constant<int, 3>());
     else go(integral_constant<int, 512>(), integral_constant<int, 2>());
   } else go(integral_constant<int, 1024>(), integral_constant<int, 1>());
 }
