@@ -2314,17 +2314,33 @@ static int jac_minb() {
   }
   return v;
 }
-// DBA_JAC=flat keeps the one-thread-per-observation kernel that gathers from the global tables
-static bool jac_tiled() {
+// Tiled (camera rows of the tile staged in shared memory) or flat (one thread per observation, gathers from the
+// global tables) Jacobian kernel.  The staging pays when a warp's 32 observations would hit 32 different rows of a
+// table that does not fit L1; with a few dozen pose blocks (the reference's rigs: 19) the tables ARE L1-resident
+// and the flat kernel wins (arc1m: 90 vs 115 us).  DBA_JAC=flat|tiled forces either.
+static bool jac_tiled(const DeviceProblem& D) {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("DBA_JAC");
-    v = (e && std::strcmp(e, "flat") == 0) ? 0 : 1;
+    v = (e && std::strcmp(e, "flat") == 0) ? 0 : ((e && std::strcmp(e, "tiled") == 0) ? 1 : 2);
   }
-  return v != 0;
+  if (!D.obs_lc) return false;
+  return v == 2 ? D.n_ext > 64 : v != 0;
 }
-int jacobian_partials(const DeviceProblem& D) { return (jac_tiled() && D.obs_lc) ? D.n_tiles : cost_grid(D); }
+int jacobian_partials(const DeviceProblem& D) { return jac_tiled(D) ? D.n_tiles : cost_grid(D); }
 
+// resident 256-thread CTAs per SM of the per-tile kernels on 256-observation tiles (the reference's rigs):
+// DBA_TILE256_MINB = 1 (whatever the register allocator takes: 2-3 CTAs) | 4 (64 registers) | 6 (40).
+// Measured on arc1m: k_point_prepare 69 / 43 / 37 us, k_back_substitute 62 / 61 / 67 us -> defaults 6 and 4.
+static int tile256_minb(int dflt) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("DBA_TILE256_MINB");
+    v = e ? std::atoi(e) : 0;
+    if (v != 1 && v != 4 && v != 6) v = 0;
+  }
+  return v ? v : dflt;
+}
 // the variant without camera planes (points-only solves, plane-less matrix-free solves) is light enough for more
 // resident CTAs, and the kernel is bound by waves x depth of its load chain (DBA_JAC0_MINB = 3..8; measured on
 // bal5m: 3: 206 us, 4: 168 us)
@@ -2341,7 +2357,7 @@ template <int CB, bool TWO>
 static void launch_jacobian_t(const DeviceProblem& D, const ParamSet& P, const WorkArrays& W, int unit_scale, double* partial_cost,
                               cudaStream_t st) {
   if constexpr (CB == 0) {
-    if (jac_tiled() && D.obs_lc) {
+    if (jac_tiled(D)) {
       switch (jac0_minb()) {
         case 3: k_jacobian_tile<0, false, 3><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost); return;
         case 5: k_jacobian_tile<0, false, 5><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost); return;
@@ -2351,7 +2367,7 @@ static void launch_jacobian_t(const DeviceProblem& D, const ParamSet& P, const W
       }
     }
   }
-  if (jac_tiled() && D.obs_lc) {
+  if (jac_tiled(D)) {
     const int mb = jac_minb();
     if (mb == 2) k_jacobian_tile<CB, TWO, 2><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost);
     else if (mb == 3) k_jacobian_tile<CB, TWO, 3><<<D.n_tiles, kJacThreads, 0, st>>>(D, P, W, unit_scale, D.intr_is_pose, partial_cost);
@@ -2406,7 +2422,12 @@ void launch_point_prepare(const DeviceProblem& D, const WorkArrays& W, double ra
     k_point_prepare<T, MB><<<D.n_tiles, T, smem, st>>>(D, W, radius, min_diag, max_diag, mode, partials);
   };
   using std::integral_constant;
-  if (D.tile == 256) go(integral_constant<int, 256>(), integral_constant<int, 1>());
+  if (D.tile == 256) {
+    const int mb = tile256_minb(6);
+    if (mb == 6) go(integral_constant<int, 256>(), integral_constant<int, 6>());
+    else if (mb == 4) go(integral_constant<int, 256>(), integral_constant<int, 4>());
+    else go(integral_constant<int, 256>(), integral_constant<int, 1>());
+  }
   else if (D.tile == 512) {
     static int prep4 = -1;  // four resident 512-thread CTAs (32 registers, 120 B of spills): 131 vs 139 us on bal5m (DBA_PREP_MINB=3 restores three)
     if (prep4 < 0) {
@@ -2669,7 +2690,12 @@ static void launch_back_substitute_t(const DeviceProblem& D, const WorkArrays& W
     k_back_substitute<CB, TWO, T, MB><<<D.n_tiles, T, smem, st>>>(D, W, partial_model);
   };
   using std::integral_constant;
-  if (D.tile == 256) go(integral_constant<int, 256>(), integral_constant<int, 1>());
+  if (D.tile == 256) {
+    const int mb = tile256_minb(4);
+    if (mb == 6) go(integral_constant<int, 256>(), integral_constant<int, 6>());
+    else if (mb == 4) go(integral_constant<int, 256>(), integral_constant<int, 4>());
+    else go(integral_constant<int, 256>(), integral_constant<int, 1>());
+  }
   else if (D.tile == 512) {
     if (tile_minb() == 3) go(integral_constant<int, 512>(), integral_constant<int, 3>());
     else go(integral_constant<int, 512>(), integral_constant<int, 2>());
