@@ -51,7 +51,8 @@ struct DzSmem {
   static constexpr size_t oEnt = oCnt + sizeof(int) * (kDnPtsCap + 4);          // entry -> (point << 16 | block), 0xffffffff = unused
   static constexpr size_t oMul = oEnt + sizeof(unsigned int) * kDnEntCap;       // incidences seen so far of each entry
   static constexpr size_t oInc = oMul + sizeof(int) * kDnEntCap;                // (observation, slot) -> entry | rank << 16
-  static constexpr size_t oLook = oInc + sizeof(unsigned int) * 2 * kDnIncObs;  // [point][block] -> entry index + 1 within the point
+  static constexpr size_t oAB = oInc + sizeof(unsigned int) * 2 * kDnIncObs;    // (block a, block b) of the batch's observations
+  static constexpr size_t oLook = oAB + sizeof(int2) * kDnIncObs;               // [point][block] -> entry index + 1 within the point
   __host__ __device__ static size_t look_bytes(int nb) { return (sizeof(unsigned short) * kDnPtsCap * ((nb + 1) & ~1) + 15) / 16 * 16; }
   // + the Z tile [kDnEntCap][3 CB + 1] of the incidence path behind the lookup
   static size_t bytes(int nb, int cb) { return oLook + look_bytes(nb) + sizeof(double) * kDnEntCap * (3 * cb + 1); }
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(kDnThreads) k_dense_z(DeviceProblem D, WorkArr
   unsigned int* sEnt = reinterpret_cast<unsigned int*>(smem_dz + L::oEnt);
   int* sMul = reinterpret_cast<int*>(smem_dz + L::oMul);
   unsigned int* sInc = reinterpret_cast<unsigned int*>(smem_dz + L::oInc);
+  int2* sAB = reinterpret_cast<int2*>(smem_dz + L::oAB);
   unsigned short* sLook = reinterpret_cast<unsigned short*>(smem_dz + L::oLook);
   __shared__ int s_rounds;
   const int tid = threadIdx.x;
@@ -96,6 +98,13 @@ __global__ void __launch_bounds__(kDnThreads) k_dense_z(DeviceProblem D, WorkArr
   if (tid == 0) s_rounds = 0;
   if (tid <= np) sSeg[tid] = D.pt_first[p0 + tid];
   __syncthreads();
+  {
+    // the batch's (block a, block b) pairs in one coalesced pass: the per-point scan below then runs out of
+    // shared memory instead of a chain of dependent global loads per thread
+    const int o_first = sSeg[0], nob = sSeg[np] - o_first;
+    if (nob <= kDnIncObs)
+      for (int i = tid; i < nob; i += kDnThreads) sAB[i] = D.obs_ab[o_first + i];
+  }
   if (tid < 32) {
     // exclusive scan of the capacities min(2 k_i, nb) (np <= kDnPtsCap = 2 per lane)
     int c[kDnPtsCap / 32], tot = 0;
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(kDnThreads) k_dense_z(DeviceProblem D, WorkArr
     const int o_first = sSeg[0];
     const bool stage_inc = sSeg[np] - o_first <= kDnIncObs;
     for (int o = sSeg[tid]; o < sSeg[tid + 1]; ++o) {
-      const int2 ab = D.obs_ab[o];
+      const int2 ab = stage_inc ? sAB[o - o_first] : D.obs_ab[o];
 #pragma unroll
       for (int slot = 0; slot < 2; ++slot) {
         const int blk = slot ? ab.y : ab.x;
