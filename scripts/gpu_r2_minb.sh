@@ -14,8 +14,4 @@ print(sys.argv[2], "value", round(d["value"], 2), "jac", f("jacobian"), "prep", 
 PY
 }
 run default X=1
-run jac0_3 DBA_JAC0_MINB=3
-run jac0_5 DBA_JAC0_MINB=5
-run jac0_6 DBA_JAC0_MINB=6
-run jac0_8 DBA_JAC0_MINB=8
-run prep4 DBA_PREP_MINB=4
+run bsub3 DBA_BSUB_MINB=3
