@@ -252,3 +252,16 @@ def test_recomputed_front_half_equals_plane_reader(engine, monkeypatch, name, ls
     np.testing.assert_allclose(sb.trace("gradient_max_norm"), sa.trace("gradient_max_norm"), rtol=1e-9)
     for k in xa:
         np.testing.assert_allclose(xb[k], xa[k], rtol=1e-8, atol=1e-10, err_msg=k)
+
+
+@pytest.mark.parametrize("n_cam", [2, 3, 9, 25, 26, 33])
+def test_dense_factorisation_sizes(engine, oracle, n_cam):
+    """Reduced systems of 12, 18, 54, 150, 156 and 198 unknowns (6-dof poses, first pose constant by the
+    gauge rule of solve() where the generator says so): the blocked LDL^T of k_dense_ldlt_small with a full
+    panel + a short one, a whole number of panels + the right-hand-side row, its largest size
+    class (n <= 152), and the first sizes of k_dense_cholesky."""
+    p = synthetic.bal_like(n_cam=n_cam, n_pts=max(60, 12 * n_cam), obs_per_point=min(4, n_cam), window=min(8, n_cam),
+                           seed=100 + n_cam, free_intrinsics=0)
+    sg, so = _compare_solve(engine, oracle, p, n_iter=3, linear_solver=capi.DBA_LS_DENSE)
+    assert sg.linear_solver_used == capi.DBA_LS_DENSE and sg.linear_solver_failures == 0
+    np.testing.assert_allclose(sg.trace("cost"), so.trace("cost"), rtol=1e-9)
