@@ -2795,6 +2795,7 @@ int dba_params_get(dba_handle* h, double* pts, double* ext_rot, double* ext_tran
   if (pts) {
     // device -> pinned arena (one asynchronous copy at link rate) -> the caller's buffer (all host cores)
     const size_t total = 3 * static_cast<size_t>(h->world == 1 ? h->n_pts : h->n_pts_global);
+    OmpThreadScope omp_scope(h->world);  // several ranks on one host: cores / world threads each, not cores each
     arena_of(h);
     PinnedArena& A = h->upload->readback;
     CU(h, cudaStreamSynchronize(h->st));
