@@ -225,6 +225,9 @@ const char* dba_last_error(const dba_handle* h); /* h may be NULL: last create e
 /* Replaces the Problem construction loop of solve() (sfm.cc:36-65): copies the SoA
  * arrays to the device, validates indices, sorts observations by point, builds the
  * shard of this rank.  May be called again with a new problem on the same handle.
+ * Input that already is sorted by point and does not compose poses (obs_pose_b all -1) is
+ * staged shard by shard and indexed on the device; anything else is sorted and indexed by
+ * the host cores first.  Same structures, same results either way.
  * Limits (DBA_ERR_UNSUPPORTED beyond them; the reference has none): a point may carry at
  * most 1024 observations (512 when observations compose two poses and cameras are free) —
  * a point and its observations are processed by one thread block; fewer than 2^30
